@@ -1,0 +1,11 @@
+"""B200-native embedding + FM / cross hot path of the reference's Deep-CTR models.
+
+The directory name carries a hyphen (it mirrors the reference's name); import it with
+`importlib.import_module("details-in-recommendation_b200")` or through the alias module
+`dir_b200` at the repository root.
+"""
+from . import _lib, synth                                    # noqa: F401
+from ._lib import LIB_PATH, build, launch_count             # noqa: F401
+from .layers import CrossNetwork, EmbeddingFM               # noqa: F401
+
+__all__ = ["EmbeddingFM", "CrossNetwork", "synth", "build", "launch_count", "LIB_PATH"]

@@ -1,0 +1,446 @@
+// K4+K5: DCN-v1 cross stack  x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l,  all L layers in one pass.
+// One warp per sample; x0 and x_l live in registers (lane owns every 32nd VEC-wide group), the
+// per-layer "matvec" is a warp-shuffle dot product: rank-1, not a GEMM, so no tensor cores.
+// Forward reads x0 once and writes x_L once.
+//
+// Backward uses the rank-1 structure:  x_l = x0 * c_l + beta_l  with  c_l = 1 + sum_{j<l} s_j  (per
+// sample) and  beta_l = sum_{j<l} b_j  (per column), so with  ds_l = dx_{l+1} . x0 :
+//     dw_l = sum_b (ds_l c_l) x0  +  beta_l * sum_b ds_l
+//     db_l = sum_b dy  +  sum_{j>l} w_j * sum_b ds_j
+// No x_l is ever stored.  Batch sums are reduced in a fixed order (per-warp sequential, per-CTA
+// fixed order, per-CTA partials combined by one finishing kernel): deterministic, no float atomics.
+//
+// Reference: models/DeepCrossNetwork/DeepCrossNetwork.py:336-367 and TF autodiff of it (:283).
+#include "common.cuh"
+
+namespace dir {
+
+template <int VEC>
+struct Pack {
+  float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> ld_pack(const float* p, bool stream) {
+  Pack<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = stream ? ldg_stream(p) : __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_pack(float* p, const float* v) {
+  if constexpr (VEC == 4) {
+    stg_stream(p, make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    *p = v[0];
+  }
+}
+
+constexpr int kCrossWarps = 8;  // warps per CTA
+
+// ------------------------------------------------------------------------------ forward
+template <int VEC, int NPL>
+__global__ void __launch_bounds__(kCrossWarps * 32)
+cross_fwd_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
+                 const float* __restrict__ bg, int64_t B, int d, int L, float* __restrict__ xLg,
+                 float* __restrict__ sg) {
+  constexpr int E = VEC * NPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCrossWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kCrossWarps;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    float x0[E], xl[E];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      Pack<VEC> p{};
+      if (c < d) p = ld_pack<VEC>(x0g + b * d + c, true);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) x0[i * VEC + e] = xl[i * VEC + e] = (c < d) ? p.v[e] : 0.f;
+    }
+    for (int l = 0; l < L; ++l) {
+      float wv[E], bv[E];
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = (i * 32 + lane) * VEC;
+        Pack<VEC> pw{}, pb{};
+        if (c < d) {
+          pw = ld_pack<VEC>(wg + l * d + c, false);
+          pb = ld_pack<VEC>(bg + l * d + c, false);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          wv[i * VEC + e] = (c < d) ? pw.v[e] : 0.f;
+          bv[i * VEC + e] = (c < d) ? pb.v[e] : 0.f;
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) dot = fmaf(xl[e], wv[e], dot);
+      dot = warp_sum(dot);
+      // ((x0 * s) + b) + x : the reference's evaluation order (DeepCrossNetwork.py:346), unfused
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        xl[e] = __fadd_rn(__fadd_rn(__fmul_rn(x0[e], dot), bv[e]), xl[e]);
+      if (sg && lane == 0) sg[b * L + l] = dot;
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      if (c < d) st_pack<VEC>(xLg + b * d + c, &xl[i * VEC]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ backward
+struct CrossBwdWs {
+  float* alpha;   // [B][L]   ds_l * c_l
+  float* Dpart;   // [G1][L]  per-CTA sum_b ds_l
+  float* dypart;  // [G1][d]  per-CTA sum_b dy
+  float* dwpart;  // [G2][L][d] per-CTA sum_b alpha_l x0
+  int G1, G2;
+  size_t total;
+};
+
+static int cross_grid1(int64_t B) {
+  const int64_t want = (B + kCrossWarps - 1) / kCrossWarps;
+  const int64_t cap = kSMs * 4;
+  return (int)(want < cap ? want : cap);
+}
+static int cross_grid2(int64_t B) {
+  const int64_t want = (B + 31) / 32;
+  const int64_t cap = kSMs * 4;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static CrossBwdWs cross_carve(void* base, int64_t B, int d, int L) {
+  CrossBwdWs w;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return reinterpret_cast<float*>(r);
+  };
+  w.G1 = cross_grid1(B);
+  w.G2 = cross_grid2(B);
+  w.alpha = take((size_t)B * L * 4);
+  w.Dpart = take((size_t)w.G1 * L * 4);
+  w.dypart = take((size_t)w.G1 * d * 4);
+  w.dwpart = take((size_t)w.G2 * L * d * 4);
+  w.total = off;
+  return w;
+}
+
+// pass 1: per-sample sweep -> dx0, alpha, and per-CTA partials of sum ds_l and sum dy
+template <int VEC, int NPL>
+__global__ void __launch_bounds__(kCrossWarps * 32)
+cross_bwd_sample_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
+                        const float* __restrict__ bg, const float* __restrict__ dyg,
+                        const float* __restrict__ sg, int64_t B, int d, int L,
+                        float* __restrict__ dx0g, float* __restrict__ alpha,
+                        float* __restrict__ Dpart, float* __restrict__ dypart) {
+  constexpr int E = VEC * NPL;
+  extern __shared__ float smem[];  // [kCrossWarps][d] then [kCrossWarps][32]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCrossWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kCrossWarps;
+  float accDy[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) accDy[e] = 0.f;
+  float Dacc = 0.f;  // lane l: sum over this warp's samples of ds_l
+
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    float x0[E], dx[E], dx0[E];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      Pack<VEC> px{}, pd{};
+      if (c < d) {
+        px = ld_pack<VEC>(x0g + b * d + c, true);
+        pd = ld_pack<VEC>(dyg + b * d + c, true);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        x0[i * VEC + e] = (c < d) ? px.v[e] : 0.f;
+        dx[i * VEC + e] = (c < d) ? pd.v[e] : 0.f;
+        dx0[i * VEC + e] = 0.f;
+        accDy[i * VEC + e] += dx[i * VEC + e];
+      }
+    }
+    // s_l = x_l . w_l : lane l keeps s_l.  Saved by the forward, or recomputed here.
+    float s_mine = 0.f;
+    if (sg) {
+      if (lane < L) s_mine = __ldg(sg + b * L + lane);
+    } else {
+      float xl[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) xl[e] = x0[e];
+      for (int l = 0; l < L; ++l) {
+        float dot = 0.f;
+        float bv[E];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = (i * 32 + lane) * VEC;
+          Pack<VEC> pw{}, pb{};
+          if (c < d) {
+            pw = ld_pack<VEC>(wg + l * d + c, false);
+            pb = ld_pack<VEC>(bg + l * d + c, false);
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            dot = fmaf(xl[i * VEC + e], (c < d) ? pw.v[e] : 0.f, dot);
+            bv[i * VEC + e] = (c < d) ? pb.v[e] : 0.f;
+          }
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          xl[e] = __fadd_rn(__fadd_rn(__fmul_rn(x0[e], dot), bv[e]), xl[e]);
+        if (lane == l) s_mine = dot;
+      }
+    }
+    // c_l = 1 + sum_{j<l} s_j  (lane l keeps c_l)
+    float c_mine = 1.f;
+    for (int j = 0; j < L; ++j) {
+      const float sj = __shfl_sync(0xffffffffu, s_mine, j);
+      if (lane > j) c_mine += sj;
+    }
+    float alpha_mine = 0.f;
+    for (int l = L - 1; l >= 0; --l) {
+      const float s_l = __shfl_sync(0xffffffffu, s_mine, l);
+      const float c_l = __shfl_sync(0xffffffffu, c_mine, l);
+      float ds = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) ds = fmaf(dx[e], x0[e], ds);
+      ds = warp_sum(ds);
+      if (lane == l) {
+        alpha_mine = ds * c_l;
+        Dacc += ds;
+      }
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = (i * 32 + lane) * VEC;
+        Pack<VEC> pw{};
+        if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          dx0[i * VEC + e] = fmaf(dx[i * VEC + e], s_l, dx0[i * VEC + e]);
+          dx[i * VEC + e] = fmaf(ds, (c < d) ? pw.v[e] : 0.f, dx[i * VEC + e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      float o[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] = dx0[i * VEC + e] + dx[i * VEC + e];
+      if (c < d) st_pack<VEC>(dx0g + b * d + c, o);
+    }
+    if (lane < L) alpha[b * L + lane] = alpha_mine;
+  }
+
+  // per-CTA partials, warps added in warp order
+  float* sdy = smem;
+  float* sD = smem + kCrossWarps * d;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = (i * 32 + lane) * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      if (c + e < d) sdy[wib * d + c + e] = accDy[i * VEC + e];
+  }
+  sD[wib * 32 + lane] = Dacc;
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) t += sdy[w * d + c];
+    dypart[(int64_t)blockIdx.x * d + c] = t;
+  }
+  if (threadIdx.x < L) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) t += sD[w * 32 + threadIdx.x];
+    Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+  }
+}
+
+// pass 2: dwpart[cta][l][c] = sum over the CTA's samples of alpha[b][l] * x0[b][c]
+// thread = one column; samples in sample order.
+constexpr int kDwUnroll = 8;
+__global__ void __launch_bounds__(256)
+cross_bwd_dw_kernel(const float* __restrict__ x0g, const float* __restrict__ alpha, int64_t B,
+                    int d, int L, float* __restrict__ dwpart) {
+  extern __shared__ float sal[];  // alpha of the current sample block [kDwUnroll][L]
+  const int64_t per = (B + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = (int64_t)blockIdx.x * per;
+  const int64_t b1 = min(B, b0 + per);
+  for (int c0 = 0; c0 < d; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    float acc[8];  // L <= 8 per sweep
+    for (int l0 = 0; l0 < L; l0 += 8) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+      for (int64_t bb = b0; bb < b1; bb += kDwUnroll) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kDwUnroll * 8; t += blockDim.x) {
+          const int64_t b = bb + t / 8;
+          const int l = l0 + (t & 7);
+          sal[t] = (b < b1 && l < L) ? __ldg(alpha + b * L + l) : 0.f;
+        }
+        __syncthreads();
+        float xv[kDwUnroll];
+#pragma unroll
+        for (int j = 0; j < kDwUnroll; ++j)
+          xv[j] = (c < d && bb + j < b1) ? __ldg(x0g + (bb + j) * d + c) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kDwUnroll; ++j)
+#pragma unroll
+          for (int l = 0; l < 8; ++l) acc[l] = fmaf(sal[j * 8 + l], xv[j], acc[l]);
+      }
+      if (c < d)
+#pragma unroll
+        for (int l = 0; l < 8; ++l)
+          if (l0 + l < L) dwpart[((int64_t)blockIdx.x * L + l0 + l) * d + c] = acc[l];
+    }
+  }
+}
+
+// pass 3: fixed-order combine.  thread = one column c.
+__global__ void __launch_bounds__(256)
+cross_bwd_finish_kernel(const float* __restrict__ wg, const float* __restrict__ bg,
+                        const float* __restrict__ Dpart, const float* __restrict__ dypart,
+                        const float* __restrict__ dwpart, int G1, int G2, int d, int L,
+                        float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float sDl[];  // [L] sum_b ds_l
+  if (threadIdx.x < L) {
+    float t = 0.f;
+    for (int g = 0; g < G1; ++g) t += Dpart[(int64_t)g * L + threadIdx.x];
+    sDl[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float sumdy = 0.f;
+  for (int g = 0; g < G1; ++g) sumdy += dypart[(int64_t)g * d + c];
+  // db_l = sum dy + sum_{j>l} w_j D_j ; walk l downwards carrying the tail
+  float tail = 0.f;
+  for (int l = L - 1; l >= 0; --l) {
+    db[l * d + c] = sumdy + tail;
+    tail = fmaf(wg[l * d + c], sDl[l], tail);
+  }
+  // dw_l = sum alpha_l x0 + beta_l D_l ; beta_l = sum_{j<l} b_j
+  float beta = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float t = 0.f;
+    for (int g = 0; g < G2; ++g) t += dwpart[((int64_t)g * L + l) * d + c];
+    dw[l * d + c] = fmaf(beta, sDl[l], t);
+    beta += bg[l * d + c];
+  }
+}
+
+struct CrossShape {
+  int vec, npl;
+};
+static bool cross_shape(int d, CrossShape& s) {
+  if (d <= 0 || d > 1024) return false;
+  if ((d & 3) == 0) {
+    const int n = (d / 4 + 31) / 32;  // float4 per lane
+    s.vec = 4;
+    s.npl = n <= 6 ? n : 8;
+    return true;
+  }
+  const int n = (d + 31) / 32;
+  s.vec = 1;
+  s.npl = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32;
+  return true;
+}
+
+#define DIR_CROSS_DISPATCH(FN)                         \
+  if (sh.vec == 4) {                                   \
+    switch (sh.npl) {                                  \
+      case 1: FN(4, 1); break;                         \
+      case 2: FN(4, 2); break;                         \
+      case 3: FN(4, 3); break;                         \
+      case 4: FN(4, 4); break;                         \
+      case 5: FN(4, 5); break;                         \
+      case 6: FN(4, 6); break;                         \
+      default: FN(4, 8); break;                        \
+    }                                                  \
+  } else {                                             \
+    switch (sh.npl) {                                  \
+      case 1: FN(1, 1); break;                         \
+      case 2: FN(1, 2); break;                         \
+      case 4: FN(1, 4); break;                         \
+      case 8: FN(1, 8); break;                         \
+      case 16: FN(1, 16); break;                       \
+      default: FN(1, 32); break;                       \
+    }                                                  \
+  }
+
+}  // namespace dir
+
+extern "C" int dir_cross_fwd(const float* x0, const float* cross_w, const float* cross_b,
+                             int64_t B, int d, int L, float* xL, float* s, dir_stream_t stream) {
+  using namespace dir;
+  CrossShape sh;
+  if (B < 0 || L < 0 || L > 32 || !cross_shape(d, sh))
+    return fail(DIR_EINVAL, "cross_fwd: need B >= 0, 0 <= L <= 32, 0 < d <= 1024");
+  if (!x0 || !xL || (L > 0 && (!cross_w || !cross_b)))
+    return fail(DIR_EINVAL, "cross_fwd: null pointer");
+  if (sh.vec == 4 && (!aligned16(x0) || !aligned16(xL) || !aligned16(cross_w) || !aligned16(cross_b)))
+    return fail(DIR_EINVAL, "cross_fwd: 16-byte alignment required when d % 4 == 0");
+  if (B == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t want = (B + kCrossWarps - 1) / kCrossWarps;
+  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
+#define DIR_FWD(V, N) \
+  cross_fwd_kernel<V, N><<<grid, kCrossWarps * 32, 0, st>>>(x0, cross_w, cross_b, B, d, L, xL, s)
+  DIR_CROSS_DISPATCH(DIR_FWD)
+#undef DIR_FWD
+  return launched("cross_fwd");
+}
+
+extern "C" size_t dir_cross_bwd_workspace_bytes(int64_t B, int d, int L) {
+  if (B <= 0 || d <= 0 || L <= 0) return 256;
+  return dir::cross_carve(nullptr, B, d, L).total;
+}
+
+extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float* cross_b,
+                             const float* dy, const float* s, int64_t B, int d, int L, float* dx0,
+                             float* dw, float* db, void* workspace, size_t workspace_bytes,
+                             dir_stream_t stream) {
+  using namespace dir;
+  CrossShape sh;
+  if (B < 0 || L <= 0 || L > 32 || !cross_shape(d, sh))
+    return fail(DIR_EINVAL, "cross_bwd: need B >= 0, 0 < L <= 32, 0 < d <= 1024");
+  if (!x0 || !cross_w || !cross_b || !dy || !dx0 || !dw || !db || !workspace)
+    return fail(DIR_EINVAL, "cross_bwd: null pointer");
+  if (sh.vec == 4 && (!aligned16(x0) || !aligned16(dy) || !aligned16(dx0) || !aligned16(cross_w) ||
+                      !aligned16(cross_b)))
+    return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0) {
+    cudaMemsetAsync(dw, 0, (size_t)L * d * 4, st);
+    cudaMemsetAsync(db, 0, (size_t)L * d * 4, st);
+    return 0;
+  }
+  CrossBwdWs w = cross_carve(workspace, B, d, L);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
+  const size_t smem1 = (size_t)kCrossWarps * (d + 32) * 4;
+#define DIR_BWD(V, N)                                                                        \
+  cross_bwd_sample_kernel<V, N><<<w.G1, kCrossWarps * 32, smem1, st>>>(                      \
+      x0, cross_w, cross_b, dy, s, B, d, L, dx0, w.alpha, w.Dpart, w.dypart)
+  DIR_CROSS_DISPATCH(DIR_BWD)
+#undef DIR_BWD
+  cross_bwd_dw_kernel<<<w.G2, 256, kDwUnroll * 8 * 4, st>>>(x0, w.alpha, B, d, L, w.dwpart);
+  cross_bwd_finish_kernel<<<(d + 255) / 256, 256, 32 * 4, st>>>(cross_w, cross_b, w.Dpart, w.dypart,
+                                                              w.dwpart, w.G1, w.G2, d, L, dw, db);
+  return launched("cross_bwd", 3);
+}

@@ -1,0 +1,416 @@
+// K6+K7: deterministic backward of lookup + first order + FM with the sparse row-wise
+// Adagrad / SGD update fused in.
+//
+//   sort      (global row, lookup position) pairs, stable LSD radix sort
+//   phase 1   the sorted list is cut into fixed chunks of C lookups; LPR = K/4 lanes walk one
+//             chunk in order, forming each lookup's gradient on the fly from g[b], S[b,:], u[b,f,:]
+//             and the row (the [B*F,K] per-lookup gradient is never materialised) and summing runs
+//             of equal rows sequentially (= sample order, the order TF's CPU UnsortedSegmentSum
+//             uses).  A run that lies inside its chunk is final: its row is updated right there.
+//             A run that crosses a chunk boundary leaves a partial sum in the workspace.
+//   phase 2   the chunk where a crossing run starts adds the partials of the following chunks in
+//             chunk order and updates the row; runs longer than kLongRun chunks go to
+//   phase 3   one CTA per long run: strided sequential sums + a fixed-shape tree.
+// Chunking depends only on positions in the sorted list, so the result is bit-identical from
+// run to run; there are no floating-point atomics.
+//
+// Reference: TF autodiff + optimizer.minimize behind models/DeepFM/deepFM.py:230-241
+// (SURVEY.md rows A8/A9).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace dir {
+
+constexpr int kChunk = 16;    // lookups per chunk (C)
+constexpr int kBatch = 4;     // lookups whose loads are in flight together
+constexpr int kLongRun = 32;  // chunks; longer crossing runs go to phase 3
+constexpr uint32_t kNoKey = 0xffffffffu;
+
+struct BwdWorkspace {
+  uint32_t* keys;      // [n] sorted global rows
+  uint32_t* pos;       // [n] lookup position b*F+f of each sorted entry
+  uint32_t* pos_in;    // [n] iota
+  void* cub_temp;
+  size_t cub_bytes;
+  float* part;         // [nchunks][2][K]
+  float* part1;        // [nchunks][2]
+  uint32_t* long_list; // [nchunks / kLongRun + 1]
+  uint32_t* long_count;
+  unsigned long long* n_unique;
+  size_t total;
+};
+
+static size_t cub_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32,
+                                  (cudaStream_t)0);
+  cudaGetLastError();  // a size query on a box without a GPU leaves an error behind
+  // onesweep needs ~ (n/ (items per tile) + digits*passes) counters; keep a generous floor
+  const size_t floor_bytes = (size_t)n / 8 + (1u << 20);
+  return bytes > floor_bytes ? bytes : floor_bytes;
+}
+
+static BwdWorkspace carve(void* base, int64_t n, int K) {
+  BwdWorkspace w;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  w.keys = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
+  w.pos = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
+  w.pos_in = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
+  w.cub_bytes = cub_temp_bytes(n);
+  w.cub_temp = take(w.cub_bytes);
+  // everything whose size does not depend on K comes first: the sort step carves with a dummy K
+  w.long_list = reinterpret_cast<uint32_t*>(take((size_t)(nchunks / kLongRun + 1) * 4));
+  w.long_count = reinterpret_cast<uint32_t*>(take(16));
+  w.n_unique = reinterpret_cast<unsigned long long*>(w.long_count ? (char*)w.long_count + 8 : nullptr);
+  w.part1 = reinterpret_cast<float*>(take((size_t)nchunks * 2 * 4));
+  w.part = reinterpret_cast<float*>(take((size_t)nchunks * 2 * K * 4));
+  w.total = off;
+  return w;
+}
+
+__global__ void iota_kernel(uint32_t* out, int64_t n, uint32_t* zero2, unsigned long long* zero1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+  if (i == 0) {
+    *zero2 = 0;
+    *zero1 = 0ull;
+  }
+}
+
+struct BwdArgs {
+  float* table;
+  float* accum;
+  int64_t row_stride;
+  float* lin;
+  float* lin_accum;
+  int64_t lin_stride;
+  const float* val;
+  const float* g_first;
+  const float* g_fm;
+  const float* S;
+  const float* u;
+  const uint32_t* keys;
+  const uint32_t* pos;
+  float* part;
+  float* part1;
+  uint32_t* long_list;
+  uint32_t* long_count;
+  unsigned long long* n_unique;
+  int64_t n;
+  int F;
+  uint32_t pruned_key;  // = n_rows
+  int opt;
+  float lr;
+};
+
+// Row update with the de-duplicated gradient.  Intrinsics pin the evaluation order to the
+// oracle's: a = acc + g*g; T = T - (lr*g)/sqrt(a)   ([TF] SparseApplyAdagrad, no epsilon).
+__device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool adagrad) {
+  if (adagrad) {
+    a = __fadd_rn(a, __fmul_rn(g, g));
+    return __fsub_rn(t, __fdiv_rn(__fmul_rn(lr, g), __fsqrt_rn(a)));
+  }
+  return __fsub_rn(t, __fmul_rn(lr, g));
+}
+
+template <int LPR>
+__device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
+                                             float g1) {
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  float4* trow = reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub;
+  float4 T = *trow;
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* arow = nullptr;
+  if (adagrad) {
+    arow = reinterpret_cast<float4*>(a.accum + (int64_t)key * a.row_stride) + sub;
+    A = *arow;
+  }
+  T.x = upd(T.x, G.x, a.lr, A.x, adagrad);
+  T.y = upd(T.y, G.y, a.lr, A.y, adagrad);
+  T.z = upd(T.z, G.z, a.lr, A.z, adagrad);
+  T.w = upd(T.w, G.w, a.lr, A.w, adagrad);
+  *trow = T;
+  if (adagrad) *arow = A;
+  if (a.lin != nullptr && sub == 0) {
+    float* wp = a.lin + (int64_t)key * a.lin_stride;
+    float a1 = 0.f;
+    float* ap = nullptr;
+    if (adagrad) {
+      ap = a.lin_accum + (int64_t)key * a.lin_stride;
+      a1 = *ap;
+    }
+    *wp = upd(*wp, g1, a.lr, a1, adagrad);
+    if (adagrad) *ap = a1;
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) {
+  constexpr int K = LPR * 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gid = tid / LPR;
+  const int sub = (int)(tid % LPR);
+  const int64_t i0 = gid * kChunk;
+  if (i0 >= a.n) return;
+  const int cnt = (int)min((int64_t)kChunk, a.n - i0);
+  const uint32_t prev_key = i0 > 0 ? __ldg(a.keys + i0 - 1) : kNoKey;
+  const uint32_t next_key = i0 + kChunk < a.n ? __ldg(a.keys + i0 + kChunk) : kNoKey;
+
+  uint32_t cur = __ldg(a.keys + i0);
+  bool left_open = cur == prev_key;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc1 = 0.f;
+  unsigned heads = (cur != prev_key && cur != a.pruned_key) ? 1u : 0u;
+
+  auto flush = [&](bool right_open) {
+    if (cur == a.pruned_key) return;
+    if (!left_open && !right_open) {
+      apply_update<LPR>(a, cur, sub, acc, acc1);
+    } else {
+      const int64_t s = gid * 2 + (left_open ? 0 : 1);
+      *(reinterpret_cast<float4*>(a.part + s * K) + sub) = acc;
+      if (sub == 0) a.part1[s] = acc1;
+    }
+  };
+
+  for (int c0 = 0; c0 < kChunk; c0 += kBatch) {
+    if (c0 >= cnt) break;
+    uint32_t k[kBatch];
+    float v[kBatch], g1[kBatch], g2[kBatch];
+    float4 Sb[kBatch], ub[kBatch], T[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int i = c0 + j;
+      k[j] = i < cnt ? __ldg(a.keys + i0 + i) : a.pruned_key;
+      v[j] = 1.f;
+      g1[j] = g2[j] = 0.f;
+      Sb[j] = ub[j] = T[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k[j] != a.pruned_key) {
+        const uint32_t p = __ldg(a.pos + i0 + i);
+        const uint32_t b = p / (uint32_t)a.F;
+        if (a.val) v[j] = __ldg(a.val + p);
+        if (a.g_first) g1[j] = __ldg(a.g_first + b);
+        g2[j] = __ldg(a.g_fm + b);
+        Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)b * K) + sub);
+        if (a.u) ub[j] = ldg_stream(a.u + (int64_t)p * K + sub * 4);
+        // plain load: the row may be rewritten later in this kernel by this same lane group
+        T[j] = *(reinterpret_cast<const float4*>(a.table + (int64_t)k[j] * a.row_stride) + sub);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      if (c0 + j < cnt) {
+        if (k[j] != cur) {
+          flush(false);
+          cur = k[j];
+          left_open = false;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc1 = 0.f;
+          if (cur != a.pruned_key) ++heads;
+        }
+        if (k[j] != a.pruned_key) {
+          // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
+          const float vv = v[j], gg = g2[j];
+          acc.x = __fadd_rn(acc.x, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(vv, T[j].x))), ub[j].x)));
+          acc.y = __fadd_rn(acc.y, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(vv, T[j].y))), ub[j].y)));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(vv, T[j].z))), ub[j].z)));
+          acc.w = __fadd_rn(acc.w, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(vv, T[j].w))), ub[j].w)));
+          acc1 = __fadd_rn(acc1, __fmul_rn(g1[j], vv));
+        }
+      }
+    }
+  }
+  flush(cur == next_key);
+  if (sub == 0 && heads && a.n_unique) atomicAdd(a.n_unique, (unsigned long long)heads);
+}
+
+// phase 2: one lane group per chunk; the chunk where a crossing run starts finishes it.
+template <int LPR>
+__global__ void __launch_bounds__(256) embed_bwd_combine_kernel(const BwdArgs a) {
+  constexpr int K = LPR * 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gid = tid / LPR;
+  const int sub = (int)(tid % LPR);
+  const int64_t i0 = gid * kChunk;
+  if (i0 >= a.n) return;
+  const int64_t end = min(a.n, i0 + kChunk);
+  if (end >= a.n) return;  // last chunk cannot be open to the right
+  const uint32_t key = __ldg(a.keys + end - 1);
+  if (key == a.pruned_key || __ldg(a.keys + end) != key) return;  // not open to the right
+  if (i0 > 0 && __ldg(a.keys + i0 - 1) == key) return;            // a middle piece, not the head
+  // long run?  chunk gid+1+kLongRun still starts with this key
+  const int64_t far = (gid + 1 + kLongRun) * kChunk;
+  if (far < a.n && __ldg(a.keys + far) == key) {
+    if (sub == 0) a.long_list[atomicAdd(a.long_count, 1u)] = (uint32_t)gid;
+    return;
+  }
+  float4 acc = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
+  float acc1 = a.part1[gid * 2 + 1];
+  for (int64_t j = gid + 1; j * kChunk < a.n && __ldg(a.keys + j * kChunk) == key; ++j) {
+    const float4 p = *(reinterpret_cast<const float4*>(a.part + (j * 2) * K) + sub);
+    acc.x = __fadd_rn(acc.x, p.x);
+    acc.y = __fadd_rn(acc.y, p.y);
+    acc.z = __fadd_rn(acc.z, p.z);
+    acc.w = __fadd_rn(acc.w, p.w);
+    acc1 = __fadd_rn(acc1, a.part1[j * 2]);
+  }
+  apply_update<LPR>(a, key, sub, acc, acc1);
+}
+
+// phase 3: one CTA per long run.
+template <int LPR>
+__global__ void __launch_bounds__(256) embed_bwd_long_kernel(const BwdArgs a) {
+  constexpr int K = LPR * 4;
+  constexpr int NG = 256 / LPR;  // lane groups per CTA
+  __shared__ float4 sm[256];
+  __shared__ float sm1[NG];
+  const int q = threadIdx.x / LPR;
+  const int sub = threadIdx.x % LPR;
+  const uint32_t n_long = *a.long_count;
+  for (uint32_t r = blockIdx.x; r < n_long; r += gridDim.x) {
+    const int64_t gid = a.long_list[r];
+    const int64_t first = (gid + 1) * kChunk;
+    const uint32_t key = __ldg(a.keys + first - 1);
+    int64_t lo = first, hi = a.n;  // upper bound of `key` in the sorted list
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(a.keys + mid) <= key) lo = mid + 1; else hi = mid;
+    }
+    const int64_t M = (lo - 1) / kChunk - gid;  // chunks gid+1 .. gid+M hold a left-open partial
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc1 = 0.f;
+    for (int64_t m = q; m < M; m += NG) {
+      const int64_t j = gid + 1 + m;
+      const float4 p = *(reinterpret_cast<const float4*>(a.part + (j * 2) * K) + sub);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      if (sub == 0) acc1 += a.part1[j * 2];
+    }
+    sm[threadIdx.x] = acc;
+    if (sub == 0) sm1[q] = acc1;
+    __syncthreads();
+#pragma unroll
+    for (int s = NG / 2; s > 0; s >>= 1) {
+      if (q < s) {
+        const float4 o = sm[threadIdx.x + s * LPR];
+        float4 m = sm[threadIdx.x];
+        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+        sm[threadIdx.x] = m;
+        if (sub == 0) sm1[q] += sm1[q + s];
+      }
+      __syncthreads();
+    }
+    if (q == 0) {
+      const float4 h = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
+      float4 t = sm[threadIdx.x];
+      t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
+      apply_update<LPR>(a, key, sub, t, a.part1[gid * 2 + 1] + sm1[0]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void copy_count_kernel(const unsigned long long* src, int64_t* dst) {
+  *dst = (int64_t)*src;
+}
+
+template <int LPR>
+static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) {
+  const int64_t nchunks = (a.n + kChunk - 1) / kChunk;
+  const int64_t threads = nchunks * LPR;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  embed_bwd_reduce_kernel<LPR><<<grid, 256, 0, st>>>(a);
+  embed_bwd_combine_kernel<LPR><<<grid, 256, 0, st>>>(a);
+  embed_bwd_long_kernel<LPR><<<kSMs, 256, 0, st>>>(a);
+  int n = 3;
+  if (n_unique_out) {
+    copy_count_kernel<<<1, 1, 0, st>>>(a.n_unique, n_unique_out);
+    ++n;
+  }
+  return launched("embed_bwd_reduce_update", n);
+}
+
+}  // namespace dir
+
+extern "C" size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K) {
+  if (n_lookups <= 0 || K <= 0) return 0;
+  return dir::carve(nullptr, n_lookups, K).total;
+}
+
+extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
+                                  void* workspace, size_t workspace_bytes, dir_stream_t stream) {
+  using namespace dir;
+  if (n_lookups < 0 || n_lookups >= 0x7fffffffLL)
+    return fail(DIR_EINVAL, "embed_bwd_sort: 0 <= n_lookups < 2^31 required");
+  if (n_rows <= 0 || n_rows >= 0xffffffffLL)
+    return fail(DIR_EINVAL, "embed_bwd_sort: 0 < n_rows < 2^32-1 required");
+  if (n_lookups == 0) return 0;
+  if (!sort_keys || !workspace) return fail(DIR_EINVAL, "embed_bwd_sort: null pointer");
+  // K only sizes the tail of the workspace; the sort part does not depend on it
+  BwdWorkspace w = carve(workspace, n_lookups, 4);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_sort: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((n_lookups + 255) / 256);
+  iota_kernel<<<grid, 256, 0, st>>>(w.pos_in, n_lookups, w.long_count, w.n_unique);
+  int rc = launched("embed_bwd_sort/iota");
+  if (rc) return rc;
+  int end_bit = 1;
+  while (end_bit < 32 && (((uint64_t)n_rows) >> end_bit) != 0) ++end_bit;  // n_rows itself is a key
+  size_t cub_bytes = w.cub_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, sort_keys, w.keys,
+                                                  (const uint32_t*)w.pos_in, w.pos, (int)n_lookups,
+                                                  0, end_bit, st);
+  if (e != cudaSuccess) return fail(DIR_EIO, "embed_bwd_sort: %s", cudaGetErrorString(e));
+  return launched("embed_bwd_sort", (end_bit + 7) / 8 + 2);
+}
+
+extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride,
+                                           float* lin, float* lin_accum, int64_t lin_stride,
+                                           const float* feature_value, const float* g_first,
+                                           const float* g_fm, const float* S, const float* u,
+                                           int64_t B, int F, int K, int64_t n_rows, int optimizer,
+                                           float lr, void* workspace, size_t workspace_bytes,
+                                           int64_t* n_unique_out, dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B >= 0, F > 0 required");
+  const int64_t n = B * F;
+  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B*F must be < 2^31");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: unknown optimizer");
+  if (!table || !g_fm || !S || !workspace)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: table, g_fm, S, workspace are required");
+  if (optimizer == DIR_OPT_ADAGRAD && (!accum || (lin && !lin_accum)))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: Adagrad needs accum (and lin_accum with lin)");
+  if (lin && !g_first) return fail(DIR_EINVAL, "embed_bwd_reduce_update: lin needs g_first");
+  if (row_stride < K || (row_stride & 3))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: row_stride must be >= K, multiple of 4");
+  if (!aligned16(table) || !aligned16(accum) || !aligned16(S) || !aligned16(u))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: table, accum, S, u must be 16-byte aligned");
+  if (n_rows <= 0 || n_rows >= 0xffffffffLL)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: 0 < n_rows < 2^32-1 required");
+  if (n == 0) return 0;
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: K must be one of 4, 8, 16, 32, 64");
+  BwdWorkspace w = carve(workspace, n, K);
+  if (workspace_bytes < w.total)
+    return fail(DIR_ENOMEM, "embed_bwd_reduce_update: workspace too small");
+  BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
+            u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
+            (uint32_t)n_rows, optimizer, lr};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 4: return launch_bwd<1>(a, n_unique_out, st);
+    case 8: return launch_bwd<2>(a, n_unique_out, st);
+    case 16: return launch_bwd<4>(a, n_unique_out, st);
+    case 32: return launch_bwd<8>(a, n_unique_out, st);
+    default: return launch_bwd<16>(a, n_unique_out, st);
+  }
+}

@@ -1,0 +1,294 @@
+"""Host-side mirror of the reference's layer API for the Deep-CTR hot path.
+
+The reference wires this path with four Python calls made while the TF graph is built
+(SURVEY.md section 8b):
+    myself_input_layer(features, columns)          models/DeepFM/deepFM.py:363-400
+    linear_logit_fn(features)                      models/DeepFM/deepFM.py:255-275
+    fm_logit_fn(inputs)                            models/DeepFM/deepFM.py:321-335
+    _cross_architecture(input_layer, params)       models/DeepCrossNetwork/DeepCrossNetwork.py:350-367
+`EmbeddingFM` stands in for the first three, `CrossNetwork` for the fourth, with the knobs the
+reference exposes (field_size = len(column_names), embedding_size = fm_embedding_size,
+cross_layer_num, cross_w / cross_b shaped [L, d]) and the dense, already-resolved inputs
+feature_index / feature_value.  PyTorch here is plumbing (device memory, streams, autograd
+hand-off); all arithmetic runs in libdir_b200.so.  There is no CPU path.
+"""
+import math
+from typing import Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+_COMBINERS = ("sum", "mean", "sqrtn")
+_OPTIMIZERS = {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD}
+_K_OK = (4, 8, 16, 32, 64)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t, name):
+    if t is not None and not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor: this layer has no CPU path" % name)
+
+
+class _Workspace:
+    """Caller-owned scratch, grown on demand (the library never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class _EmbeddingFMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, bias, layer, idx, val, train):
+        B, F = idx.shape
+        K = layer.embedding_size
+        dev = idx.device
+        emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
+        fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        first = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
+        keys = torch.empty((B * F,), dtype=torch.int32, device=dev) if train else None
+        lin = layer.w1 if layer.first_order else None
+        check(_lib.lib().dir_embed_fm_fwd(
+            ptr(layer.table), layer.row_stride, ptr(lin), layer.lin_stride,
+            ptr(bias) if layer.first_order else None, ptr(idx), ptr(val), ptr(layer.field_offset),
+            ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first), ptr(fm), ptr(keys),
+            ptr(layer.oob_flag) if layer.check_bounds else None, _stream()), "dir_embed_fm_fwd")
+        if not layer.first_order:
+            first.zero_()
+        ctx.layer, ctx.train = layer, train
+        ctx.shape = (B, F, K)
+        ctx.set_materialize_grads(False)
+        if train:
+            ctx.save_for_backward(val, S, keys)
+        if emb is None:
+            emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(emb)
+        return first, fm, emb
+
+    @staticmethod
+    def backward(ctx, g_first, g_fm, u):
+        if not ctx.train:
+            raise RuntimeError("EmbeddingFM.backward: forward ran without gradient tracking")
+        layer = ctx.layer
+        val, S, keys = ctx.saved_tensors
+        B, F, K = ctx.shape
+        dev = S.device
+        g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
+                   else g_first.reshape(B).contiguous().float())
+        g_fm = (torch.zeros(B, dtype=torch.float32, device=dev) if g_fm is None
+                else g_fm.reshape(B).contiguous().float())
+        if u is not None:
+            u = u.contiguous().float()
+        layer.apply_gradients(keys, val, g_first, g_fm, S, u, B)
+        g_bias = g_first.sum().reshape(1) if layer.first_order else None
+        return None, g_bias, None, None, None, None
+
+
+class EmbeddingFM(torch.nn.Module):
+    """Multi-field embedding lookup + first-order term + FM second-order interaction, with the
+    backward's sparse row-wise Adagrad / SGD update fused in (tables are optimizer-owned state,
+    not autograd Parameters; `.backward()` through the outputs updates them in place).
+
+    forward(feature_index[B,F] int64, feature_value[B,F] fp32 | None)
+        -> (first_order[B,1], fm_second_order[B,1], embeddings[B, F*K])
+    which map 1:1 to `linear_logit_fn(features)`, `fm_logit_fn(inputs)` and the `net` fed to
+    `dnn_logit_fn` (models/DeepFM/deepFM.py:214, 321-335, 288-291); `embeddings` is also DCN's
+    x0 (models/DeepCrossNetwork/DeepCrossNetwork.py:126).
+
+    rows_per_field: N_f per field (one reference embedding variable per column,
+    deepFM.py:385-390), stored concatenated; or a single int `feature_size` with global ids.
+    Storage is B200-first: with Adagrad each row and its accumulator share one 128-byte line
+    ([N, 2K] fp32), and each first-order weight sits next to its accumulator ([N, 2]).
+    """
+
+    def __init__(self, field_size: int, embedding_size: int,
+                 rows_per_field: Union[int, Sequence[int]], optimizer: str = "adagrad",
+                 lr: float = 0.01, initial_accumulator_value: float = 0.1,
+                 combiner: str = "sum", first_order: bool = True, emit_embeddings: bool = True,
+                 check_bounds: bool = False, device="cuda"):
+        super().__init__()
+        if field_size <= 0:
+            raise ValueError("empty columns.")                      # deepFM.py:104-105
+        if embedding_size not in _K_OK:
+            raise ValueError("embedding_size must be one of %r" % (_K_OK,))
+        if optimizer not in _OPTIMIZERS:
+            raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        if combiner not in _COMBINERS:
+            raise ValueError("combiner must be one of %r" % (_COMBINERS,))
+        if isinstance(rows_per_field, int):                         # global ids: one shared table
+            n_rows, offsets, rows = int(rows_per_field), [0] * field_size, None
+        else:
+            rows = [int(r) for r in rows_per_field]
+            if len(rows) != field_size:
+                raise ValueError("rows_per_field must have field_size entries")
+            offsets = [0]
+            for r in rows[:-1]:
+                offsets.append(offsets[-1] + r)
+            n_rows = sum(rows)
+        if not 0 < n_rows < 2 ** 32 - 1:
+            raise ValueError("total rows must be in (0, 2^32-1)")
+        self.field_size, self.embedding_size, self.n_rows = field_size, embedding_size, n_rows
+        self.shared_table = isinstance(rows_per_field, int)
+        self.optimizer, self.lr = optimizer, float(lr)
+        self.combiner, self.first_order = combiner, first_order
+        self.emit_embeddings, self.check_bounds = emit_embeddings, check_bounds
+        K = embedding_size
+        adagrad = optimizer == "adagrad"
+        self.row_stride = 2 * K if adagrad else K
+        self.lin_stride = 2 if adagrad else 1
+        dev = torch.device(device)
+        self.register_buffer("field_offset", torch.tensor(offsets, dtype=torch.int64, device=dev))
+        self.register_buffer("field_rows", None if rows is None else
+                             torch.tensor(rows, dtype=torch.int64, device=dev))
+        self.register_buffer("rows", torch.empty((n_rows, self.row_stride), dtype=torch.float32, device=dev))
+        self.register_buffer("lin_rows", torch.zeros((n_rows, self.lin_stride), dtype=torch.float32, device=dev))
+        self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
+        self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
+        self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
+        self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._ws = _Workspace()
+        with torch.no_grad():
+            # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
+            torch.nn.init.trunc_normal_(self.table, 0.0, 1.0 / math.sqrt(K), -2.0 / math.sqrt(K), 2.0 / math.sqrt(K))
+            if adagrad:
+                self.accum.fill_(initial_accumulator_value)
+                self.w1_accum.fill_(initial_accumulator_value)
+
+    # views into the interleaved storage
+    @property
+    def table(self):
+        return self.rows[:, :self.embedding_size]
+
+    @property
+    def accum(self):
+        return self.rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+
+    @property
+    def w1(self):
+        return self.lin_rows[:, 0]
+
+    @property
+    def w1_accum(self):
+        return self.lin_rows[:, 1] if self.optimizer == "adagrad" else None
+
+    @torch.no_grad()
+    def load_tables(self, table=None, w1=None, accum=None, w1_accum=None):
+        for dst, src in ((self.table, table), (self.w1, w1), (self.accum, accum), (self.w1_accum, w1_accum)):
+            if src is not None:
+                dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(dst.device))
+
+    def _prepare(self, feature_index, feature_value):
+        if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
+            raise ValueError("feature_index must be [B, field_size=%d]" % self.field_size)
+        if feature_index.dtype != torch.int64:
+            raise ValueError("feature_index must be int64")
+        _need_cuda(feature_index, "feature_index")
+        idx = feature_index.contiguous()
+        val = None
+        if feature_value is not None:
+            if feature_value.shape != feature_index.shape:
+                raise ValueError("feature_value must have feature_index's shape")
+            _need_cuda(feature_value, "feature_value")
+            val = feature_value.contiguous().float()
+            if self.combiner != "sum":       # one id per field: mean / sqrtn reduce to a pruned gather
+                val = (val > 0).float()
+        return idx, val
+
+    def forward(self, feature_index, feature_value=None):
+        idx, val = self._prepare(feature_index, feature_value)
+        train = self.training and torch.is_grad_enabled()
+        first, fm, emb = _EmbeddingFMFunction.apply(self._anchor, self.bias, self, idx, val, train)
+        if self.check_bounds and int(self.oob_flag.item()) != 0:
+            self.oob_flag.zero_()
+            raise IndexError("feature_index out of range for its field")   # TF CPU Gather raises
+        return first, fm, emb
+
+    @torch.no_grad()
+    def apply_gradients(self, sort_keys, feature_value, g_first, g_fm, S, u, B):
+        """sort -> segmented reduce -> fused row update (dir_embed_bwd_sort + _reduce_update)."""
+        F, K = self.field_size, self.embedding_size
+        L = _lib.lib()
+        nbytes = L.dir_embed_bwd_workspace_bytes(B * F, K)
+        ws = self._ws.get(nbytes, S.device)
+        check(L.dir_embed_bwd_sort(ptr(sort_keys), B * F, self.n_rows, ptr(ws), ws.numel(), _stream()),
+              "dir_embed_bwd_sort")
+        adagrad = self.optimizer == "adagrad"
+        check(L.dir_embed_bwd_reduce_update(
+            ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
+            ptr(self.w1) if self.first_order else None,
+            ptr(self.w1_accum) if (adagrad and self.first_order) else None, self.lin_stride,
+            ptr(feature_value), ptr(g_first), ptr(g_fm), ptr(S), ptr(u), B, F, K, self.n_rows,
+            _OPTIMIZERS[self.optimizer], self.lr, ptr(ws), ws.numel(), ptr(self.last_n_unique),
+            _stream()), "dir_embed_bwd_reduce_update")
+
+
+class _CrossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, cross_w, cross_b, layer):
+        B, d = x0.shape
+        L = cross_w.shape[0]
+        xL = torch.empty_like(x0)
+        train = layer.training and (x0.requires_grad or cross_w.requires_grad or cross_b.requires_grad)
+        s = torch.empty((B, L), dtype=torch.float32, device=x0.device) if train else None
+        check(_lib.lib().dir_cross_fwd(ptr(x0), ptr(cross_w), ptr(cross_b), B, d, L, ptr(xL), ptr(s),
+                                       _stream()), "dir_cross_fwd")
+        ctx.layer = layer
+        ctx.save_for_backward(x0, cross_w, cross_b, s)
+        return xL
+
+    @staticmethod
+    def backward(ctx, dy):
+        x0, cross_w, cross_b, s = ctx.saved_tensors
+        B, d = x0.shape
+        L = cross_w.shape[0]
+        dy = dy.contiguous().float()
+        dx0 = torch.empty_like(x0)
+        dw = torch.empty_like(cross_w)
+        db = torch.empty_like(cross_b)
+        lib = _lib.lib()
+        ws = ctx.layer._ws.get(lib.dir_cross_bwd_workspace_bytes(B, d, L), x0.device)
+        check(lib.dir_cross_bwd(ptr(x0), ptr(cross_w), ptr(cross_b), ptr(dy), ptr(s), B, d, L,
+                                ptr(dx0), ptr(dw), ptr(db), ptr(ws), ws.numel(), _stream()),
+              "dir_cross_bwd")
+        return dx0, dw, db, None
+
+
+class CrossNetwork(torch.nn.Module):
+    """DCN cross stack: x_{l+1} = x0 * (x_l . w_l) + b_l + x_l for l < cross_layer_num.
+
+    Mirrors `_cross_architecture` / `_cross_variable_creat`
+    (models/DeepCrossNetwork/DeepCrossNetwork.py:322-367): parameters `cross_w`, `cross_b`
+    of shape [cross_layer_num, input_dim], both truncated_normal(0, 0.1) (the bias is not
+    zero-initialised in the reference).  forward(x0[B,d]) -> x_L[B,d].
+    """
+
+    def __init__(self, input_dim: int, cross_layer_num: int = 2, device="cuda"):
+        super().__init__()
+        if not 0 < input_dim <= 1024:
+            raise ValueError("input_dim must be in (0, 1024]")
+        if not 0 < cross_layer_num <= 32:
+            raise ValueError("cross_layer_num must be in (0, 32]")
+        self.input_dim, self.cross_layer_num = input_dim, cross_layer_num
+        w = torch.empty((cross_layer_num, input_dim), dtype=torch.float32, device=device)
+        b = torch.empty((cross_layer_num, input_dim), dtype=torch.float32, device=device)
+        torch.nn.init.trunc_normal_(w, 0.0, 0.1, -0.2, 0.2)
+        torch.nn.init.trunc_normal_(b, 0.0, 0.1, -0.2, 0.2)
+        self.cross_w = torch.nn.Parameter(w)
+        self.cross_b = torch.nn.Parameter(b)
+        self._ws = _Workspace()
+
+    def forward(self, x0):
+        _need_cuda(x0, "x0")
+        if x0.dim() != 2 or x0.shape[1] != self.input_dim:
+            raise ValueError("x0 must be [B, input_dim=%d]" % self.input_dim)
+        return _CrossFunction.apply(x0.contiguous().float(), self.cross_w, self.cross_b, self)

@@ -1,0 +1,129 @@
+/*
+ * dir_b200.h -- C ABI of libdir_b200.so: the B200 (sm_100a) embedding + FM / cross hot path.
+ *
+ * The reference (yinyajun/Details-In-Recommendation) is pure Python over TensorFlow 1.x and
+ * has no FFI for this path; its boundary is four Python calls made while the graph is built
+ * (SURVEY.md section 8b).  Each entry point below names the reference lines it stands in for.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name ends
+ *    in _host.  The caller owns all memory, including workspaces (query the size first).
+ *  - Nothing here allocates, frees or caches device memory, creates streams or synchronises
+ *    the device: all work is enqueued on `stream` (a cudaStream_t; NULL = legacy default stream).
+ *  - Return value: 0 on success, a negative errno-style code otherwise
+ *      DIR_EINVAL  bad shape / alignment / unsupported size
+ *      DIR_ENOMEM  workspace too small
+ *      DIR_EIO     CUDA launch error (text in dir_last_error())
+ *  - fp32 data, int64 feature ids (the reference's dtypes: DeepCrossNetwork.py:330-332,
+ *    models/DeepFM/test01.py:11-13).  Row-major.  `table`, `accum`, `emb`, `S`, `u` need
+ *    16-byte alignment of every row: row strides are multiples of 4 floats.
+ *  - Re-entrant: no global mutable state except a thread-local error string and an atomic
+ *    launch counter.
+ */
+#ifndef DIR_B200_H
+#define DIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIR_EINVAL (-22)
+#define DIR_ENOMEM (-12)
+#define DIR_EIO (-5)
+
+#define DIR_OPT_SGD 0     /* T[r] -= lr*g                         (models/LFM/Biased LFM/train.py:44) */
+#define DIR_OPT_ADAGRAD 1 /* acc[r] += g*g; T[r] -= lr*g/sqrt(acc[r])  (deepFM.py:61 'Adagrad')    */
+
+typedef void* dir_stream_t; /* cudaStream_t */
+
+int dir_version(void);
+const char* dir_last_error(void);
+/* kernels this library has launched since it was loaded (process-wide) */
+uint64_t dir_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward: multi-field lookup + first order + FM second order, one pass over the ids.
+ * Replaces, for one-id-per-field inputs,
+ *   myself_input_layer                     models/DeepFM/deepFM.py:363-400  -> emb
+ *   linear_logit_fn (linear_model, 'sum')  models/DeepFM/deepFM.py:255-275  -> first
+ *   fm_logit_fn                            models/DeepFM/deepFM.py:321-335  -> fm
+ *   tf.feature_column.input_layer          models/DeepCrossNetwork/DeepCrossNetwork.py:126 -> emb (= x0)
+ *
+ *   table[n_rows] rows of K floats, `row_stride` floats apart (row_stride >= K, multiple of 4)
+ *   lin[n_rows]   first-order weight of each row, `lin_stride` floats apart (may be NULL: no first order)
+ *   bias          1 float (may be NULL)
+ *   feature_index [B,F] int64 ids local to their field; feature_value [B,F] or NULL (= all 1.0)
+ *   field_offset  [F] int64: global row = field_offset[f] + id
+ *   field_rows    [F] int64 rows of each field, or NULL (then only row < n_rows is checked: the
+ *                 classic one-shared-table / global-id layout passes field_offset = 0, NULL)
+ *   n_rows        rows in `table`
+ * Lookups with id < 0 or feature_value <= 0 are pruned ([TF] _safe_embedding_lookup_sparse):
+ * zero vector, no gradient.  Ids beyond their field are pruned too and, when `oob_flag` is not
+ * NULL, *oob_flag is set to 1 (TF's CPU Gather raises InvalidArgumentError there).
+ *   emb  [B,F,K] or NULL   e[b,f,:] = value * table[row]
+ *   S    [B,K]   or NULL   sum over fields of e (the backward needs it)
+ *   first[B], fm[B]  (first may be NULL when lin is NULL)
+ *   sort_keys [B*F] uint32 or NULL: global row of each lookup, n_rows for pruned ones
+ *                 (input of dir_embed_bwd_sort; requires n_rows < 2^32-1)
+ * K in {4, 8, 16, 32, 64}.
+ */
+int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
+                     const float* bias, const int64_t* feature_index, const float* feature_value,
+                     const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows,
+                     int64_t B, int F, int K, float* emb, float* S, float* first, float* fm,
+                     uint32_t* sort_keys, int* oob_flag, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward + sparse row-wise update.  Replaces TF autodiff of the ops above plus
+ * optimizer.minimize (models/DeepFM/deepFM.py:230-241; Unique + UnsortedSegmentSum +
+ * _deduplicate_indexed_slices + SparseApplyAdagrad / ScatterSub inside TF).
+ *
+ * Step 1, dir_embed_bwd_sort: stable LSD radix sort of (global row, lookup position).
+ *   workspace layout is private; sorted keys / positions are found again by step 2 in the
+ *   same workspace.
+ * Step 2, dir_embed_bwd_reduce_update: for each run of equal rows, in lookup order,
+ *     G_r  = sum value * (g_fm[b] * (S[b] - value*T_r) + u[b,f])     (K floats)
+ *     g1_r = sum value * g_first[b]
+ *   then T_r / lin_r are updated in place with `optimizer`.  Deterministic: fixed chunking of
+ *   the sorted list, sequential sums inside a chunk, fixed-order combine across chunks; no
+ *   floating-point atomics.  Pruned lookups do not touch their row.
+ *   accum / lin_accum: Adagrad accumulators with the same strides as table / lin (NULL for SGD).
+ *   lin == NULL skips the first-order update.  u == NULL means no upstream embedding gradient.
+ *   n_unique_out (device int64, may be NULL) receives the number of distinct rows updated.
+ */
+size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K);
+int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
+                       void* workspace, size_t workspace_bytes, dir_stream_t stream);
+int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
+                                float* lin_accum, int64_t lin_stride, const float* feature_value,
+                                const float* g_first, const float* g_fm, const float* S,
+                                const float* u, int64_t B, int F, int K, int64_t n_rows,
+                                int optimizer, float lr, void* workspace, size_t workspace_bytes,
+                                int64_t* n_unique_out, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DCN cross network, all L layers in one pass.  Replaces _cross_architecture / _cross_op
+ * (models/DeepCrossNetwork/DeepCrossNetwork.py:336-367): x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l.
+ *   x0 [B,d], cross_w / cross_b [L,d] (names as DeepCrossNetwork.py:329-332), xL [B,d],
+ *   s [B,L] or NULL (s[b,l] = x_l . w_l, reusable by the backward).   d <= 1024.
+ */
+int dir_cross_fwd(const float* x0, const float* cross_w, const float* cross_b, int64_t B, int d,
+                  int L, float* xL, float* s, dir_stream_t stream);
+
+/* Backward of the cross stack (TF autodiff behind compute_gradients, DeepCrossNetwork.py:283).
+ *   dy [B,d] -> dx0 [B,d], dw [L,d], db [L,d]; s [B,L] from the forward or NULL (recomputed).
+ * dw / db are reduced in a fixed order (per-CTA partials in `workspace`, then one combine).
+ */
+size_t dir_cross_bwd_workspace_bytes(int64_t B, int d, int L);
+int dir_cross_bwd(const float* x0, const float* cross_w, const float* cross_b, const float* dy,
+                  const float* s, int64_t B, int d, int L, float* dx0, float* dw, float* db,
+                  void* workspace, size_t workspace_bytes, dir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIR_B200_H */

@@ -1,0 +1,203 @@
+"""TEST INFRASTRUCTURE -- CPU restatement (numpy) of the reference's Deep-CTR hot path.
+
+PARITY UNPINNED at the TensorFlow boundary (see oracle/tf_semantics.py): the
+reference's TF 1.x graph cannot run here and the reference ships no golden
+vectors.  This module restates, op by op and in the reference's evaluation
+order, the lines cited on each function; tests/test_oracle.py pins it against
+closed-form known-answer tests and against torch autograd (an independent
+implementation).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import it; the product never does.
+
+Layout: ONE concatenated table `table[N, K]` (the reference holds one variable
+per column, deepFM.py:385-390; concatenation is a storage choice) with
+`field_offset[F]`, global row = field_offset[f] + feature_index[b, f].
+`dtype` selects fp32 (the reference's arithmetic) or fp64 (the adjudicator).
+"""
+import numpy as np
+
+from . import tf_semantics as tfs
+
+
+def global_rows(feature_index, field_offset):
+    """int64 [B,F]; the index arithmetic that must be bit-exact."""
+    return feature_index.astype(np.int64) + np.asarray(field_offset, dtype=np.int64)[None, :]
+
+
+# ----------------------------------------------------------------------------
+# forward
+# ----------------------------------------------------------------------------
+def embedding_lookup(table, field_offset, feature_index, feature_value=None,
+                     combiner="sum", dtype=np.float32):
+    """models/DeepFM/deepFM.py:363-400 (myself_input_layer): per column
+    `column._get_dense_tensor` (:387) then reshape to [B, K] (:393).
+    Returns e[B, F, K] (column c at [:, c, :]) and the keep mask.
+    """
+    dt = np.dtype(dtype).type
+    eff, keep = tfs.effective_value(feature_index, feature_value, combiner, dt)
+    rows = global_rows(np.where(keep, feature_index, 0), field_offset)
+    e = table[rows].astype(dt) * eff[:, :, None]
+    return e, keep
+
+
+def first_order(w1, bias, field_offset, feature_index, feature_value=None,
+                dtype=np.float32):
+    """models/DeepFM/deepFM.py:255-263 linear_model(units=1, sparse_combiner='sum'):
+    per column sum-combined scalar weight, summed over columns in column order
+    (AddN), plus bias.  -> [B, 1]
+    """
+    dt = np.dtype(dtype).type
+    eff, keep = tfs.effective_value(feature_index, feature_value, "sum", dt)
+    rows = global_rows(np.where(keep, feature_index, 0), field_offset)
+    per_col = w1[rows].astype(dt) * eff                     # [B, F]
+    acc = np.zeros(per_col.shape[0], dtype=dt)
+    for f in range(per_col.shape[1]):                       # AddN in column order
+        acc = acc + per_col[:, f]
+    return (acc + dt(bias))[:, None]
+
+
+def fm_second_order(e):
+    """models/DeepFM/deepFM.py:329-334, op for op:
+    summed_squared = square(reduce_sum(e, -2)); squared_summed = reduce_sum(square(e), -2)
+    logits = 0.5 * reduce_sum(summed_squared - squared_summed, -1); expand_dims(-1)
+    """
+    dt = e.dtype.type
+    summed_squared = np.square(np.sum(e, axis=-2, dtype=e.dtype))
+    squared_summed = np.sum(np.square(e), axis=-2, dtype=e.dtype)
+    logits = dt(0.5) * np.sum(summed_squared - squared_summed, axis=-1, dtype=e.dtype)
+    return logits[:, None]
+
+
+def fm_pairwise(e):
+    """Sum_{i<j} <v_i, v_j>: the definition fm_second_order simplifies (KAT-2)."""
+    B, F, K = e.shape
+    out = np.zeros(B, dtype=e.dtype)
+    for i in range(F):
+        for j in range(i + 1, F):
+            out += np.sum(e[:, i, :] * e[:, j, :], axis=-1)
+    return out[:, None]
+
+
+def cross_op(x0, x, w, b):
+    """models/DeepCrossNetwork/DeepCrossNetwork.py:336-347:
+    x_w = tensordot(x, w, axes=1); y = x0 * expand_dims(x_w, -1) + b + x
+    evaluated ((x0*s) + b) + x.
+    """
+    x_w = np.tensordot(x, w, axes=1).astype(x.dtype)
+    return x0 * x_w[:, None] + b + x, x_w
+
+
+def cross_forward(x0, cross_w, cross_b):
+    """models/DeepCrossNetwork/DeepCrossNetwork.py:350-367 (_cross_architecture).
+    Returns x_L[B,d] and s[B,L] (s[:, l] = x_l . w_l)."""
+    xl = x0
+    s = np.zeros((x0.shape[0], cross_w.shape[0]), dtype=x0.dtype)
+    for l in range(cross_w.shape[0]):
+        xl, s[:, l] = cross_op(x0, xl, cross_w[l], cross_b[l])
+    return xl, s
+
+
+# ----------------------------------------------------------------------------
+# backward (TF autodiff of the ops above, restated analytically)
+# ----------------------------------------------------------------------------
+def cross_backward(x0, cross_w, cross_b, dy):
+    """Reverse sweep of _cross_architecture.
+    -> dx0[B,d], dw[L,d], db[L,d]
+    """
+    L = cross_w.shape[0]
+    xs = [x0]
+    for l in range(L):
+        xs.append(cross_op(x0, xs[-1], cross_w[l], cross_b[l])[0])
+    dx = dy.copy()
+    dx0 = np.zeros_like(x0)
+    dw = np.zeros_like(cross_w)
+    db = np.zeros_like(cross_b)
+    for l in range(L - 1, -1, -1):
+        s_l = np.tensordot(xs[l], cross_w[l], axes=1).astype(x0.dtype)
+        db[l] = dx.sum(axis=0, dtype=x0.dtype)
+        ds = np.sum(dx * x0, axis=1, dtype=x0.dtype)
+        dx0 = dx0 + dx * s_l[:, None]
+        dw[l] = np.sum(ds[:, None] * xs[l], axis=0, dtype=x0.dtype)
+        dx = dx + ds[:, None] * cross_w[l][None, :]
+    dx0 = dx0 + dx
+    return dx0, dw, db
+
+
+def embedding_backward(table, field_offset, feature_index, feature_value,
+                       g_first, g_fm, u=None, combiner="sum", dtype=np.float32):
+    """Backward of lookup + first order + FM (implicit in
+    optimizer.minimize, models/DeepFM/deepFM.py:230-241).
+
+    g_first[B], g_fm[B]: dL/d(first_order), dL/d(fm_second_order);
+    u[B,F,K] or None:    dL/d(embeddings) from the DNN / cross consumer.
+    Returns (rows[U] int64 sorted unique, G[U,K], g1[U], dbias): per-unique-row
+    gradients, duplicates summed in sample order ([TF] Unique + UnsortedSegmentSum,
+    then _deduplicate_indexed_slices).  Pruned lookups contribute nothing and do
+    not touch their row.
+    """
+    dt = np.dtype(dtype).type
+    eff, keep = tfs.effective_value(feature_index, feature_value, combiner, dt)
+    eff1, _ = tfs.effective_value(feature_index, feature_value, "sum", dt)
+    rows = global_rows(np.where(keep, feature_index, 0), field_offset)
+    e = table[rows].astype(dt) * eff[:, :, None]
+    S = np.sum(e, axis=1, dtype=e.dtype)                                # [B,K]
+    de = g_fm.astype(dt)[:, None, None] * (S[:, None, :] - e)
+    if u is not None:
+        de = de + u.astype(dt)
+    per_lookup = eff[:, :, None] * de                                   # [B,F,K]
+    per_lookup1 = g_first.astype(dt)[:, None] * eff1                    # [B,F]
+    flat_rows = rows[keep]                                              # sample-major order
+    uniq, inv = np.unique(flat_rows, return_inverse=True)
+    G = np.zeros((uniq.shape[0], table.shape[1]), dtype=dt)
+    g1 = np.zeros(uniq.shape[0], dtype=dt)
+    np.add.at(G, inv, per_lookup[keep])                                 # sequential, sample order
+    np.add.at(g1, inv, per_lookup1[keep])
+    dbias = np.sum(g_first.astype(dt), dtype=dt)
+    return uniq, G, g1, dbias
+
+
+# ----------------------------------------------------------------------------
+# sparse row-wise optimizers
+# ----------------------------------------------------------------------------
+def sparse_adagrad(var, accum, rows, grad, lr):
+    """[TF] SparseApplyAdagrad after dedupe: accum[r] += g*g; var[r] -= lr*g/sqrt(accum[r]).
+    No epsilon; rows not listed are untouched.  In place; `rows` unique."""
+    dt = var.dtype.type
+    a = accum[rows] + grad * grad
+    accum[rows] = a
+    var[rows] = var[rows] - dt(lr) * grad / np.sqrt(a)
+
+
+def sparse_sgd(var, rows, grad, lr):
+    """[TF] ScatterSub of the de-duplicated IndexedSlices: var[r] -= lr*g."""
+    var[rows] = var[rows] - var.dtype.type(lr) * grad
+
+
+# ----------------------------------------------------------------------------
+# one training step of the layer, as the bench times it
+# ----------------------------------------------------------------------------
+def deepfm_layer_step(table, accum, w1, accum1, bias, field_offset, feature_index,
+                      feature_value, labels, lr, u=None, optimizer="adagrad",
+                      update_first_order=True, dtype=np.float32):
+    """fwd (lookup + first order + FM) -> SUM-reduced sigmoid CE (deepFM.py:72)
+    -> bwd -> fused sparse update.  Mutates table/accum/w1/accum1 in place.
+    Returns dict(first, fm, logits, e, rows, G, g1, dbias, g)."""
+    dt = np.dtype(dtype).type
+    e, _ = embedding_lookup(table, field_offset, feature_index, feature_value, "sum", dt)
+    first = first_order(w1, bias, field_offset, feature_index, feature_value, dt)
+    fm = fm_second_order(e)
+    logits = first + fm                                   # deepFM.py:218-223 add_n
+    g = (tfs.sigmoid(logits[:, 0]) - labels.astype(dt)).astype(dt)     # SUM reduction: no 1/B
+    rows, G, g1, dbias = embedding_backward(table, field_offset, feature_index,
+                                            feature_value, g, g, u, "sum", dt)
+    if optimizer == "adagrad":
+        sparse_adagrad(table, accum, rows, G, lr)
+        if update_first_order:
+            sparse_adagrad(w1, accum1, rows, g1, lr)
+    elif optimizer == "sgd":
+        sparse_sgd(table, rows, G, lr)
+        if update_first_order:
+            sparse_sgd(w1, rows, g1, lr)
+    else:
+        raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+    return dict(first=first, fm=fm, logits=logits, e=e, rows=rows, G=G, g1=g1,
+                dbias=dbias, g=g)

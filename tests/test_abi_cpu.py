@@ -1,0 +1,72 @@
+"""CPU-side checks of the boundary: the C-ABI library loads here (no GPU) and exports every symbol
+include/dir_b200.h declares; argument validation runs before any launch."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "dir_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dir_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from dir_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = _lib.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), "libdir_b200.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "no ctypes signature for %s" % s
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.dir_version() >= 100
+
+
+def test_argument_validation_without_gpu(pkg):
+    from dir_b200 import _lib
+    lib = _lib.lib()
+    # K = 12 is unsupported; no launch happens before validation
+    rc = lib.dir_embed_fm_fwd(16, 12, None, 1, None, 16, None, 16, None, 10, 4, 3, 12, None, None, None, 16,
+                              None, None, None)
+    assert rc == -22 and b"K must be" in lib.dir_last_error()
+    rc = lib.dir_cross_fwd(16, 16, 16, 4, 2000, 2, 16, None, None)
+    assert rc == -22
+    with pytest.raises(ValueError):
+        _lib.check(rc, "dir_cross_fwd")
+    assert lib.dir_embed_bwd_workspace_bytes(0, 16) == 0
+    assert lib.dir_embed_bwd_workspace_bytes(39 * 1024, 16) > 39 * 1024 * 12
+
+
+def test_layers_refuse_cpu_tensors(pkg):
+    import torch
+    layer_cls = pkg.EmbeddingFM
+    with pytest.raises(ValueError):
+        layer_cls(0, 16, [])
+    with pytest.raises(ValueError):
+        layer_cls(2, 16, [4, 4], optimizer="ftrl", device="cpu")
+    layer = layer_cls(2, 16, [4, 4], device="cpu")       # construction is host-only plumbing
+    with pytest.raises(ValueError, match="no CPU path"):
+        layer(torch.zeros((3, 2), dtype=torch.int64))
+
+
+def test_synth_workloads(pkg):
+    import numpy as np
+    s = pkg.synth
+    w2 = s.cfg("cfg2")
+    assert w2.field_size == 39 and w2.embedding_size == 16 and abs(w2.n_rows - 10_000_000) < 100
+    w4 = s.cfg("cfg4")
+    assert w4.field_size == 39 and w4.n_rows == 880_000_000 + 13
+    w5 = s.cfg("cfg5", batch=4096)
+    idx, val, lab = s.make_inputs(w5)
+    assert idx.shape == (4096, 39) and idx.dtype == np.int64 and (idx[:, 26:] == 0).all()
+    share = (idx[:, 0] == 0).mean()
+    assert 0.08 < share < 0.18          # Zipf(1.1): hottest row ~ 12.8 % of lookups
+    assert ((val[:, :26] == 1).all() and (val[:, 26:] < 1).all())
+    idx2, _, _ = s.make_inputs(w5)
+    assert np.array_equal(idx, idx2)    # seeded

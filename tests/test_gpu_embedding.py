@@ -1,0 +1,183 @@
+"""GPU parity of the embedding + first-order + FM path (forward, backward, fused update) against
+the oracle, through the reference-facing layer and the C ABI.  Bars (north_star): indices and
+gathered rows bit-exact; logits and gradients (here: the updated rows) within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deepctr_oracle as O
+from tests._util import REL, make_case, make_layer, oracle_forward, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (B, rows_per_field, K)
+    (1, [5], 4),
+    (3, [7, 1, 2], 8),
+    (64, [50, 1, 9, 1000, 3, 17, 1], 16),
+    (257, [100] * 26 + [1] * 13, 16),          # Criteo-shaped: 26 sparse + 13 dense
+    (1024, [10_000] * 26 + [1] * 13, 8),       # cfg1 (BASELINE.json configs[0])
+    (130, [33] * 70, 32),
+    (65, [12, 40, 7], 64),
+]
+
+
+@pytest.mark.parametrize("B,rows,K", SHAPES)
+@pytest.mark.parametrize("weighted", [False, True])
+def test_forward_parity(pkg, cuda, B, rows, K, weighted):
+    case = make_case(11, B, rows, K, weighted=weighted, prune=weighted)
+    layer = make_layer(pkg, case).eval()
+    with torch.no_grad():
+        layer.bias.fill_(0.125)
+        first, fm, emb = layer(to_dev(case["idx"]), to_dev(case["val"]))
+    e, first_o, fm_o, _ = oracle_forward(case, bias=0.125)
+    F = case["F"]
+    assert np.array_equal(emb.cpu().numpy().reshape(B, F, K), e), "gathered rows must be bit-exact"
+    e64, first64, fm64, _ = oracle_forward(case, bias=0.125, dtype=np.float64)
+    floor_fm = 0.5 * (e64 ** 2).sum((1, 2))[:, None] + 1e-30
+    floor_first = np.abs(case["w1"]).max() * F + 0.125
+    assert rel_err(fm.cpu().numpy(), fm64, floor_fm) <= REL
+    assert rel_err(first.cpu().numpy(), first64, floor_first) <= REL
+    # and the fp32 oracle itself sits inside the same band (sanity of the bar)
+    assert rel_err(fm_o, fm64, floor_fm) <= REL
+
+
+def _run_step(pkg, case, optimizer, g_first, g_fm, u, lr=0.05):
+    layer = make_layer(pkg, case, optimizer=optimizer, lr=lr).train()
+    first, fm, emb = layer(to_dev(case["idx"]), to_dev(case["val"]))
+    loss = (first[:, 0] * to_dev(g_first)).sum() + (fm[:, 0] * to_dev(g_fm)).sum()
+    if u is not None:
+        loss = loss + (emb * to_dev(u.reshape(case["B"], -1))).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return layer
+
+
+def _oracle_step(case, optimizer, g_first, g_fm, u, lr=0.05, dtype=np.float32):
+    t, w = case["table"].astype(dtype), case["w1"].astype(dtype)
+    acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+    rows, G, g1, dbias = O.embedding_backward(t, case["off"], case["idx"], case["val"], g_first, g_fm,
+                                              u, "sum", dtype)
+    if optimizer == "adagrad":
+        O.sparse_adagrad(t, acc, rows, G, lr)
+        O.sparse_adagrad(w, acc1, rows, g1, lr)
+    else:
+        O.sparse_sgd(t, rows, G, lr)
+        O.sparse_sgd(w, rows, g1, lr)
+    return t, acc, w, acc1, rows, G, dbias
+
+
+@pytest.mark.parametrize("B,rows,K", SHAPES)
+@pytest.mark.parametrize("optimizer", ["adagrad", "sgd"])
+@pytest.mark.parametrize("with_u", [False, True])
+def test_backward_update_parity(pkg, cuda, B, rows, K, optimizer, with_u):
+    case = make_case(12, B, rows, K, weighted=True, prune=True)
+    rng = case["rng"]
+    F = case["F"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = rng.standard_normal(B).astype(np.float32)
+    u = (rng.standard_normal((B, F, K)) * 0.1).astype(np.float32) if with_u else None
+    layer = _run_step(pkg, case, optimizer, g_first, g_fm, u)
+    t64, acc64, w64, acc1_64, urows, G64, dbias = _oracle_step(case, optimizer, g_first, g_fm, u, dtype=np.float64)
+    got_t = layer.table.cpu().numpy()
+    got_w = layer.w1.cpu().numpy()
+    assert int(layer.last_n_unique.item()) == len(urows)
+    # rows the batch did not touch are bit-identical (sparse update semantics)
+    untouched = np.ones(case["N"], bool)
+    untouched[urows] = False
+    assert np.array_equal(got_t[untouched], case["table"][untouched])
+    assert np.array_equal(got_w[untouched], case["w1"][untouched])
+    assert rel_err(got_t[urows], t64[urows], np.abs(case["table"]).max()) <= REL
+    assert rel_err(got_w[urows], w64[urows], np.abs(case["w1"]).max() + 1e-3) <= REL
+    if optimizer == "adagrad":
+        assert rel_err(layer.accum.cpu().numpy()[urows], acc64[urows], 0.1) <= REL
+        assert rel_err(layer.w1_accum.cpu().numpy()[urows], acc1_64[urows], 0.1) <= REL
+        assert np.all(layer.accum.cpu().numpy()[untouched] == np.float32(0.1))
+    if layer.bias.grad is not None:
+        assert abs(float(layer.bias.grad.item()) - dbias) <= 1e-4 * (np.abs(g_first).sum() + 1)
+
+
+def test_sgd_delta_is_gradient(pkg, cuda):
+    """With SGD and lr=1 the row delta IS the de-duplicated gradient: check it at 1e-5 relative."""
+    B, rows, K = 300, [40, 1, 500, 3], 16
+    case = make_case(13, B, rows, K, weighted=True, prune=False, skew=3.0)
+    rng = case["rng"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = rng.standard_normal(B).astype(np.float32)
+    u = rng.standard_normal((B, len(rows), K)).astype(np.float32)
+    layer = _run_step(pkg, case, "sgd", g_first, g_fm, u, lr=1.0)
+    _, _, _, _, urows, G64, _ = _oracle_step(case, "sgd", g_first, g_fm, u, lr=1.0, dtype=np.float64)
+    G_got = case["table"][urows].astype(np.float64) - layer.table.cpu().numpy()[urows]
+    # subtraction T - G rounds at ulp(T): allow that on top of the gradient tolerance
+    floor = np.abs(G64).max()
+    assert rel_err(G_got, G64, floor) <= REL + 2 ** -23 * np.abs(case["table"]).max() / floor
+
+
+@pytest.mark.parametrize("B,rows", [(5000, [1]), (40_000, [3, 1]), (9000, [2] * 5)])
+def test_long_runs_and_determinism(pkg, cuda, B, rows):
+    """Heavy hitters: every lookup of a field hits 1-3 rows -> runs of thousands of duplicates that
+    cross many chunks (phase 2 and the one-CTA-per-run phase 3).  Two runs must agree bit for bit."""
+    K = 16
+    case = make_case(14, B, rows, K, weighted=True)
+    rng = case["rng"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = (rng.standard_normal(B) * 0.01).astype(np.float32)
+    u = (rng.standard_normal((B, len(rows), K)) * 0.01).astype(np.float32)
+    a = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    b = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    assert torch.equal(a.rows, b.rows) and torch.equal(a.lin_rows, b.lin_rows)
+    t64, acc64, w64, _, urows, G64, _ = _oracle_step(case, "adagrad", g_first, g_fm, u, dtype=np.float64)
+    assert rel_err(a.table.cpu().numpy(), t64, np.abs(case["table"]).max()) <= REL
+    assert rel_err(a.accum.cpu().numpy(), acc64, np.abs(acc64).max()) <= 10 * REL
+    assert rel_err(a.w1.cpu().numpy(), w64, np.abs(case["w1"]).max()) <= REL
+
+
+def test_sort_keys_bit_exact_and_oob(pkg, cuda):
+    from dir_b200 import _lib
+    case = make_case(15, 200, [9, 1, 30], 8, weighted=True, prune=True)
+    layer = make_layer(pkg, case, check_bounds=True).train()
+    idx = case["idx"].copy()
+    B, F = idx.shape
+    keys = torch.empty(B * F, dtype=torch.int32, device="cuda")
+    fm = torch.empty(B, device="cuda")
+    first = torch.empty(B, device="cuda")
+    d_idx, d_val = to_dev(idx), to_dev(case["val"])
+    _lib.check(_lib.lib().dir_embed_fm_fwd(
+        layer.table.data_ptr(), layer.row_stride, layer.w1.data_ptr(), layer.lin_stride, None,
+        d_idx.data_ptr(), d_val.data_ptr(), layer.field_offset.data_ptr(), layer.field_rows.data_ptr(),
+        layer.n_rows, B, F, 8, None, None, first.data_ptr(), fm.data_ptr(), keys.data_ptr(), None,
+        torch.cuda.current_stream().cuda_stream), "fwd")
+    keep = (idx >= 0) & (case["val"] > 0)
+    want = np.where(keep, idx + case["off"][None, :], case["N"]).astype(np.uint32).reshape(-1)
+    assert np.array_equal(keys.cpu().numpy().view(np.uint32), want)
+    idx[7, 0] = 9            # one past the end of field 0
+    with pytest.raises(IndexError):
+        layer(to_dev(idx), d_val)
+
+
+def test_errors_and_empty_batch(pkg, cuda):
+    with pytest.raises(ValueError):
+        pkg.EmbeddingFM(0, 16, [])
+    with pytest.raises(ValueError):
+        pkg.EmbeddingFM(2, 12, [3, 3])
+    layer = pkg.EmbeddingFM(2, 16, [3, 3])
+    with pytest.raises(ValueError):
+        layer(torch.zeros((4, 3), dtype=torch.int64, device="cuda"))
+    with pytest.raises(ValueError):
+        layer(torch.zeros((4, 2), dtype=torch.int64))        # CPU tensor: no CPU path
+    first, fm, emb = layer(torch.zeros((0, 2), dtype=torch.int64, device="cuda"))
+    assert first.shape == (0, 1) and fm.shape == (0, 1) and emb.shape == (0, 32)
+
+
+def test_shared_table_global_ids(pkg, cuda):
+    """Classic DeepFM layout: one feature_size-row table, feature_index holds global ids."""
+    rng = np.random.default_rng(16)
+    N, F, K, B = 500, 6, 16, 77
+    layer = pkg.EmbeddingFM(F, K, N).eval()
+    idx = rng.integers(0, N, size=(B, F)).astype(np.int64)
+    with torch.no_grad():
+        first, fm, emb = layer(to_dev(idx))
+    t = layer.table.cpu().numpy()
+    e = t[idx]
+    assert np.array_equal(emb.cpu().numpy().reshape(B, F, K), e)
+    fm64 = O.fm_second_order(e.astype(np.float64))
+    assert rel_err(fm.cpu().numpy(), fm64, 0.5 * (e.astype(np.float64) ** 2).sum((1, 2))[:, None]) <= REL

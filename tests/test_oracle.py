@@ -1,0 +1,192 @@
+"""The oracle against closed-form known-answer tests and against
+torch autograd, an independent implementation.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deepctr_oracle as O
+from oracle import tf_semantics as tfs
+
+
+def _rand_case(seed, B=7, F=5, K=4, rows=(6, 3, 1, 9, 2), weighted=True, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    rows = np.asarray(rows)
+    off = np.concatenate([[0], np.cumsum(rows)[:-1]])
+    N = int(rows.sum())
+    table = rng.standard_normal((N, K)).astype(dtype)
+    w1 = rng.standard_normal(N).astype(dtype)
+    idx = np.stack([rng.integers(0, r, size=B) for r in rows], axis=1).astype(np.int64)
+    val = (rng.random((B, F)) + 0.1).astype(dtype) if weighted else None
+    return table, w1, off, idx, val, rng
+
+
+# ---- KAT-1: models/DeepFM/test01.py graph, duplicate-id batch ---------------------------------
+def test_kat1_test01_graph():
+    # embedding [5,3]; x = lookup; logit = dense(ones)(x) + sum(x^2); sigmoid CE; Adagrad(0.1)
+    table = np.array([[0.1, -0.2, 0.3], [0.4, 0.5, -0.6], [0.7, 0.8, 0.9],
+                      [-1.0, 1.1, 1.2], [1.3, -1.4, 1.5]], dtype=np.float64)
+    ids = np.array([0, 1, 0])
+    labels = np.array([1.0, 0.0, 1.0])
+    x = table[ids]
+    z = x.sum(-1) + (x * x).sum(-1)
+    g = tfs.sigmoid(z) - labels
+    # closed form: dL/dT[r] = sum_{b: id=r} g_b * (1 + 2 x_r)
+    want = {0: (g[0] + g[2]) * (1 + 2 * table[0]), 1: g[1] * (1 + 2 * table[1])}
+    # the same through the oracle's segment-sum + Adagrad machinery: feed d(logit)/dx as `u`
+    K = 3
+    # one padded column so K stays 3 but the layer sees F=1
+    per_lookup_u = (g[:, None] * (1 + 2 * x))[:, None, :]
+    rows, G, g1, _ = O.embedding_backward(table, [0], ids[:, None], None, np.zeros(3), np.zeros(3),
+                                          u=per_lookup_u, dtype=np.float64)
+    assert rows.tolist() == [0, 1]
+    np.testing.assert_allclose(G[0], want[0], rtol=1e-14)
+    np.testing.assert_allclose(G[1], want[1], rtol=1e-14)
+    acc = np.full_like(table, 0.1)
+    t2 = table.copy()
+    O.sparse_adagrad(t2, acc, rows, G, 0.1)
+    for r in (0, 1):
+        a = 0.1 + want[r] ** 2
+        np.testing.assert_allclose(acc[r], a, rtol=1e-14)
+        np.testing.assert_allclose(t2[r], table[r] - 0.1 * want[r] / np.sqrt(a), rtol=1e-14)
+    assert np.array_equal(t2[2:], table[2:]) and np.all(acc[2:] == 0.1)   # untouched rows
+
+
+# ---- KAT-2/3: FM identity ------------------------------------------------------------------------
+def test_kat2_fm_equals_pairwise_exact_on_integers():
+    rng = np.random.default_rng(0)
+    e = rng.integers(-3, 4, size=(11, 6, 4)).astype(np.float32)     # exact in fp32
+    assert np.array_equal(O.fm_second_order(e), O.fm_pairwise(e))
+
+
+def test_kat3_fm_degenerate():
+    rng = np.random.default_rng(1)
+    e1 = rng.standard_normal((5, 1, 8))
+    np.testing.assert_allclose(O.fm_second_order(e1), 0.0, atol=1e-15)         # F = 1
+    v = rng.standard_normal((5, 1, 8))
+    F = 7
+    eF = np.repeat(v, F, axis=1)
+    np.testing.assert_allclose(O.fm_second_order(eF)[:, 0], 0.5 * F * (F - 1) * (v[:, 0] ** 2).sum(-1), rtol=1e-12)
+
+
+def test_fm_permutation_invariant():
+    rng = np.random.default_rng(2)
+    e = rng.standard_normal((9, 6, 4))
+    p = rng.permutation(6)
+    np.testing.assert_allclose(O.fm_second_order(e), O.fm_second_order(e[:, p]), rtol=1e-12)
+
+
+# ---- KAT-4: cross ---------------------------------------------------------------------------------
+def test_kat4_cross_closed_forms():
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal((6, 10))
+    b = rng.standard_normal((3, 10))
+    xL, s = O.cross_forward(x0, np.zeros((3, 10)), b)
+    np.testing.assert_allclose(xL, x0 + b.sum(0), rtol=1e-13)                   # w = 0
+    assert np.all(s == 0)
+    x0 = rng.standard_normal((6, 1))
+    w = rng.standard_normal((4, 1))
+    xL, _ = O.cross_forward(x0, w, np.zeros((4, 1)))
+    x = x0.copy()
+    for l in range(4):
+        x = x * (1 + x0 * w[l, 0])                                            # d = 1, b = 0
+    np.testing.assert_allclose(xL, x, rtol=1e-13)
+
+
+def test_cross_backward_vs_autograd():
+    rng = np.random.default_rng(4)
+    B, d, L = 9, 13, 4
+    x0, w, b, dy = (rng.standard_normal(s) for s in ((B, d), (L, d), (L, d), (B, d)))
+    tx0, tw, tb = (torch.tensor(a, requires_grad=True) for a in (x0, w, b))
+    xl = tx0
+    for l in range(L):
+        xl = tx0 * (xl @ tw[l])[:, None] + tb[l] + xl
+    xl.backward(torch.tensor(dy))
+    dx0, dw, db = O.cross_backward(x0, w, b, dy)
+    np.testing.assert_allclose(O.cross_forward(x0, w, b)[0], xl.detach().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(dx0, tx0.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dw, tw.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(db, tb.grad.numpy(), rtol=1e-10, atol=1e-12)
+
+
+# ---- embedding backward vs autograd -------------------------------------------------------------
+@pytest.mark.parametrize("weighted", [False, True])
+def test_embedding_backward_vs_autograd(weighted):
+    table, w1, off, idx, val, rng = _rand_case(5, weighted=weighted)
+    B, F = idx.shape
+    K = table.shape[1]
+    u = rng.standard_normal((B, F, K))
+    g_first, g_fm = rng.standard_normal(B), rng.standard_normal(B)
+    tt = torch.tensor(table, requires_grad=True)
+    tw = torch.tensor(w1, requires_grad=True)
+    rows = torch.tensor(idx + off[None, :])
+    v = torch.ones((B, F), dtype=torch.float64) if val is None else torch.tensor(val)
+    e = tt[rows] * v[:, :, None]
+    fm = 0.5 * ((e.sum(1) ** 2) - (e ** 2).sum(1)).sum(-1)
+    first = (tw[rows] * v).sum(1)
+    loss = (fm * torch.tensor(g_fm)).sum() + (first * torch.tensor(g_first)).sum() + (e * torch.tensor(u)).sum()
+    loss.backward()
+    ur, G, g1, dbias = O.embedding_backward(table, off, idx, val, g_first, g_fm, u, dtype=np.float64)
+    dense = np.zeros_like(table)
+    dense[ur] = G
+    dense1 = np.zeros_like(w1)
+    dense1[ur] = g1
+    np.testing.assert_allclose(dense, tt.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dense1, tw.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dbias, g_first.sum(), rtol=1e-12)
+    e_o, _ = O.embedding_lookup(table, off, idx, val, dtype=np.float64)
+    np.testing.assert_allclose(O.fm_second_order(e_o)[:, 0], fm.detach().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(O.first_order(w1, 0.0, off, idx, val, np.float64)[:, 0], first.detach().numpy(), rtol=1e-10)
+
+
+# ---- KAT-5: dedupe + Adagrad == torch sparse Adagrad --------------------------------------------
+def test_kat5_adagrad_matches_torch_sparse_adagrad():
+    rng = np.random.default_rng(6)
+    N, K, B = 12, 4, 20
+    table = rng.standard_normal((N, K)).astype(np.float32)
+    ids = rng.integers(0, 5, size=B)          # heavy duplication; rows 5.. untouched
+    g = rng.standard_normal((B, K)).astype(np.float32)
+    emb = torch.nn.Embedding(N, K, sparse=True)
+    emb.weight.data.copy_(torch.tensor(table))
+    opt = torch.optim.Adagrad(emb.parameters(), lr=0.05, initial_accumulator_value=0.1, eps=0)
+    (emb(torch.tensor(ids)) * torch.tensor(g)).sum().backward()
+    opt.step()
+    t2, acc = table.copy(), np.full_like(table, 0.1)
+    uniq, inv = np.unique(ids, return_inverse=True)
+    G = np.zeros((len(uniq), K), np.float32)
+    np.add.at(G, inv, g)
+    O.sparse_adagrad(t2, acc, uniq, G, 0.05)
+    np.testing.assert_allclose(t2, emb.weight.detach().numpy(), rtol=2e-6, atol=1e-7)
+    assert np.array_equal(t2[5:], table[5:])
+
+
+# ---- KAT-6: weighted semantics --------------------------------------------------------------------
+def test_kat6_weighted_semantics_and_pruning():
+    table, w1, off, idx, val, _ = _rand_case(7)
+    val[0, 0] = 0.0
+    val[1, 2] = -1.5
+    idx[2, 1] = -1
+    e, keep = O.embedding_lookup(table, off, idx, val, "sum", np.float64)
+    assert not keep[0, 0] and not keep[1, 2] and not keep[2, 1]
+    assert np.all(e[0, 0] == 0) and np.all(e[1, 2] == 0) and np.all(e[2, 1] == 0)
+    rows = idx + off[None, :]
+    np.testing.assert_allclose(e[3, 1], val[3, 1] * table[rows[3, 1]])
+    em, _ = O.embedding_lookup(table, off, idx, val, "mean", np.float64)
+    np.testing.assert_allclose(em[3, 1], table[rows[3, 1]])
+    assert np.all(em[0, 0] == 0)
+    # pruned lookups do not touch their row
+    g = np.ones(idx.shape[0])
+    ur, G, g1, _ = O.embedding_backward(table, off, idx, val, g, g, None, dtype=np.float64)
+    kept_rows = np.unique(rows[keep])
+    assert np.array_equal(ur, kept_rows)
+
+
+def test_step_fp32_close_to_fp64():
+    table, w1, off, idx, val, rng = _rand_case(8, B=64, dtype=np.float32)
+    labels = (rng.random(64) < 0.25).astype(np.float32)
+    outs = {}
+    for dt in (np.float32, np.float64):
+        t, w = table.astype(dt), w1.astype(dt)
+        acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+        outs[dt] = (O.deepfm_layer_step(t, acc, w, acc1, 0.0, off, idx, val.astype(dt), labels, 0.05, dtype=dt), t)
+    np.testing.assert_allclose(outs[np.float32][0]["logits"], outs[np.float64][0]["logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(outs[np.float32][1], outs[np.float64][1], rtol=1e-4, atol=1e-5)
