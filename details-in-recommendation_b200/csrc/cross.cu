@@ -392,11 +392,11 @@ extern "C" int dir_cross_fwd(const float* x0, const float* cross_w, const float*
   CrossShape sh;
   if (B < 0 || L < 0 || L > 32 || !cross_shape(d, sh))
     return fail(DIR_EINVAL, "cross_fwd: need B >= 0, 0 <= L <= 32, 0 < d <= 1024");
+  if (B == 0) return 0;
   if (!x0 || !xL || (L > 0 && (!cross_w || !cross_b)))
     return fail(DIR_EINVAL, "cross_fwd: null pointer");
   if (sh.vec == 4 && (!aligned16(x0) || !aligned16(xL) || !aligned16(cross_w) || !aligned16(cross_b)))
     return fail(DIR_EINVAL, "cross_fwd: 16-byte alignment required when d % 4 == 0");
-  if (B == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t want = (B + kCrossWarps - 1) / kCrossWarps;
   const unsigned grid = (unsigned)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
@@ -420,17 +420,17 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   CrossShape sh;
   if (B < 0 || L <= 0 || L > 32 || !cross_shape(d, sh))
     return fail(DIR_EINVAL, "cross_bwd: need B >= 0, 0 < L <= 32, 0 < d <= 1024");
-  if (!x0 || !cross_w || !cross_b || !dy || !dx0 || !dw || !db || !workspace)
+  if (!dw || !db || (B > 0 && (!x0 || !cross_w || !cross_b || !dy || !dx0 || !workspace)))
     return fail(DIR_EINVAL, "cross_bwd: null pointer");
-  if (sh.vec == 4 && (!aligned16(x0) || !aligned16(dy) || !aligned16(dx0) || !aligned16(cross_w) ||
-                      !aligned16(cross_b)))
-    return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (B == 0) {
     cudaMemsetAsync(dw, 0, (size_t)L * d * 4, st);
     cudaMemsetAsync(db, 0, (size_t)L * d * 4, st);
     return 0;
   }
+  if (sh.vec == 4 && (!aligned16(x0) || !aligned16(dy) || !aligned16(dx0) || !aligned16(cross_w) ||
+                      !aligned16(cross_b)))
+    return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
   const size_t smem1 = (size_t)kCrossWarps * (d + 32) * 4;

@@ -162,6 +162,9 @@ extern "C" int dir_embed_fm_fwd(const float* table, int64_t row_stride, const fl
                                 dir_stream_t stream) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_fm_fwd: B >= 0 and F > 0 required");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_fm_fwd: K must be one of 4, 8, 16, 32, 64");
+  if (B == 0) return 0;  // empty batch: nothing to read or write (pointers may be NULL)
   if (!table || !feature_index || !field_offset || !fm)
     return fail(DIR_EINVAL, "embed_fm_fwd: table, feature_index, field_offset, fm are required");
   if (lin && !first) return fail(DIR_EINVAL, "embed_fm_fwd: `first` is required when `lin` is given");
@@ -172,7 +175,6 @@ extern "C" int dir_embed_fm_fwd(const float* table, int64_t row_stride, const fl
   if (n_rows <= 0 || (sort_keys && n_rows >= 0xffffffffLL))
     return fail(DIR_EINVAL, "embed_fm_fwd: 0 < n_rows (< 2^32-1 when sort_keys is given) required");
   if ((B + 7) / 8 > 0x7fffffffLL) return fail(DIR_EINVAL, "embed_fm_fwd: B too large");
-  if (B == 0) return 0;
   FwdArgs a{table, row_stride, lin,        lin_stride, bias, feature_index, feature_value,
             field_offset, field_rows, n_rows, B, F, emb, S, first, fm, sort_keys, oob_flag};
   cudaStream_t st = static_cast<cudaStream_t>(stream);

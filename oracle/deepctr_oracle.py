@@ -123,7 +123,7 @@ def cross_backward(x0, cross_w, cross_b, dy):
 
 
 def embedding_backward(table, field_offset, feature_index, feature_value,
-                       g_first, g_fm, u=None, combiner="sum", dtype=np.float32):
+                       g_first, g_fm, u=None, combiner="sum", dtype=np.float32, return_abs=False):
     """Backward of lookup + first order + FM (implicit in
     optimizer.minimize, models/DeepFM/deepFM.py:230-241).
 
@@ -132,7 +132,8 @@ def embedding_backward(table, field_offset, feature_index, feature_value,
     Returns (rows[U] int64 sorted unique, G[U,K], g1[U], dbias): per-unique-row
     gradients, duplicates summed in sample order ([TF] Unique + UnsortedSegmentSum,
     then _deduplicate_indexed_slices).  Pruned lookups contribute nothing and do
-    not touch their row.
+    not touch their row.  return_abs=True appends Gabs[U,K] = sum |per-lookup term| per row:
+    the magnitude being summed, i.e. the honest denominator for a relative error on G.
     """
     dt = np.dtype(dtype).type
     eff, keep = tfs.effective_value(feature_index, feature_value, combiner, dt)
@@ -152,6 +153,12 @@ def embedding_backward(table, field_offset, feature_index, feature_value,
     np.add.at(G, inv, per_lookup[keep])                                 # sequential, sample order
     np.add.at(g1, inv, per_lookup1[keep])
     dbias = np.sum(g_first.astype(dt), dtype=dt)
+    if return_abs:
+        Gabs = np.zeros_like(G)
+        g1abs = np.zeros_like(g1)
+        np.add.at(Gabs, inv, np.abs(per_lookup[keep]))
+        np.add.at(g1abs, inv, np.abs(per_lookup1[keep]))
+        return uniq, G, g1, dbias, Gabs, g1abs
     return uniq, G, g1, dbias
 
 
