@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of fwd + bwd (+ fused Adagrad update) of the embedding + FM / cross layer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg5] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic Criteo-shaped input
+(BASELINE.json configs[1] by default: 26 sparse + 13 dense fields, 10 M rows, K = 16, B = 65 536,
+embeddings emitted to / upstream gradients consumed from the DNN side):
+    dir_embed_fm_fwd -> g = sigmoid(first + fm) - y -> dir_embed_bwd_sort -> dir_embed_bwd_reduce_update
+(cfg3 adds dir_cross_fwd / dir_cross_bwd between the two halves).  Prints ONE JSON line.
+
+  value     device-resident inputs, CUDA-event timed, max over ranks
+  e2e       the same step fed from pinned HOST buffers through `HostFeeder` (H2D of ids / values /
+            labels and D2H of the logits inside the timed region, copies overlapped with compute)
+  roofline  the dominant C-ABI call, algorithmic bytes (details-in-recommendation_b200/roofline.py)
+            / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the PyTorch-CPU op-by-op restatement of the reference's TF graph
+            (oracle/torch_restatement.py; TF 1.x itself cannot be installed here) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "samples/sec fwd+bwd embedding+FM/cross layer"
+UNIT = "samples/s"
+LR = 0.05
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    p.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    p.add_argument("--rotate", type=int, default=4, help="distinct input sets cycled through")
+    p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of CUDA graphs")
+    p.add_argument("--no-emit", action="store_true", help="FM only: no embeddings out / upstream in")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def workload_config(w, args, n_gpus):
+    B = args.batch or w.batch
+    return {
+        "workload": "%s: DeepFM embedding + first-order + FM%s, fwd + bwd + fused Adagrad row update" % (
+            w.name, " + %d-layer DCN cross" % w.cross_layer_num if w.cross_layer_num else ""),
+        "batch_per_gpu": B, "global_batch": B * n_gpus, "field_size": w.field_size,
+        "sparse_fields": w.field_size - w.n_dense, "dense_fields": w.n_dense,
+        "embedding_size": w.embedding_size, "table_rows": w.n_rows, "ids": w.ids,
+        "cross_layer_num": w.cross_layer_num, "optimizer": "adagrad",
+        "emit_embeddings_and_upstream_grad": not args.no_emit,
+        "parallelism": "single GPU" if n_gpus == 1 else "row-sharded tables (row mod %d), all-to-all, dp%d" % (n_gpus, n_gpus),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the PyTorch-CPU restatement of the reference graph on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_restatement(w, steps, warmup, budget_s, full_batch):
+    """Times oracle/torch_restatement.DeepFMLayerCPU (one variable per column, separate materialising
+    ops, sparse Adagrad) on a bounded sample: the per-step batch is cut so that (steps + warmup)
+    steps fit in `budget_s`.  Returns dict(value, ms_per_step, cores, sample, batch)."""
+    import torch
+    from oracle import torch_restatement as TR
+    import dir_b200
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, F = w.embedding_size, w.field_size
+    model = TR.DeepFMLayerCPU(w.rows_per_field, K, lr=LR)
+
+    def batch_of(B, shift):
+        i, v, y = dir_b200.synth.make_inputs(w, batch=B, seed_shift=shift)
+        U = torch.randn((B, F * K)) * 1e-2
+        return torch.as_tensor(i), torch.as_tensor(v), torch.as_tensor(y), U
+
+    # calibrate on a small batch, then size the sample
+    probe = min(4096, full_batch)
+    b = batch_of(probe, 100)
+    model.step(*b)
+    t0 = time.perf_counter()
+    model.step(*b)
+    per_sample = (time.perf_counter() - t0) / probe
+    B = int(min(full_batch, max(256, budget_s / max(1, steps + warmup) / per_sample)))
+    sets = [batch_of(B, 200 + r) for r in range(2)]
+    for s in range(warmup):
+        model.step(*sets[s % 2])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        model.step(*sets[s % 2])
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": cores, "batch": B,
+            "sample": "%d steps of B=%d (of the workload's %d) %s rows, torch %d threads" % (
+                steps, B, full_batch, w.name, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import dir_b200
+    w = dir_b200.synth.cfg("cfg2" if args.workload == "cfg3" else args.workload)
+    full = args.batch or w.batch
+    r = cpu_restatement(w, args.steps, args.warmup, 150.0, full)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(w, args, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"] + "; PyTorch-CPU restatement of the TF 1.x graph (TF not installable)"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80)]
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.h = [], set(), None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.wait(0.02):
+            self.sample()
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.sample()               # at least one sample while the queue is still draining
+        self._stop.set()
+        self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dir_b200
+    from dir_b200 import roofline as RL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    dir_b200._lib.lib()                    # raises if libdir_b200.so is missing
+
+    w = dir_b200.synth.cfg(args.workload)
+    B, F, K = args.batch or w.batch, w.field_size, w.embedding_size
+    L, d = w.cross_layer_num, w.field_size * w.embedding_size
+    emit = (not args.no_emit) or L > 0
+    R = max(1, args.rotate)
+    torch.manual_seed(dir_b200.synth.SEED_TABLES + rank)
+
+    if world == 1:
+        layer = dir_b200.EmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
+                                     emit_embeddings=emit, device=dev).train()
+    else:
+        layer = dir_b200.ShardedEmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
+                                            emit_embeddings=emit, device=dev).train()
+    layer.w1.normal_(0.0, 0.01)            # TF's zero init would make the first-order path trivial
+    cross = dir_b200.CrossNetwork(d, L, device=dev).train() if L else None
+
+    # R rotating input sets: pinned host copies (for e2e) and device-resident copies (for value)
+    host, devs, ups = [], [], []
+    for r in range(R):
+        i, v, y = dir_b200.synth.make_inputs(w, batch=B, seed_shift=r + 16 * rank)
+        hs = [torch.as_tensor(a).pin_memory() for a in (i, v, y)]
+        host.append(hs)
+        devs.append([t.to(dev) for t in hs])
+        ups.append(torch.randn((B, d), device=dev) * 1e-2 if emit else None)
+    n_rows_touched = []
+
+    def step(idx, val, y, up):
+        first, fm, emb = layer(idx, val)
+        with torch.no_grad():
+            logits = first + fm
+            g = torch.sigmoid(logits).sub_(y.unsqueeze(1))          # SUM-reduced CE: no 1/B (deepFM.py:72)
+        if cross is not None:
+            xL = cross(emb)
+            torch.autograd.backward((first, fm, xL), (g, g, up))
+        elif emit:
+            torch.autograd.backward((first, fm, emb), (g, g, up))
+        else:
+            torch.autograd.backward((first, fm), (g, g))
+        return logits
+
+    # warm every slot eagerly (allocates workspaces), note U per slot
+    out = None
+    for r in range(R):
+        out = step(*devs[r], ups[r])
+        n_rows_touched.append(int(layer.last_n_unique.item()))
+    torch.cuda.synchronize()
+
+    graphs, graph_out = [None] * R, [None] * R
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for r in range(R):
+                    step(*devs[r], ups[r])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            pool = None
+            for r in range(R):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, pool=pool):
+                    graph_out[r] = step(*devs[r], ups[r])
+                pool = g_.pool()
+                graphs[r] = g_
+        except Exception as e:                                       # eager launches are still our kernels
+            if rank == 0:
+                print("bench.py: CUDA graph capture failed (%s); launching eagerly" % e, file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
+
+    def run(slot):
+        if use_graph:
+            graphs[slot].replay()
+            return graph_out[slot]
+        return step(*devs[slot], ups[slot])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = dir_b200._lib.lib()
+    # per-step launch count of OUR kernels (graph replays do not pass through the library's counter)
+    n0 = lib.dir_launch_count()
+    step(*devs[0], ups[0])
+    launches_per_step = int(lib.dir_launch_count() - n0)
+
+    # ---------------- value: device-resident inputs -------------------------------------------
+    for s in range(args.warmup):
+        run(s % R)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for s in range(args.steps):
+            run(s % R)
+        ev1.record()
+        clocks.sample()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    barrier()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region ---------------
+    e2e = None
+    if not args.no_e2e:
+        feeder = dir_b200.HostFeeder(devs[0], devs[1 % R] if R > 1 else devs[0])
+        out_host = [torch.empty((B, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        d2h = out_host[0].numel() * 4
+        slots = [0, 1 % R]
+
+        def e2e_loop(n):
+            feeder.prefetch(0, host[0])
+            for s in range(n):
+                cur = s & 1
+                if s + 1 < n:
+                    feeder.prefetch(cur ^ 1, host[(s + 1) % R])
+                feeder.wait(cur)
+                o = run(slots[cur])
+                feeder.release(cur)
+                out_host[cur].copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        if R > 1:
+            e2e_loop(max(3, args.warmup))
+            barrier()
+            ev0.record()
+            e2e_loop(args.steps)
+            ev1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "how": "EmbeddingFM.forward/backward fed by HostFeeder from pinned host memory "
+                          "(double-buffered H2D on a copy stream), logits read back each step"}
+            # the feeder overwrote slots 0/1: restore the resident sets
+            for r in range(min(2, R)):
+                for dst, src in zip(devs[r], host[r]):
+                    dst.copy_(src)
+            torch.cuda.synchronize()
+
+    # ---------------- roofline: each C-ABI call timed on its own (rank 0's GPU) ---------------
+    roof, kernels = None, []
+    if world == 1:
+        roof, kernels = time_calls(dir_b200, RL, layer, cross, devs, ups, w, B, emit, n_rows_touched,
+                                   min(50, max(5, args.steps)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        wc = dir_b200.synth.cfg("cfg2") if w.name == "cfg3" else w
+        r = cpu_restatement(wc, 3, 1, args.cpu_seconds, B)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": r["sample"] + "; PyTorch-CPU restatement of the reference's TF 1.x graph"}
+
+    if rank == 0:
+        cfg = workload_config(w, args, world)
+        cfg.update({"l2_policy": "%d rotating input sets (%.0f MB of ids/values/upstream each) + a %.2f GB table: "
+                                 "inputs larger than L2, no flush" % (
+                                     R, (B * F * 12 + (B * d * 4 if emit else 0)) / 1e6,
+                                     layer.rows.numel() * 4 / 1e9),
+                    "cuda_graphs": use_graph, "rows_touched_per_step": int(np.mean(n_rows_touched))})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": launches_per_step * args.steps, "roofline": roof, "kernels": kernels,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
+    """CUDA-event time of each C-ABI call on torch's current stream (the one they are launched on),
+    rotating inputs; returns (roofline of the dominant call, per-call table)."""
+    import torch
+    from dir_b200._lib import check, ptr
+    lib = pkg._lib.lib()
+    F, K = w.field_size, w.embedding_size
+    L, d = w.cross_layer_num, F * K
+    R = len(devs)
+    dev = devs[0][0].device
+    st = torch.cuda.current_stream().cuda_stream
+    emb = torch.empty((B, d), device=dev) if emit else None
+    S = torch.empty((B, K), device=dev)
+    first, fm = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    keys = torch.empty(B * F, dtype=torch.int32, device=dev)
+    g = torch.randn(B, device=dev) * 0.1
+    ws = torch.empty(int(lib.dir_embed_bwd_workspace_bytes(B * F, K)), dtype=torch.uint8, device=dev)
+    peak, src = RL.measured_peaks()
+    U = sum(n_unique) / len(n_unique)
+
+    def fwd(r):
+        idx, val, _ = devs[r]
+        check(lib.dir_embed_fm_fwd(ptr(layer.table), layer.row_stride, ptr(layer.w1), layer.lin_stride,
+                                   ptr(layer.bias), ptr(idx), ptr(val), ptr(layer.field_offset),
+                                   ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first),
+                                   ptr(fm), ptr(keys), None, st), "fwd")
+
+    def sort(r):
+        check(lib.dir_embed_bwd_sort(ptr(keys), B * F, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
+
+    def upd(r):
+        check(lib.dir_embed_bwd_reduce_update(
+            ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
+            layer.lin_stride, ptr(devs[r][1]), ptr(g), ptr(g), ptr(S), ptr(ups[r]) if emit else None, B, F, K,
+            layer.n_rows, 1, LR, ptr(ws), ws.numel(), None, st), "update")
+
+    calls = [("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
+             ("dir_embed_bwd_sort", sort, 0),
+             ("dir_embed_bwd_reduce_update", upd, RL.embed_bwd_bytes(B, F, K, U, True, emit, "adagrad"))]
+    if cross is not None:
+        xL, s = torch.empty((B, d), device=dev), torch.empty((B, L), device=dev)
+        dx0, dw, db = torch.empty((B, d), device=dev), torch.empty((L, d), device=dev), torch.empty((L, d), device=dev)
+        cws = torch.empty(int(lib.dir_cross_bwd_workspace_bytes(B, d, L)), dtype=torch.uint8, device=dev)
+
+        def cf(r):
+            check(lib.dir_cross_fwd(ptr(emb), ptr(cross.cross_w), ptr(cross.cross_b), B, d, L, ptr(xL), ptr(s), st), "cf")
+
+        def cb(r):
+            check(lib.dir_cross_bwd(ptr(emb), ptr(cross.cross_w), ptr(cross.cross_b), ptr(ups[r]), ptr(s), B, d, L,
+                                    ptr(dx0), ptr(dw), ptr(db), ptr(cws), cws.numel(), st), "cb")
+        calls += [("dir_cross_fwd", cf, RL.cross_fwd_bytes(B, d, L)), ("dir_cross_bwd", cb, RL.cross_bwd_bytes(B, d, L))]
+
+    # one pass in order keeps each call's inputs valid; events bracket every call
+    evs = {name: [] for name, _, _ in calls}
+    for it in range(3 + iters):
+        r = it % R
+        for name, fn, _ in calls:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(r)
+            b.record()
+            if it >= 3:
+                evs[name].append((a, b))
+    torch.cuda.synchronize()
+    table = []
+    for name, _, nbytes in calls:
+        ms = sum(a.elapsed_time(b) for a, b in evs[name]) / len(evs[name])
+        table.append({"call": name, "us": ms * 1e3, "algorithmic_bytes": int(nbytes),
+                      "achieved_gbs": nbytes / (ms * 1e-3) / 1e9 if nbytes else None})
+    top = max((t for t in table if t["algorithmic_bytes"]), key=lambda t: t["us"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(w.name, {}).get(top["call"])
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "kernel": top["call"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": top["achieved_gbs"] / peak, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
+            if src == "measured" else "fallback (B200_PROFILING.md)", "traffic": traffic,
+            "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "us_per_launch": top["us"]}
+    return roof, table
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,8 +4,9 @@ The directory name carries a hyphen (it mirrors the reference's name); import it
 `importlib.import_module("details-in-recommendation_b200")` or through the alias module
 `dir_b200` at the repository root.
 """
-from . import _lib, synth                                    # noqa: F401
+from . import _lib, roofline, synth                          # noqa: F401
 from ._lib import LIB_PATH, build, launch_count             # noqa: F401
+from .feeder import HostFeeder                              # noqa: F401
 from .layers import CrossNetwork, EmbeddingFM               # noqa: F401
 
-__all__ = ["EmbeddingFM", "CrossNetwork", "synth", "build", "launch_count", "LIB_PATH"]
+__all__ = ["EmbeddingFM", "CrossNetwork", "HostFeeder", "synth", "roofline", "build", "launch_count", "LIB_PATH"]
