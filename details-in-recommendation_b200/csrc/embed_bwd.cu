@@ -22,8 +22,8 @@
 
 namespace dir {
 
-constexpr int kChunk = 16;    // lookups per chunk (C)
-constexpr int kBatch = 4;     // lookups whose loads are in flight together
+constexpr int kTile = 32;     // lookups a warp handles at a time
+constexpr int kChunk = 128;   // lookups per chunk (C): one warp walks one chunk
 constexpr int kLongRun = 32;  // chunks; longer crossing runs go to phase 3
 constexpr uint32_t kNoKey = 0xffffffffu;
 
@@ -110,6 +110,8 @@ struct BwdArgs {
   uint32_t pruned_key;  // = n_rows
   int opt;
   float lr;
+  uint32_t div_magic;   // position / F == (position * div_magic) >> div_shift for position < 2^31
+  int div_shift;
 };
 
 // Row update with the de-duplicated gradient.  Intrinsics pin the evaluation order to the
@@ -153,84 +155,187 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int
   }
 }
 
+// Row update from values already in registers (same arithmetic as apply_update).
+__device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int sub, float4 T,
+                                             float4 A, float4 G, float w, float a1, float g1) {
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  T.x = upd(T.x, G.x, a.lr, A.x, adagrad);
+  T.y = upd(T.y, G.y, a.lr, A.y, adagrad);
+  T.z = upd(T.z, G.z, a.lr, A.z, adagrad);
+  T.w = upd(T.w, G.w, a.lr, A.w, adagrad);
+  *(reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub) = T;
+  if (adagrad) *(reinterpret_cast<float4*>(a.accum + (int64_t)key * a.row_stride) + sub) = A;
+  if (a.lin != nullptr && sub == 0) {
+    a.lin[(int64_t)key * a.lin_stride] = upd(w, g1, a.lr, a1, adagrad);
+    if (adagrad) a.lin_accum[(int64_t)key * a.lin_stride] = a1;
+  }
+}
+
+// phase 1: one warp per chunk of kChunk sorted lookups, kTile = 32 at a time.
+//   lane-per-lookup stage : key, position, sample = position / F, value, g_first, g_fm
+//   vector stage          : LPR lanes hold one K-vector as float4s, so a pass covers 32/LPR lookups;
+//                           PB passes have their S / u / row loads in flight together.  Each pass forms
+//                           the per-lookup gradients, sums runs of equal rows with a segmented
+//                           inclusive scan over the row slots (fixed shuffle pattern) and adds the
+//                           running sum carried from the previous pass.
+//   At the last lookup of a run: the run lies inside the chunk -> update the row right here with the
+//   row / accumulator already in registers; otherwise leave a partial for phase 2 / 3.
 template <int LPR>
 __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) {
   constexpr int K = LPR * 4;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gid = tid / LPR;
-  const int sub = (int)(tid % LPR);
-  const int64_t i0 = gid * kChunk;
-  if (i0 >= a.n) return;
-  const int cnt = (int)min((int64_t)kChunk, a.n - i0);
+  constexpr int SLOTS = 32 / LPR;             // lookups per pass
+  constexpr int PASSES = LPR;                 // passes per tile of 32 lookups
+  constexpr int PB = PASSES < 2 ? PASSES : 2; // passes whose loads are in flight together
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int slot = lane / LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t i0 = chunk * kChunk;
+  if (i0 >= a.n) return;  // whole warp
+  const int64_t chunk_end = min(a.n, i0 + (int64_t)kChunk);
   const uint32_t prev_key = i0 > 0 ? __ldg(a.keys + i0 - 1) : kNoKey;
-  const uint32_t next_key = i0 + kChunk < a.n ? __ldg(a.keys + i0 + kChunk) : kNoKey;
+  const uint32_t next_chunk_key = chunk_end < a.n ? __ldg(a.keys + chunk_end) : kNoKey;
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const uint64_t pol_once = policy_evict_first();  // upstream gradients are read exactly once
 
-  uint32_t cur = __ldg(a.keys + i0);
-  bool left_open = cur == prev_key;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float acc1 = 0.f;
-  unsigned heads = (cur != prev_key && cur != a.pruned_key) ? 1u : 0u;
+  uint32_t carry_key = kNoKey, last_key = prev_key;
+  float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+  float carry1 = 0.f;
+  unsigned heads = 0;
 
-  auto flush = [&](bool right_open) {
-    if (cur == a.pruned_key) return;
-    if (!left_open && !right_open) {
-      apply_update<LPR>(a, cur, sub, acc, acc1);
-    } else {
-      const int64_t s = gid * 2 + (left_open ? 0 : 1);
-      *(reinterpret_cast<float4*>(a.part + s * K) + sub) = acc;
-      if (sub == 0) a.part1[s] = acc1;
+  // software pipeline: the next tile's keys / positions are requested before this tile's gathers
+  int64_t i = i0 + lane;
+  uint32_t key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
+  uint32_t pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
+
+  for (int64_t base = i0; base < chunk_end; base += kTile) {
+    const uint32_t key = key_nx, pos = pos_nx;
+    i = base + kTile + lane;
+    key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
+    pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
+
+    // ---- lane-per-lookup stage
+    const bool valid = key != a.pruned_key;
+    uint32_t keyp = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) keyp = last_key;
+    uint32_t keyn = __shfl_down_sync(FULL, key, 1);
+    const uint32_t first_nx = __shfl_sync(FULL, key_nx, 0);
+    if (lane == 31) keyn = base + kTile < chunk_end ? first_nx : next_chunk_key;
+    const bool last_in_chunk = base + lane == chunk_end - 1;
+    if (last_in_chunk) keyn = next_chunk_key;
+    last_key = __shfl_sync(FULL, key, 31);
+    heads += __popc(__ballot_sync(FULL, valid && key != keyp));
+    const uint32_t b = (uint32_t)(((uint64_t)pos * a.div_magic) >> a.div_shift);  // pos / F
+    float v = 1.f, g1 = 0.f, g2 = 0.f;
+    if (valid) {
+      if (a.val) v = __ldg(a.val + pos);
+      if (a.g_first) g1 = __ldg(a.g_first + b);
+      g2 = __ldg(a.g_fm + b);
     }
-  };
-
-  for (int c0 = 0; c0 < kChunk; c0 += kBatch) {
-    if (c0 >= cnt) break;
-    uint32_t k[kBatch];
-    float v[kBatch], g1[kBatch], g2[kBatch];
-    float4 Sb[kBatch], ub[kBatch], T[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const int i = c0 + j;
-      k[j] = i < cnt ? __ldg(a.keys + i0 + i) : a.pruned_key;
-      v[j] = 1.f;
-      g1[j] = g2[j] = 0.f;
-      Sb[j] = ub[j] = T[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k[j] != a.pruned_key) {
-        const uint32_t p = __ldg(a.pos + i0 + i);
-        const uint32_t b = p / (uint32_t)a.F;
-        if (a.val) v[j] = __ldg(a.val + p);
-        if (a.g_first) g1[j] = __ldg(a.g_first + b);
-        g2[j] = __ldg(a.g_fm + b);
-        Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)b * K) + sub);
-        if (a.u) ub[j] = ldg_stream(a.u + (int64_t)p * K + sub * 4);
-        // plain load: the row may be rewritten later in this kernel by this same lane group
-        T[j] = *(reinterpret_cast<const float4*>(a.table + (int64_t)k[j] * a.row_stride) + sub);
-      }
+    // what happens at this lookup: 0 nothing, 1 update the row, 2 partial (run open to the left),
+    // 3 partial (run starts here, open to the right)
+    int act = 0;
+    if (valid && (keyn != key || last_in_chunk)) {
+      const bool left_open = key == prev_key;
+      const bool right_open = last_in_chunk && keyn == key;
+      act = (!left_open && !right_open) ? 1 : (left_open ? 2 : 3);
     }
+
+    // ---- vector stage
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      if (c0 + j < cnt) {
-        if (k[j] != cur) {
-          flush(false);
-          cur = k[j];
-          left_open = false;
-          acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          acc1 = 0.f;
-          if (cur != a.pruned_key) ++heads;
-        }
+    for (int j0 = 0; j0 < PASSES; j0 += PB) {
+      uint32_t k[PB];
+      int ac[PB];
+      float vv[PB], gg1[PB], gg2[PB], w[PB], a1[PB];
+      float4 Sb[PB], ub[PB], T[PB], A[PB];
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int l = (j0 + j) * SLOTS + slot;
+        k[j] = __shfl_sync(FULL, key, l);
+        const uint32_t p = __shfl_sync(FULL, pos, l);
+        const uint32_t bb = __shfl_sync(FULL, b, l);
+        ac[j] = __shfl_sync(FULL, act, l);
+        Sb[j] = ub[j] = T[j] = A[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[j] = a1[j] = 0.f;
         if (k[j] != a.pruned_key) {
-          // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
-          const float vv = v[j], gg = g2[j];
-          acc.x = __fadd_rn(acc.x, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(vv, T[j].x))), ub[j].x)));
-          acc.y = __fadd_rn(acc.y, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(vv, T[j].y))), ub[j].y)));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(vv, T[j].z))), ub[j].z)));
-          acc.w = __fadd_rn(acc.w, __fmul_rn(vv, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(vv, T[j].w))), ub[j].w)));
-          acc1 = __fadd_rn(acc1, __fmul_rn(g1[j], vv));
+          if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
+          Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
+          // plain load: this warp may rewrite the row further down
+          T[j] = *(reinterpret_cast<const float4*>(a.table + (int64_t)k[j] * a.row_stride) + sub);
+          if (ac[j] == 1) {
+            if (adagrad)
+              A[j] = *(reinterpret_cast<const float4*>(a.accum + (int64_t)k[j] * a.row_stride) + sub);
+            if (a.lin != nullptr && sub == 0) {
+              w[j] = a.lin[(int64_t)k[j] * a.lin_stride];
+              if (adagrad) a1[j] = a.lin_accum[(int64_t)k[j] * a.lin_stride];
+            }
+          }
         }
+      }
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int l = (j0 + j) * SLOTS + slot;
+        vv[j] = __shfl_sync(FULL, v, l);
+        gg1[j] = __shfl_sync(FULL, g1, l);
+        gg2[j] = __shfl_sync(FULL, g2, l);
+      }
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
+        const float x = vv[j], gg = gg2[j];
+        float4 d;
+        d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(x, T[j].x))), ub[j].x));
+        d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(x, T[j].y))), ub[j].y));
+        d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(x, T[j].z))), ub[j].z));
+        d.w = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(x, T[j].w))), ub[j].w));
+        float d1 = __fmul_rn(gg1[j], x);
+        if (k[j] == a.pruned_key) {
+          d = make_float4(0.f, 0.f, 0.f, 0.f);
+          d1 = 0.f;
+        }
+        // segmented inclusive scan over the row slots (sorted: equal keys are contiguous)
+#pragma unroll
+        for (int dl = 1; dl < SLOTS; dl <<= 1) {
+          const uint32_t ko = __shfl_up_sync(FULL, k[j], dl * LPR);
+          const float ox = __shfl_up_sync(FULL, d.x, dl * LPR);
+          const float oy = __shfl_up_sync(FULL, d.y, dl * LPR);
+          const float oz = __shfl_up_sync(FULL, d.z, dl * LPR);
+          const float ow = __shfl_up_sync(FULL, d.w, dl * LPR);
+          const float o1 = __shfl_up_sync(FULL, d1, dl * LPR);
+          if (slot >= dl && ko == k[j]) {
+            d.x = __fadd_rn(ox, d.x);
+            d.y = __fadd_rn(oy, d.y);
+            d.z = __fadd_rn(oz, d.z);
+            d.w = __fadd_rn(ow, d.w);
+            d1 = __fadd_rn(o1, d1);
+          }
+        }
+        if (k[j] == carry_key) {  // the run came in from an earlier pass of this chunk
+          d.x = __fadd_rn(carry.x, d.x);
+          d.y = __fadd_rn(carry.y, d.y);
+          d.z = __fadd_rn(carry.z, d.z);
+          d.w = __fadd_rn(carry.w, d.w);
+          d1 = __fadd_rn(carry1, d1);
+        }
+        if (ac[j] == 1) {
+          apply_loaded(a, k[j], sub, T[j], A[j], d, w[j], a1[j], d1);
+        } else if (ac[j] >= 2) {
+          const int64_t s = chunk * 2 + (ac[j] == 2 ? 0 : 1);
+          *(reinterpret_cast<float4*>(a.part + s * K) + sub) = d;
+          if (sub == 0) a.part1[s] = d1;
+        }
+        const int src = (SLOTS - 1) * LPR + sub;
+        carry_key = __shfl_sync(FULL, k[j], src);
+        carry.x = __shfl_sync(FULL, d.x, src);
+        carry.y = __shfl_sync(FULL, d.y, src);
+        carry.z = __shfl_sync(FULL, d.z, src);
+        carry.w = __shfl_sync(FULL, d.w, src);
+        carry1 = __shfl_sync(FULL, d1, src);
       }
     }
   }
-  flush(cur == next_key);
-  if (sub == 0 && heads && a.n_unique) atomicAdd(a.n_unique, (unsigned long long)heads);
+  if (lane == 0 && heads && a.n_unique) atomicAdd(a.n_unique, (unsigned long long)heads);
 }
 
 // phase 2: one lane group per chunk; the chunk where a crossing run starts finishes it.
@@ -327,7 +432,7 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
   const int64_t nchunks = (a.n + kChunk - 1) / kChunk;
   const int64_t threads = nchunks * LPR;
   const unsigned grid = (unsigned)((threads + 255) / 256);
-  embed_bwd_reduce_kernel<LPR><<<grid, 256, 0, st>>>(a);
+  embed_bwd_reduce_kernel<LPR><<<(unsigned)((nchunks + 7) / 8), 256, 0, st>>>(a);
   embed_bwd_combine_kernel<LPR><<<grid, 256, 0, st>>>(a);
   embed_bwd_long_kernel<LPR><<<kSMs, 256, 0, st>>>(a);
   int n = 3;
@@ -404,7 +509,12 @@ extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t r
     return fail(DIR_ENOMEM, "embed_bwd_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0};
+  // exact for positions < 2^31: shift = 31 + ceil(log2 F), magic = ceil(2^shift / F) < 2^32
+  int lg = 0;
+  while ((1 << lg) < F) ++lg;
+  a.div_shift = 31 + lg;
+  a.div_magic = (uint32_t)((((uint64_t)1 << a.div_shift) + (uint64_t)F - 1) / (uint64_t)F);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (K) {
     case 4: return launch_bwd<1>(a, n_unique_out, st);

@@ -27,6 +27,7 @@ struct FwdArgs {
   float* fm;
   uint32_t* sort_keys;
   int* oob_flag;
+  int tune;  // experiment bits (DIR_B200_TUNE): 1 lin evict_last, 2 emb stores evict_first, 4 rows evict_first
 };
 
 template <int LPR, int UNR>
@@ -45,6 +46,8 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
   float4 Sv = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 Qv = make_float4(0.f, 0.f, 0.f, 0.f);
   float fo = 0.f;
+  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_once = policy_evict_first();
 
   for (int f0 = 0; f0 < F; f0 += RPW * UNR) {
     float4 t[UNR];
@@ -79,8 +82,12 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
       t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       w[j] = 0.f;
       if (keep[j]) {
-        t[j] = __ldg(reinterpret_cast<const float4*>(a.table + row[j] * a.row_stride) + sub);
-        if (a.lin != nullptr && sub == 0) w[j] = __ldg(a.lin + row[j] * a.lin_stride);
+        const float* rp = a.table + row[j] * a.row_stride + sub * 4;
+        t[j] = (a.tune & 4) ? ldg_hint(rp, pol_once) : __ldg(reinterpret_cast<const float4*>(rp));
+        if (a.lin != nullptr && sub == 0) {
+          const float* lp = a.lin + row[j] * a.lin_stride;
+          w[j] = (a.tune & 1) ? ldg_hint1(lp, pol_keep) : __ldg(lp);
+        }
       }
     }
 #pragma unroll
@@ -96,7 +103,10 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
         Qv.x = fmaf(e.x, e.x, Qv.x); Qv.y = fmaf(e.y, e.y, Qv.y);
         Qv.z = fmaf(e.z, e.z, Qv.z); Qv.w = fmaf(e.w, e.w, Qv.w);
         fo = fmaf(v[j], w[j], fo);
-        if (a.emb) stg_stream(a.emb + (base + f) * K + sub * 4, e);
+        if (a.emb) {
+          float* ep = a.emb + (base + f) * K + sub * 4;
+          if (a.tune & 2) stg_hint(ep, e, pol_once); else stg_stream(ep, e);
+        }
         if (a.sort_keys && sub == 0)
           a.sort_keys[base + f] = keep[j] ? (uint32_t)row[j] : pruned_key;
       }
@@ -176,7 +186,7 @@ extern "C" int dir_embed_fm_fwd(const float* table, int64_t row_stride, const fl
     return fail(DIR_EINVAL, "embed_fm_fwd: 0 < n_rows (< 2^32-1 when sort_keys is given) required");
   if ((B + 7) / 8 > 0x7fffffffLL) return fail(DIR_EINVAL, "embed_fm_fwd: B too large");
   FwdArgs a{table, row_stride, lin,        lin_stride, bias, feature_index, feature_value,
-            field_offset, field_rows, n_rows, B, F, emb, S, first, fm, sort_keys, oob_flag};
+            field_offset, field_rows, n_rows, B, F, emb, S, first, fm, sort_keys, oob_flag, tune()};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (K) {
     case 4: return launch_fwd<1>(a, st);

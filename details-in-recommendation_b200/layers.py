@@ -13,6 +13,7 @@ feature_index / feature_value.  PyTorch here is plumbing (device memory, streams
 hand-off); all arithmetic runs in libdir_b200.so.  There is no CPU path.
 """
 import math
+import os
 from typing import Optional, Sequence, Union
 
 import torch
@@ -115,8 +116,10 @@ class EmbeddingFM(torch.nn.Module):
                  rows_per_field: Union[int, Sequence[int]], optimizer: str = "adagrad",
                  lr: float = 0.01, initial_accumulator_value: float = 0.1,
                  combiner: str = "sum", first_order: bool = True, emit_embeddings: bool = True,
-                 check_bounds: bool = False, device="cuda"):
+                 check_bounds: bool = False, lin_interleaved: Optional[bool] = None, device="cuda"):
         super().__init__()
+        if lin_interleaved is None:
+            lin_interleaved = os.environ.get("DIR_B200_LIN_SEPARATE", "0") != "1"
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
         if embedding_size not in _K_OK:
@@ -145,13 +148,15 @@ class EmbeddingFM(torch.nn.Module):
         K = embedding_size
         adagrad = optimizer == "adagrad"
         self.row_stride = 2 * K if adagrad else K
-        self.lin_stride = 2 if adagrad else 1
+        self.lin_stride = 2 if (adagrad and lin_interleaved) else 1
         dev = torch.device(device)
         self.register_buffer("field_offset", torch.tensor(offsets, dtype=torch.int64, device=dev))
         self.register_buffer("field_rows", None if rows is None else
                              torch.tensor(rows, dtype=torch.int64, device=dev))
         self.register_buffer("rows", torch.empty((n_rows, self.row_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_rows", torch.zeros((n_rows, self.lin_stride), dtype=torch.float32, device=dev))
+        self.register_buffer("lin_acc", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)
+                             if (adagrad and not lin_interleaved) else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
@@ -179,7 +184,9 @@ class EmbeddingFM(torch.nn.Module):
 
     @property
     def w1_accum(self):
-        return self.lin_rows[:, 1] if self.optimizer == "adagrad" else None
+        if self.optimizer != "adagrad":
+            return None
+        return self.lin_rows[:, 1] if self.lin_acc is None else self.lin_acc[:, 0]
 
     @torch.no_grad()
     def load_tables(self, table=None, w1=None, accum=None, w1_accum=None):
