@@ -251,7 +251,7 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     graphs, graph_out = [None] * R, [None] * R
-    use_graph = not args.no_graph
+    use_graph = not args.no_graph and world == 1     # the sharded step reads split sizes on the host
     if use_graph:
         try:
             side = torch.cuda.Stream()

@@ -8,5 +8,6 @@ from . import _lib, roofline, synth                          # noqa: F401
 from ._lib import LIB_PATH, build, launch_count             # noqa: F401
 from .feeder import HostFeeder                              # noqa: F401
 from .layers import CrossNetwork, EmbeddingFM               # noqa: F401
+from .sharded import ShardedEmbeddingFM, ShardPlan          # noqa: F401
 
-__all__ = ["EmbeddingFM", "CrossNetwork", "HostFeeder", "synth", "roofline", "build", "launch_count", "LIB_PATH"]
+__all__ = ["EmbeddingFM", "CrossNetwork", "ShardedEmbeddingFM", "ShardPlan", "HostFeeder", "synth", "roofline", "build", "launch_count", "LIB_PATH"]

@@ -28,6 +28,20 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_int, c_float,
                                             c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dir_embed_bwd_sorted": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p]),
+    "dir_shard_unique_workspace_bytes": (c_size_t, [c_int64]),
+    "dir_shard_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dir_rows_gather": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
+                                c_int64, c_void_p]),
+    "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int64,
+                                          c_void_p, c_size_t, c_void_p]),
+    "dir_rows_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                       c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_size_t,
+                                       c_void_p, c_void_p]),
     "dir_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                               c_void_p, c_void_p]),
     "dir_cross_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),

@@ -112,14 +112,27 @@ struct BwdArgs {
   float lr;
   uint32_t div_magic;   // position / F == (position * div_magic) >> div_shift for position < 2^31
   int div_shift;
+  // sharded-table modes (see kMode*)
+  int mode;
+  const uint32_t* rowidx;  // kModeEmit: row of `table` (the exchanged unique-row buffer) per sorted entry
+  float* emit;             // kModeEmit: [n_unique, emit_stride] receives (G[K], g1) per run
+  int64_t emit_stride;
+  const float* gbuf;       // kModeGiven: [n, gbuf_stride] per-lookup (G[K], g1), indexed by position
+  int64_t gbuf_stride;
 };
 
-// Row update with the de-duplicated gradient.  Intrinsics pin the evaluation order to the
-// oracle's: a = acc + g*g; T = T - (lr*g)/sqrt(a)   ([TF] SparseApplyAdagrad, no epsilon).
+constexpr int kModeLocal = 0;  // gradients formed from g, S, u, row; the row is updated in place
+constexpr int kModeEmit = 1;   // requester side of a sharded table: per-row sums go to `emit`
+constexpr int kModeGiven = 2;  // owner side: per-lookup gradients arrive in `gbuf`; update in place
+
+// Row update with the de-duplicated gradient: a = acc + g*g; T = T - (lr*g) * rsqrt(a)
+// ([TF] SparseApplyAdagrad, no epsilon; Eigen evaluates it as lr * g * rsqrt(a) as well).  rsqrtf
+// is MUFU.RSQ (<= 2 ulp): an IEEE divide + square root per component made this line a quarter of
+// all instructions the kernel issued (profiles/r01_reduce_v1_source.txt).
 __device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool adagrad) {
   if (adagrad) {
     a = __fadd_rn(a, __fmul_rn(g, g));
-    return __fsub_rn(t, __fdiv_rn(__fmul_rn(lr, g), __fsqrt_rn(a)));
+    return __fsub_rn(t, __fmul_rn(__fmul_rn(lr, g), rsqrtf(a)));
   }
   return __fsub_rn(t, __fmul_rn(lr, g));
 }
@@ -127,6 +140,12 @@ __device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool 
 template <int LPR>
 __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
                                              float g1) {
+  if (a.mode == kModeEmit) {  // `key` is the row of the emit buffer here
+    float* e = a.emit + (int64_t)key * a.emit_stride;
+    *(reinterpret_cast<float4*>(e) + sub) = G;
+    if (sub == 0) e[LPR * 4] = g1;
+    return;
+  }
   const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
   float4* trow = reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub;
   float4 T = *trow;
@@ -180,8 +199,8 @@ __device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int
 //                           running sum carried from the previous pass.
 //   At the last lookup of a run: the run lies inside the chunk -> update the row right here with the
 //   row / accumulator already in registers; otherwise leave a partial for phase 2 / 3.
-template <int LPR>
-__global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) {
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs a) {
   constexpr int K = LPR * 4;
   constexpr int SLOTS = 32 / LPR;             // lookups per pass
   constexpr int PASSES = LPR;                 // passes per tile of 32 lookups
@@ -208,12 +227,16 @@ __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) 
   int64_t i = i0 + lane;
   uint32_t key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
   uint32_t pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
+  uint32_t row_nx = key_nx;  // row of `table` this lookup reads
+  if (MODE == kModeEmit) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
 
   for (int64_t base = i0; base < chunk_end; base += kTile) {
-    const uint32_t key = key_nx, pos = pos_nx;
+    const uint32_t key = key_nx, pos = pos_nx, row = row_nx;
     i = base + kTile + lane;
     key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
     pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
+    row_nx = key_nx;
+    if (MODE == kModeEmit) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
 
     // ---- lane-per-lookup stage
     const bool valid = key != a.pruned_key;
@@ -226,49 +249,66 @@ __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) 
     if (last_in_chunk) keyn = next_chunk_key;
     last_key = __shfl_sync(FULL, key, 31);
     heads += __popc(__ballot_sync(FULL, valid && key != keyp));
+    const unsigned cont = __ballot_sync(FULL, valid && keyn == key);  // run goes on after this lookup
     const uint32_t b = (uint32_t)(((uint64_t)pos * a.div_magic) >> a.div_shift);  // pos / F
-    float v = 1.f, g1 = 0.f, g2 = 0.f;
+    float v = 1.f, g2 = 0.f, d1l = 0.f;
     if (valid) {
-      if (a.val) v = __ldg(a.val + pos);
-      if (a.g_first) g1 = __ldg(a.g_first + b);
-      g2 = __ldg(a.g_fm + b);
+      if (MODE == kModeGiven) {
+        d1l = __ldg(a.gbuf + (int64_t)pos * a.gbuf_stride + K);
+      } else {
+        if (a.val) v = __ldg(a.val + pos);
+        if (a.g_first) d1l = __fmul_rn(__ldg(a.g_first + b), v);
+        g2 = __ldg(a.g_fm + b);
+      }
     }
-    // what happens at this lookup: 0 nothing, 1 update the row, 2 partial (run open to the left),
-    // 3 partial (run starts here, open to the right)
+    // what happens at this lookup: 0 nothing, 1 finish the row (update / emit), 2 partial (run open
+    // to the left), 3 partial (run starts here, open to the right); bits 2.. = scan mask: bit t set
+    // when the lookup 2^t places earlier in the same pass has the same key
     int act = 0;
     if (valid && (keyn != key || last_in_chunk)) {
       const bool left_open = key == prev_key;
       const bool right_open = last_in_chunk && keyn == key;
       act = (!left_open && !right_open) ? 1 : (left_open ? 2 : 3);
     }
+#pragma unroll
+    for (int t = 0; (1 << t) < SLOTS; ++t) {
+      const uint32_t ko = __shfl_up_sync(FULL, key, 1 << t);
+      if ((lane % SLOTS) >= (1 << t) && ko == key && valid) act |= 4 << t;
+    }
 
     // ---- vector stage
 #pragma unroll
     for (int j0 = 0; j0 < PASSES; j0 += PB) {
-      uint32_t k[PB];
+      uint32_t k[PB], rw[PB];
       int ac[PB];
-      float vv[PB], gg1[PB], gg2[PB], w[PB], a1[PB];
+      float a1[PB], lw[PB];
       float4 Sb[PB], ub[PB], T[PB], A[PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int l = (j0 + j) * SLOTS + slot;
         k[j] = __shfl_sync(FULL, key, l);
+        rw[j] = MODE == kModeEmit ? __shfl_sync(FULL, row, l) : k[j];
         const uint32_t p = __shfl_sync(FULL, pos, l);
-        const uint32_t bb = __shfl_sync(FULL, b, l);
+        const uint32_t bb = MODE == kModeGiven ? 0u : __shfl_sync(FULL, b, l);
         ac[j] = __shfl_sync(FULL, act, l);
         Sb[j] = ub[j] = T[j] = A[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w[j] = a1[j] = 0.f;
+        lw[j] = a1[j] = 0.f;
         if (k[j] != a.pruned_key) {
-          if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
-          Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
-          // plain load: this warp may rewrite the row further down
-          T[j] = *(reinterpret_cast<const float4*>(a.table + (int64_t)k[j] * a.row_stride) + sub);
-          if (ac[j] == 1) {
-            if (adagrad)
-              A[j] = *(reinterpret_cast<const float4*>(a.accum + (int64_t)k[j] * a.row_stride) + sub);
+          const int64_t ro = (int64_t)rw[j] * a.row_stride;
+          if (MODE == kModeGiven) {  // the per-lookup gradient was formed by the requester
+            ub[j] = ldg_hint(a.gbuf + (int64_t)p * a.gbuf_stride + sub * 4, pol_once);
+          } else {
+            if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
+            Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
+            // plain load: this warp may rewrite the row further down
+            T[j] = *(reinterpret_cast<const float4*>(a.table + ro) + sub);
+          }
+          if (MODE != kModeEmit && (ac[j] & 3) == 1) {
+            if (MODE == kModeGiven) T[j] = *(reinterpret_cast<const float4*>(a.table + ro) + sub);
+            if (adagrad) A[j] = *(reinterpret_cast<const float4*>(a.accum + ro) + sub);
             if (a.lin != nullptr && sub == 0) {
-              w[j] = a.lin[(int64_t)k[j] * a.lin_stride];
-              if (adagrad) a1[j] = a.lin_accum[(int64_t)k[j] * a.lin_stride];
+              lw[j] = a.lin[(int64_t)rw[j] * a.lin_stride];
+              if (adagrad) a1[j] = a.lin_accum[(int64_t)rw[j] * a.lin_stride];
             }
           }
         }
@@ -276,121 +316,139 @@ __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const BwdArgs a) 
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int l = (j0 + j) * SLOTS + slot;
-        vv[j] = __shfl_sync(FULL, v, l);
-        gg1[j] = __shfl_sync(FULL, g1, l);
-        gg2[j] = __shfl_sync(FULL, g2, l);
-      }
-#pragma unroll
-      for (int j = 0; j < PB; ++j) {
-        // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
-        const float x = vv[j], gg = gg2[j];
-        float4 d;
-        d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(x, T[j].x))), ub[j].x));
-        d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(x, T[j].y))), ub[j].y));
-        d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(x, T[j].z))), ub[j].z));
-        d.w = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(x, T[j].w))), ub[j].w));
-        float d1 = __fmul_rn(gg1[j], x);
+        float4 d = ub[j];
+        float d1 = __shfl_sync(FULL, d1l, l);
+        if (MODE != kModeGiven) {
+          // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
+          const float x = __shfl_sync(FULL, v, l), gg = __shfl_sync(FULL, g2, l);
+          d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(x, T[j].x))), ub[j].x));
+          d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(x, T[j].y))), ub[j].y));
+          d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(x, T[j].z))), ub[j].z));
+          d.w = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(x, T[j].w))), ub[j].w));
+        }
         if (k[j] == a.pruned_key) {
           d = make_float4(0.f, 0.f, 0.f, 0.f);
           d1 = 0.f;
         }
-        // segmented inclusive scan over the row slots (sorted: equal keys are contiguous)
+        // segmented inclusive scan over the row slots (sorted: equal keys are contiguous); a step is
+        // skipped when no lookup of the pass needs it (most runs are short)
 #pragma unroll
-        for (int dl = 1; dl < SLOTS; dl <<= 1) {
-          const uint32_t ko = __shfl_up_sync(FULL, k[j], dl * LPR);
-          const float ox = __shfl_up_sync(FULL, d.x, dl * LPR);
-          const float oy = __shfl_up_sync(FULL, d.y, dl * LPR);
-          const float oz = __shfl_up_sync(FULL, d.z, dl * LPR);
-          const float ow = __shfl_up_sync(FULL, d.w, dl * LPR);
-          const float o1 = __shfl_up_sync(FULL, d1, dl * LPR);
-          if (slot >= dl && ko == k[j]) {
-            d.x = __fadd_rn(ox, d.x);
-            d.y = __fadd_rn(oy, d.y);
-            d.z = __fadd_rn(oz, d.z);
-            d.w = __fadd_rn(ow, d.w);
-            d1 = __fadd_rn(o1, d1);
+        for (int t = 0; (1 << t) < SLOTS; ++t) {
+          if (__any_sync(FULL, ac[j] & (4 << t))) {
+            const int dl = (1 << t) * LPR;
+            const float ox = __shfl_up_sync(FULL, d.x, dl);
+            const float oy = __shfl_up_sync(FULL, d.y, dl);
+            const float oz = __shfl_up_sync(FULL, d.z, dl);
+            const float ow = __shfl_up_sync(FULL, d.w, dl);
+            const float o1 = __shfl_up_sync(FULL, d1, dl);
+            if (ac[j] & (4 << t)) {
+              d.x = __fadd_rn(ox, d.x);
+              d.y = __fadd_rn(oy, d.y);
+              d.z = __fadd_rn(oz, d.z);
+              d.w = __fadd_rn(ow, d.w);
+              d1 = __fadd_rn(o1, d1);
+            }
           }
         }
-        if (k[j] == carry_key) {  // the run came in from an earlier pass of this chunk
+        if (carry_key != kNoKey && k[j] == carry_key) {  // the run came in from an earlier pass
           d.x = __fadd_rn(carry.x, d.x);
           d.y = __fadd_rn(carry.y, d.y);
           d.z = __fadd_rn(carry.z, d.z);
           d.w = __fadd_rn(carry.w, d.w);
           d1 = __fadd_rn(carry1, d1);
         }
-        if (ac[j] == 1) {
-          apply_loaded(a, k[j], sub, T[j], A[j], d, w[j], a1[j], d1);
-        } else if (ac[j] >= 2) {
-          const int64_t s = chunk * 2 + (ac[j] == 2 ? 0 : 1);
+        if ((ac[j] & 3) == 1) {
+          if (MODE == kModeEmit) {
+            float* e = a.emit + (int64_t)rw[j] * a.emit_stride;
+            *(reinterpret_cast<float4*>(e) + sub) = d;
+            if (sub == 0) e[K] = d1;
+          } else {
+            apply_loaded(a, rw[j], sub, T[j], A[j], d, lw[j], a1[j], d1);
+          }
+        } else if ((ac[j] & 3) >= 2) {
+          const int64_t s = chunk * 2 + ((ac[j] & 3) == 2 ? 0 : 1);
           *(reinterpret_cast<float4*>(a.part + s * K) + sub) = d;
           if (sub == 0) a.part1[s] = d1;
         }
-        const int src = (SLOTS - 1) * LPR + sub;
-        carry_key = __shfl_sync(FULL, k[j], src);
-        carry.x = __shfl_sync(FULL, d.x, src);
-        carry.y = __shfl_sync(FULL, d.y, src);
-        carry.z = __shfl_sync(FULL, d.z, src);
-        carry.w = __shfl_sync(FULL, d.w, src);
-        carry1 = __shfl_sync(FULL, d1, src);
+        // hand the running sum to the next pass only when the run really continues (warp-uniform)
+        carry_key = kNoKey;
+        if ((cont >> ((j0 + j) * SLOTS + SLOTS - 1)) & 1u) {
+          const int src = (SLOTS - 1) * LPR + sub;
+          carry_key = __shfl_sync(FULL, k[j], src);
+          carry.x = __shfl_sync(FULL, d.x, src);
+          carry.y = __shfl_sync(FULL, d.y, src);
+          carry.z = __shfl_sync(FULL, d.z, src);
+          carry.w = __shfl_sync(FULL, d.w, src);
+          carry1 = __shfl_sync(FULL, d1, src);
+        }
       }
     }
   }
   if (lane == 0 && heads && a.n_unique) atomicAdd(a.n_unique, (unsigned long long)heads);
 }
 
-// phase 2: one lane group per chunk; the chunk where a crossing run starts finishes it.
+// phase 2 + 3 in one launch.  Phase 2: one lane group per chunk; the chunk where a crossing run
+// starts adds the partials of the following chunks in chunk order and finishes the row.  A run that
+// spans more than kLongRun chunks is left to phase 3: the whole CTA finds its end by probing chunk
+// heads in parallel, sums the partials strided over lane groups (sequential per group) and combines
+// the groups with a fixed-shape tree.
 template <int LPR>
-__global__ void __launch_bounds__(256) embed_bwd_combine_kernel(const BwdArgs a) {
-  constexpr int K = LPR * 4;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gid = tid / LPR;
-  const int sub = (int)(tid % LPR);
-  const int64_t i0 = gid * kChunk;
-  if (i0 >= a.n) return;
-  const int64_t end = min(a.n, i0 + kChunk);
-  if (end >= a.n) return;  // last chunk cannot be open to the right
-  const uint32_t key = __ldg(a.keys + end - 1);
-  if (key == a.pruned_key || __ldg(a.keys + end) != key) return;  // not open to the right
-  if (i0 > 0 && __ldg(a.keys + i0 - 1) == key) return;            // a middle piece, not the head
-  // long run?  chunk gid+1+kLongRun still starts with this key
-  const int64_t far = (gid + 1 + kLongRun) * kChunk;
-  if (far < a.n && __ldg(a.keys + far) == key) {
-    if (sub == 0) a.long_list[atomicAdd(a.long_count, 1u)] = (uint32_t)gid;
-    return;
-  }
-  float4 acc = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
-  float acc1 = a.part1[gid * 2 + 1];
-  for (int64_t j = gid + 1; j * kChunk < a.n && __ldg(a.keys + j * kChunk) == key; ++j) {
-    const float4 p = *(reinterpret_cast<const float4*>(a.part + (j * 2) * K) + sub);
-    acc.x = __fadd_rn(acc.x, p.x);
-    acc.y = __fadd_rn(acc.y, p.y);
-    acc.z = __fadd_rn(acc.z, p.z);
-    acc.w = __fadd_rn(acc.w, p.w);
-    acc1 = __fadd_rn(acc1, a.part1[j * 2]);
-  }
-  apply_update<LPR>(a, key, sub, acc, acc1);
-}
-
-// phase 3: one CTA per long run.
-template <int LPR>
-__global__ void __launch_bounds__(256) embed_bwd_long_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, int64_t* n_unique_out) {
   constexpr int K = LPR * 4;
   constexpr int NG = 256 / LPR;  // lane groups per CTA
   __shared__ float4 sm[256];
   __shared__ float sm1[NG];
+  __shared__ uint32_t s_long[NG];
+  __shared__ int s_nlong;
+  if (threadIdx.x == 0) s_nlong = 0;
+  __syncthreads();
   const int q = threadIdx.x / LPR;
   const int sub = threadIdx.x % LPR;
-  const uint32_t n_long = *a.long_count;
-  for (uint32_t r = blockIdx.x; r < n_long; r += gridDim.x) {
-    const int64_t gid = a.long_list[r];
+  {
+    const int64_t gid = (int64_t)blockIdx.x * NG + q;
+    const int64_t i0 = gid * kChunk;
+    const int64_t end = min(a.n, i0 + (int64_t)kChunk);
+    bool head = i0 < a.n && end < a.n;  // the last chunk cannot be open to the right
+    uint32_t key = 0;
+    if (head) {
+      key = __ldg(a.keys + end - 1);
+      head = key != a.pruned_key && __ldg(a.keys + end) == key &&      // open to the right
+             !(i0 > 0 && __ldg(a.keys + i0 - 1) == key);               // and not a middle piece
+    }
+    if (head) {
+      const int64_t far = (gid + 1 + kLongRun) * kChunk;  // chunk gid+1+kLongRun still starts with key?
+      if (far < a.n && __ldg(a.keys + far) == key) {
+        if (sub == 0) s_long[atomicAdd(&s_nlong, 1)] = (uint32_t)gid;
+      } else {
+        float4 acc = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
+        float acc1 = a.part1[gid * 2 + 1];
+        for (int64_t j = gid + 1; j * kChunk < a.n && __ldg(a.keys + j * kChunk) == key; ++j) {
+          const float4 p = *(reinterpret_cast<const float4*>(a.part + (j * 2) * K) + sub);
+          acc.x = __fadd_rn(acc.x, p.x);
+          acc.y = __fadd_rn(acc.y, p.y);
+          acc.z = __fadd_rn(acc.z, p.z);
+          acc.w = __fadd_rn(acc.w, p.w);
+          acc1 = __fadd_rn(acc1, a.part1[j * 2]);
+        }
+        apply_update<LPR>(a, a.mode == kModeEmit ? __ldg(a.rowidx + end - 1) : key, sub, acc, acc1);
+      }
+    }
+  }
+  __syncthreads();
+  const int n_long = s_nlong;
+  for (int r = 0; r < n_long; ++r) {
+    // the order of s_long depends on the atomics, but each run is finished on its own
+    const int64_t gid = s_long[r];
     const int64_t first = (gid + 1) * kChunk;
     const uint32_t key = __ldg(a.keys + first - 1);
-    int64_t lo = first, hi = a.n;  // upper bound of `key` in the sorted list
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(a.keys + mid) <= key) lo = mid + 1; else hi = mid;
+    int64_t M = 0;  // chunks gid+1 .. gid+M start with `key`: they hold a left-open partial
+    for (;;) {
+      const int64_t c = gid + 1 + M + threadIdx.x;
+      const int ok = c * kChunk < a.n && __ldg(a.keys + c * kChunk) == key;
+      const int cnt = __syncthreads_count(ok);
+      M += cnt;
+      if (cnt < 256) break;
     }
-    const int64_t M = (lo - 1) / kChunk - gid;  // chunks gid+1 .. gid+M hold a left-open partial
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float acc1 = 0.f;
     for (int64_t m = q; m < M; m += NG) {
@@ -403,13 +461,13 @@ __global__ void __launch_bounds__(256) embed_bwd_long_kernel(const BwdArgs a) {
     if (sub == 0) sm1[q] = acc1;
     __syncthreads();
 #pragma unroll
-    for (int s = NG / 2; s > 0; s >>= 1) {
-      if (q < s) {
-        const float4 o = sm[threadIdx.x + s * LPR];
+    for (int st = NG / 2; st > 0; st >>= 1) {
+      if (q < st) {
+        const float4 o = sm[threadIdx.x + st * LPR];
         float4 m = sm[threadIdx.x];
         m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
         sm[threadIdx.x] = m;
-        if (sub == 0) sm1[q] += sm1[q + s];
+        if (sub == 0) sm1[q] += sm1[q + st];
       }
       __syncthreads();
     }
@@ -417,30 +475,47 @@ __global__ void __launch_bounds__(256) embed_bwd_long_kernel(const BwdArgs a) {
       const float4 h = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
       float4 t = sm[threadIdx.x];
       t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
-      apply_update<LPR>(a, key, sub, t, a.part1[gid * 2 + 1] + sm1[0]);
+      apply_update<LPR>(a, a.mode == kModeEmit ? __ldg(a.rowidx + first - 1) : key, sub, t,
+                        a.part1[gid * 2 + 1] + sm1[0]);
     }
     __syncthreads();
   }
-}
-
-__global__ void copy_count_kernel(const unsigned long long* src, int64_t* dst) {
-  *dst = (int64_t)*src;
+  // every atomicAdd of phase 1 has landed: publish the number of distinct rows
+  if (n_unique_out && blockIdx.x == 0 && threadIdx.x == 0) *n_unique_out = (int64_t)*a.n_unique;
 }
 
 template <int LPR>
 static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) {
   const int64_t nchunks = (a.n + kChunk - 1) / kChunk;
-  const int64_t threads = nchunks * LPR;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
-  embed_bwd_reduce_kernel<LPR><<<(unsigned)((nchunks + 7) / 8), 256, 0, st>>>(a);
-  embed_bwd_combine_kernel<LPR><<<grid, 256, 0, st>>>(a);
-  embed_bwd_long_kernel<LPR><<<kSMs, 256, 0, st>>>(a);
-  int n = 3;
-  if (n_unique_out) {
-    copy_count_kernel<<<1, 1, 0, st>>>(a.n_unique, n_unique_out);
-    ++n;
+  const unsigned rgrid = (unsigned)((nchunks + 7) / 8);
+  if (a.mode == kModeEmit)
+    embed_bwd_reduce_kernel<LPR, kModeEmit><<<rgrid, 256, 0, st>>>(a);
+  else if (a.mode == kModeGiven)
+    embed_bwd_reduce_kernel<LPR, kModeGiven><<<rgrid, 256, 0, st>>>(a);
+  else
+    embed_bwd_reduce_kernel<LPR, kModeLocal><<<rgrid, 256, 0, st>>>(a);
+  constexpr int NG = 256 / LPR;
+  embed_bwd_finish_kernel<LPR><<<(unsigned)((nchunks + NG - 1) / NG), 256, 0, st>>>(a, n_unique_out);
+  return launched("embed_bwd_reduce_update", 2);
+}
+
+// position / F == (position * magic) >> shift, exact for positions < 2^31:
+// shift = 31 + ceil(log2 F), magic = ceil(2^shift / F) <= 2^32 - 1
+static void set_div(BwdArgs& a, int F) {
+  int lg = 0;
+  while ((1 << lg) < F) ++lg;
+  a.div_shift = 31 + lg;
+  a.div_magic = (uint32_t)((((uint64_t)1 << a.div_shift) + (uint64_t)F - 1) / (uint64_t)F);
+}
+
+static int dispatch_bwd(const BwdArgs& a, int K, int64_t* n_unique_out, cudaStream_t st) {
+  switch (K) {
+    case 4: return launch_bwd<1>(a, n_unique_out, st);
+    case 8: return launch_bwd<2>(a, n_unique_out, st);
+    case 16: return launch_bwd<4>(a, n_unique_out, st);
+    case 32: return launch_bwd<8>(a, n_unique_out, st);
+    default: return launch_bwd<16>(a, n_unique_out, st);
   }
-  return launched("embed_bwd_reduce_update", n);
 }
 
 }  // namespace dir
@@ -448,6 +523,17 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
 extern "C" size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K) {
   if (n_lookups <= 0 || K <= 0) return 0;
   return dir::carve(nullptr, n_lookups, K).total;
+}
+
+extern "C" int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups,
+                                    const uint32_t** sorted_keys, const uint32_t** sorted_pos) {
+  using namespace dir;
+  if (!workspace || n_lookups <= 0 || !sorted_keys || !sorted_pos)
+    return fail(DIR_EINVAL, "embed_bwd_sorted: workspace, n_lookups > 0 and both outputs are required");
+  BwdWorkspace w = carve(const_cast<void*>(workspace), n_lookups, 4);
+  *sorted_keys = w.keys;
+  *sorted_pos = w.pos;
+  return 0;
 }
 
 extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
@@ -509,18 +595,73 @@ extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t r
     return fail(DIR_ENOMEM, "embed_bwd_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0};
-  // exact for positions < 2^31: shift = 31 + ceil(log2 F), magic = ceil(2^shift / F) < 2^32
-  int lg = 0;
-  while ((1 << lg) < F) ++lg;
-  a.div_shift = 31 + lg;
-  a.div_magic = (uint32_t)((((uint64_t)1 << a.div_shift) + (uint64_t)F - 1) / (uint64_t)F);
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, kModeLocal, nullptr, nullptr, 0, nullptr, 0};
+  set_div(a, F);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (K) {
-    case 4: return launch_bwd<1>(a, n_unique_out, st);
-    case 8: return launch_bwd<2>(a, n_unique_out, st);
-    case 16: return launch_bwd<4>(a, n_unique_out, st);
-    case 32: return launch_bwd<8>(a, n_unique_out, st);
-    default: return launch_bwd<16>(a, n_unique_out, st);
-  }
+  return dispatch_bwd(a, K, n_unique_out, st);
+}
+
+/* requester side of a row-sharded table: per-unique-row gradient sums -> gu (include/dir_b200.h) */
+extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
+                                         const float* feature_value, const float* g_first,
+                                         const float* g_fm, const float* S, const float* u,
+                                         const uint32_t* uidx, int64_t B, int F, int K,
+                                         int64_t n_keys, float* gu, int64_t gu_stride,
+                                         void* workspace, size_t workspace_bytes,
+                                         dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_emit: B >= 0, F > 0 required");
+  const int64_t n = B * F;
+  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_emit: B*F must be < 2^31");
+  if (n == 0) return 0;
+  if (!ubuf || !g_fm || !S || !uidx || !gu || !workspace)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: ubuf, g_fm, S, uidx, gu, workspace are required");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: K must be one of 4, 8, 16, 32, 64");
+  if (ubuf_stride < K || (ubuf_stride & 3) || gu_stride < K + 1 || (gu_stride & 3))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: strides must be multiples of 4, >= K (ubuf), >= K+1 (gu)");
+  if (!aligned16(ubuf) || !aligned16(gu) || !aligned16(S) || !aligned16(u))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: ubuf, gu, S, u must be 16-byte aligned");
+  if (n_keys <= 0 || n_keys >= 0xffffffffLL)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: 0 < n_keys < 2^32-1 required");
+  BwdWorkspace w = carve(workspace, n, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_reduce_emit: workspace too small");
+  BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
+            g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0};
+  set_div(a, F);
+  return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+/* owner side: per-lookup gradients arrive from the requesters; segmented sum + fused row update */
+extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
+                                      float* lin_accum, int64_t lin_stride, const float* gbuf,
+                                      int64_t gbuf_stride, int64_t n, int K, int64_t n_rows,
+                                      int optimizer, float lr, void* workspace,
+                                      size_t workspace_bytes, int64_t* n_unique_out,
+                                      dir_stream_t stream) {
+  using namespace dir;
+  if (n < 0 || n >= 0x7fffffffLL) return fail(DIR_EINVAL, "rows_reduce_update: 0 <= n < 2^31 required");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+    return fail(DIR_EINVAL, "rows_reduce_update: unknown optimizer");
+  if (n == 0) return 0;
+  if (!table || !gbuf || !workspace)
+    return fail(DIR_EINVAL, "rows_reduce_update: table, gbuf, workspace are required");
+  if (optimizer == DIR_OPT_ADAGRAD && (!accum || (lin && !lin_accum)))
+    return fail(DIR_EINVAL, "rows_reduce_update: Adagrad needs accum (and lin_accum with lin)");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "rows_reduce_update: K must be one of 4, 8, 16, 32, 64");
+  if (row_stride < K || (row_stride & 3) || gbuf_stride < K + 1 || (gbuf_stride & 3))
+    return fail(DIR_EINVAL, "rows_reduce_update: strides must be multiples of 4, >= K (rows), >= K+1 (gbuf)");
+  if (!aligned16(table) || !aligned16(accum) || !aligned16(gbuf))
+    return fail(DIR_EINVAL, "rows_reduce_update: table, accum, gbuf must be 16-byte aligned");
+  if (n_rows <= 0 || n_rows >= 0xffffffffLL)
+    return fail(DIR_EINVAL, "rows_reduce_update: 0 < n_rows < 2^32-1 required");
+  BwdWorkspace w = carve(workspace, n, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
+  BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
+            nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
+  set_div(a, 1);
+  return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,290 @@
+"""Row-sharded embedding + FM layer: one process per GPU, tables sharded by row over the ranks of a
+process group, NCCL all-to-all for the lookup and the gradient exchange, the FM / first-order /
+cross interaction data-parallel on the requesting rank.
+
+The reference's only hook for this is the partitioner around its embedding variables
+(`input_layer_partitioner`, models/DeepFM/deepFM.py:163-175): with a TF parameter-server cluster
+the variables are split by row and ids / IndexedSlices travel over gRPC.  Here the exchange is two
+all-to-alls per direction (counts, then payload) over NVLink, and only DISTINCT rows travel:
+the requester sorts its lookups by (owner, local row), numbers the distinct ones, and after the
+owner answered runs the ordinary forward kernel on the received buffer; in the backward it sums
+the gradients of each distinct row before shipping them, so a one-row "dense" field or a Zipf-hot
+row costs one row of traffic per rank and step instead of one per sample.
+
+`ShardPlan` (pure index arithmetic) and `exchange` / `exchange_counts` (the collectives) carry no
+CUDA-only code: tests run them under gloo with world_size 2 on CPU.
+"""
+import math
+import os
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr
+from .layers import _K_OK, _OPTIMIZERS, _Workspace, _need_cuda, _stream
+
+
+class ShardPlan:
+    """owner = global row mod G, local row = global row div G (modulo, so hot low rows spread)."""
+
+    def __init__(self, rows_per_field: Sequence[int], world_size: int, rank: int):
+        if world_size <= 0 or not 0 <= rank < world_size:
+            raise ValueError("need 0 <= rank < world_size")
+        self.rows_per_field = [int(r) for r in rows_per_field]
+        self.world_size, self.rank = world_size, rank
+        self.n_rows = sum(self.rows_per_field)
+        off = [0]
+        for r in self.rows_per_field[:-1]:
+            off.append(off[-1] + r)
+        self.field_offset = off
+        self.cap = (self.n_rows + world_size - 1) // world_size          # rows every rank allocates
+        self.n_local = (self.n_rows - rank + world_size - 1) // world_size if self.n_rows > rank else 0
+        if self.cap * world_size >= 2 ** 32 - 1:
+            raise ValueError("ceil(n_rows / world_size) * world_size must be < 2^32-1")
+
+    def owner(self, global_rows):
+        return global_rows % self.world_size
+
+    def local_row(self, global_rows):
+        return global_rows // self.world_size
+
+    def global_row(self, local_rows, rank=None):
+        return local_rows * self.world_size + (self.rank if rank is None else rank)
+
+    def shard_of(self, full):
+        """This rank's rows of a full [n_rows, ...] array (numpy or torch)."""
+        return full[self.rank::self.world_size]
+
+
+def exchange_counts(send_counts: torch.Tensor, group=None) -> torch.Tensor:
+    """all-to-all of one int64 per peer: recv[g] = what rank g will send to this rank."""
+    if not dist.is_initialized():                 # a single process owns every row
+        return send_counts.clone()
+    recv = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv, send_counts.contiguous(), group=group)
+    return recv
+
+
+def exchange(payload: torch.Tensor, send_splits, recv_splits, group=None) -> torch.Tensor:
+    """Variable-size all-to-all along dim 0: rows [sum(send_splits), ...] grouped by destination ->
+    rows [sum(recv_splits), ...] grouped by source."""
+    if not dist.is_initialized():
+        return payload.contiguous()
+    out = payload.new_empty((int(sum(recv_splits)),) + tuple(payload.shape[1:]))
+    dist.all_to_all_single(out, payload.contiguous(), output_split_sizes=list(recv_splits),
+                           input_split_sizes=list(send_splits), group=group)
+    return out
+
+
+class _ShardedFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, bias, layer, idx, val, train):
+        B, F = idx.shape
+        K, G = layer.embedding_size, layer.plan.world_size
+        dev = idx.device
+        L = _lib.lib()
+        n = B * F
+        st = _stream()
+        pad = layer.pad_stride
+        # 1-3: composite keys, sort, distinct keys
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
+                               layer.plan.n_rows, B, F, G, ptr(keys),
+                               ptr(layer.oob_flag) if layer.check_bounds else None, st), "dir_shard_keys")
+        n_keys = layer.plan.cap * G
+        ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
+        check(L.dir_embed_bwd_sort(ptr(keys), n, n_keys, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
+        skeys, spos = _lib.c_void_p(), _lib.c_void_p()
+        check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
+              "dir_embed_bwd_sorted")
+        uidx = torch.empty(n, dtype=torch.int32, device=dev)
+        ulocal = torch.empty(n, dtype=torch.int32, device=dev)
+        inv = torch.empty((B, F), dtype=torch.int64, device=dev)
+        owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
+        ws2 = layer._ws2.get(L.dir_shard_unique_workspace_bytes(n), dev)
+        check(L.dir_shard_unique(skeys, spos, n, layer.plan.n_rows, G, ptr(uidx), ptr(ulocal), ptr(inv),
+                                 ptr(owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+        # 4: counts (one host sync: NCCL needs the split sizes), ids out, rows back
+        send_counts = owner_off[1:] - owner_off[:-1]
+        recv_counts = exchange_counts(send_counts, layer.group)
+        both = torch.stack([send_counts, recv_counts]).cpu()
+        send_splits, recv_splits = both[0].tolist(), both[1].tolist()
+        U, R = int(sum(send_splits)), int(sum(recv_splits))
+        recv_ids = exchange(ulocal[:U], send_splits, recv_splits, layer.group)
+        answer = torch.empty((R, pad), dtype=torch.float32, device=dev)
+        check(L.dir_rows_gather(ptr(layer.table), layer.row_stride, ptr(layer.w1) if layer.first_order else None,
+                                layer.lin_stride, ptr(recv_ids), R, K, ptr(answer), pad, st), "dir_rows_gather")
+        ubuf = exchange(answer, recv_splits, send_splits, layer.group)          # [U, K+4]
+        if U == 0:
+            ubuf = torch.zeros((1, pad), dtype=torch.float32, device=dev)
+        # 5: the ordinary forward on the received rows
+        emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
+        fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        first = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
+        lin = ubuf[:, K] if layer.first_order else None
+        check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
+                                 ptr(inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
+                                 ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
+        if not layer.first_order:
+            first.zero_()
+        layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": n}
+        ctx.layer, ctx.train, ctx.shape = layer, train, (B, F, K)
+        ctx.splits = (send_splits, recv_splits)
+        ctx.set_materialize_grads(False)
+        if train:
+            ctx.save_for_backward(val, S, ubuf, uidx, recv_ids)
+        if emb is None:
+            emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(emb)
+        return first, fm, emb
+
+    @staticmethod
+    def backward(ctx, g_first, g_fm, u):
+        if not ctx.train:
+            raise RuntimeError("ShardedEmbeddingFM.backward: forward ran without gradient tracking")
+        layer = ctx.layer
+        val, S, ubuf, uidx, recv_ids = ctx.saved_tensors
+        B, F, K = ctx.shape
+        send_splits, recv_splits = ctx.splits
+        U, R = int(sum(send_splits)), int(sum(recv_splits))
+        dev = S.device
+        L = _lib.lib()
+        st = _stream()
+        pad = layer.pad_stride
+        n = B * F
+        g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
+                   else g_first.reshape(B).contiguous().float())
+        g_fm = (torch.zeros(B, dtype=torch.float32, device=dev) if g_fm is None
+                else g_fm.reshape(B).contiguous().float())
+        if u is not None:
+            u = u.contiguous().float()
+        with torch.no_grad():
+            # 6: per-distinct-row sums on the requester (the sorted list is still in the workspace)
+            ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
+            gu = torch.empty((max(U, 1), pad), dtype=torch.float32, device=dev)
+            check(L.dir_embed_bwd_reduce_emit(ptr(ubuf), pad, ptr(val), ptr(g_first) if layer.first_order else None,
+                                              ptr(g_fm), ptr(S), ptr(u), ptr(uidx), B, F, K,
+                                              layer.plan.cap * layer.plan.world_size, ptr(gu), pad,
+                                              ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
+            # 7: sums to their owners; the owner merges the ranks' contributions and updates
+            grecv = exchange(gu[:U], send_splits, recv_splits, layer.group)      # [R, K+4]
+            if R > 0:
+                ws3 = layer._ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)
+                check(L.dir_embed_bwd_sort(ptr(recv_ids), R, layer.plan.cap, ptr(ws3), ws3.numel(), st),
+                      "dir_embed_bwd_sort")
+                adagrad = layer.optimizer == "adagrad"
+                check(L.dir_rows_reduce_update(
+                    ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
+                    ptr(layer.w1) if layer.first_order else None,
+                    ptr(layer.w1_accum) if (adagrad and layer.first_order) else None, layer.lin_stride,
+                    ptr(grecv), pad, R, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
+                    ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
+            else:
+                layer.last_n_unique.zero_()
+        g_bias = g_first.sum().reshape(1) if layer.first_order else None
+        return None, g_bias, None, None, None, None
+
+
+class ShardedEmbeddingFM(torch.nn.Module):
+    """`EmbeddingFM` with its tables sharded by row over a process group (one process per GPU).
+
+    Same call as EmbeddingFM: forward(feature_index[B_local, F] int64, feature_value | None) ->
+    (first_order, fm_second_order, embeddings) for THIS rank's samples; `.backward()` updates the
+    rows this rank owns with the gradients of every rank's samples.  `bias` is an ordinary
+    replicated parameter: all-reduce its gradient like any dense parameter.
+    """
+
+    def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
+                 optimizer: str = "adagrad", lr: float = 0.01, initial_accumulator_value: float = 0.1,
+                 first_order: bool = True, emit_embeddings: bool = True, check_bounds: bool = False,
+                 process_group=None, device="cuda"):
+        super().__init__()
+        if field_size <= 0:
+            raise ValueError("empty columns.")                      # deepFM.py:104-105
+        if embedding_size not in _K_OK:
+            raise ValueError("embedding_size must be one of %r" % (_K_OK,))
+        if optimizer not in _OPTIMIZERS:
+            raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        rows = [int(r) for r in rows_per_field]
+        if len(rows) != field_size:
+            raise ValueError("rows_per_field must have field_size entries")
+        self.group = process_group
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.plan = ShardPlan(rows, world, rank)
+        self.field_size, self.embedding_size = field_size, embedding_size
+        self.optimizer, self.lr = optimizer, float(lr)
+        self.first_order, self.emit_embeddings, self.check_bounds = first_order, emit_embeddings, check_bounds
+        K = embedding_size
+        adagrad = optimizer == "adagrad"
+        self.row_stride = 2 * K if adagrad else K
+        self.lin_stride = 1
+        self.pad_stride = K + 4                                     # (row[K], first-order weight, 3 pad)
+        self.n_rows = self.plan.cap                                 # local rows allocated
+        dev = torch.device(device)
+        cap = max(self.plan.cap, 1)
+        self.register_buffer("field_offset", torch.tensor(self.plan.field_offset, dtype=torch.int64, device=dev))
+        self.register_buffer("field_rows", torch.tensor(rows, dtype=torch.int64, device=dev))
+        self.register_buffer("zero_offset", torch.zeros(field_size, dtype=torch.int64, device=dev))
+        self.register_buffer("rows", torch.empty((cap, self.row_stride), dtype=torch.float32, device=dev))
+        self.register_buffer("lin_rows", torch.zeros((cap, 1), dtype=torch.float32, device=dev))
+        self.register_buffer("lin_acc", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if adagrad else None)
+        self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
+        self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
+        self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
+        self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.last_exchange = {}
+        self._ws, self._ws2, self._ws3 = _Workspace(), _Workspace(), _Workspace()
+        with torch.no_grad():
+            sd = 1.0 / math.sqrt(K)
+            torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)
+            if adagrad:
+                self.accum.fill_(initial_accumulator_value)
+                self.lin_acc.fill_(initial_accumulator_value)
+
+    @property
+    def table(self):
+        return self.rows[:, :self.embedding_size]
+
+    @property
+    def accum(self):
+        return self.rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+
+    @property
+    def w1(self):
+        return self.lin_rows[:, 0]
+
+    @property
+    def w1_accum(self):
+        return self.lin_acc[:, 0] if self.optimizer == "adagrad" else None
+
+    @torch.no_grad()
+    def load_tables(self, table=None, w1=None):
+        """Takes the FULL [n_rows, K] table / [n_rows] first-order weights and keeps this rank's rows."""
+        for dst, src in ((self.table, table), (self.w1, w1)):
+            if src is not None:
+                mine = torch.as_tensor(self.plan.shard_of(src), dtype=torch.float32)
+                dst[:mine.shape[0]].copy_(mine.to(dst.device))
+
+    def forward(self, feature_index, feature_value=None):
+        if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
+            raise ValueError("feature_index must be [B, field_size=%d]" % self.field_size)
+        if feature_index.dtype != torch.int64:
+            raise ValueError("feature_index must be int64")
+        _need_cuda(feature_index, "feature_index")
+        idx = feature_index.contiguous()
+        val = None
+        if feature_value is not None:
+            if feature_value.shape != feature_index.shape:
+                raise ValueError("feature_value must have feature_index's shape")
+            _need_cuda(feature_value, "feature_value")
+            val = feature_value.contiguous().float()
+        train = self.training and torch.is_grad_enabled()
+        first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train)
+        if self.check_bounds and int(self.oob_flag.item()) != 0:
+            self.oob_flag.zero_()
+            raise IndexError("feature_index out of range for its field")
+        return first, fm, emb

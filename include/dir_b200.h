@@ -105,6 +105,63 @@ int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, 
                                 int optimizer, float lr, void* workspace, size_t workspace_bytes,
                                 int64_t* n_unique_out, dir_stream_t stream);
 
+/* Where step 1 left the sorted (row, position) pairs inside its workspace (read-only views). */
+int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_t** sorted_keys,
+                         const uint32_t** sorted_pos);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded tables over G ranks of one NVSwitch box: owner = global row mod G, local row =
+ * global row div G, every rank keeps ceil(n_rows / G) rows; the batch stays data-parallel.
+ * The reference has no counterpart beyond the partitioner hook around its embedding variables
+ * (models/DeepFM/deepFM.py:163-175: under a TF parameter-server cluster the variables are
+ * sharded by row and ids / IndexedSlices travel over gRPC).  Here only DISTINCT rows cross
+ * NVLink, once per step in each direction (NCCL all-to-all, issued by the host layer):
+ *
+ *   requester                                          owner
+ *   dir_shard_keys      (owner, local row) per lookup
+ *   dir_embed_bwd_sort  sort (key, position)
+ *   dir_shard_unique    number distinct keys  --ids-->  dir_rows_gather  (row | first-order weight)
+ *   dir_embed_fm_fwd    on the returned buffer <-rows--
+ *   dir_embed_bwd_reduce_emit  per-row sums   --grads-> dir_embed_bwd_sort + dir_rows_reduce_update
+ *
+ * dir_shard_keys: keys[b*F+f] = owner * cap + local row, cap = ceil(n_rows / G); pruned lookups
+ *   (id < 0, value <= 0, id beyond its field) get G * cap, the `n_rows` to pass to dir_embed_bwd_sort.
+ * dir_shard_unique, on the sorted list:
+ *   uidx[i]               index of sorted entry i's key among the distinct keys
+ *   unique_local_rows[u]  local row (at its owner) of distinct key u; grouped by owner, ascending
+ *   inv[b*F+f]            int64 index of that lookup's row in the exchanged buffer, -1 if pruned:
+ *                         the feature_index to hand to dir_embed_fm_fwd
+ *   owner_off[g], g = 0..G   distinct keys owned by ranks < g (owner_off[G] = their total)
+ * dir_rows_gather: out[i, 0:K] = table[local_rows[i]], out[i, K] = lin[local_rows[i]] (0 if lin is
+ *   NULL); out rows are out_stride floats apart (multiple of 4, >= K + 1).
+ * dir_embed_bwd_reduce_emit: as dir_embed_bwd_reduce_update, but rows are read from the exchanged
+ *   buffer `ubuf` at uidx[i] and each distinct row's (G[K], g1) is written to gu[u] instead of
+ *   being applied.  Deterministic, same chunking.
+ * dir_rows_reduce_update: the owner's half.  gbuf[j] = (G[K], g1) received for the j-th id it
+ *   answered; dir_embed_bwd_sort(ids, n, n_local_rows) must have run on `workspace`.  Sums the
+ *   contributions of each local row in arrival order (source rank major) and applies the update.
+ */
+int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
+                   const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
+                   int F, int G, uint32_t* keys, int* oob_flag, dir_stream_t stream);
+size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
+int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
+                     int64_t n_rows, int G, uint32_t* uidx, int32_t* unique_local_rows, int64_t* inv,
+                     int64_t* owner_off, void* workspace, size_t workspace_bytes, dir_stream_t stream);
+int dir_rows_gather(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
+                    const int32_t* local_rows, int64_t n, int K, float* out, int64_t out_stride,
+                    dir_stream_t stream);
+int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
+                              const float* g_first, const float* g_fm, const float* S, const float* u,
+                              const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
+                              int64_t gu_stride, void* workspace, size_t workspace_bytes,
+                              dir_stream_t stream);
+int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
+                           float* lin_accum, int64_t lin_stride, const float* gbuf,
+                           int64_t gbuf_stride, int64_t n, int K, int64_t n_rows, int optimizer,
+                           float lr, void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
+                           dir_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * DCN cross network, all L layers in one pass.  Replaces _cross_architecture / _cross_op
  * (models/DeepCrossNetwork/DeepCrossNetwork.py:336-367): x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l.
