@@ -366,6 +366,16 @@ def run_b200(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": r["sample"] + "; PyTorch-CPU restatement of the reference's TF 1.x graph"}
 
+    if world > 1 and getattr(layer, "trace", None) is not None and layer.trace.on:
+        layer.trace.report()
+        t0 = time.perf_counter()
+        for s_ in range(20):
+            run(s_ % R)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 20 * 1e6
+        if rank == 0:
+            print("stage trace (us/step, rank 0; wall %.0f us/step): %s" % (wall, json.dumps(
+                {k: round(v, 1) for k, v in layer.trace.report().items()})), file=sys.stderr)
     if rank == 0:
         cfg = workload_config(w, args, world)
         cfg.update({"l2_policy": "%d rotating input sets (%.0f MB of ids/values/upstream each) + a %.2f GB table: "
@@ -404,12 +414,17 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     peak, src = RL.measured_peaks()
     U = sum(n_unique) / len(n_unique)
 
+    def mkkeys(r):
+        idx, val, _ = devs[r]
+        check(lib.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
+                                 layer.n_rows, B, F, 1, ptr(keys), None, st), "keys")
+
     def fwd(r):
         idx, val, _ = devs[r]
         check(lib.dir_embed_fm_fwd(ptr(layer.table), layer.row_stride, ptr(layer.w1), layer.lin_stride,
                                    ptr(layer.bias), ptr(idx), ptr(val), ptr(layer.field_offset),
                                    ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first),
-                                   ptr(fm), ptr(keys), None, st), "fwd")
+                                   ptr(fm), None, None, st), "fwd")
 
     def sort(r):
         check(lib.dir_embed_bwd_sort(ptr(keys), B * F, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
@@ -420,7 +435,8 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
             layer.lin_stride, ptr(devs[r][1]), ptr(g), ptr(g), ptr(S), ptr(ups[r]) if emit else None, B, F, K,
             layer.n_rows, 1, LR, ptr(ws), ws.numel(), None, st), "update")
 
-    calls = [("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
+    calls = [("dir_shard_keys", mkkeys, 0),
+             ("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
              ("dir_embed_bwd_sort", sort, 0),
              ("dir_embed_bwd_reduce_update", upd, RL.embed_bwd_bytes(B, F, K, U, True, emit, "adagrad"))]
     if cross is not None:

@@ -69,6 +69,15 @@ __device__ __forceinline__ float4 ldg_hint(const float* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return r;
 }
+// coherent (not .nc) 16-B load with an L2 policy: for rows this kernel also writes
+__device__ __forceinline__ float4 ld_hint(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ float ldg_hint1(const float* p, uint64_t pol) {
   float r;
   asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));

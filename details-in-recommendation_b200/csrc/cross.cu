@@ -110,6 +110,11 @@ static int cross_grid1(int64_t B) {
   const int64_t cap = kSMs * 4;
   return (int)(want < cap ? want : cap);
 }
+static int cross_grid_fused(int64_t B) {  // persistent: two CTAs per SM
+  const int64_t want = (B + 15) / 16;
+  const int64_t cap = kSMs * 2;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
 static int cross_grid2(int64_t B) {
   const int64_t want = (B + 31) / 32;
   const int64_t cap = kSMs * 4;
@@ -125,9 +130,10 @@ static CrossBwdWs cross_carve(void* base, int64_t B, int d, int L) {
     off += align_up(bytes, 256);
     return reinterpret_cast<float*>(r);
   };
-  w.G1 = cross_grid1(B);
-  w.G2 = cross_grid2(B);
-  w.alpha = take((size_t)B * L * 4);
+  const bool fused = L <= 8;
+  w.G1 = fused ? cross_grid_fused(B) : cross_grid1(B);
+  w.G2 = fused ? w.G1 : cross_grid2(B);
+  w.alpha = take(fused ? 0 : (size_t)B * L * 4);
   w.Dpart = take((size_t)w.G1 * L * 4);
   w.dypart = take((size_t)w.G1 * d * 4);
   w.dwpart = take((size_t)w.G2 * L * d * 4);
@@ -345,6 +351,248 @@ cross_bwd_finish_kernel(const float* __restrict__ wg, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------ fused backward (L <= 8)
+// One pass over x0 and dy.  A CTA walks tiles of kTS samples:
+//   phase A  one warp per sample, registers: the reverse sweep -> dx0 to HBM, alpha_l = ds_l c_l to
+//            shared memory; the warp also leaves its x0 / dy rows in shared memory
+//   phase B  one thread per column: dw_l[c] += alpha_l[b] x0[b][c], db[c] += dy[b][c] over the tile,
+//            samples in order, accumulators in registers for the whole kernel
+// so x0 is read from HBM once (the separate dw pass re-read all of it).  Per-CTA partials are
+// combined by cross_bwd_finish2_kernel in a fixed order.
+constexpr int kTS = 16;  // samples per tile: two per warp
+
+template <int VEC, int NPL>
+__global__ void __launch_bounds__(kCrossWarps * 32, 2)
+cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
+                       const float* __restrict__ bg, const float* __restrict__ dyg,
+                       const float* __restrict__ sg, int64_t B, int d, int L,
+                       float* __restrict__ dx0g, float* __restrict__ Dpart,
+                       float* __restrict__ dypart, float* __restrict__ dwpart) {
+  constexpr int E = VEC * NPL;
+  constexpr int CI = (E * 32 + 255) / 256;  // columns per thread in phase B
+  extern __shared__ float smem[];
+  float* x0s = smem;                   // [kTS][d]
+  float* dys = x0s + kTS * d;          // [kTS][d]
+  float* als = dys + kTS * d;          // [kTS][8]
+  float* sD = als + kTS * 8;           // [kCrossWarps][32]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  float acc[CI][8], accdy[CI];
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) {
+    accdy[ci] = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[ci][l] = 0.f;
+  }
+  float Dacc = 0.f;  // lane l: sum over this warp's samples of ds_l
+
+  const int64_t ntiles = (B + kTS - 1) / kTS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t b0 = tile * kTS;
+    // ---- phase A
+#pragma unroll 1
+    for (int h = 0; h < kTS / kCrossWarps; ++h) {
+      const int tb = h * kCrossWarps + wib;
+      const int64_t b = b0 + tb;
+      float x0[E], dx[E], dx0[E];
+      const bool live = b < B;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = (i * 32 + lane) * VEC;
+        Pack<VEC> px{}, pd{};
+        if (live && c < d) {
+          px = ld_pack<VEC>(x0g + b * d + c, true);
+          pd = ld_pack<VEC>(dyg + b * d + c, true);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const bool in = live && c < d;
+          x0[i * VEC + e] = in ? px.v[e] : 0.f;
+          dx[i * VEC + e] = in ? pd.v[e] : 0.f;
+          dx0[i * VEC + e] = 0.f;
+        }
+        if (c < d) {  // the tile copy phase B reads (zeros for samples past the end)
+          if constexpr (VEC == 4) {
+            *reinterpret_cast<float4*>(x0s + tb * d + c) =
+                make_float4(x0[i * 4], x0[i * 4 + 1], x0[i * 4 + 2], x0[i * 4 + 3]);
+            *reinterpret_cast<float4*>(dys + tb * d + c) =
+                make_float4(dx[i * 4], dx[i * 4 + 1], dx[i * 4 + 2], dx[i * 4 + 3]);
+          } else {
+            x0s[tb * d + c] = x0[i];
+            dys[tb * d + c] = dx[i];
+          }
+        }
+      }
+      float s_mine = 0.f;  // lane l keeps s_l = x_l . w_l
+      if (sg) {
+        if (live && lane < L) s_mine = __ldg(sg + b * L + lane);
+      } else {
+        float xl[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) xl[e] = x0[e];
+        for (int l = 0; l < L; ++l) {
+          float dot = 0.f;
+          float bv[E];
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int c = (i * 32 + lane) * VEC;
+            Pack<VEC> pw{}, pb{};
+            if (c < d) {
+              pw = ld_pack<VEC>(wg + l * d + c, false);
+              pb = ld_pack<VEC>(bg + l * d + c, false);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              dot = fmaf(xl[i * VEC + e], (c < d) ? pw.v[e] : 0.f, dot);
+              bv[i * VEC + e] = (c < d) ? pb.v[e] : 0.f;
+            }
+          }
+          dot = warp_sum(dot);
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            xl[e] = __fadd_rn(__fadd_rn(__fmul_rn(x0[e], dot), bv[e]), xl[e]);
+          if (lane == l) s_mine = dot;
+        }
+      }
+      float c_mine = 1.f;  // c_l = 1 + sum_{j<l} s_j
+      for (int j = 0; j < L; ++j) {
+        const float sj = __shfl_sync(0xffffffffu, s_mine, j);
+        if (lane > j) c_mine += sj;
+      }
+      float alpha_mine = 0.f;
+      for (int l = L - 1; l >= 0; --l) {
+        const float s_l = __shfl_sync(0xffffffffu, s_mine, l);
+        const float c_l = __shfl_sync(0xffffffffu, c_mine, l);
+        float ds = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) ds = fmaf(dx[e], x0[e], ds);
+        ds = warp_sum(ds);
+        if (lane == l) {
+          alpha_mine = ds * c_l;
+          Dacc += ds;
+        }
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = (i * 32 + lane) * VEC;
+          Pack<VEC> pw{};
+          if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            dx0[i * VEC + e] = fmaf(dx[i * VEC + e], s_l, dx0[i * VEC + e]);
+            dx[i * VEC + e] = fmaf(ds, (c < d) ? pw.v[e] : 0.f, dx[i * VEC + e]);
+          }
+        }
+      }
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = (i * 32 + lane) * VEC;
+          float o[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) o[e] = dx0[i * VEC + e] + dx[i * VEC + e];
+          if (c < d) st_pack<VEC>(dx0g + b * d + c, o);
+        }
+      }
+      if (lane < 8) als[tb * 8 + lane] = (live && lane < L) ? alpha_mine : 0.f;
+    }
+    __syncthreads();
+    // ---- phase B: thread = column, samples of the tile in order
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      const int c = ci * 256 + threadIdx.x;
+      if (c < d) {
+#pragma unroll 4
+        for (int tb = 0; tb < kTS; ++tb) {
+          const float xv = x0s[tb * d + c];
+          const float4 a0 = *reinterpret_cast<const float4*>(als + tb * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
+          acc[ci][0] = fmaf(a0.x, xv, acc[ci][0]);
+          acc[ci][1] = fmaf(a0.y, xv, acc[ci][1]);
+          acc[ci][2] = fmaf(a0.z, xv, acc[ci][2]);
+          acc[ci][3] = fmaf(a0.w, xv, acc[ci][3]);
+          acc[ci][4] = fmaf(a1.x, xv, acc[ci][4]);
+          acc[ci][5] = fmaf(a1.y, xv, acc[ci][5]);
+          acc[ci][6] = fmaf(a1.z, xv, acc[ci][6]);
+          acc[ci][7] = fmaf(a1.w, xv, acc[ci][7]);
+          accdy[ci] += dys[tb * d + c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // per-CTA partials
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) {
+    const int c = ci * 256 + threadIdx.x;
+    if (c < d) {
+      dypart[(int64_t)blockIdx.x * d + c] = accdy[ci];
+#pragma unroll
+      for (int l = 0; l < 8; ++l)
+        if (l < L) dwpart[((int64_t)blockIdx.x * L + l) * d + c] = acc[ci][l];
+    }
+  }
+  sD[wib * 32 + lane] = Dacc;
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) t += sD[w * 32 + threadIdx.x];
+    Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+  }
+}
+
+// Fixed-order combine of per-CTA partials: a CTA owns 32 columns; 8 "g-lanes" per column each sum
+// every 8th partial in order, then the 8 sums are added in order.
+__global__ void __launch_bounds__(256)
+cross_bwd_finish2_kernel(const float* __restrict__ wg, const float* __restrict__ bg,
+                         const float* __restrict__ Dpart, const float* __restrict__ dypart,
+                         const float* __restrict__ dwpart, int G1, int G2, int d, int L,
+                         float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sDl[32];       // sum_b ds_l
+  __shared__ float red[8][33];
+  __shared__ float rows[33][32];  // row 0: sum dy; row 1+l: sum alpha_l x0
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+    if (threadIdx.x < L)
+      for (int g = 0; g < G1; ++g) t += Dpart[(int64_t)g * L + threadIdx.x];
+    sDl[threadIdx.x] = t;
+  }
+  for (int r = 0; r <= L; ++r) {
+    float t = 0.f;
+    if (c < d) {
+      if (r == 0) {
+        for (int g = gy; g < G1; g += 8) t += dypart[(int64_t)g * d + c];
+      } else {
+        for (int g = gy; g < G2; g += 8) t += dwpart[((int64_t)g * L + (r - 1)) * d + c];
+      }
+    }
+    red[gy][cx] = t;
+    __syncthreads();
+    if (gy == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][cx];
+      rows[r][cx] = v;
+    }
+    __syncthreads();
+  }
+  if (gy != 0 || c >= d) return;
+  // db_l = sum dy + sum_{j>l} w_j D_j ; walk l downwards carrying the tail
+  float tail = 0.f;
+  for (int l = L - 1; l >= 0; --l) {
+    db[l * d + c] = rows[0][cx] + tail;
+    tail = fmaf(wg[l * d + c], sDl[l], tail);
+  }
+  // dw_l = sum alpha_l x0 + beta_l D_l ; beta_l = sum_{j<l} b_j
+  float beta = 0.f;
+  for (int l = 0; l < L; ++l) {
+    dw[l * d + c] = fmaf(beta, sDl[l], rows[1 + l][cx]);
+    beta += bg[l * d + c];
+  }
+}
+
 struct CrossShape {
   int vec, npl;
 };
@@ -433,6 +681,21 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
     return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
+  if (L <= 8) {
+    const size_t smemf = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32) * 4;
+#define DIR_BWDF(V, N)                                                                          \
+  {                                                                                             \
+    cudaFuncSetAttribute(cross_bwd_fused_kernel<V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smemf);                                                           \
+    cross_bwd_fused_kernel<V, N><<<w.G1, kCrossWarps * 32, smemf, st>>>(                        \
+        x0, cross_w, cross_b, dy, s, B, d, L, dx0, w.Dpart, w.dypart, w.dwpart);                \
+  }
+    DIR_CROSS_DISPATCH(DIR_BWDF)
+#undef DIR_BWDF
+    cross_bwd_finish2_kernel<<<(d + 31) / 32, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
+                                                           w.G1, w.G2, d, L, dw, db);
+    return launched("cross_bwd", 2);
+  }
   const size_t smem1 = (size_t)kCrossWarps * (d + 32) * 4;
 #define DIR_BWD(V, N)                                                                        \
   cross_bwd_sample_kernel<V, N><<<w.G1, kCrossWarps * 32, smem1, st>>>(                      \
@@ -440,7 +703,7 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   DIR_CROSS_DISPATCH(DIR_BWD)
 #undef DIR_BWD
   cross_bwd_dw_kernel<<<w.G2, 256, kDwUnroll * 8 * 4, st>>>(x0, w.alpha, B, d, L, w.dwpart);
-  cross_bwd_finish_kernel<<<(d + 255) / 256, 256, 32 * 4, st>>>(cross_w, cross_b, w.Dpart, w.dypart,
-                                                              w.dwpart, w.G1, w.G2, d, L, dw, db);
+  cross_bwd_finish2_kernel<<<(d + 31) / 32, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
+                                                         w.G1, w.G2, d, L, dw, db);
   return launched("cross_bwd", 3);
 }

@@ -112,6 +112,7 @@ struct BwdArgs {
   float lr;
   uint32_t div_magic;   // position / F == (position * div_magic) >> div_shift for position < 2^31
   int div_shift;
+  int tune;             // DIR_B200_TUNE experiment bits
   // sharded-table modes (see kMode*)
   int mode;
   const uint32_t* rowidx;  // kModeEmit: row of `table` (the exchanged unique-row buffer) per sorted entry
@@ -216,7 +217,13 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
   const uint32_t prev_key = i0 > 0 ? __ldg(a.keys + i0 - 1) : kNoKey;
   const uint32_t next_chunk_key = chunk_end < a.n ? __ldg(a.keys + chunk_end) : kNoKey;
   const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
-  const uint64_t pol_once = policy_evict_first();  // upstream gradients are read exactly once
+  // L2 policies.  A 64-byte gradient / row gather pulls a whole 128-byte line from HBM (measured,
+  // tools/gather_probe.cu); the other half of a `u` line belongs to the neighbouring field of the
+  // same sample and is wanted later by some other warp, so `u` lines are asked to stay (evict_last)
+  // while row / accumulator lines, read and rewritten exactly once, are asked to leave first.
+  const int tune = a.tune;
+  const uint64_t pol_once = (tune & 8) ? policy_evict_first() : policy_evict_last();
+  const uint64_t pol_row = policy_evict_first();
 
   uint32_t carry_key = kNoKey, last_key = prev_key;
   float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -300,12 +307,13 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
           } else {
             if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
             Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
-            // plain load: this warp may rewrite the row further down
-            T[j] = *(reinterpret_cast<const float4*>(a.table + ro) + sub);
+            // coherent load: this warp may rewrite the row further down
+            T[j] = (tune & 16) ? *(reinterpret_cast<const float4*>(a.table + ro) + sub)
+                               : ld_hint(a.table + ro + sub * 4, pol_row);
           }
           if (MODE != kModeEmit && (ac[j] & 3) == 1) {
-            if (MODE == kModeGiven) T[j] = *(reinterpret_cast<const float4*>(a.table + ro) + sub);
-            if (adagrad) A[j] = *(reinterpret_cast<const float4*>(a.accum + ro) + sub);
+            if (MODE == kModeGiven) T[j] = ld_hint(a.table + ro + sub * 4, pol_row);
+            if (adagrad) A[j] = ld_hint(a.accum + ro + sub * 4, pol_row);
             if (a.lin != nullptr && sub == 0) {
               lw[j] = a.lin[(int64_t)rw[j] * a.lin_stride];
               if (adagrad) a1[j] = a.lin_accum[(int64_t)rw[j] * a.lin_stride];
@@ -595,7 +603,7 @@ extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t r
     return fail(DIR_ENOMEM, "embed_bwd_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, kModeLocal, nullptr, nullptr, 0, nullptr, 0};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), kModeLocal, nullptr, nullptr, 0, nullptr, 0};
   set_div(a, F);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return dispatch_bwd(a, K, n_unique_out, st);
@@ -628,7 +636,7 @@ extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_reduce_emit: workspace too small");
   BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0};
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), kModeEmit, uidx, gu, gu_stride, nullptr, 0};
   set_div(a, F);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -661,7 +669,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }

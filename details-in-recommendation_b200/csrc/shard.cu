@@ -27,7 +27,7 @@ shard_keys_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val
                   int* oob_flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int f = (int)(i % F);
+  const int f = (int)((uint32_t)i % (uint32_t)F);  // n < 2^31
   const int64_t id = __ldg(idx + i);
   const float v = val ? __ldg(val + i) : 1.f;
   const int64_t lo = __ldg(field_offset + f);
@@ -37,8 +37,10 @@ shard_keys_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val
     keep = false;
     if (oob_flag) *oob_flag = 1;
   }
-  const int64_t row = lo + id;
-  keys[i] = keep ? (uint32_t)((row % G) * cap + row / G) : (uint32_t)(G * cap);
+  const uint32_t row = (uint32_t)(lo + id);  // n_rows < 2^32
+  uint32_t key = row;                        // one rank: the key is the global row
+  if (G > 1) key = (row % (uint32_t)G) * (uint32_t)cap + row / (uint32_t)G;
+  keys[i] = keep ? key : (uint32_t)(G * cap);
 }
 
 struct HeadFlag {
@@ -143,6 +145,7 @@ extern "C" int dir_shard_keys(const int64_t* feature_index, const float* feature
   if ((uint64_t)cap * (uint64_t)G >= 0xffffffffULL)
     return fail(DIR_EINVAL, "shard_keys: ceil(n_rows / G) * G must be < 2^32-1");
   const int64_t n = B * F;
+  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "shard_keys: B*F must be < 2^31");
   if (n == 0) return 0;
   if (!feature_index || !field_offset || !keys) return fail(DIR_EINVAL, "shard_keys: null pointer");
   shard_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -53,24 +53,43 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         B, F = idx.shape
         K = layer.embedding_size
         dev = idx.device
+        L = _lib.lib()
         emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
         fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
         first = torch.empty((B, 1), dtype=torch.float32, device=dev)
         S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
-        keys = torch.empty((B * F,), dtype=torch.int32, device=dev) if train else None
         lin = layer.w1 if layer.first_order else None
-        check(_lib.lib().dir_embed_fm_fwd(
+        sort_done = None
+        if train and B > 0:
+            # The backward needs the lookups sorted by row.  That sort is latency-bound and leaves
+            # HBM mostly idle, the gather below is HBM-bound: form the keys first and let the sort
+            # run on a side stream underneath the forward kernel (and whatever the model does
+            # between this layer's forward and backward).
+            keys = torch.empty((B * F,), dtype=torch.int32, device=dev)
+            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
+                                   layer.n_rows, B, F, 1, ptr(keys), None, _stream()), "dir_shard_keys")
+            ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(B * F, K), dev)
+            main, side = torch.cuda.current_stream(), layer.side_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            check(L.dir_embed_bwd_sort(ptr(keys), B * F, layer.n_rows, ptr(ws), ws.numel(), side.cuda_stream),
+                  "dir_embed_bwd_sort")
+            sort_done = torch.cuda.Event()
+            sort_done.record(side)
+            ctx.keys = keys                      # keeps the side stream's input alive until the backward
+        check(L.dir_embed_fm_fwd(
             ptr(layer.table), layer.row_stride, ptr(lin), layer.lin_stride,
             ptr(bias) if layer.first_order else None, ptr(idx), ptr(val), ptr(layer.field_offset),
-            ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first), ptr(fm), ptr(keys),
+            ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first), ptr(fm), None,
             ptr(layer.oob_flag) if layer.check_bounds else None, _stream()), "dir_embed_fm_fwd")
         if not layer.first_order:
             first.zero_()
-        ctx.layer, ctx.train = layer, train
+        ctx.layer, ctx.train, ctx.sort_done = layer, train, sort_done
         ctx.shape = (B, F, K)
         ctx.set_materialize_grads(False)
         if train:
-            ctx.save_for_backward(val, S, keys)
+            ctx.save_for_backward(val, S)
         if emb is None:
             emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(emb)
@@ -81,7 +100,7 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         if not ctx.train:
             raise RuntimeError("EmbeddingFM.backward: forward ran without gradient tracking")
         layer = ctx.layer
-        val, S, keys = ctx.saved_tensors
+        val, S = ctx.saved_tensors
         B, F, K = ctx.shape
         dev = S.device
         g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
@@ -90,7 +109,9 @@ class _EmbeddingFMFunction(torch.autograd.Function):
                 else g_fm.reshape(B).contiguous().float())
         if u is not None:
             u = u.contiguous().float()
-        layer.apply_gradients(keys, val, g_first, g_fm, S, u, B)
+        if ctx.sort_done is not None:
+            torch.cuda.current_stream().wait_event(ctx.sort_done)
+            layer.apply_sorted_gradients(val, g_first, g_fm, S, u, B)
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None
 
@@ -119,7 +140,7 @@ class EmbeddingFM(torch.nn.Module):
                  check_bounds: bool = False, lin_interleaved: Optional[bool] = None, device="cuda"):
         super().__init__()
         if lin_interleaved is None:
-            lin_interleaved = os.environ.get("DIR_B200_LIN_SEPARATE", "0") != "1"
+            lin_interleaved = os.environ.get("DIR_B200_LIN_INTERLEAVED", "0") == "1"
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
         if embedding_size not in _K_OK:
@@ -162,6 +183,7 @@ class EmbeddingFM(torch.nn.Module):
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
         self._ws = _Workspace()
+        self._side = None
         with torch.no_grad():
             # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
             torch.nn.init.trunc_normal_(self.table, 0.0, 1.0 / math.sqrt(K), -2.0 / math.sqrt(K), 2.0 / math.sqrt(K))
@@ -220,15 +242,19 @@ class EmbeddingFM(torch.nn.Module):
             raise IndexError("feature_index out of range for its field")   # TF CPU Gather raises
         return first, fm, emb
 
+    def side_stream(self, device):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
     @torch.no_grad()
-    def apply_gradients(self, sort_keys, feature_value, g_first, g_fm, S, u, B):
-        """sort -> segmented reduce -> fused row update (dir_embed_bwd_sort + _reduce_update)."""
+    def apply_sorted_gradients(self, feature_value, g_first, g_fm, S, u, B):
+        """segmented reduce -> fused row update (dir_embed_bwd_reduce_update) on the (row, position)
+        list the forward left sorted in the workspace."""
         F, K = self.field_size, self.embedding_size
         L = _lib.lib()
         nbytes = L.dir_embed_bwd_workspace_bytes(B * F, K)
         ws = self._ws.get(nbytes, S.device)
-        check(L.dir_embed_bwd_sort(ptr(sort_keys), B * F, self.n_rows, ptr(ws), ws.numel(), _stream()),
-              "dir_embed_bwd_sort")
         adagrad = self.optimizer == "adagrad"
         check(L.dir_embed_bwd_reduce_update(
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,

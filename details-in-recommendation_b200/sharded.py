@@ -78,6 +78,34 @@ def exchange(payload: torch.Tensor, send_splits, recv_splits, group=None) -> tor
     return out
 
 
+class StageTrace:
+    """Optional per-stage CUDA-event timing of the sharded step (DIR_B200_TRACE=1): mark(name) closes
+    the stage that just ran; report() averages over the steps seen since the last report."""
+
+    def __init__(self):
+        self.on = os.environ.get("DIR_B200_TRACE", "0") == "1"
+        self.marks, self.tot, self.steps = [], {}, 0
+
+    def mark(self, name):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def close_step(self):
+        if not self.on or len(self.marks) < 2:
+            return
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            self.tot[name] = self.tot.get(name, 0.0) + a.elapsed_time(b) * 1e3
+        self.marks, self.steps = [], self.steps + 1
+
+    def report(self):
+        out = {k: v / max(1, self.steps) for k, v in self.tot.items()}
+        self.tot, self.steps = {}, 0
+        return out
+
+
 class _ShardedFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, bias, layer, idx, val, train):
@@ -88,14 +116,18 @@ class _ShardedFunction(torch.autograd.Function):
         n = B * F
         st = _stream()
         pad = layer.pad_stride
+        tr = layer.trace
+        tr.mark("start")
         # 1-3: composite keys, sort, distinct keys
         keys = torch.empty(n, dtype=torch.int32, device=dev)
         check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
                                layer.plan.n_rows, B, F, G, ptr(keys),
                                ptr(layer.oob_flag) if layer.check_bounds else None, st), "dir_shard_keys")
+        tr.mark("fwd.keys")
         n_keys = layer.plan.cap * G
         ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
         check(L.dir_embed_bwd_sort(ptr(keys), n, n_keys, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
+        tr.mark("fwd.sort")
         skeys, spos = _lib.c_void_p(), _lib.c_void_p()
         check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
               "dir_embed_bwd_sorted")
@@ -106,17 +138,22 @@ class _ShardedFunction(torch.autograd.Function):
         ws2 = layer._ws2.get(L.dir_shard_unique_workspace_bytes(n), dev)
         check(L.dir_shard_unique(skeys, spos, n, layer.plan.n_rows, G, ptr(uidx), ptr(ulocal), ptr(inv),
                                  ptr(owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+        tr.mark("fwd.unique")
         # 4: counts (one host sync: NCCL needs the split sizes), ids out, rows back
         send_counts = owner_off[1:] - owner_off[:-1]
         recv_counts = exchange_counts(send_counts, layer.group)
         both = torch.stack([send_counts, recv_counts]).cpu()
         send_splits, recv_splits = both[0].tolist(), both[1].tolist()
         U, R = int(sum(send_splits)), int(sum(recv_splits))
+        tr.mark("fwd.counts+sync")
         recv_ids = exchange(ulocal[:U], send_splits, recv_splits, layer.group)
+        tr.mark("fwd.a2a_ids")
         answer = torch.empty((R, pad), dtype=torch.float32, device=dev)
         check(L.dir_rows_gather(ptr(layer.table), layer.row_stride, ptr(layer.w1) if layer.first_order else None,
                                 layer.lin_stride, ptr(recv_ids), R, K, ptr(answer), pad, st), "dir_rows_gather")
+        tr.mark("fwd.gather")
         ubuf = exchange(answer, recv_splits, send_splits, layer.group)          # [U, K+4]
+        tr.mark("fwd.a2a_rows")
         if U == 0:
             ubuf = torch.zeros((1, pad), dtype=torch.float32, device=dev)
         # 5: the ordinary forward on the received rows
@@ -128,6 +165,7 @@ class _ShardedFunction(torch.autograd.Function):
         check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
                                  ptr(inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
                                  ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
+        tr.mark("fwd.fm")
         if not layer.first_order:
             first.zero_()
         layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": n}
@@ -161,6 +199,8 @@ class _ShardedFunction(torch.autograd.Function):
                 else g_fm.reshape(B).contiguous().float())
         if u is not None:
             u = u.contiguous().float()
+        tr = layer.trace
+        tr.mark("between")
         with torch.no_grad():
             # 6: per-distinct-row sums on the requester (the sorted list is still in the workspace)
             ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
@@ -169,12 +209,15 @@ class _ShardedFunction(torch.autograd.Function):
                                               ptr(g_fm), ptr(S), ptr(u), ptr(uidx), B, F, K,
                                               layer.plan.cap * layer.plan.world_size, ptr(gu), pad,
                                               ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
+            tr.mark("bwd.emit")
             # 7: sums to their owners; the owner merges the ranks' contributions and updates
             grecv = exchange(gu[:U], send_splits, recv_splits, layer.group)      # [R, K+4]
+            tr.mark("bwd.a2a_grads")
             if R > 0:
                 ws3 = layer._ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)
                 check(L.dir_embed_bwd_sort(ptr(recv_ids), R, layer.plan.cap, ptr(ws3), ws3.numel(), st),
                       "dir_embed_bwd_sort")
+                tr.mark("bwd.owner_sort")
                 adagrad = layer.optimizer == "adagrad"
                 check(L.dir_rows_reduce_update(
                     ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
@@ -182,8 +225,10 @@ class _ShardedFunction(torch.autograd.Function):
                     ptr(layer.w1_accum) if (adagrad and layer.first_order) else None, layer.lin_stride,
                     ptr(grecv), pad, R, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
                     ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
+                tr.mark("bwd.owner_update")
             else:
                 layer.last_n_unique.zero_()
+            tr.close_step()
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None
 
@@ -238,6 +283,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
         self.last_exchange = {}
         self._ws, self._ws2, self._ws3 = _Workspace(), _Workspace(), _Workspace()
+        self.trace = StageTrace()
         with torch.no_grad():
             sd = 1.0 / math.sqrt(K)
             torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)

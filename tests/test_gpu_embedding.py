@@ -156,6 +156,12 @@ def test_sort_keys_bit_exact_and_oob(pkg, cuda):
     keep = (idx >= 0) & (case["val"] > 0)
     want = np.where(keep, idx + case["off"][None, :], case["N"]).astype(np.uint32).reshape(-1)
     assert np.array_equal(keys.cpu().numpy().view(np.uint32), want)
+    # the stand-alone key kernel (what the layer uses, so that the sort can overlap the gather) agrees
+    keys2 = torch.empty(B * F, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().dir_shard_keys(d_idx.data_ptr(), d_val.data_ptr(), layer.field_offset.data_ptr(),
+                                         layer.field_rows.data_ptr(), layer.n_rows, B, F, 1, keys2.data_ptr(), None,
+                                         torch.cuda.current_stream().cuda_stream), "keys")
+    assert torch.equal(keys, keys2)
     idx[7, 0] = 9            # one past the end of field 0
     with pytest.raises(IndexError):
         layer(to_dev(idx), d_val)
