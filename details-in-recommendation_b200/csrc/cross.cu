@@ -541,31 +541,39 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
   }
 }
 
-// Fixed-order combine of per-CTA partials: a CTA owns 32 columns; 8 "g-lanes" per column each sum
-// every 8th partial in order, then the 8 sums are added in order.
+// Fixed-order combine of per-CTA partials: a CTA owns 8 columns; 32 "g-lanes" per column each sum
+// every 32nd partial in order, then the 32 sums are added in lane order.
 __global__ void __launch_bounds__(256)
 cross_bwd_finish2_kernel(const float* __restrict__ wg, const float* __restrict__ bg,
                          const float* __restrict__ Dpart, const float* __restrict__ dypart,
                          const float* __restrict__ dwpart, int G1, int G2, int d, int L,
                          float* __restrict__ dw, float* __restrict__ db) {
   __shared__ float sDl[32];       // sum_b ds_l
-  __shared__ float red[8][33];
-  __shared__ float rows[33][32];  // row 0: sum dy; row 1+l: sum alpha_l x0
-  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  if (threadIdx.x < 32) {
+  __shared__ float red[32][9];
+  __shared__ float rows[33][8];   // row 0: sum dy; row 1+l: sum alpha_l x0
+  const int cx = threadIdx.x & 7, gy = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cx;
+  {  // D_l: thread (l = gy, part = cx) sums every 8th partial, then the 8 parts in order
     float t = 0.f;
-    if (threadIdx.x < L)
-      for (int g = 0; g < G1; ++g) t += Dpart[(int64_t)g * L + threadIdx.x];
-    sDl[threadIdx.x] = t;
+    if (gy < L)
+      for (int g = cx; g < G1; g += 8) t += Dpart[(int64_t)g * L + gy];
+    red[gy][cx] = t;
+    __syncthreads();
+    if (cx == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[gy][k];
+      sDl[gy] = v;
+    }
+    __syncthreads();
   }
   for (int r = 0; r <= L; ++r) {
     float t = 0.f;
     if (c < d) {
       if (r == 0) {
-        for (int g = gy; g < G1; g += 8) t += dypart[(int64_t)g * d + c];
+        for (int g = gy; g < G1; g += 32) t += dypart[(int64_t)g * d + c];
       } else {
-        for (int g = gy; g < G2; g += 8) t += dwpart[((int64_t)g * L + (r - 1)) * d + c];
+        for (int g = gy; g < G2; g += 32) t += dwpart[((int64_t)g * L + (r - 1)) * d + c];
       }
     }
     red[gy][cx] = t;
@@ -573,7 +581,7 @@ cross_bwd_finish2_kernel(const float* __restrict__ wg, const float* __restrict__
     if (gy == 0) {
       float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v += red[k][cx];
+      for (int k = 0; k < 32; ++k) v += red[k][cx];
       rows[r][cx] = v;
     }
     __syncthreads();
@@ -692,7 +700,7 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   }
     DIR_CROSS_DISPATCH(DIR_BWDF)
 #undef DIR_BWDF
-    cross_bwd_finish2_kernel<<<(d + 31) / 32, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
+    cross_bwd_finish2_kernel<<<(d + 7) / 8, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
                                                            w.G1, w.G2, d, L, dw, db);
     return launched("cross_bwd", 2);
   }
@@ -703,7 +711,7 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   DIR_CROSS_DISPATCH(DIR_BWD)
 #undef DIR_BWD
   cross_bwd_dw_kernel<<<w.G2, 256, kDwUnroll * 8 * 4, st>>>(x0, w.alpha, B, d, L, w.dwpart);
-  cross_bwd_finish2_kernel<<<(d + 31) / 32, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
+  cross_bwd_finish2_kernel<<<(d + 7) / 8, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
                                                          w.G1, w.G2, d, L, dw, db);
   return launched("cross_bwd", 3);
 }

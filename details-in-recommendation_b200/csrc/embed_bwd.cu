@@ -17,6 +17,7 @@
 // Reference: TF autodiff + optimizer.minimize behind models/DeepFM/deepFM.py:230-241
 // (SURVEY.md rows A8/A9).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/dispatch/dispatch_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -41,11 +42,54 @@ struct BwdWorkspace {
   size_t total;
 };
 
+// cub's onesweep with a smaller tile than its sm_90+ default (384 threads x 23 items = 8832 pairs):
+// at 2.5 M pairs the default gives 290 tiles, < 2 per SM, and each pass is latency-bound.
+template <int THREADS, int ITEMS>
+struct SmallTileHub {
+  using Base = cub::detail::radix::policy_hub<uint32_t, uint32_t, int>;
+  struct Policy300 : cub::ChainedPolicy<300, Policy300, Policy300> {
+    static constexpr bool ONESWEEP = true;
+    static constexpr int ONESWEEP_RADIX_BITS = 8;
+    using HistogramPolicy = typename Base::Policy900::HistogramPolicy;
+    using ExclusiveSumPolicy = typename Base::Policy900::ExclusiveSumPolicy;
+    using OnesweepPolicy =
+        cub::AgentRadixSortOnesweepPolicy<THREADS, ITEMS, uint32_t, 1, cub::RADIX_RANK_MATCH_EARLY_COUNTS_ANY,
+                                          cub::BLOCK_SCAN_RAKING_MEMOIZE, cub::RADIX_SORT_STORE_DIRECT, 8>;
+    using ScanPolicy = typename Base::Policy900::ScanPolicy;
+    using DownsweepPolicy = typename Base::Policy900::DownsweepPolicy;
+    using AltDownsweepPolicy = typename Base::Policy900::AltDownsweepPolicy;
+    using UpsweepPolicy = typename Base::Policy900::UpsweepPolicy;
+    using AltUpsweepPolicy = typename Base::Policy900::AltUpsweepPolicy;
+    using SingleTilePolicy = typename Base::Policy900::SingleTilePolicy;
+    using SegmentedPolicy = typename Base::Policy900::SegmentedPolicy;
+    using AltSegmentedPolicy = typename Base::Policy900::AltSegmentedPolicy;
+  };
+  using MaxPolicy = Policy300;
+};
+
+template <class Hub>
+static cudaError_t sort_pairs_hub(void* temp, size_t& bytes, const uint32_t* kin, uint32_t* kout,
+                                  const uint32_t* vin, uint32_t* vout, int n, int end_bit, cudaStream_t st) {
+  cub::DoubleBuffer<uint32_t> dk(const_cast<uint32_t*>(kin), kout);
+  cub::DoubleBuffer<uint32_t> dv(const_cast<uint32_t*>(vin), vout);
+  return cub::DispatchRadixSort<false, uint32_t, uint32_t, int, Hub>::Dispatch(temp, bytes, dk, dv, n, 0, end_bit,
+                                                                              false, st);
+}
+
+static cudaError_t sort_pairs(void* temp, size_t& bytes, const uint32_t* kin, uint32_t* kout,
+                              const uint32_t* vin, uint32_t* vout, int n, int end_bit, cudaStream_t st,
+                              int variant) {
+  if (variant == 1) return sort_pairs_hub<SmallTileHub<256, 8>>(temp, bytes, kin, kout, vin, vout, n, end_bit, st);
+  if (variant == 2) return sort_pairs_hub<SmallTileHub<384, 12>>(temp, bytes, kin, kout, vin, vout, n, end_bit, st);
+  if (variant == 3) return sort_pairs_hub<SmallTileHub<512, 8>>(temp, bytes, kin, kout, vin, vout, n, end_bit, st);
+  return cub::DeviceRadixSort::SortPairs(temp, bytes, kin, kout, vin, vout, n, 0, end_bit, st);
+}
+
+static int sort_variant() { return (tune() >> 5) & 3; }  // DIR_B200_TUNE bits 32, 64
+
 static size_t cub_temp_bytes(int64_t n) {
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32,
-                                  (cudaStream_t)0);
+  sort_pairs(nullptr, bytes, nullptr, nullptr, nullptr, nullptr, (int)n, 32, (cudaStream_t)0, sort_variant());
   cudaGetLastError();  // a size query on a box without a GPU leaves an error behind
   // onesweep needs ~ (n/ (items per tile) + digits*passes) counters; keep a generous floor
   const size_t floor_bytes = (size_t)n / 8 + (1u << 20);
@@ -564,9 +608,8 @@ extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, 
   int end_bit = 1;
   while (end_bit < 32 && (((uint64_t)n_rows) >> end_bit) != 0) ++end_bit;  // n_rows itself is a key
   size_t cub_bytes = w.cub_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, sort_keys, w.keys,
-                                                  (const uint32_t*)w.pos_in, w.pos, (int)n_lookups,
-                                                  0, end_bit, st);
+  cudaError_t e = sort_pairs(w.cub_temp, cub_bytes, sort_keys, w.keys, (const uint32_t*)w.pos_in, w.pos,
+                             (int)n_lookups, end_bit, st, sort_variant());
   if (e != cudaSuccess) return fail(DIR_EIO, "embed_bwd_sort: %s", cudaGetErrorString(e));
   return launched("embed_bwd_sort", (end_bit + 7) / 8 + 2);
 }

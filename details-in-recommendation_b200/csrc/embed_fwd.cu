@@ -27,7 +27,7 @@ struct FwdArgs {
   float* fm;
   uint32_t* sort_keys;
   int* oob_flag;
-  int tune;  // experiment bits (DIR_B200_TUNE): 1 lin evict_last, 2 emb stores evict_first, 4 rows evict_first
+  int tune;  // DIR_B200_TUNE bits switch a policy OFF: 1 lin evict_last, 2 emb stores evict_first, 4 rows evict_first
 };
 
 template <int LPR, int UNR>
@@ -83,10 +83,10 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
       w[j] = 0.f;
       if (keep[j]) {
         const float* rp = a.table + row[j] * a.row_stride + sub * 4;
-        t[j] = (a.tune & 4) ? ldg_hint(rp, pol_once) : __ldg(reinterpret_cast<const float4*>(rp));
+        t[j] = (a.tune & 4) ? __ldg(reinterpret_cast<const float4*>(rp)) : ldg_hint(rp, pol_once);
         if (a.lin != nullptr && sub == 0) {
           const float* lp = a.lin + row[j] * a.lin_stride;
-          w[j] = (a.tune & 1) ? ldg_hint1(lp, pol_keep) : __ldg(lp);
+          w[j] = (a.tune & 1) ? __ldg(lp) : ldg_hint1(lp, pol_keep);
         }
       }
     }
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
         fo = fmaf(v[j], w[j], fo);
         if (a.emb) {
           float* ep = a.emb + (base + f) * K + sub * 4;
-          if (a.tune & 2) stg_hint(ep, e, pol_once); else stg_stream(ep, e);
+          if (a.tune & 2) stg_stream(ep, e); else stg_hint(ep, e, pol_once);
         }
         if (a.sort_keys && sub == 0)
           a.sort_keys[base + f] = keep[j] ? (uint32_t)row[j] : pruned_key;
