@@ -413,11 +413,12 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     ws = torch.empty(int(lib.dir_embed_bwd_workspace_bytes(B * F, K)), dtype=torch.uint8, device=dev)
     peak, src = RL.measured_peaks()
     U = sum(n_unique) / len(n_unique)
+    n_sel = layer.n_sorted_fields
 
     def mkkeys(r):
         idx, val, _ = devs[r]
         check(lib.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                                 layer.n_rows, B, F, 1, ptr(keys), None, st), "keys")
+                                 layer.n_rows, B, F, 1, ptr(layer.sorted_fields), n_sel, ptr(keys), None, st), "keys")
 
     def fwd(r):
         idx, val, _ = devs[r]
@@ -427,13 +428,14 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
                                    ptr(fm), None, None, st), "fwd")
 
     def sort(r):
-        check(lib.dir_embed_bwd_sort(ptr(keys), B * F, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
+        check(lib.dir_embed_bwd_sort(ptr(keys), B * n_sel, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
 
     def upd(r):
         check(lib.dir_embed_bwd_reduce_update(
             ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
-            layer.lin_stride, ptr(devs[r][1]), ptr(g), ptr(g), ptr(S), ptr(ups[r]) if emit else None, B, F, K,
-            layer.n_rows, 1, LR, ptr(ws), ws.numel(), None, st), "update")
+            layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
+            ptr(ups[r]) if emit else None, B, F, K, layer.n_rows, ptr(layer.sorted_fields), n_sel,
+            ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, ptr(ws), ws.numel(), None, st), "update")
 
     calls = [("dir_shard_keys", mkkeys, 0),
              ("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),

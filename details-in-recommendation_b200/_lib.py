@@ -25,12 +25,12 @@ SIGNATURES = {
     "dir_embed_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dir_embed_bwd_sort": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_embed_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_int64, c_int, c_int, c_int64, c_int, c_float,
-                                            c_void_p, c_size_t, c_void_p, c_void_p]),
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
+                                            c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_sorted": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
-                               c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dir_shard_unique_workspace_bytes": (c_size_t, [c_int64]),
     "dir_shard_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -571,9 +571,11 @@ cross_bwd_finish2_kernel(const float* __restrict__ wg, const float* __restrict__
     float t = 0.f;
     if (c < d) {
       if (r == 0) {
-        for (int g = gy; g < G1; g += 32) t += dypart[(int64_t)g * d + c];
+#pragma unroll 8
+        for (int g = gy; g < G1; g += 32) t += __ldg(dypart + (int64_t)g * d + c);
       } else {
-        for (int g = gy; g < G2; g += 32) t += dwpart[((int64_t)g * L + (r - 1)) * d + c];
+#pragma unroll 8
+        for (int g = gy; g < G2; g += 32) t += __ldg(dwpart + ((int64_t)g * L + (r - 1)) * d + c);
       }
     }
     red[gy][cx] = t;

@@ -39,6 +39,8 @@ struct BwdWorkspace {
   uint32_t* long_list; // [nchunks / kLongRun + 1]
   uint32_t* long_count;
   unsigned long long* n_unique;
+  int* onerow_flags;   // [64]
+  float* onerow_part;  // [296][64][K + 4]
   size_t total;
 };
 
@@ -115,8 +117,10 @@ static BwdWorkspace carve(void* base, int64_t n, int K) {
   w.long_list = reinterpret_cast<uint32_t*>(take((size_t)(nchunks / kLongRun + 1) * 4));
   w.long_count = reinterpret_cast<uint32_t*>(take(16));
   w.n_unique = reinterpret_cast<unsigned long long*>(w.long_count ? (char*)w.long_count + 8 : nullptr);
+  w.onerow_flags = reinterpret_cast<int*>(take(64 * 4));
   w.part1 = reinterpret_cast<float*>(take((size_t)nchunks * 2 * 4));
   w.part = reinterpret_cast<float*>(take((size_t)nchunks * 2 * K * 4));
+  w.onerow_part = reinterpret_cast<float*>(take((size_t)296 * 64 * (K + 4) * 4));
   w.total = off;
   return w;
 }
@@ -157,6 +161,8 @@ struct BwdArgs {
   uint32_t div_magic;   // position / F == (position * div_magic) >> div_shift for position < 2^31
   int div_shift;
   int tune;             // DIR_B200_TUNE experiment bits
+  const int32_t* field_sel;  // sorted entries index the compact [B, n_sel] list of these fields (or NULL)
+  int n_sel;
   // sharded-table modes (see kMode*)
   int mode;
   const uint32_t* rowidx;  // kModeEmit: row of `table` (the exchanged unique-row buffer) per sorted entry
@@ -282,7 +288,8 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
   if (MODE == kModeEmit) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
 
   for (int64_t base = i0; base < chunk_end; base += kTile) {
-    const uint32_t key = key_nx, pos = pos_nx, row = row_nx;
+    const uint32_t key = key_nx, row = row_nx;
+    uint32_t pos = pos_nx;
     i = base + kTile + lane;
     key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
     pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
@@ -301,15 +308,19 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
     last_key = __shfl_sync(FULL, key, 31);
     heads += __popc(__ballot_sync(FULL, valid && key != keyp));
     const unsigned cont = __ballot_sync(FULL, valid && keyn == key);  // run goes on after this lookup
-    const uint32_t b = (uint32_t)(((uint64_t)pos * a.div_magic) >> a.div_shift);  // pos / F
+    // sample of this lookup: entry / (fields per sample in the sorted list)
+    const uint32_t b = (uint32_t)(((uint64_t)pos * a.div_magic) >> a.div_shift);
+    if (a.field_sel != nullptr)  // compact list of selected fields -> position in the [B, F] inputs
+      pos = b * (uint32_t)a.F + (uint32_t)__ldg(a.field_sel + (pos - b * (uint32_t)a.n_sel));
     float v = 1.f, g2 = 0.f, d1l = 0.f;
     if (valid) {
       if (MODE == kModeGiven) {
         d1l = __ldg(a.gbuf + (int64_t)pos * a.gbuf_stride + K);
       } else {
         if (a.val) v = __ldg(a.val + pos);
-        if (a.g_first) d1l = __fmul_rn(__ldg(a.g_first + b), v);
+        if (a.g_first) d1l = __ldg(a.g_first + b);
         g2 = __ldg(a.g_fm + b);
+        d1l = __fmul_rn(d1l, v);
       }
     }
     // what happens at this lookup: 0 nothing, 1 finish the row (update / emit), 2 partial (run open
@@ -551,6 +562,219 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
   return launched("embed_bwd_reduce_update", 2);
 }
 
+// ------------------------------------------------------------------------------------------
+// One-row fields.  A numeric ("dense") feature is a field whose table has a single row scaled by
+// feature_value (weighted-column semantics, dataset/SequenceTensorFlowDataset/test4.py:50-55), so
+// every sample looks up the same row: no sort is needed, the row's gradient is a column sum over
+// the batch.  Warps stride over samples and keep one accumulator per field (LPR lanes per field);
+// warps, then CTAs, are combined in a fixed order and the finish kernel applies the update.
+constexpr int kOneRowPasses = 4;   // fields per launch = kOneRowPasses * 32 / LPR
+constexpr int kOneRowCtas = 296;   // two per SM
+constexpr int kOneRowMax = 64;     // one-row fields per call
+
+struct OneRowArgs {
+  float* table;
+  float* accum;
+  int64_t row_stride;
+  float* lin;
+  float* lin_accum;
+  int64_t lin_stride;
+  const int64_t* idx;
+  const float* val;
+  const int64_t* field_offset;
+  const float* g_first;
+  const float* g_fm;
+  const float* S;
+  const float* u;
+  const int32_t* fields;
+  int64_t B;
+  int F;
+  int opt;
+  float lr;
+  float* part;   // [kOneRowCtas][kOneRowMax][K + 4]
+  int* flags;    // [kOneRowMax] some sample had a surviving lookup
+  unsigned long long* n_unique;
+};
+
+template <int LPR, int P>
+__global__ void __launch_bounds__(256)
+embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
+  constexpr int K = LPR * 4;
+  constexpr int SLOTS = 32 / LPR;
+  constexpr int UN = 4;  // samples whose loads are in flight together
+  __shared__ float4 sm4[8][P][32];
+  __shared__ float sm1[8][P][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane % LPR, slot = lane / LPR;
+  float4 T[P], acc[P];
+  float acc1[P];
+  int fld[P];
+  bool any[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int j = p * SLOTS + slot;
+    fld[p] = j < nf ? __ldg(a.fields + f0 + j) : -1;
+    acc[p] = T[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc1[p] = 0.f;
+    any[p] = false;
+    if (fld[p] >= 0)
+      T[p] = *(reinterpret_cast<const float4*>(a.table + __ldg(a.field_offset + fld[p]) * a.row_stride) + sub);
+  }
+  const int64_t W = (int64_t)gridDim.x * 8;
+  for (int64_t b0 = (int64_t)blockIdx.x * 8 + wib; b0 < a.B; b0 += W * UN) {
+    float4 Sb[UN], ub[UN][P];
+    float g1[UN], g2[UN], v[UN][P];
+    bool ok[UN][P];
+#pragma unroll
+    for (int s = 0; s < UN; ++s) {
+      const int64_t b = b0 + s * W < a.B ? b0 + s * W : a.B - 1;  // clamped; masked by `ok` below
+      Sb[s] = __ldg(reinterpret_cast<const float4*>(a.S + b * K) + sub);
+      g1[s] = __ldg((a.g_first ? a.g_first : a.g_fm) + b);
+      g2[s] = __ldg(a.g_fm + b);
+    }
+    // Loads only, no branches on the nullable pointers and no consumer in between (a NULL array is
+    // replaced by a harmless valid address): every load of the UN samples is in flight before the
+    // first value is looked at.
+    int64_t id[UN][P];
+#pragma unroll
+    for (int s = 0; s < UN; ++s) {
+      const int64_t b = b0 + s * W < a.B ? b0 + s * W : a.B - 1;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int64_t pos = b * a.F + (fld[p] >= 0 ? fld[p] : 0);
+        v[s][p] = __ldg(a.val ? a.val + pos : a.S);
+        id[s][p] = __ldg(a.idx ? a.idx + pos : a.field_offset);
+        ub[s][p] = ldg_stream(a.u ? a.u + pos * K + sub * 4 : a.S);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < UN; ++s) {
+      const bool live = b0 + s * W < a.B;
+      if (!a.g_first) g1[s] = 0.f;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        if (!a.val) v[s][p] = 1.f;
+        if (!a.u) ub[s][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // pruned: id < 0, value <= 0, or id beyond the field's single row
+        ok[s][p] = live && fld[p] >= 0 && (!a.idx || id[s][p] == 0) && v[s][p] > 0.f;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < UN; ++s) {  // samples in ascending order
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        if (!ok[s][p]) continue;
+        const float x = v[s][p], gg = g2[s];
+        acc[p].x = __fadd_rn(acc[p].x, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].x, __fmul_rn(x, T[p].x))), ub[s][p].x)));
+        acc[p].y = __fadd_rn(acc[p].y, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].y, __fmul_rn(x, T[p].y))), ub[s][p].y)));
+        acc[p].z = __fadd_rn(acc[p].z, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].z, __fmul_rn(x, T[p].z))), ub[s][p].z)));
+        acc[p].w = __fadd_rn(acc[p].w, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].w, __fmul_rn(x, T[p].w))), ub[s][p].w)));
+        acc1[p] = __fadd_rn(acc1[p], __fmul_rn(g1[s], x));
+        any[p] = true;
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    sm4[wib][p][lane] = acc[p];
+    sm1[wib][p][lane] = acc1[p];
+    if (any[p] && sub == 0) a.flags[f0 + p * SLOTS + slot] = 1;  // benign race: everyone writes 1
+  }
+  __syncthreads();
+  if (wib < P) {  // warp p adds the 8 warps' sums of pass p in warp order
+    const int p = wib;
+    const int j = p * SLOTS + slot;
+    if (j < nf) {
+      float4 t = sm4[0][p][lane];
+      float t1 = sm1[0][p][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const float4 o = sm4[w][p][lane];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        t1 += sm1[w][p][lane];
+      }
+      float* dst = a.part + ((int64_t)blockIdx.x * kOneRowMax + f0 + j) * (K + 4);
+      *(reinterpret_cast<float4*>(dst) + sub) = t;
+      if (sub == 0) dst[K] = t1;
+    }
+  }
+}
+
+// one CTA per one-row field: 32 component lanes x 8 "g-lanes" sum the CTA partials in a fixed order
+template <int LPR>
+__global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneRowArgs a, int G) {
+  constexpr int K = LPR * 4;
+  __shared__ float red[8][33];
+  __shared__ float tot[K + 1];
+  const int j = blockIdx.x;
+  if (a.flags[j] == 0) return;  // no surviving lookup: the row is not touched
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  for (int c0 = 0; c0 <= K; c0 += 32) {
+    const int c = c0 + cx;
+    float t = 0.f;
+    if (c <= K)
+#pragma unroll 8
+      for (int g = gy; g < G; g += 8) t += __ldg(a.part + ((int64_t)g * kOneRowMax + j) * (K + 4) + c);
+    red[gy][cx] = t;
+    __syncthreads();
+    if (gy == 0 && c <= K) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][cx];
+      tot[c] = v;
+    }
+    __syncthreads();
+  }
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const int64_t row = a.field_offset[a.fields[j]];
+  if (threadIdx.x < K) {
+    float* tp = a.table + row * a.row_stride + threadIdx.x;
+    float acc = 0.f;
+    float* ap = nullptr;
+    if (adagrad) {
+      ap = a.accum + row * a.row_stride + threadIdx.x;
+      acc = *ap;
+    }
+    *tp = upd(*tp, tot[threadIdx.x], a.lr, acc, adagrad);
+    if (adagrad) *ap = acc;
+  } else if (threadIdx.x == K) {
+    if (a.lin != nullptr) {
+      float* wp = a.lin + row * a.lin_stride;
+      float a1 = 0.f;
+      float* ap = nullptr;
+      if (adagrad) {
+        ap = a.lin_accum + row * a.lin_stride;
+        a1 = *ap;
+      }
+      *wp = upd(*wp, tot[K], a.lr, a1, adagrad);
+      if (adagrad) *ap = a1;
+    }
+    if (a.n_unique) atomicAdd(a.n_unique, 1ull);
+  }
+}
+
+template <int LPR>
+static int launch_onerow(const OneRowArgs& a, int n_fields, cudaStream_t st) {
+  constexpr int PER = kOneRowPasses * (32 / LPR);
+  const int64_t want = (a.B + 7) / 8;
+  const int G = (int)(want < kOneRowCtas ? want : kOneRowCtas);
+  constexpr int SLOTS = 32 / LPR;
+  int n = 0;
+  for (int f0 = 0; f0 < n_fields; f0 += PER, ++n) {
+    const int nf = n_fields - f0 < PER ? n_fields - f0 : PER;
+    switch ((nf + SLOTS - 1) / SLOTS) {
+      case 1: embed_bwd_onerow_kernel<LPR, 1><<<G, 256, 0, st>>>(a, f0, nf); break;
+      case 2: embed_bwd_onerow_kernel<LPR, 2><<<G, 256, 0, st>>>(a, f0, nf); break;
+      case 3: embed_bwd_onerow_kernel<LPR, 3><<<G, 256, 0, st>>>(a, f0, nf); break;
+      default: embed_bwd_onerow_kernel<LPR, 4><<<G, 256, 0, st>>>(a, f0, nf); break;
+    }
+  }
+  embed_bwd_onerow_finish_kernel<LPR><<<n_fields, 256, 0, st>>>(a, G);
+  return launched("embed_bwd_onerow", n + 1);
+}
+
+__global__ void publish_count_kernel(const unsigned long long* src, int64_t* dst) { *dst = (int64_t)*src; }
+
 // position / F == (position * magic) >> shift, exact for positions < 2^31:
 // shift = 31 + ceil(log2 F), magic = ceil(2^shift / F) <= 2^32 - 1
 static void set_div(BwdArgs& a, int F) {
@@ -614,17 +838,16 @@ extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, 
   return launched("embed_bwd_sort", (end_bit + 7) / 8 + 2);
 }
 
-extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride,
-                                           float* lin, float* lin_accum, int64_t lin_stride,
-                                           const float* feature_value, const float* g_first,
-                                           const float* g_fm, const float* S, const float* u,
-                                           int64_t B, int F, int K, int64_t n_rows, int optimizer,
-                                           float lr, void* workspace, size_t workspace_bytes,
-                                           int64_t* n_unique_out, dir_stream_t stream) {
+extern "C" int dir_embed_bwd_reduce_update(
+    float* table, float* accum, int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
+    const int64_t* feature_index, const float* feature_value, const int64_t* field_offset,
+    const float* g_first, const float* g_fm, const float* S, const float* u, int64_t B, int F, int K,
+    int64_t n_rows, const int32_t* field_sel, int n_sel, const int32_t* onerow_fields, int n_onerow,
+    int optimizer, float lr, void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
+    dir_stream_t stream) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B >= 0, F > 0 required");
-  const int64_t n = B * F;
-  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B*F must be < 2^31");
+  if (B * F >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B*F must be < 2^31");
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: unknown optimizer");
   if (!table || !g_fm || !S || !workspace)
@@ -638,17 +861,46 @@ extern "C" int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t r
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: table, accum, S, u must be 16-byte aligned");
   if (n_rows <= 0 || n_rows >= 0xffffffffLL)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: 0 < n_rows < 2^32-1 required");
-  if (n == 0) return 0;
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: K must be one of 4, 8, 16, 32, 64");
-  BwdWorkspace w = carve(workspace, n, K);
+  if (field_sel == nullptr) n_sel = F;
+  if (n_sel < 0 || n_sel > F || n_onerow < 0 || n_onerow > kOneRowMax || (n_onerow > 0 && !onerow_fields))
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: need 0 <= n_sel <= F and 0 <= n_onerow <= 64");
+  if (n_onerow > 0 && !field_offset)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: one-row fields need field_offset");
+  if (B == 0) return 0;
+  const int64_t n = B * n_sel;  // entries the sort step left in the workspace
+  BwdWorkspace w = carve(workspace, n > 0 ? n : 1, K);
   if (workspace_bytes < w.total)
     return fail(DIR_ENOMEM, "embed_bwd_reduce_update: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) cudaMemsetAsync(w.n_unique, 0, 8, st);  // no sort ran: nobody zeroed the counter
+  if (n_onerow > 0) {
+    cudaMemsetAsync(w.onerow_flags, 0, kOneRowMax * 4, st);
+    OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value,
+                 field_offset, g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.onerow_part,
+                 w.onerow_flags, w.n_unique};
+    int rc;
+    switch (K) {
+      case 4: rc = launch_onerow<1>(o, n_onerow, st); break;
+      case 8: rc = launch_onerow<2>(o, n_onerow, st); break;
+      case 16: rc = launch_onerow<4>(o, n_onerow, st); break;
+      case 32: rc = launch_onerow<8>(o, n_onerow, st); break;
+      default: rc = launch_onerow<16>(o, n_onerow, st); break;
+    }
+    if (rc) return rc;
+  }
+  if (n == 0) {
+    if (n_unique_out) {
+      publish_count_kernel<<<1, 1, 0, st>>>(w.n_unique, n_unique_out);
+      return launched("embed_bwd_reduce_update/count");
+    }
+    return 0;
+  }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), kModeLocal, nullptr, nullptr, 0, nullptr, 0};
-  set_div(a, F);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0};
+  set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
 
@@ -679,7 +931,7 @@ extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_reduce_emit: workspace too small");
   BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), kModeEmit, uidx, gu, gu_stride, nullptr, 0};
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0};
   set_div(a, F);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -712,7 +964,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }

@@ -65,19 +65,24 @@ class _EmbeddingFMFunction(torch.autograd.Function):
             # HBM mostly idle, the gather below is HBM-bound: form the keys first and let the sort
             # run on a side stream underneath the forward kernel (and whatever the model does
             # between this layer's forward and backward).
-            keys = torch.empty((B * F,), dtype=torch.int32, device=dev)
-            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                                   layer.n_rows, B, F, 1, ptr(keys), None, _stream()), "dir_shard_keys")
             ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(B * F, K), dev)
-            main, side = torch.cuda.current_stream(), layer.side_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side.wait_event(fork)
-            check(L.dir_embed_bwd_sort(ptr(keys), B * F, layer.n_rows, ptr(ws), ws.numel(), side.cuda_stream),
-                  "dir_embed_bwd_sort")
+            n_sel = layer.n_sorted_fields
             sort_done = torch.cuda.Event()
-            sort_done.record(side)
-            ctx.keys = keys                      # keeps the side stream's input alive until the backward
+            if n_sel > 0:
+                keys = torch.empty((B * n_sel,), dtype=torch.int32, device=dev)
+                check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
+                                       layer.n_rows, B, F, 1, ptr(layer.sorted_fields), n_sel, ptr(keys), None,
+                                       _stream()), "dir_shard_keys")
+                main, side = torch.cuda.current_stream(), layer.side_stream(dev)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                check(L.dir_embed_bwd_sort(ptr(keys), B * n_sel, layer.n_rows, ptr(ws), ws.numel(),
+                                           side.cuda_stream), "dir_embed_bwd_sort")
+                sort_done.record(side)
+                ctx.keys = keys                  # keeps the side stream's input alive until the backward
+            else:
+                sort_done.record(torch.cuda.current_stream())
         check(L.dir_embed_fm_fwd(
             ptr(layer.table), layer.row_stride, ptr(lin), layer.lin_stride,
             ptr(bias) if layer.first_order else None, ptr(idx), ptr(val), ptr(layer.field_offset),
@@ -89,7 +94,7 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         ctx.shape = (B, F, K)
         ctx.set_materialize_grads(False)
         if train:
-            ctx.save_for_backward(val, S)
+            ctx.save_for_backward(idx, val, S)
         if emb is None:
             emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(emb)
@@ -100,7 +105,7 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         if not ctx.train:
             raise RuntimeError("EmbeddingFM.backward: forward ran without gradient tracking")
         layer = ctx.layer
-        val, S = ctx.saved_tensors
+        idx, val, S = ctx.saved_tensors
         B, F, K = ctx.shape
         dev = S.device
         g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
@@ -111,7 +116,7 @@ class _EmbeddingFMFunction(torch.autograd.Function):
             u = u.contiguous().float()
         if ctx.sort_done is not None:
             torch.cuda.current_stream().wait_event(ctx.sort_done)
-            layer.apply_sorted_gradients(val, g_first, g_fm, S, u, B)
+            layer.apply_sorted_gradients(idx, val, g_first, g_fm, S, u, B)
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None
 
@@ -179,6 +184,15 @@ class EmbeddingFM(torch.nn.Module):
         self.register_buffer("lin_acc", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)
                              if (adagrad and not lin_interleaved) else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
+        # Field plan: a field whose table has ONE row (a numeric feature scaled by feature_value) needs no
+        # sort -- every sample hits the same row -- so only the other fields' lookups are sorted.
+        onerow = [f for f in range(field_size) if rows is not None and rows[f] == 1][:64]
+        if os.environ.get("DIR_B200_SORT_ALL_FIELDS", "0") == "1":
+            onerow = []
+        srt = [f for f in range(field_size) if f not in set(onerow)]
+        self.n_sorted_fields, self.n_onerow_fields = len(srt), len(onerow)
+        self.register_buffer("sorted_fields", torch.tensor(srt or [0], dtype=torch.int32, device=dev))
+        self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -244,11 +258,14 @@ class EmbeddingFM(torch.nn.Module):
 
     def side_stream(self, device):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=device)
+            # high priority: the sort's few, latency-bound CTAs must not queue behind the thousands
+            # of CTAs of the forward gather it is meant to run underneath
+            prio = 0 if os.environ.get("DIR_B200_SIDE_PRIORITY", "1") == "0" else -1
+            self._side = torch.cuda.Stream(device=device, priority=prio)
         return self._side
 
     @torch.no_grad()
-    def apply_sorted_gradients(self, feature_value, g_first, g_fm, S, u, B):
+    def apply_sorted_gradients(self, feature_index, feature_value, g_first, g_fm, S, u, B):
         """segmented reduce -> fused row update (dir_embed_bwd_reduce_update) on the (row, position)
         list the forward left sorted in the workspace."""
         F, K = self.field_size, self.embedding_size
@@ -260,7 +277,9 @@ class EmbeddingFM(torch.nn.Module):
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
             ptr(self.w1) if self.first_order else None,
             ptr(self.w1_accum) if (adagrad and self.first_order) else None, self.lin_stride,
-            ptr(feature_value), ptr(g_first), ptr(g_fm), ptr(S), ptr(u), B, F, K, self.n_rows,
+            ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
+            ptr(u), B, F, K, self.n_rows, ptr(self.sorted_fields), self.n_sorted_fields,
+            ptr(self.onerow_fields), self.n_onerow_fields,
             _OPTIMIZERS[self.optimizer], self.lr, ptr(ws), ws.numel(), ptr(self.last_n_unique),
             _stream()), "dir_embed_bwd_reduce_update")
 

@@ -121,7 +121,7 @@ class _ShardedFunction(torch.autograd.Function):
         # 1-3: composite keys, sort, distinct keys
         keys = torch.empty(n, dtype=torch.int32, device=dev)
         check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                               layer.plan.n_rows, B, F, G, ptr(keys),
+                               layer.plan.n_rows, B, F, G, None, F, ptr(keys),
                                ptr(layer.oob_flag) if layer.check_bounds else None, st), "dir_shard_keys")
         tr.mark("fwd.keys")
         n_keys = layer.plan.cap * G

@@ -91,6 +91,11 @@ int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, i
  *   then T_r / lin_r are updated in place with `optimizer`.  Deterministic: fixed chunking of
  *   the sorted list, sequential sums inside a chunk, fixed-order combine across chunks; no
  *   floating-point atomics.  Pruned lookups do not touch their row.
+ *   field_sel / n_sel: the fields whose lookups were sorted (dir_shard_keys with the same list:
+ *   sorted entries index the compact [B, n_sel] list); NULL = all F fields.
+ *   onerow_fields / n_onerow (<= 64): fields whose table has ONE row (a numeric feature scaled by
+ *   feature_value).  Every sample hits the same row, so these are left out of the sort and reduced
+ *   as a column sum over the batch (fixed order); they need feature_index / field_offset.
  *   accum / lin_accum: Adagrad accumulators with the same strides as table / lin (NULL for SGD).
  *   lin == NULL skips the first-order update.  u == NULL means no upstream embedding gradient.
  *   n_unique_out (device int64, may be NULL) receives the number of distinct rows updated.
@@ -99,11 +104,13 @@ size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K);
 int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
                        void* workspace, size_t workspace_bytes, dir_stream_t stream);
 int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
-                                float* lin_accum, int64_t lin_stride, const float* feature_value,
+                                float* lin_accum, int64_t lin_stride, const int64_t* feature_index,
+                                const float* feature_value, const int64_t* field_offset,
                                 const float* g_first, const float* g_fm, const float* S,
                                 const float* u, int64_t B, int F, int K, int64_t n_rows,
-                                int optimizer, float lr, void* workspace, size_t workspace_bytes,
-                                int64_t* n_unique_out, dir_stream_t stream);
+                                const int32_t* field_sel, int n_sel, const int32_t* onerow_fields,
+                                int n_onerow, int optimizer, float lr, void* workspace,
+                                size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
 /* Where step 1 left the sorted (row, position) pairs inside its workspace (read-only views). */
 int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_t** sorted_keys,
@@ -126,6 +133,8 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  *
  * dir_shard_keys: keys[b*F+f] = owner * cap + local row, cap = ceil(n_rows / G); pruned lookups
  *   (id < 0, value <= 0, id beyond its field) get G * cap, the `n_rows` to pass to dir_embed_bwd_sort.
+ *   With G = 1 the key is the global row: this is also how the single-GPU layer forms its sort keys.
+ *   field_sel / n_sel restrict the list to some fields: keys[b*n_sel + j] for field field_sel[j].
  * dir_shard_unique, on the sorted list:
  *   uidx[i]               index of sorted entry i's key among the distinct keys
  *   unique_local_rows[u]  local row (at its owner) of distinct key u; grouped by owner, ascending
@@ -143,7 +152,8 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  */
 int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
                    const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
-                   int F, int G, uint32_t* keys, int* oob_flag, dir_stream_t stream);
+                   int F, int G, const int32_t* field_sel, int n_sel, uint32_t* keys, int* oob_flag,
+                   dir_stream_t stream);
 size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
 int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
                      int64_t n_rows, int G, uint32_t* uidx, int32_t* unique_local_rows, int64_t* inv,

@@ -159,7 +159,7 @@ def test_sort_keys_bit_exact_and_oob(pkg, cuda):
     # the stand-alone key kernel (what the layer uses, so that the sort can overlap the gather) agrees
     keys2 = torch.empty(B * F, dtype=torch.int32, device="cuda")
     _lib.check(_lib.lib().dir_shard_keys(d_idx.data_ptr(), d_val.data_ptr(), layer.field_offset.data_ptr(),
-                                         layer.field_rows.data_ptr(), layer.n_rows, B, F, 1, keys2.data_ptr(), None,
+                                         layer.field_rows.data_ptr(), layer.n_rows, B, F, 1, None, F, keys2.data_ptr(), None,
                                          torch.cuda.current_stream().cuda_stream), "keys")
     assert torch.equal(keys, keys2)
     idx[7, 0] = 9            # one past the end of field 0
@@ -194,3 +194,28 @@ def test_shared_table_global_ids(pkg, cuda):
     assert np.array_equal(emb.cpu().numpy().reshape(B, F, K), e)
     fm64 = O.fm_second_order(e.astype(np.float64))
     assert rel_err(fm.cpu().numpy(), fm64, 0.5 * (e.astype(np.float64) ** 2).sum((1, 2))[:, None]) <= REL
+
+
+def test_onerow_path_equals_sorted_path(pkg, cuda, monkeypatch):
+    """One-row (numeric) fields reduced as a column sum must agree with pushing them through the sort."""
+    B, rows, K = 700, [1, 40, 1, 1, 9, 1], 16
+    case = make_case(17, B, rows, K, weighted=True, prune=True)
+    rng = case["rng"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = (rng.standard_normal(B) * 0.1).astype(np.float32)
+    u = (rng.standard_normal((B, len(rows), K)) * 0.1).astype(np.float32)
+    a = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    assert a.n_onerow_fields == 4 and a.n_sorted_fields == 2
+    monkeypatch.setenv("DIR_B200_SORT_ALL_FIELDS", "1")
+    b = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    assert b.n_onerow_fields == 0 and b.n_sorted_fields == 6
+    assert int(a.last_n_unique.item()) == int(b.last_n_unique.item())
+    t64, acc64, w64, _, urows, _, _ = _oracle_step(case, "adagrad", g_first, g_fm, u, dtype=np.float64)
+    for layer in (a, b):
+        assert rel_err(layer.table.cpu().numpy(), t64, np.abs(case["table"]).max()) <= REL
+        assert rel_err(layer.w1.cpu().numpy(), w64, np.abs(case["w1"]).max() + 1e-3) <= REL
+    # a field whose every lookup is pruned leaves its row untouched, bit for bit
+    case["val"][:, 0] = 0.0
+    c = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    assert np.array_equal(c.table.cpu().numpy()[0], case["table"][0])
+    assert float(c.accum.cpu().numpy()[0].max()) == np.float32(0.1)
