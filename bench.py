@@ -229,8 +229,18 @@ def run_b200(args):
         ups.append(torch.randn((B, d), device=dev) * 1e-2 if emit else None)
     n_rows_touched = []
 
-    def step(idx, val, y, up):
-        first, fm, emb = layer(idx, val)
+    # The sort of a batch needs its ids only, so the sort for batch i+1 is issued (side stream) at the
+    # start of step i and runs underneath it: every step still performs exactly one sort.
+    pipelined = world == 1
+    handles = [dir_b200.SortedLookups() for _ in range(R)] if pipelined else None
+
+    def step(idx, val, y, up, slot=None, events=True):
+        pre = None
+        if pipelined and slot is not None:
+            nxt = (slot + 1) % R
+            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=events)
+            pre = handles[slot]
+        first, fm, emb = layer(idx, val, presorted=pre) if pipelined else layer(idx, val)
         with torch.no_grad():
             logits = first + fm
             g = torch.sigmoid(logits).sub_(y.unsqueeze(1))          # SUM-reduced CE: no 1/B (deepFM.py:72)
@@ -241,12 +251,16 @@ def run_b200(args):
             torch.autograd.backward((first, fm, emb), (g, g, up))
         else:
             torch.autograd.backward((first, fm), (g, g))
+        if pipelined and slot is not None and not events:      # captured: join the side branch ourselves
+            torch.cuda.current_stream().wait_stream(layer.side_stream(dev))
         return logits
 
     # warm every slot eagerly (allocates workspaces), note U per slot
     out = None
+    if pipelined:
+        layer.presort(devs[0][0], devs[0][1], handle=handles[0])
     for r in range(R):
-        out = step(*devs[r], ups[r])
+        out = step(*devs[r], ups[r], slot=r)
         n_rows_touched.append(int(layer.last_n_unique.item()))
     torch.cuda.synchronize()
 
@@ -258,16 +272,19 @@ def run_b200(args):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for r in range(R):
-                    step(*devs[r], ups[r])
+                    step(*devs[r], ups[r], slot=r, events=False)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             pool = None
             for r in range(R):
                 g_ = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_, pool=pool):
-                    graph_out[r] = step(*devs[r], ups[r])
+                    graph_out[r] = step(*devs[r], ups[r], slot=r, events=False)
                 pool = g_.pool()
                 graphs[r] = g_
+            if pipelined:                       # slot 0's list for the first replay
+                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
+                torch.cuda.synchronize()
         except Exception as e:                                       # eager launches are still our kernels
             if rank == 0:
                 print("bench.py: CUDA graph capture failed (%s); launching eagerly" % e, file=sys.stderr)
@@ -278,7 +295,7 @@ def run_b200(args):
         if use_graph:
             graphs[slot].replay()
             return graph_out[slot]
-        return step(*devs[slot], ups[slot])
+        return step(*devs[slot], ups[slot], slot=slot)
 
     def barrier():
         if world > 1:
@@ -288,8 +305,11 @@ def run_b200(args):
     lib = dir_b200._lib.lib()
     # per-step launch count of OUR kernels (graph replays do not pass through the library's counter)
     n0 = lib.dir_launch_count()
-    step(*devs[0], ups[0])
+    step(*devs[0], ups[0], slot=0)
     launches_per_step = int(lib.dir_launch_count() - n0)
+    if pipelined:                               # that step presorted slot 1; slot 0 runs next
+        layer.presort(devs[0][0], devs[0][1], handle=handles[0])
+        torch.cuda.synchronize()
 
     # ---------------- value: device-resident inputs -------------------------------------------
     for s in range(args.warmup):
@@ -315,25 +335,33 @@ def run_b200(args):
     # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region ---------------
     e2e = None
     if not args.no_e2e:
-        feeder = dir_b200.HostFeeder(devs[0], devs[1 % R] if R > 1 else devs[0])
+        # R device slots form a ring: while step s computes on slot s%R, the sort of batch s+1 (already on
+        # the device) runs on the side stream and batch s+2 lands through the copy stream.
+        feeder = dir_b200.HostFeeder(*devs)
         out_host = [torch.empty((B, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         d2h = out_host[0].numel() * 4
-        slots = [0, 1 % R]
+        ahead = 2 if R >= 3 else 1
 
         def e2e_loop(n):
-            feeder.prefetch(0, host[0])
+            for s in range(min(ahead, n)):
+                feeder.prefetch(s % R, host[s % R])
+            if pipelined:                                    # batch 0's list; later ones are sorted a step ahead
+                feeder.wait(0)
+                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
             for s in range(n):
-                cur = s & 1
-                if s + 1 < n:
-                    feeder.prefetch(cur ^ 1, host[(s + 1) % R])
+                cur = s % R
+                if s + ahead < n:
+                    feeder.prefetch((s + ahead) % R, host[(s + ahead) % R])
                 feeder.wait(cur)
-                o = run(slots[cur])
+                if pipelined and s + 1 < n:
+                    feeder.wait((s + 1) % R)                 # this step presorts the next batch
+                o = run(cur)
                 feeder.release(cur)
-                out_host[cur].copy_(o, non_blocking=True)
+                out_host[s & 1].copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-        if R > 1:
+        if R >= 3 or not pipelined:
             e2e_loop(max(3, args.warmup))
             barrier()
             ev0.record()
@@ -345,12 +373,14 @@ def run_b200(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "how": "EmbeddingFM.forward/backward fed by HostFeeder from pinned host memory "
-                          "(double-buffered H2D on a copy stream), logits read back each step"}
-            # the feeder overwrote slots 0/1: restore the resident sets
-            for r in range(min(2, R)):
+                   "how": "EmbeddingFM.presort/forward/backward fed by HostFeeder from pinned host memory "
+                          "(ring of %d device slots, H2D on a copy stream), logits read back each step" % R}
+            # the feeder overwrote the slots: restore the resident sets
+            for r in range(R):
                 for dst, src in zip(devs[r], host[r]):
                     dst.copy_(src)
+            if pipelined:
+                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
             torch.cuda.synchronize()
 
     # ---------------- roofline: each C-ABI call timed on its own (rank 0's GPU) ---------------

@@ -47,9 +47,29 @@ class _Workspace:
         return self.buf
 
 
+class SortedLookups:
+    """What `EmbeddingFM.presort` leaves behind for one batch: the (row, position) list of its lookups
+    sorted by row, inside a workspace of its own, and the event that marks the sort done.  The sort
+    depends on the ids only -- not on the tables -- so it can run as soon as a batch is on the device,
+    underneath the previous step (the reference's input pipeline likewise prefetches decoded batches,
+    models/DeepCrossNetwork/train.py:148-156)."""
+
+    def __init__(self):
+        self.ws = _Workspace()
+        self.keys = None
+        self.event = None
+        self.B = -1
+        self.src = None
+
+    @staticmethod
+    def key_of(feature_index, feature_value):
+        return (feature_index.data_ptr(), None if feature_value is None else feature_value.data_ptr(),
+                tuple(feature_index.shape))
+
+
 class _EmbeddingFMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, bias, layer, idx, val, train):
+    def forward(ctx, anchor, bias, layer, idx, val, train, presorted):
         B, F = idx.shape
         K = layer.embedding_size
         dev = idx.device
@@ -59,30 +79,15 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         first = torch.empty((B, 1), dtype=torch.float32, device=dev)
         S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
         lin = layer.w1 if layer.first_order else None
-        sort_done = None
+        handle = None
         if train and B > 0:
-            # The backward needs the lookups sorted by row.  That sort is latency-bound and leaves
-            # HBM mostly idle, the gather below is HBM-bound: form the keys first and let the sort
-            # run on a side stream underneath the forward kernel (and whatever the model does
-            # between this layer's forward and backward).
-            ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(B * F, K), dev)
-            n_sel = layer.n_sorted_fields
-            sort_done = torch.cuda.Event()
-            if n_sel > 0:
-                keys = torch.empty((B * n_sel,), dtype=torch.int32, device=dev)
-                check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                                       layer.n_rows, B, F, 1, ptr(layer.sorted_fields), n_sel, ptr(keys), None,
-                                       _stream()), "dir_shard_keys")
-                main, side = torch.cuda.current_stream(), layer.side_stream(dev)
-                fork = torch.cuda.Event()
-                fork.record(main)
-                side.wait_event(fork)
-                check(L.dir_embed_bwd_sort(ptr(keys), B * n_sel, layer.n_rows, ptr(ws), ws.numel(),
-                                           side.cuda_stream), "dir_embed_bwd_sort")
-                sort_done.record(side)
-                ctx.keys = keys                  # keeps the side stream's input alive until the backward
-            else:
-                sort_done.record(torch.cuda.current_stream())
+            # The backward needs the lookups sorted by row.  That sort is latency-bound and leaves HBM
+            # mostly idle, the gather below is HBM-bound: unless the caller already had the batch
+            # sorted ahead of time (`presort`), fork it onto the side stream right here, underneath
+            # the forward kernel and whatever the model does before this layer's backward.
+            handle = presorted
+            if handle is None:
+                handle = layer.presort(idx, val, handle=layer._inline_sort)
         check(L.dir_embed_fm_fwd(
             ptr(layer.table), layer.row_stride, ptr(lin), layer.lin_stride,
             ptr(bias) if layer.first_order else None, ptr(idx), ptr(val), ptr(layer.field_offset),
@@ -90,7 +95,7 @@ class _EmbeddingFMFunction(torch.autograd.Function):
             ptr(layer.oob_flag) if layer.check_bounds else None, _stream()), "dir_embed_fm_fwd")
         if not layer.first_order:
             first.zero_()
-        ctx.layer, ctx.train, ctx.sort_done = layer, train, sort_done
+        ctx.layer, ctx.train, ctx.handle = layer, train, handle
         ctx.shape = (B, F, K)
         ctx.set_materialize_grads(False)
         if train:
@@ -114,11 +119,12 @@ class _EmbeddingFMFunction(torch.autograd.Function):
                 else g_fm.reshape(B).contiguous().float())
         if u is not None:
             u = u.contiguous().float()
-        if ctx.sort_done is not None:
-            torch.cuda.current_stream().wait_event(ctx.sort_done)
-            layer.apply_sorted_gradients(idx, val, g_first, g_fm, S, u, B)
+        if ctx.handle is not None:
+            if ctx.handle.event is not None:
+                torch.cuda.current_stream().wait_event(ctx.handle.event)
+            layer.apply_sorted_gradients(ctx.handle, idx, val, g_first, g_fm, S, u, B)
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
-        return None, g_bias, None, None, None, None
+        return None, g_bias, None, None, None, None, None
 
 
 class EmbeddingFM(torch.nn.Module):
@@ -198,6 +204,7 @@ class EmbeddingFM(torch.nn.Module):
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
         self._ws = _Workspace()
         self._side = None
+        self._inline_sort = SortedLookups()
         with torch.no_grad():
             # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
             torch.nn.init.trunc_normal_(self.table, 0.0, 1.0 / math.sqrt(K), -2.0 / math.sqrt(K), 2.0 / math.sqrt(K))
@@ -247,14 +254,56 @@ class EmbeddingFM(torch.nn.Module):
                 val = (val > 0).float()
         return idx, val
 
-    def forward(self, feature_index, feature_value=None):
+    def forward(self, feature_index, feature_value=None, presorted=None):
         idx, val = self._prepare(feature_index, feature_value)
         train = self.training and torch.is_grad_enabled()
-        first, fm, emb = _EmbeddingFMFunction.apply(self._anchor, self.bias, self, idx, val, train)
+        if presorted is not None and presorted.src != SortedLookups.key_of(feature_index, feature_value):
+            raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
+        first, fm, emb = _EmbeddingFMFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
         if self.check_bounds and int(self.oob_flag.item()) != 0:
             self.oob_flag.zero_()
             raise IndexError("feature_index out of range for its field")   # TF CPU Gather raises
         return first, fm, emb
+
+    @torch.no_grad()
+    def presort(self, feature_index, feature_value=None, handle=None, after=None, record_event=True):
+        """Sort the lookups of a batch by row on the side stream, ahead of `forward`.
+
+        The sort needs only the ids, so a training loop can issue it for batch i+1 as soon as that batch
+        is on the device and let it run underneath step i; pass the returned handle to
+        `forward(..., presorted=handle)` with the SAME tensors.  `after`: an event the side stream must
+        wait for first (e.g. the H2D copy of the batch).  `record_event=False` leaves the ordering to the
+        caller (needed when the presort and its consumer are captured in different CUDA graphs).
+        """
+        idx, val = self._prepare(feature_index, feature_value)
+        B, F, K = idx.shape[0], self.field_size, self.embedding_size
+        dev = idx.device
+        L = _lib.lib()
+        h = handle if handle is not None else SortedLookups()
+        ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), dev)
+        n_sel = self.n_sorted_fields
+        main, side = torch.cuda.current_stream(), self.side_stream(dev)
+        if n_sel > 0 and B > 0:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            if after is not None:
+                side.wait_event(after)
+            if h.keys is None or h.keys.numel() != B * n_sel or h.keys.device != dev:
+                h.keys = torch.empty((B * n_sel,), dtype=torch.int32, device=dev)
+                h.keys.record_stream(side)
+            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
+                                   self.n_rows, B, F, 1, ptr(self.sorted_fields), n_sel, ptr(h.keys), None,
+                                   side.cuda_stream), "dir_shard_keys")
+            check(L.dir_embed_bwd_sort(ptr(h.keys), B * n_sel, self.n_rows, ptr(ws), ws.numel(),
+                                       side.cuda_stream), "dir_embed_bwd_sort")
+        h.event = None
+        if record_event:
+            h.event = torch.cuda.Event()
+            h.event.record(side if (n_sel > 0 and B > 0) else main)
+        h.B = B
+        h.src = SortedLookups.key_of(feature_index, feature_value)
+        return h
 
     def side_stream(self, device):
         if self._side is None:
@@ -265,13 +314,12 @@ class EmbeddingFM(torch.nn.Module):
         return self._side
 
     @torch.no_grad()
-    def apply_sorted_gradients(self, feature_index, feature_value, g_first, g_fm, S, u, B):
+    def apply_sorted_gradients(self, handle, feature_index, feature_value, g_first, g_fm, S, u, B):
         """segmented reduce -> fused row update (dir_embed_bwd_reduce_update) on the (row, position)
-        list the forward left sorted in the workspace."""
+        list `presort` left sorted in the handle's workspace."""
         F, K = self.field_size, self.embedding_size
         L = _lib.lib()
-        nbytes = L.dir_embed_bwd_workspace_bytes(B * F, K)
-        ws = self._ws.get(nbytes, S.device)
+        ws = handle.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), S.device)
         adagrad = self.optimizer == "adagrad"
         check(L.dir_embed_bwd_reduce_update(
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,

@@ -219,3 +219,26 @@ def test_onerow_path_equals_sorted_path(pkg, cuda, monkeypatch):
     c = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
     assert np.array_equal(c.table.cpu().numpy()[0], case["table"][0])
     assert float(c.accum.cpu().numpy()[0].max()) == np.float32(0.1)
+
+
+def test_presort_ahead_of_forward(pkg, cuda):
+    """presort(batch) ahead of forward(batch, presorted=handle) gives the same update as sorting inline;
+    a handle made for other tensors is refused."""
+    B, rows, K = 513, [30, 1, 200, 5], 16
+    case = make_case(18, B, rows, K, weighted=True, prune=True)
+    rng = case["rng"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = (rng.standard_normal(B) * 0.1).astype(np.float32)
+    u = (rng.standard_normal((B, len(rows), K)) * 0.1).astype(np.float32)
+    ref = _run_step(pkg, case, "adagrad", g_first, g_fm, u)
+    layer = make_layer(pkg, case, optimizer="adagrad", lr=0.05).train()
+    idx, val = to_dev(case["idx"]), to_dev(case["val"])
+    h = layer.presort(idx, val)
+    other = idx.clone()
+    with pytest.raises(ValueError):
+        layer(other, val, presorted=h)
+    first, fm, emb = layer(idx, val, presorted=h)
+    loss = (first[:, 0] * to_dev(g_first)).sum() + (fm[:, 0] * to_dev(g_fm)).sum() + (emb * to_dev(u.reshape(B, -1))).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(layer.rows, ref.rows) and torch.equal(layer.lin_rows, ref.lin_rows)
