@@ -198,6 +198,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if "DIR_B200_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["DIR_B200_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)                   # its banner would share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
@@ -215,7 +219,7 @@ def run_b200(args):
                                      emit_embeddings=emit, device=dev).train()
     else:
         layer = dir_b200.ShardedEmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
-                                            emit_embeddings=emit, device=dev).train()
+                                            emit_embeddings=emit, max_batch=B, device=dev).train()
     layer.w1.normal_(0.0, 0.01)            # TF's zero init would make the first-order path trivial
     cross = dir_b200.CrossNetwork(d, L, device=dev).train() if L else None
 
@@ -231,16 +235,18 @@ def run_b200(args):
 
     # The sort of a batch needs its ids only, so the sort for batch i+1 is issued (side stream) at the
     # start of step i and runs underneath it: every step still performs exactly one sort.
-    pipelined = world == 1
-    handles = [dir_b200.SortedLookups() for _ in range(R)] if pipelined else None
+    pipelined = True
+    ready_events = {}          # e2e: slot -> event of its H2D copy (the sharded presort waits for it)
+    handles = [dir_b200.SortedLookups() if world == 1 else dir_b200.ShardedLookups() for _ in range(R)]
 
     def step(idx, val, y, up, slot=None, events=True):
         pre = None
-        if pipelined and slot is not None:
+        if slot is not None:
             nxt = (slot + 1) % R
-            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=events)
+            if world == 1:
+                layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=events)
             pre = handles[slot]
-        first, fm, emb = layer(idx, val, presorted=pre) if pipelined else layer(idx, val)
+        first, fm, emb = layer(idx, val, presorted=pre)
         with torch.no_grad():
             logits = first + fm
             g = torch.sigmoid(logits).sub_(y.unsqueeze(1))          # SUM-reduced CE: no 1/B (deepFM.py:72)
@@ -251,8 +257,13 @@ def run_b200(args):
             torch.autograd.backward((first, fm, emb), (g, g, up))
         else:
             torch.autograd.backward((first, fm), (g, g))
-        if pipelined and slot is not None and not events:      # captured: join the side branch ourselves
+        if world == 1 and slot is not None and not events:     # captured: join the side branch ourselves
             torch.cuda.current_stream().wait_stream(layer.side_stream(dev))
+        if world > 1 and slot is not None:
+            # sharded: the next batch's id-only work (incl. the one host read of the split sizes) is issued
+            # AFTER this step's kernels are queued, so the host wait does not starve the main stream
+            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False,
+                          after=ready_events.get(nxt))
         return logits
 
     # warm every slot eagerly (allocates workspaces), note U per slot
@@ -355,7 +366,10 @@ def run_b200(args):
                     feeder.prefetch((s + ahead) % R, host[(s + ahead) % R])
                 feeder.wait(cur)
                 if pipelined and s + 1 < n:
-                    feeder.wait((s + 1) % R)                 # this step presorts the next batch
+                    if world == 1:
+                        feeder.wait((s + 1) % R)             # this step presorts the next batch
+                    else:
+                        ready_events[(s + 1) % R] = feeder.ready[(s + 1) % R]
                 o = run(cur)
                 feeder.release(cur)
                 out_host[s & 1].copy_(o, non_blocking=True)
@@ -375,6 +389,7 @@ def run_b200(args):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "how": "EmbeddingFM.presort/forward/backward fed by HostFeeder from pinned host memory "
                           "(ring of %d device slots, H2D on a copy stream), logits read back each step" % R}
+            ready_events.clear()
             # the feeder overwrote the slots: restore the resident sets
             for r in range(R):
                 for dst, src in zip(devs[r], host[r]):
@@ -398,14 +413,16 @@ def run_b200(args):
 
     if world > 1 and getattr(layer, "trace", None) is not None and layer.trace.on:
         layer.trace.report()
+        layer.trace_pre.report()
         t0 = time.perf_counter()
         for s_ in range(20):
             run(s_ % R)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) / 20 * 1e6
         if rank == 0:
-            print("stage trace (us/step, rank 0; wall %.0f us/step): %s" % (wall, json.dumps(
-                {k: round(v, 1) for k, v in layer.trace.report().items()})), file=sys.stderr)
+            print("stage trace (us/step, rank 0; wall %.0f us/step): %s | side stream: %s" % (wall, json.dumps(
+                {k: round(v, 1) for k, v in layer.trace.report().items()}), json.dumps(
+                {k: round(v, 1) for k, v in layer.trace_pre.report().items()})), file=sys.stderr)
     if rank == 0:
         cfg = workload_config(w, args, world)
         cfg.update({"l2_policy": "%d rotating input sets (%.0f MB of ids/values/upstream each) + a %.2f GB table: "

@@ -8,6 +8,6 @@ from . import _lib, roofline, synth                          # noqa: F401
 from ._lib import LIB_PATH, build, launch_count             # noqa: F401
 from .feeder import HostFeeder                              # noqa: F401
 from .layers import CrossNetwork, EmbeddingFM, SortedLookups # noqa: F401
-from .sharded import ShardedEmbeddingFM, ShardPlan          # noqa: F401
+from .sharded import ShardedEmbeddingFM, ShardedLookups, ShardPlan  # noqa: F401
 
 __all__ = ["EmbeddingFM", "CrossNetwork", "ShardedEmbeddingFM", "ShardPlan", "HostFeeder", "synth", "roofline", "build", "launch_count", "LIB_PATH"]

@@ -36,6 +36,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "dir_rows_gather": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                 c_int64, c_void_p]),
+    "dir_rows_gather_to": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dir_rows_push": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int64,
                                           c_void_p, c_size_t, c_void_p]),

@@ -110,6 +110,87 @@ rows_gather_kernel(const float* __restrict__ table, int64_t row_stride, const fl
   if (sub == 0) out[i * out_stride + K] = lin ? __ldg(lin + r * lin_stride) : 0.f;
 }
 
+// ---- exchange over NVLink peer memory (no NCCL on the payload path) ---------------------------------
+// The n rows are grouped into G segments (seg_start[G+1]); segment q goes to rank q's buffer
+// (peer_ptrs[q], a peer-mapped device pointer from symmetric memory) starting at row dst_row_off[q].
+// Stores to a peer pointer travel over NVLink; the caller runs a cross-rank barrier afterwards.
+__device__ __forceinline__ int segment_of(const int64_t* __restrict__ seg_start, int G, int64_t i) {
+  int q = 0;
+  while (q + 1 < G && i >= __ldg(seg_start + q + 1)) ++q;
+  return q;
+}
+
+// owner side, fused gather + send: LPR lanes carry the row, one more lane carries (w, 0, 0, 0).
+// A thread handles kRowsPerThread rows a grid-stride apart, loads first, so several 128-byte lines
+// per thread are in flight before the first NVLink store.
+constexpr int kRowsPerThread = 4;
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+rows_gather_to_kernel(const float* __restrict__ table, int64_t row_stride, const float* __restrict__ lin,
+                      int64_t lin_stride, const int32_t* __restrict__ ids, int64_t n, int G,
+                      const int64_t* __restrict__ seg_start, const int64_t* __restrict__ peer_ptrs,
+                      const int64_t* __restrict__ dst_row_off, int64_t out_stride) {
+  constexpr int TPR = LPR + 1;  // threads per row
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = t / TPR;
+  const int sub = (int)(t % TPR);
+  const int64_t step = ((int64_t)gridDim.x * blockDim.x) / TPR;
+  float4 v[kRowsPerThread];
+  int64_t r[kRowsPerThread];
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int64_t i = i0 + k * step;
+    r[k] = i < n ? (int64_t)__ldg(ids + i) : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r[k] >= 0) {
+      if (sub < LPR)
+        v[k] = __ldg(reinterpret_cast<const float4*>(table + r[k] * row_stride) + sub);
+      else if (lin)
+        v[k].x = __ldg(lin + r[k] * lin_stride);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int64_t i = i0 + k * step;
+    if (r[k] < 0) continue;
+    const int q = segment_of(seg_start, G, i);
+    float* dst = reinterpret_cast<float*>(__ldg(peer_ptrs + q)) +
+                 (__ldg(dst_row_off + q) + i - __ldg(seg_start + q)) * out_stride;
+    *(reinterpret_cast<float4*>(dst) + sub) = v[k];
+  }
+}
+
+// requester side: ship rows [n, stride] to their owners' buffers
+__global__ void __launch_bounds__(256)
+rows_push_kernel(const float* __restrict__ src, int64_t n, int stride4, int G,
+                 const int64_t* __restrict__ seg_start, const int64_t* __restrict__ peer_ptrs,
+                 const int64_t* __restrict__ dst_row_off) {
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t total = n * stride4;
+  float4 v[kRowsPerThread];
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int64_t t = t0 + k * step;
+    v[k] = t < total ? ldg_stream(src + t * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int64_t t = t0 + k * step;
+    if (t >= total) continue;
+    const int64_t i = t / stride4;
+    const int c = (int)(t % stride4);
+    const int q = segment_of(seg_start, G, i);
+    float4* dst = reinterpret_cast<float4*>(__ldg(peer_ptrs + q)) +
+                  (__ldg(dst_row_off + q) + i - __ldg(seg_start + q)) * stride4 + c;
+    *dst = v[k];
+  }
+}
+
 struct UniqueWs {
   uint32_t* incl;
   void* cub_temp;
@@ -222,4 +303,48 @@ extern "C" int dir_rows_gather(const float* table, int64_t row_stride, const flo
     default: rows_gather_kernel<16><<<grid, 256, 0, st>>>(table, row_stride, lin, lin_stride, local_rows, n, out, out_stride); break;
   }
   return launched("rows_gather");
+}
+
+extern "C" int dir_rows_gather_to(const float* table, int64_t row_stride, const float* lin,
+                                  int64_t lin_stride, const int32_t* local_rows, int64_t n, int K, int G,
+                                  const int64_t* seg_start, const int64_t* peer_ptrs,
+                                  const int64_t* dst_row_off, int64_t out_stride, dir_stream_t stream) {
+  using namespace dir;
+  if (n < 0 || G <= 0) return fail(DIR_EINVAL, "rows_gather_to: n >= 0, G > 0 required");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "rows_gather_to: K must be one of 4, 8, 16, 32, 64");
+  if (n == 0) return 0;
+  if (!table || !local_rows || !seg_start || !peer_ptrs || !dst_row_off)
+    return fail(DIR_EINVAL, "rows_gather_to: null pointer");
+  if (row_stride < K || (row_stride & 3) || out_stride < K + 4 || (out_stride & 3))
+    return fail(DIR_EINVAL, "rows_gather_to: strides must be multiples of 4, >= K (rows), >= K+4 (out)");
+  if (!aligned16(table)) return fail(DIR_EINVAL, "rows_gather_to: 16-byte alignment required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int lpr = K / 4;
+  const unsigned grid = (unsigned)((n * (lpr + 1) + 256 * kRowsPerThread - 1) / (256 * kRowsPerThread));
+#define DIR_GT(L) rows_gather_to_kernel<L><<<grid, 256, 0, st>>>(table, row_stride, lin, lin_stride, local_rows, n, G, seg_start, peer_ptrs, dst_row_off, out_stride)
+  switch (lpr) {
+    case 1: DIR_GT(1); break;
+    case 2: DIR_GT(2); break;
+    case 4: DIR_GT(4); break;
+    case 8: DIR_GT(8); break;
+    default: DIR_GT(16); break;
+  }
+#undef DIR_GT
+  return launched("rows_gather_to");
+}
+
+extern "C" int dir_rows_push(const float* src, int64_t n, int64_t stride, int G, const int64_t* seg_start,
+                             const int64_t* peer_ptrs, const int64_t* dst_row_off, dir_stream_t stream) {
+  using namespace dir;
+  if (n < 0 || G <= 0 || stride <= 0 || (stride & 3))
+    return fail(DIR_EINVAL, "rows_push: n >= 0, G > 0, stride a positive multiple of 4 required");
+  if (n == 0) return 0;
+  if (!src || !seg_start || !peer_ptrs || !dst_row_off) return fail(DIR_EINVAL, "rows_push: null pointer");
+  if (!aligned16(src)) return fail(DIR_EINVAL, "rows_push: 16-byte alignment required");
+  const int stride4 = (int)(stride / 4);
+  const unsigned grid = (unsigned)((n * stride4 + 256 * kRowsPerThread - 1) / (256 * kRowsPerThread));
+  rows_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, stride4, G, seg_start, peer_ptrs,
+                                                                         dst_row_off);
+  return launched("rows_push");
 }

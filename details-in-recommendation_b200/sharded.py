@@ -16,6 +16,7 @@ CUDA-only code: tests run them under gloo with world_size 2 on CPU.
 """
 import math
 import os
+import sys
 from typing import Optional, Sequence
 
 import torch
@@ -106,56 +107,91 @@ class StageTrace:
         return out
 
 
+class PeerBuffers:
+    """Double-buffered symmetric memory for the payload exchange: every rank allocates the same buffers and
+    maps its peers' copies (torch.distributed._symmetric_memory, CUDA IPC over NVLink).  `ptrs[p]` is a
+    device int64[G] of peer-mapped addresses of buffer p; `barrier(p)` is a device-side cross-rank barrier
+    on the current stream (no host involvement)."""
+
+    def __init__(self, group, rows_cap, stride, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.bufs, self.handles, self.ptrs = [], [], []
+        name = group if group is not None else dist.group.WORLD
+        for _ in range(2):
+            t = symm_mem.empty((rows_cap, stride), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, name)
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptrs.append(torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=device))
+        self.rows_cap = rows_cap
+
+    def barrier(self, p, channel=0):
+        self.handles[p].barrier(channel=channel)
+
+
+class ShardedLookups:
+    """What `ShardedEmbeddingFM.presort` leaves behind for one batch -- everything that depends on the
+    ids only: this rank's lookups sorted by (owner, local row), the distinct rows numbered, the ids
+    already exchanged, and the owner's half (the ids it received, sorted for the gradient merge)."""
+
+    def __init__(self):
+        self.ws, self.ws2, self.ws3 = _Workspace(), _Workspace(), _Workspace()
+        self.keys = self.uidx = self.ulocal = self.inv = self.owner_off = self.recv_ids = None
+        self.send_splits = self.recv_splits = None
+        self.recv_off = self.fwd_dst_off = self.bwd_dst_off = None     # device offsets of the peer exchange
+        self.U = self.R = 0
+        self.event = None
+        self.src = None
+
+    @staticmethod
+    def key_of(feature_index, feature_value):
+        return (feature_index.data_ptr(), None if feature_value is None else feature_value.data_ptr(),
+                tuple(feature_index.shape))
+
+
 class _ShardedFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, bias, layer, idx, val, train):
+    def forward(ctx, anchor, bias, layer, idx, val, train, h):
         B, F = idx.shape
-        K, G = layer.embedding_size, layer.plan.world_size
+        K = layer.embedding_size
         dev = idx.device
         L = _lib.lib()
-        n = B * F
         st = _stream()
         pad = layer.pad_stride
         tr = layer.trace
         tr.mark("start")
-        # 1-3: composite keys, sort, distinct keys
-        keys = torch.empty(n, dtype=torch.int32, device=dev)
-        check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                               layer.plan.n_rows, B, F, G, None, F, ptr(keys),
-                               ptr(layer.oob_flag) if layer.check_bounds else None, st), "dir_shard_keys")
-        tr.mark("fwd.keys")
-        n_keys = layer.plan.cap * G
-        ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
-        check(L.dir_embed_bwd_sort(ptr(keys), n, n_keys, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
-        tr.mark("fwd.sort")
-        skeys, spos = _lib.c_void_p(), _lib.c_void_p()
-        check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
-              "dir_embed_bwd_sorted")
-        uidx = torch.empty(n, dtype=torch.int32, device=dev)
-        ulocal = torch.empty(n, dtype=torch.int32, device=dev)
-        inv = torch.empty((B, F), dtype=torch.int64, device=dev)
-        owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
-        ws2 = layer._ws2.get(L.dir_shard_unique_workspace_bytes(n), dev)
-        check(L.dir_shard_unique(skeys, spos, n, layer.plan.n_rows, G, ptr(uidx), ptr(ulocal), ptr(inv),
-                                 ptr(owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
-        tr.mark("fwd.unique")
-        # 4: counts (one host sync: NCCL needs the split sizes), ids out, rows back
-        send_counts = owner_off[1:] - owner_off[:-1]
-        recv_counts = exchange_counts(send_counts, layer.group)
-        both = torch.stack([send_counts, recv_counts]).cpu()
-        send_splits, recv_splits = both[0].tolist(), both[1].tolist()
-        U, R = int(sum(send_splits)), int(sum(recv_splits))
-        tr.mark("fwd.counts+sync")
-        recv_ids = exchange(ulocal[:U], send_splits, recv_splits, layer.group)
-        tr.mark("fwd.a2a_ids")
-        answer = torch.empty((R, pad), dtype=torch.float32, device=dev)
-        check(L.dir_rows_gather(ptr(layer.table), layer.row_stride, ptr(layer.w1) if layer.first_order else None,
-                                layer.lin_stride, ptr(recv_ids), R, K, ptr(answer), pad, st), "dir_rows_gather")
-        tr.mark("fwd.gather")
-        ubuf = exchange(answer, recv_splits, send_splits, layer.group)          # [U, K+4]
-        tr.mark("fwd.a2a_rows")
-        if U == 0:
-            ubuf = torch.zeros((1, pad), dtype=torch.float32, device=dev)
+        if h.event is not None:
+            torch.cuda.current_stream().wait_event(h.event)
+        U, R = h.U, h.R
+        # 4b: the owner answers the ids it received; rows back over NVLink
+        G = layer.plan.world_size
+        parity = layer._step_parity
+        layer._step_parity ^= 1
+        if layer.peer is not None:
+            if B > layer.max_batch:
+                raise ValueError("batch %d exceeds max_batch=%d the peer buffers were sized for" % (B, layer.max_batch))
+            # one kernel gathers the rows and writes them straight into the requesters' buffers
+            pb = layer.peer["rows"]
+            check(L.dir_rows_gather_to(ptr(layer.table), layer.row_stride,
+                                       ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
+                                       ptr(h.recv_ids), R, K, G, ptr(h.recv_off), ptr(pb.ptrs[parity]),
+                                       ptr(h.fwd_dst_off), pad, st), "dir_rows_gather_to")
+            tr.mark("fwd.gather+send")
+            pb.barrier(parity)
+            tr.mark("fwd.barrier")
+            ubuf = pb.bufs[parity]
+            use_peer = True
+        else:
+            answer = torch.empty((R, pad), dtype=torch.float32, device=dev)
+            check(L.dir_rows_gather(ptr(layer.table), layer.row_stride,
+                                    ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
+                                    ptr(h.recv_ids), R, K, ptr(answer), pad, st), "dir_rows_gather")
+            tr.mark("fwd.gather")
+            ubuf = exchange(answer, h.recv_splits, h.send_splits, layer.group)          # [U, K+4]
+            tr.mark("fwd.a2a_rows")
+            if U == 0:
+                ubuf = torch.zeros((1, pad), dtype=torch.float32, device=dev)
+            use_peer = False
         # 5: the ordinary forward on the received rows
         emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
         fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
@@ -163,17 +199,17 @@ class _ShardedFunction(torch.autograd.Function):
         S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
         lin = ubuf[:, K] if layer.first_order else None
         check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
-                                 ptr(inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
+                                 ptr(h.inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
                                  ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
         tr.mark("fwd.fm")
         if not layer.first_order:
             first.zero_()
-        layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": n}
-        ctx.layer, ctx.train, ctx.shape = layer, train, (B, F, K)
-        ctx.splits = (send_splits, recv_splits)
+        layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": B * F}
+        ctx.layer, ctx.train, ctx.shape, ctx.h = layer, train, (B, F, K), h
+        ctx.use_peer, ctx.parity = use_peer, parity
         ctx.set_materialize_grads(False)
         if train:
-            ctx.save_for_backward(val, S, ubuf, uidx, recv_ids)
+            ctx.save_for_backward(val, S, ubuf)
         if emb is None:
             emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(emb)
@@ -183,11 +219,10 @@ class _ShardedFunction(torch.autograd.Function):
     def backward(ctx, g_first, g_fm, u):
         if not ctx.train:
             raise RuntimeError("ShardedEmbeddingFM.backward: forward ran without gradient tracking")
-        layer = ctx.layer
-        val, S, ubuf, uidx, recv_ids = ctx.saved_tensors
+        layer, h = ctx.layer, ctx.h
+        val, S, ubuf = ctx.saved_tensors
         B, F, K = ctx.shape
-        send_splits, recv_splits = ctx.splits
-        U, R = int(sum(send_splits)), int(sum(recv_splits))
+        U, R = h.U, h.R
         dev = S.device
         L = _lib.lib()
         st = _stream()
@@ -202,22 +237,28 @@ class _ShardedFunction(torch.autograd.Function):
         tr = layer.trace
         tr.mark("between")
         with torch.no_grad():
-            # 6: per-distinct-row sums on the requester (the sorted list is still in the workspace)
-            ws = layer._ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
+            # 6: per-distinct-row sums on the requester (the sorted list is in the handle's workspace)
+            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
             gu = torch.empty((max(U, 1), pad), dtype=torch.float32, device=dev)
             check(L.dir_embed_bwd_reduce_emit(ptr(ubuf), pad, ptr(val), ptr(g_first) if layer.first_order else None,
-                                              ptr(g_fm), ptr(S), ptr(u), ptr(uidx), B, F, K,
+                                              ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K,
                                               layer.plan.cap * layer.plan.world_size, ptr(gu), pad,
                                               ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
             tr.mark("bwd.emit")
             # 7: sums to their owners; the owner merges the ranks' contributions and updates
-            grecv = exchange(gu[:U], send_splits, recv_splits, layer.group)      # [R, K+4]
-            tr.mark("bwd.a2a_grads")
+            if ctx.use_peer:
+                pb = layer.peer["grads"]
+                check(L.dir_rows_push(ptr(gu), U, pad, layer.plan.world_size, ptr(h.owner_off),
+                                      ptr(pb.ptrs[ctx.parity]), ptr(h.bwd_dst_off), st), "dir_rows_push")
+                tr.mark("bwd.push")
+                pb.barrier(ctx.parity)
+                tr.mark("bwd.barrier")
+                grecv = pb.bufs[ctx.parity]
+            else:
+                grecv = exchange(gu[:U], h.send_splits, h.recv_splits, layer.group)      # [R, K+4]
+                tr.mark("bwd.a2a_grads")
             if R > 0:
-                ws3 = layer._ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)
-                check(L.dir_embed_bwd_sort(ptr(recv_ids), R, layer.plan.cap, ptr(ws3), ws3.numel(), st),
-                      "dir_embed_bwd_sort")
-                tr.mark("bwd.owner_sort")
+                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)      # sorted by presort
                 adagrad = layer.optimizer == "adagrad"
                 check(L.dir_rows_reduce_update(
                     ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
@@ -230,7 +271,7 @@ class _ShardedFunction(torch.autograd.Function):
                 layer.last_n_unique.zero_()
             tr.close_step()
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
-        return None, g_bias, None, None, None, None
+        return None, g_bias, None, None, None, None, None
 
 
 class ShardedEmbeddingFM(torch.nn.Module):
@@ -245,7 +286,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
     def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
                  optimizer: str = "adagrad", lr: float = 0.01, initial_accumulator_value: float = 0.1,
                  first_order: bool = True, emit_embeddings: bool = True, check_bounds: bool = False,
-                 process_group=None, device="cuda"):
+                 process_group=None, max_batch: int = 65536, device="cuda"):
         super().__init__()
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
@@ -282,8 +323,29 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
         self.last_exchange = {}
-        self._ws, self._ws2, self._ws3 = _Workspace(), _Workspace(), _Workspace()
-        self.trace = StageTrace()
+        self._side = None
+        self._inline = ShardedLookups()
+        # the id exchange of the NEXT batch runs concurrently with this batch's row / gradient exchange:
+        # give it a communicator of its own so the two never queue behind each other
+        self.side_group = (dist.new_group(ranks=dist.get_process_group_ranks(process_group or dist.group.WORLD))
+                           if dist.is_initialized() and dist.get_backend(process_group) == "nccl" else process_group)
+        self.trace, self.trace_pre = StageTrace(), StageTrace()
+        # Payload exchange: NVLink peer memory (symmetric buffers + a device-side barrier) when there is
+        # more than one rank and torch's symmetric memory is usable, else NCCL all-to-all.
+        self.peer, self._step_parity = None, 0
+        self.max_batch = int(max_batch)
+        want_peer = os.environ.get("DIR_B200_EXCHANGE", "peer") == "peer"
+        if want_peer and dist.is_initialized() and world > 1 and dev.type == "cuda" \
+                and dist.get_backend(process_group) == "nccl":
+            try:
+                cap = min(self.max_batch * field_size, max(self.plan.cap, 1))       # distinct rows a rank can want
+                self.peer = {"rows": PeerBuffers(process_group, cap, self.pad_stride, dev),         # <- owners
+                             "grads": PeerBuffers(process_group, cap * world, self.pad_stride, dev)}  # <- requesters
+            except Exception as e:                                              # no IPC / fabric support
+                if rank == 0:
+                    print("ShardedEmbeddingFM: symmetric memory unavailable (%s); using NCCL all-to-all" % e,
+                          file=sys.stderr)
+                self.peer = None
         with torch.no_grad():
             sd = 1.0 / math.sqrt(K)
             torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)
@@ -315,7 +377,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 mine = torch.as_tensor(self.plan.shard_of(src), dtype=torch.float32)
                 dst[:mine.shape[0]].copy_(mine.to(dst.device))
 
-    def forward(self, feature_index, feature_value=None):
+    def _prepare(self, feature_index, feature_value):
         if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
             raise ValueError("feature_index must be [B, field_size=%d]" % self.field_size)
         if feature_index.dtype != torch.int64:
@@ -328,8 +390,104 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 raise ValueError("feature_value must have feature_index's shape")
             _need_cuda(feature_value, "feature_value")
             val = feature_value.contiguous().float()
+        return idx, val
+
+    def side_stream(self, device):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device, priority=-1)
+        return self._side
+
+    @torch.no_grad()
+    def presort(self, feature_index, feature_value=None, handle=None, after=None, fork=True):
+        """Everything of a step that depends on the ids only, on the side stream and on a process group of
+        its own: composite keys, sort, distinct-row numbering, the counts / ids all-to-all, and the owner's
+        sort of the ids it received.  Issue it for batch i+1 right after enqueueing step i: it then runs
+        underneath step i, and the one host read of the split sizes waits on the side stream only.
+        `fork=False`: do not order the side stream after the work already queued on the current stream (the
+        ids are already on the device, or `after` marks their arrival) -- this is what lets it overlap.
+        """
+        idx, val = self._prepare(feature_index, feature_value)
+        B, F = idx.shape
+        K, G = self.embedding_size, self.plan.world_size
+        dev = idx.device
+        L = _lib.lib()
+        n = B * F
+        h = handle if handle is not None else ShardedLookups()
+        main, side = torch.cuda.current_stream(), self.side_stream(dev)
+        if fork:        # order after whatever the current stream has queued (it may be producing the ids)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        if after is not None:
+            side.wait_event(after)
+        tr = self.trace_pre
+        with torch.cuda.stream(side):
+            st = side.cuda_stream
+            tr.mark("pre.start")
+            if h.keys is None or h.keys.numel() != n or h.keys.device != dev:
+                h.keys = torch.empty(n, dtype=torch.int32, device=dev)
+                h.uidx = torch.empty(n, dtype=torch.int32, device=dev)
+                h.ulocal = torch.empty(n, dtype=torch.int32, device=dev)
+                h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
+                h.owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
+            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
+                                   self.plan.n_rows, B, F, G, None, F, ptr(h.keys),
+                                   ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
+            tr.mark("pre.keys")
+            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n, 1), K), dev)
+            check(L.dir_embed_bwd_sort(ptr(h.keys), n, self.plan.cap * G, ptr(ws), ws.numel(), st),
+                  "dir_embed_bwd_sort")
+            tr.mark("pre.sort")
+            if n > 0:
+                skeys, spos = _lib.c_void_p(), _lib.c_void_p()
+                check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
+                      "dir_embed_bwd_sorted")
+            else:
+                skeys = spos = None
+            ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(n), 1), dev)
+            check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, ptr(h.uidx), ptr(h.ulocal), ptr(h.inv),
+                                     ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+            tr.mark("pre.unique")
+            # counts: the one host read per step (NCCL needs the split sizes); it waits on the side stream only
+            send_counts = h.owner_off[1:] - h.owner_off[:-1]
+            if self.peer is not None:
+                # everybody's counts: M[q, o] = distinct rows q wants from o.  From it, on the device, where
+                # each rank's segment starts inside its peers' exchange buffers.
+                M = torch.empty((G, G), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(M, send_counts.contiguous(), group=self.side_group)
+                me = self.plan.rank
+                recv_counts = M[:, me].contiguous()
+                zero = torch.zeros(1, dtype=torch.int64, device=dev)
+                h.recv_off = torch.cat([zero, torch.cumsum(recv_counts, 0)])
+                h.fwd_dst_off = (torch.cumsum(M, 1) - M)[:, me].contiguous()   # my segment inside q's row buffer
+                h.bwd_dst_off = (torch.cumsum(M, 0) - M)[me, :].contiguous()   # my segment inside o's grad buffer
+            else:
+                recv_counts = exchange_counts(send_counts, self.side_group)
+            both = torch.stack([send_counts, recv_counts]).cpu()
+            h.send_splits, h.recv_splits = both[0].tolist(), both[1].tolist()
+            h.U, h.R = int(sum(h.send_splits)), int(sum(h.recv_splits))
+            tr.mark("pre.counts+sync")
+            h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
+            tr.mark("pre.a2a_ids")
+            if h.R > 0:                       # the owner's half: arrival order -> local-row order
+                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(h.R, K), dev)
+                check(L.dir_embed_bwd_sort(ptr(h.recv_ids), h.R, self.plan.cap, ptr(ws3), ws3.numel(), st),
+                      "dir_embed_bwd_sort")
+            tr.mark("pre.owner_sort")
+            h.event = torch.cuda.Event()
+            h.event.record(side)
+            tr.close_step()
+        h.src = ShardedLookups.key_of(feature_index, feature_value)
+        return h
+
+    def forward(self, feature_index, feature_value=None, presorted=None):
+        idx, val = self._prepare(feature_index, feature_value)
         train = self.training and torch.is_grad_enabled()
-        first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train)
+        if presorted is None:
+            presorted = self.presort(feature_index, feature_value, handle=self._inline)
+        elif presorted.src != ShardedLookups.key_of(feature_index, feature_value):
+            raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
+        first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
         if self.check_bounds and int(self.oob_flag.item()) != 0:
             self.oob_flag.zero_()
             raise IndexError("feature_index out of range for its field")

@@ -161,6 +161,21 @@ int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, in
 int dir_rows_gather(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
                     const int32_t* local_rows, int64_t n, int K, float* out, int64_t out_stride,
                     dir_stream_t stream);
+/* Payload exchange over NVLink peer memory instead of an NCCL all-to-all (one kernel does the
+ * gather AND the transfer).  The n rows are grouped into G segments, seg_start[G+1] (device);
+ * segment q is written into rank q's buffer: peer_ptrs[q] is that buffer's peer-mapped device
+ * address (symmetric memory), dst_row_off[q] the row at which this rank's segment starts there
+ * (both device arrays).  The caller runs a cross-rank barrier before the buffer is read.
+ *   dir_rows_gather_to  owner side: row q-segment j = (table[local_rows[j]] | lin | 0 0 0),
+ *                       out_stride >= K + 4 floats
+ *   dir_rows_push       requester side: ships rows [n, stride] (per-row gradient sums) as they are
+ */
+int dir_rows_gather_to(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
+                       const int32_t* local_rows, int64_t n, int K, int G, const int64_t* seg_start,
+                       const int64_t* peer_ptrs, const int64_t* dst_row_off, int64_t out_stride,
+                       dir_stream_t stream);
+int dir_rows_push(const float* src, int64_t n, int64_t stride, int G, const int64_t* seg_start,
+                  const int64_t* peer_ptrs, const int64_t* dst_row_off, dir_stream_t stream);
 int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
                               const float* g_first, const float* g_fm, const float* S, const float* u,
                               const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,

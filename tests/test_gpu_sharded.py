@@ -77,10 +77,10 @@ def _free_port():
     return p
 
 
-def _rank_main(rank, world, port, out):
+def _rank_main(rank, world, port, out, exchange_mode):
     import torch.distributed as dist
     import dir_b200
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), DIR_B200_EXCHANGE=exchange_mode)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -91,7 +91,9 @@ def _rank_main(rank, world, port, out):
         g_fm = (rng.standard_normal(Bl * world) * 0.1).astype(np.float32)
         u = (rng.standard_normal((Bl * world, F, K)) * 0.1).astype(np.float32)
         sl = slice(rank * Bl, (rank + 1) * Bl)
-        layer = dir_b200.ShardedEmbeddingFM(F, K, rows, optimizer="adagrad", lr=0.05, device="cuda").train()
+        layer = dir_b200.ShardedEmbeddingFM(F, K, rows, optimizer="adagrad", lr=0.05, max_batch=Bl,
+                                            device="cuda").train()
+        assert (layer.peer is not None) == (exchange_mode == "peer"), "exchange mode not honoured"
         layer.load_tables(case["table"], case["w1"])
         d = "cuda"
         first, fm, emb = layer(to_dev(case["idx"][sl], d), to_dev(case["val"][sl], d))
@@ -133,7 +135,8 @@ def _rank_main(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_world2_nccl_matches_oracle(pkg, cuda):
+@pytest.mark.parametrize("exchange_mode", ["peer", "nccl"])
+def test_world2_nccl_matches_oracle(pkg, cuda, exchange_mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -141,7 +144,7 @@ def test_world2_nccl_matches_oracle(pkg, cuda):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, out, exchange_mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in procs]
