@@ -47,6 +47,8 @@ def parse_args():
     p.add_argument("--no-emit", action="store_true", help="FM only: no embeddings out / upstream in")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--feed", default="columns", choices=["columns", "resolved"],
+                   help="e2e host format: one column per feature (the reference's input_fn form) or the [B,F] pair")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -348,7 +350,17 @@ def run_b200(args):
     if not args.no_e2e:
         # R device slots form a ring: while step s computes on slot s%R, the sort of batch s+1 (already on
         # the device) runs on the side stream and batch s+2 lands through the copy stream.
-        feeder = dir_b200.HostFeeder(*devs)
+        # The host ships what the reference's input_fn yields -- one column per feature: int32 ids of the
+        # categorical fields, floats of the numeric ones, labels -- and dir_expand_features widens them into
+        # feature_index / feature_value on the copy stream (--feed resolved ships the [B,F] pair instead).
+        if args.feed == "columns":
+            sp_f = [f for f, n in enumerate(w.rows_per_field) if n > 1]
+            de_f = [f for f, n in enumerate(w.rows_per_field) if n == 1]
+            feeder = dir_b200.ColumnFeeder(sp_f, de_f, *devs, index_dtype=torch.int32)
+            host = [[hs[0][:, sp_f].to(torch.int32).contiguous().pin_memory(),
+                     hs[1][:, de_f].contiguous().pin_memory(), hs[2]] for hs in host]
+        else:
+            feeder = dir_b200.HostFeeder(*devs)
         out_host = [torch.empty((B, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         d2h = out_host[0].numel() * 4
@@ -387,13 +399,17 @@ def run_b200(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "how": "EmbeddingFM.presort/forward/backward fed by HostFeeder from pinned host memory "
-                          "(ring of %d device slots, H2D on a copy stream), logits read back each step" % R}
+                   "feed": "columns: int32 ids [B,%d] + fp32 values [B,%d] + labels [B], widened on the device by "
+                           "dir_expand_features" % (len(sp_f), len(de_f)) if args.feed == "columns"
+                           else "resolved: feature_index [B,F] int64 + feature_value [B,F] fp32 + labels [B]",
+                   "how": "EmbeddingFM.presort/forward/backward fed by %s from pinned host memory "
+                          "(ring of %d device slots, H2D on a copy stream), logits read back each step" % (
+                              type(feeder).__name__, R)}
             ready_events.clear()
             # the feeder overwrote the slots: restore the resident sets
             for r in range(R):
-                for dst, src in zip(devs[r], host[r]):
-                    dst.copy_(src)
+                feeder.prefetch(r, host[r])
+                feeder.wait(r)
             if pipelined:
                 layer.presort(devs[0][0], devs[0][1], handle=handles[0])
             torch.cuda.synchronize()

@@ -1,14 +1,22 @@
 // K4+K5: DCN-v1 cross stack  x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l,  all L layers in one pass.
-// One warp per sample; x0 and x_l live in registers (lane owns every 32nd VEC-wide group), the
-// per-layer "matvec" is a warp-shuffle dot product: rank-1, not a GEMM, so no tensor cores.
-// Forward reads x0 once and writes x_L once.
+// Not a GEMM (the per-layer "matvec" is one dot product per sample), so no tensor cores: the kernels
+// are HBM-bound streams over x0 / dy with the per-sample work done by one warp in registers.
 //
-// Backward uses the rank-1 structure:  x_l = x0 * c_l + beta_l  with  c_l = 1 + sum_{j<l} s_j  (per
-// sample) and  beta_l = sum_{j<l} b_j  (per column), so with  ds_l = dx_{l+1} . x0 :
+// Both directions use the rank-1 structure of the recurrence.  With  p_l = x0 . w_l  (per sample),
+// beta_l = sum_{j<l} b_j  (per column) and  q_l = beta_l . w_l  (one scalar per layer):
+//     x_l = x0 * c_l + beta_l,      s_l = x_l . w_l = c_l p_l + q_l,      c_{l+1} = c_l + s_l,  c_0 = 1
+// so the forward is L dot products of x0 with the w_l, a scalar recurrence, and one fused
+// multiply-add per output element ( x_L = x0 * c_L + beta_L ): 7 FMAs per element at L = 6 instead of
+// the 18 flops + 12 parameter loads of the layer-by-layer sweep, which was issue-bound (ncu: 0.64 IPC
+// per scheduler, 31 % DRAM; profiles/r01_kernels_v3_ncu.txt).  The backward, with a = dy . x0 :
+//     ds_l = a + sum_{j>l} ds_j p_j                       (scalar recurrence, l = L-1 .. 0)
+//     dx0  = c_L dy + sum_l (ds_l c_l) w_l
 //     dw_l = sum_b (ds_l c_l) x0  +  beta_l * sum_b ds_l
 //     db_l = sum_b dy  +  sum_{j>l} w_j * sum_b ds_j
-// No x_l is ever stored.  Batch sums are reduced in a fixed order (per-warp sequential, per-CTA
-// fixed order, per-CTA partials combined by one finishing kernel): deterministic, no float atomics.
+// No x_l is ever stored.  Batch sums are reduced in a fixed order (per-thread sequential over the
+// CTA's tiles, per-CTA partials combined by one finishing kernel): deterministic, no float atomics.
+// Results differ from the reference's ((x0*s)+b)+x evaluation order by rounding only (a few ulp of
+// the largest term; the parity tests hold 1e-5 relative against the fp64 oracle).
 //
 // Reference: models/DeepCrossNetwork/DeepCrossNetwork.py:336-367 and TF autodiff of it (:283).
 #include "common.cuh"
@@ -41,56 +49,125 @@ __device__ __forceinline__ void st_pack(float* p, const float* v) {
 
 constexpr int kCrossWarps = 8;  // warps per CTA
 
+// ------------------------------------------------------------------------------ per-CTA constants
+// beta_L[c] = sum_l b_l[c] (layer order) and q_l = beta_l . w_l, computed once per CTA by its 256
+// threads in a fixed order (thread t owns columns t, t+256, ...; warp sums, then warps in order).
+// s_beta may be NULL.  Ends with a __syncthreads().
+__device__ __forceinline__ void cross_constants(const float* __restrict__ wg,
+                                                const float* __restrict__ bg, int d, int L,
+                                                float* s_beta, float* s_q, float* s_red) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float beta[4] = {0.f, 0.f, 0.f, 0.f};  // d <= 1024 = 4 * 256
+  for (int l = 0; l < L; ++l) {
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = threadIdx.x + j * 256;
+      if (c < d) {
+        part = fmaf(beta[j], __ldg(wg + l * d + c), part);
+        beta[j] += __ldg(bg + l * d + c);
+      }
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_red[wib] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCrossWarps; ++w) t += s_red[w];
+      s_q[l] = t;
+    }
+    __syncthreads();
+  }
+  if (s_beta != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = threadIdx.x + j * 256;
+      if (c < d) s_beta[c] = beta[j];
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------ forward
+// One warp per PAIR of samples (the w_l loads are shared by the pair), persistent grid.
+// pg [B,L] (nullable) receives p_l = x0 . w_l for the backward.
 template <int VEC, int NPL>
 __global__ void __launch_bounds__(kCrossWarps * 32)
 cross_fwd_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
                  const float* __restrict__ bg, int64_t B, int d, int L, float* __restrict__ xLg,
-                 float* __restrict__ sg) {
+                 float* __restrict__ pg) {
   constexpr int E = VEC * NPL;
+  __shared__ float s_beta[1024];
+  __shared__ float s_q[32];
+  __shared__ float s_red[kCrossWarps];
+  cross_constants(wg, bg, d, L, s_beta, s_q, s_red);
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * kCrossWarps + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kCrossWarps;
-  for (int64_t b = warp0; b < B; b += nwarps) {
-    float x0[E], xl[E];
+  const float q_mine = lane < L ? s_q[lane] : 0.f;
+  float betaL[E];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = (i * 32 + lane) * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) betaL[i * VEC + e] = (c + e < d) ? s_beta[c + e] : 0.f;
+  }
+  const int64_t pair0 = (int64_t)blockIdx.x * kCrossWarps + (threadIdx.x >> 5);
+  const int64_t npairs = (int64_t)gridDim.x * kCrossWarps;
+  for (int64_t b = pair0 * 2; b < B; b += npairs * 2) {
+    const bool two = b + 1 < B;
+    float xa[E], xb[E];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int c = (i * 32 + lane) * VEC;
-      Pack<VEC> p{};
-      if (c < d) p = ld_pack<VEC>(x0g + b * d + c, true);
+      Pack<VEC> pa{}, pb{};
+      if (c < d) {
+        pa = ld_pack<VEC>(x0g + b * d + c, true);
+        if (two) pb = ld_pack<VEC>(x0g + (b + 1) * d + c, true);
+      }
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) x0[i * VEC + e] = xl[i * VEC + e] = (c < d) ? p.v[e] : 0.f;
+      for (int e = 0; e < VEC; ++e) {
+        xa[i * VEC + e] = (c < d) ? pa.v[e] : 0.f;
+        xb[i * VEC + e] = (c < d && two) ? pb.v[e] : 0.f;
+      }
     }
+    float ca = 1.f, cb = 1.f;  // c_l = 1 + sum_{j<l} s_j
     for (int l = 0; l < L; ++l) {
-      float wv[E], bv[E];
+      float da = 0.f, db = 0.f;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int c = (i * 32 + lane) * VEC;
-        Pack<VEC> pw{}, pb{};
-        if (c < d) {
-          pw = ld_pack<VEC>(wg + l * d + c, false);
-          pb = ld_pack<VEC>(bg + l * d + c, false);
-        }
+        Pack<VEC> pw{};
+        if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          wv[i * VEC + e] = (c < d) ? pw.v[e] : 0.f;
-          bv[i * VEC + e] = (c < d) ? pb.v[e] : 0.f;
+          const float wv = (c < d) ? pw.v[e] : 0.f;
+          da = fmaf(xa[i * VEC + e], wv, da);
+          db = fmaf(xb[i * VEC + e], wv, db);
         }
       }
-      float dot = 0.f;
-#pragma unroll
-      for (int e = 0; e < E; ++e) dot = fmaf(xl[e], wv[e], dot);
-      dot = warp_sum(dot);
-      // ((x0 * s) + b) + x : the reference's evaluation order (DeepCrossNetwork.py:346), unfused
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        xl[e] = __fadd_rn(__fadd_rn(__fmul_rn(x0[e], dot), bv[e]), xl[e]);
-      if (sg && lane == 0) sg[b * L + l] = dot;
+      da = warp_sum(da);
+      db = warp_sum(db);
+      const float q = __shfl_sync(0xffffffffu, q_mine, l);
+      if (pg && lane == 0) {
+        pg[b * L + l] = da;
+        if (two) pg[(b + 1) * L + l] = db;
+      }
+      ca += fmaf(ca, da, q);  // s_l = c_l p_l + q_l
+      cb += fmaf(cb, db, q);
     }
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int c = (i * 32 + lane) * VEC;
-      if (c < d) st_pack<VEC>(xLg + b * d + c, &xl[i * VEC]);
+      float oa[VEC], ob[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        oa[e] = fmaf(xa[i * VEC + e], ca, betaL[i * VEC + e]);  // x_L = x0 c_L + beta_L
+        ob[e] = fmaf(xb[i * VEC + e], cb, betaL[i * VEC + e]);
+      }
+      if (c < d) {
+        st_pack<VEC>(xLg + b * d + c, oa);
+        if (two) st_pack<VEC>(xLg + (b + 1) * d + c, ob);
+      }
     }
   }
 }
@@ -353,19 +430,21 @@ cross_bwd_finish_kernel(const float* __restrict__ wg, const float* __restrict__ 
 
 // ------------------------------------------------------------------------------ fused backward (L <= 8)
 // One pass over x0 and dy.  A CTA walks tiles of kTS samples:
-//   phase A  one warp per sample, registers: the reverse sweep -> dx0 to HBM, alpha_l = ds_l c_l to
-//            shared memory; the warp also leaves its x0 / dy rows in shared memory
+//   phase A  one warp per sample: a = dy . x0, p_l (saved by the forward, or recomputed), the two
+//            scalar recurrences (every lane runs them redundantly), dx0 = c_L dy + sum_l alpha_l w_l
+//            to HBM, alpha_l = ds_l c_l to shared memory; the warp also leaves its x0 / dy rows in
+//            shared memory
 //   phase B  one thread per column: dw_l[c] += alpha_l[b] x0[b][c], db[c] += dy[b][c] over the tile,
 //            samples in order, accumulators in registers for the whole kernel
-// so x0 is read from HBM once (the separate dw pass re-read all of it).  Per-CTA partials are
-// combined by cross_bwd_finish2_kernel in a fixed order.
+// so x0 and dy are read from HBM once.  Per-CTA partials are combined by cross_bwd_finish2_kernel
+// in a fixed order.
 constexpr int kTS = 16;  // samples per tile: two per warp
 
 template <int VEC, int NPL>
 __global__ void __launch_bounds__(kCrossWarps * 32, 2)
 cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
                        const float* __restrict__ bg, const float* __restrict__ dyg,
-                       const float* __restrict__ sg, int64_t B, int d, int L,
+                       const float* __restrict__ pg, int64_t B, int d, int L,
                        float* __restrict__ dx0g, float* __restrict__ Dpart,
                        float* __restrict__ dypart, float* __restrict__ dwpart) {
   constexpr int E = VEC * NPL;
@@ -375,8 +454,12 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
   float* dys = x0s + kTS * d;          // [kTS][d]
   float* als = dys + kTS * d;          // [kTS][8]
   float* sD = als + kTS * 8;           // [kCrossWarps][32]
+  float* s_q = sD + kCrossWarps * 32;  // [32]
+  float* s_red = s_q + 32;             // [kCrossWarps]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
+  cross_constants(wg, bg, d, L, nullptr, s_q, s_red);
+  const float q_mine = lane < L ? s_q[lane] : 0.f;
   float acc[CI][8], accdy[CI];
 #pragma unroll
   for (int ci = 0; ci < CI; ++ci) {
@@ -394,8 +477,9 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
     for (int h = 0; h < kTS / kCrossWarps; ++h) {
       const int tb = h * kCrossWarps + wib;
       const int64_t b = b0 + tb;
-      float x0[E], dx[E], dx0[E];
+      float x0[E], dx[E];
       const bool live = b < B;
+      float a = 0.f;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int c = (i * 32 + lane) * VEC;
@@ -409,7 +493,7 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
           const bool in = live && c < d;
           x0[i * VEC + e] = in ? px.v[e] : 0.f;
           dx[i * VEC + e] = in ? pd.v[e] : 0.f;
-          dx0[i * VEC + e] = 0.f;
+          a = fmaf(dx[i * VEC + e], x0[i * VEC + e], a);
         }
         if (c < d) {  // the tile copy phase B reads (zeros for samples past the end)
           if constexpr (VEC == 4) {
@@ -423,77 +507,76 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
           }
         }
       }
-      float s_mine = 0.f;  // lane l keeps s_l = x_l . w_l
-      if (sg) {
-        if (live && lane < L) s_mine = __ldg(sg + b * L + lane);
+      a = warp_sum(a);
+      float p_mine = 0.f;  // lane l keeps p_l = x0 . w_l (0 for l >= L and for samples past the end)
+      if (pg) {
+        if (live && lane < L) p_mine = __ldg(pg + b * L + lane);
       } else {
-        float xl[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) xl[e] = x0[e];
         for (int l = 0; l < L; ++l) {
           float dot = 0.f;
-          float bv[E];
 #pragma unroll
           for (int i = 0; i < NPL; ++i) {
             const int c = (i * 32 + lane) * VEC;
-            Pack<VEC> pw{}, pb{};
-            if (c < d) {
-              pw = ld_pack<VEC>(wg + l * d + c, false);
-              pb = ld_pack<VEC>(bg + l * d + c, false);
-            }
+            Pack<VEC> pw{};
+            if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              dot = fmaf(xl[i * VEC + e], (c < d) ? pw.v[e] : 0.f, dot);
-              bv[i * VEC + e] = (c < d) ? pb.v[e] : 0.f;
-            }
+            for (int e = 0; e < VEC; ++e) dot = fmaf(x0[i * VEC + e], (c < d) ? pw.v[e] : 0.f, dot);
           }
           dot = warp_sum(dot);
-#pragma unroll
-          for (int e = 0; e < E; ++e)
-            xl[e] = __fadd_rn(__fadd_rn(__fmul_rn(x0[e], dot), bv[e]), xl[e]);
-          if (lane == l) s_mine = dot;
+          if (lane == l) p_mine = dot;
         }
       }
-      float c_mine = 1.f;  // c_l = 1 + sum_{j<l} s_j
-      for (int j = 0; j < L; ++j) {
-        const float sj = __shfl_sync(0xffffffffu, s_mine, j);
-        if (lane > j) c_mine += sj;
+      // scalar recurrences, every lane redundantly.  Layers l >= L have p = q = 0: c stays, ds = 0.
+      float pv[8], cv[9];
+      cv[0] = 1.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        pv[l] = __shfl_sync(0xffffffffu, p_mine, l);
+        const float q = __shfl_sync(0xffffffffu, q_mine, l);
+        cv[l + 1] = cv[l] + fmaf(cv[l], pv[l], q);  // c_{l+1} = c_l + s_l,  s_l = c_l p_l + q_l
       }
-      float alpha_mine = 0.f;
-      for (int l = L - 1; l >= 0; --l) {
-        const float s_l = __shfl_sync(0xffffffffu, s_mine, l);
-        const float c_l = __shfl_sync(0xffffffffu, c_mine, l);
+      float al[8];  // alpha_l = ds_l c_l
+      float t = 0.f, ds_mine = 0.f, al_mine = 0.f;
+#pragma unroll
+      for (int l = 7; l >= 0; --l) {
         float ds = 0.f;
-#pragma unroll
-        for (int e = 0; e < E; ++e) ds = fmaf(dx[e], x0[e], ds);
-        ds = warp_sum(ds);
-        if (lane == l) {
-          alpha_mine = ds * c_l;
-          Dacc += ds;
+        if (l < L) {
+          ds = a + t;  // ds_l = a + sum_{j>l} ds_j p_j
+          t = fmaf(ds, pv[l], t);
         }
+        al[l] = ds * cv[l];
+        if (lane == l) {
+          ds_mine = ds;
+          al_mine = al[l];
+        }
+      }
+      Dacc += ds_mine;
+      if (lane < 8) als[tb * 8 + lane] = al_mine;
+      // dx0 = c_L dy + sum_l alpha_l w_l
+      const float cL = cv[8];
+#pragma unroll
+      for (int e = 0; e < E; ++e) dx[e] *= cL;
+      for (int l = 0; l < L; ++l) {
+        float alv = al[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) alv = (l == j) ? al[j] : alv;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
           const int c = (i * 32 + lane) * VEC;
           Pack<VEC> pw{};
           if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            dx0[i * VEC + e] = fmaf(dx[i * VEC + e], s_l, dx0[i * VEC + e]);
-            dx[i * VEC + e] = fmaf(ds, (c < d) ? pw.v[e] : 0.f, dx[i * VEC + e]);
-          }
+          for (int e = 0; e < VEC; ++e)
+            dx[i * VEC + e] = fmaf(alv, (c < d) ? pw.v[e] : 0.f, dx[i * VEC + e]);
         }
       }
       if (live) {
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
           const int c = (i * 32 + lane) * VEC;
-          float o[VEC];
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) o[e] = dx0[i * VEC + e] + dx[i * VEC + e];
-          if (c < d) st_pack<VEC>(dx0g + b * d + c, o);
+          if (c < d) st_pack<VEC>(dx0g + b * d + c, &dx[i * VEC]);
         }
       }
-      if (lane < 8) als[tb * 8 + lane] = (live && lane < L) ? alpha_mine : 0.f;
     }
     __syncthreads();
     // ---- phase B: thread = column, samples of the tile in order
@@ -656,8 +739,9 @@ extern "C" int dir_cross_fwd(const float* x0, const float* cross_w, const float*
   if (sh.vec == 4 && (!aligned16(x0) || !aligned16(xL) || !aligned16(cross_w) || !aligned16(cross_b)))
     return fail(DIR_EINVAL, "cross_fwd: 16-byte alignment required when d % 4 == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t want = (B + kCrossWarps - 1) / kCrossWarps;
-  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
+  // one warp per pair of samples; persistent beyond 4 CTAs per SM (each CTA recomputes beta_L, q_l)
+  const int64_t want = (B + 2 * kCrossWarps - 1) / (2 * kCrossWarps);
+  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 4 ? want : (int64_t)kSMs * 4);
 #define DIR_FWD(V, N) \
   cross_fwd_kernel<V, N><<<grid, kCrossWarps * 32, 0, st>>>(x0, cross_w, cross_b, B, d, L, xL, s)
   DIR_CROSS_DISPATCH(DIR_FWD)
@@ -692,7 +776,7 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
   if (L <= 8) {
-    const size_t smemf = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32) * 4;
+    const size_t smemf = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps) * 4;
 #define DIR_BWDF(V, N)                                                                          \
   {                                                                                             \
     cudaFuncSetAttribute(cross_bwd_fused_kernel<V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -709,7 +793,7 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   const size_t smem1 = (size_t)kCrossWarps * (d + 32) * 4;
 #define DIR_BWD(V, N)                                                                        \
   cross_bwd_sample_kernel<V, N><<<w.G1, kCrossWarps * 32, smem1, st>>>(                      \
-      x0, cross_w, cross_b, dy, s, B, d, L, dx0, w.alpha, w.Dpart, w.dypart)
+      x0, cross_w, cross_b, dy, nullptr, B, d, L, dx0, w.alpha, w.Dpart, w.dypart)
   DIR_CROSS_DISPATCH(DIR_BWD)
 #undef DIR_BWD
   cross_bwd_dw_kernel<<<w.G2, 256, kDwUnroll * 8 * 4, st>>>(x0, w.alpha, B, d, L, w.dwpart);

@@ -188,16 +188,36 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
                            dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Column feed -> [B,F] inputs.  The reference's input_fn hands the graph one tensor per column --
+ * ids for categorical columns, floats for numeric ones (models/DeepCrossNetwork/train.py:127-156,
+ * columns built at :57-100; DeepFM consumes the same dict, models/DeepFM/deepFM.py:159-177).  The
+ * host ships those columns only; this widens them, on the device, into the resolved pair the
+ * kernels above read:
+ *   sparse_index [B, n_sparse] int32 (index_bytes = 4) or int64 (index_bytes = 8)
+ *   dense_value  [B, n_dense]  fp32
+ *   field_src    [F] int32: j >= 0 -> field f is categorical column j: (id, 1.0)
+ *                           j <  0 -> field f is numeric column -j-1, a one-row table: (0, x)
+ *   feature_index [B,F] int64, feature_value [B,F] fp32 (outputs)
+ */
+int dir_expand_features(const void* sparse_index, int index_bytes, const float* dense_value,
+                        const int32_t* field_src, int64_t B, int F, int n_sparse, int n_dense,
+                        int64_t* feature_index, float* feature_value, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DCN cross network, all L layers in one pass.  Replaces _cross_architecture / _cross_op
  * (models/DeepCrossNetwork/DeepCrossNetwork.py:336-367): x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l.
  *   x0 [B,d], cross_w / cross_b [L,d] (names as DeepCrossNetwork.py:329-332), xL [B,d],
- *   s [B,L] or NULL (s[b,l] = x_l . w_l, reusable by the backward).   d <= 1024.
+ *   s [B,L] or NULL: per-sample scalars saved for the backward (s[b,l] = x0[b] . w_l; the
+ *   kernels use x_l = x0 * c_l + sum_{j<l} b_j, so x_l . w_l follows from these).   d <= 1024.
+ * Evaluated as x_L = x0 * c_L + sum_l b_l with c_L from a scalar recurrence: equal to the
+ * reference's layer-by-layer ((x0*s)+b)+x up to rounding (a few ulp of the largest term).
  */
 int dir_cross_fwd(const float* x0, const float* cross_w, const float* cross_b, int64_t B, int d,
                   int L, float* xL, float* s, dir_stream_t stream);
 
 /* Backward of the cross stack (TF autodiff behind compute_gradients, DeepCrossNetwork.py:283).
- *   dy [B,d] -> dx0 [B,d], dw [L,d], db [L,d]; s [B,L] from the forward or NULL (recomputed).
+ *   dy [B,d] -> dx0 [B,d], dw [L,d], db [L,d]; s [B,L] as written by dir_cross_fwd, or NULL
+ *   (recomputed; always recomputed when L > 8).
  * dw / db are reduced in a fixed order (per-CTA partials in `workspace`, then one combine).
  */
 size_t dir_cross_bwd_workspace_bytes(int64_t B, int d, int L);
