@@ -241,7 +241,9 @@ def run_b200(args):
     ready_events = {}          # e2e: slot -> event of its H2D copy (the sharded presort waits for it)
     handles = [dir_b200.SortedLookups() if world == 1 else dir_b200.ShardedLookups() for _ in range(R)]
 
-    def step(idx, val, y, up, slot=None, events=True):
+    def step(idx, val, y, up, slot=None, events=True, id_work=True):
+        """One step on resident inputs.  id_work=False leaves the sharded layer's id-only work for the next
+        batch (NCCL + one host read: not capturable) to the caller."""
         pre = None
         if slot is not None:
             nxt = (slot + 1) % R
@@ -261,12 +263,14 @@ def run_b200(args):
             torch.autograd.backward((first, fm), (g, g))
         if world == 1 and slot is not None and not events:     # captured: join the side branch ourselves
             torch.cuda.current_stream().wait_stream(layer.side_stream(dev))
-        if world > 1 and slot is not None:
-            # sharded: the next batch's id-only work (incl. the one host read of the split sizes) is issued
-            # AFTER this step's kernels are queued, so the host wait does not starve the main stream
-            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False,
-                          after=ready_events.get(nxt))
+        if world > 1 and slot is not None and id_work:
+            sharded_id_work(nxt)
         return logits
+
+    def sharded_id_work(nxt):
+        # sharded: the next batch's id-only work (incl. the one host read of the split sizes) is issued
+        # AFTER this step's kernels are queued, so the host wait does not starve the main stream
+        layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False, after=ready_events.get(nxt))
 
     # warm every slot eagerly (allocates workspaces), note U per slot
     out = None
@@ -278,8 +282,42 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     graphs, graph_out = [None] * R, [None] * R
-    use_graph = not args.no_graph and world == 1     # the sharded step reads split sizes on the host
-    if use_graph:
+    # Sharded: the main-stream half of a step (rows over NVLink, FM, gradient sums over NVLink, owner update) has
+    # device-side sizes and fixed addresses in the layer's static mode, so it is captured too; the id-only half
+    # (sort, NCCL id exchange, the one host read of the split sizes) stays eager on the side stream.
+    sharded_graph = (world > 1 and getattr(layer, "static", False) and R % 2 == 0
+                     and os.environ.get("DIR_B200_SHARDED_GRAPH", "1") == "1")
+    use_graph = not args.no_graph and (world == 1 or sharded_graph)
+    if use_graph and world > 1:
+        try:
+            for r in range(R):
+                handles[r].parity = r % 2          # captured: the half of the peer buffers is baked in
+            for r in range(R):                      # every slot once more, eagerly, with its fixed parity
+                step(*devs[r], ups[r], slot=r)
+            torch.cuda.synchronize()
+            dist.barrier()
+            layer.capturing = True                 # the wait for the side stream happens outside the graph
+            pool = None
+            for r in range(R):
+                # handle r holds batch r's id work at fixed addresses (the eager pass above left it there)
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, pool=pool, capture_error_mode="thread_local"):
+                    graph_out[r] = step(*devs[r], ups[r], slot=r, id_work=False)
+                pool = g_.pool()
+                graphs[r] = g_
+            layer.capturing = False
+            torch.cuda.synchronize()
+            dist.barrier()
+        except Exception as e:
+            layer.capturing = False
+            if rank == 0:
+                print("bench.py: CUDA graph capture of the sharded step failed (%s); launching eagerly" % e,
+                      file=sys.stderr)
+            use_graph = False
+            for r in range(R):
+                handles[r].parity = None
+            torch.cuda.synchronize()
+    elif use_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -305,6 +343,11 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     def run(slot):
+        if use_graph and world > 1:
+            torch.cuda.current_stream().wait_event(handles[slot].event)    # this batch's id work (side stream)
+            graphs[slot].replay()
+            sharded_id_work((slot + 1) % R)
+            return graph_out[slot]
         if use_graph:
             graphs[slot].replay()
             return graph_out[slot]

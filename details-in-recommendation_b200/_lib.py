@@ -24,6 +24,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dir_embed_bwd_sort": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "dir_embed_bwd_sort_in": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_embed_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
@@ -42,9 +43,12 @@ SIGNATURES = {
     "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int64,
                                           c_void_p, c_size_t, c_void_p]),
+    "dir_embed_bwd_reduce_emit_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_rows_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
-                                       c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_size_t,
-                                       c_void_p, c_void_p]),
+                                       c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
+                                       c_size_t, c_void_p, c_void_p]),
     "dir_expand_features": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "dir_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

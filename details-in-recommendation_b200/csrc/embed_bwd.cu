@@ -170,7 +170,45 @@ struct BwdArgs {
   int64_t emit_stride;
   const float* gbuf;       // kModeGiven: [n, gbuf_stride] per-lookup (G[K], g1), indexed by position
   int64_t gbuf_stride;
+  // kModeEmit straight into the owners' buffers over NVLink (NULL: rows go to `emit`): distinct row u
+  // of segment q (emit_seg[q] <= u < emit_seg[q+1]) is row emit_dst_off[q] + u - emit_seg[q] of the
+  // buffer at the peer-mapped address emit_peers[q]
+  const int64_t* emit_seg;
+  const int64_t* emit_peers;
+  const int64_t* emit_dst_off;
+  int emit_G;
+  // entries actually in the sorted list, read on the device (NULL: n).  `n` then only bounds the launch
+  // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
+  const int64_t* n_dev;
 };
+
+__device__ __forceinline__ int64_t entries(const BwdArgs& a) {
+  if (a.n_dev == nullptr) return a.n;
+  const int64_t m = __ldg(a.n_dev);
+  return m < a.n ? m : a.n;
+}
+
+// where distinct row u's (G[K], g1) goes
+__device__ __forceinline__ float* emit_row(const BwdArgs& a, uint32_t u) {
+  if (a.emit_peers == nullptr) return a.emit + (int64_t)u * a.emit_stride;
+  int q = 0;
+  for (int g = 1; g < a.emit_G; ++g) q += ((int64_t)u >= __ldg(a.emit_seg + g)) ? 1 : 0;
+  float* base = reinterpret_cast<float*>(__ldg(a.emit_peers + q));
+  return base + (__ldg(a.emit_dst_off + q) + (int64_t)u - __ldg(a.emit_seg + q)) * a.emit_stride;
+}
+// one distinct row's sums: LPR lanes store the K-vector, lane 0 of the group the 16-byte tail (g1, 0, 0, 0)
+// when the rows cross NVLink (whole 16-byte stores only), the bare g1 otherwise
+template <int LPR>
+__device__ __forceinline__ void emit_store(const BwdArgs& a, uint32_t u, int sub, float4 G, float g1) {
+  float* e = emit_row(a, u);
+  *(reinterpret_cast<float4*>(e) + sub) = G;
+  if (sub == 0) {
+    if (a.emit_peers != nullptr)
+      *(reinterpret_cast<float4*>(e) + LPR) = make_float4(g1, 0.f, 0.f, 0.f);
+    else
+      e[LPR * 4] = g1;
+  }
+}
 
 constexpr int kModeLocal = 0;  // gradients formed from g, S, u, row; the row is updated in place
 constexpr int kModeEmit = 1;   // requester side of a sharded table: per-row sums go to `emit`
@@ -192,9 +230,7 @@ template <int LPR>
 __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
                                              float g1) {
   if (a.mode == kModeEmit) {  // `key` is the row of the emit buffer here
-    float* e = a.emit + (int64_t)key * a.emit_stride;
-    *(reinterpret_cast<float4*>(e) + sub) = G;
-    if (sub == 0) e[LPR * 4] = g1;
+    emit_store<LPR>(a, key, sub, G, g1);
     return;
   }
   const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
@@ -262,10 +298,11 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
   const int slot = lane / LPR;
   const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t i0 = chunk * kChunk;
-  if (i0 >= a.n) return;  // whole warp
-  const int64_t chunk_end = min(a.n, i0 + (int64_t)kChunk);
+  const int64_t n = entries(a);
+  if (i0 >= n) return;  // whole warp
+  const int64_t chunk_end = min(n, i0 + (int64_t)kChunk);
   const uint32_t prev_key = i0 > 0 ? __ldg(a.keys + i0 - 1) : kNoKey;
-  const uint32_t next_chunk_key = chunk_end < a.n ? __ldg(a.keys + chunk_end) : kNoKey;
+  const uint32_t next_chunk_key = chunk_end < n ? __ldg(a.keys + chunk_end) : kNoKey;
   const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
   // L2 policies.  A 64-byte gradient / row gather pulls a whole 128-byte line from HBM (measured,
   // tools/gather_probe.cu); the other half of a `u` line belongs to the neighbouring field of the
@@ -422,9 +459,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
         }
         if ((ac[j] & 3) == 1) {
           if (MODE == kModeEmit) {
-            float* e = a.emit + (int64_t)rw[j] * a.emit_stride;
-            *(reinterpret_cast<float4*>(e) + sub) = d;
-            if (sub == 0) e[K] = d1;
+            emit_store<LPR>(a, rw[j], sub, d, d1);
           } else {
             apply_loaded(a, rw[j], sub, T[j], A[j], d, lw[j], a1[j], d1);
           }
@@ -467,11 +502,12 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
   __syncthreads();
   const int q = threadIdx.x / LPR;
   const int sub = threadIdx.x % LPR;
+  const int64_t n = entries(a);
   {
     const int64_t gid = (int64_t)blockIdx.x * NG + q;
     const int64_t i0 = gid * kChunk;
-    const int64_t end = min(a.n, i0 + (int64_t)kChunk);
-    bool head = i0 < a.n && end < a.n;  // the last chunk cannot be open to the right
+    const int64_t end = min(n, i0 + (int64_t)kChunk);
+    bool head = i0 < n && end < n;  // the last chunk cannot be open to the right
     uint32_t key = 0;
     if (head) {
       key = __ldg(a.keys + end - 1);
@@ -480,12 +516,12 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
     }
     if (head) {
       const int64_t far = (gid + 1 + kLongRun) * kChunk;  // chunk gid+1+kLongRun still starts with key?
-      if (far < a.n && __ldg(a.keys + far) == key) {
+      if (far < n && __ldg(a.keys + far) == key) {
         if (sub == 0) s_long[atomicAdd(&s_nlong, 1)] = (uint32_t)gid;
       } else {
         float4 acc = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
         float acc1 = a.part1[gid * 2 + 1];
-        for (int64_t j = gid + 1; j * kChunk < a.n && __ldg(a.keys + j * kChunk) == key; ++j) {
+        for (int64_t j = gid + 1; j * kChunk < n && __ldg(a.keys + j * kChunk) == key; ++j) {
           const float4 p = *(reinterpret_cast<const float4*>(a.part + (j * 2) * K) + sub);
           acc.x = __fadd_rn(acc.x, p.x);
           acc.y = __fadd_rn(acc.y, p.y);
@@ -507,7 +543,7 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
     int64_t M = 0;  // chunks gid+1 .. gid+M start with `key`: they hold a left-open partial
     for (;;) {
       const int64_t c = gid + 1 + M + threadIdx.x;
-      const int ok = c * kChunk < a.n && __ldg(a.keys + c * kChunk) == key;
+      const int ok = c * kChunk < n && __ldg(a.keys + c * kChunk) == key;
       const int cnt = __syncthreads_count(ok);
       M += cnt;
       if (cnt < 256) break;
@@ -814,17 +850,30 @@ extern "C" int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups,
 
 extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
                                   void* workspace, size_t workspace_bytes, dir_stream_t stream) {
+  return dir_embed_bwd_sort_in(sort_keys, n_lookups, n_lookups, n_rows, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dir_embed_bwd_sort_in(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_capacity,
+                                     int64_t n_rows, void* workspace, size_t workspace_bytes,
+                                     dir_stream_t stream) {
   using namespace dir;
-  if (n_lookups < 0 || n_lookups >= 0x7fffffffLL)
-    return fail(DIR_EINVAL, "embed_bwd_sort: 0 <= n_lookups < 2^31 required");
+  if (n_lookups < 0 || n_lookups >= 0x7fffffffLL || n_capacity < n_lookups || n_capacity >= 0x7fffffffLL)
+    return fail(DIR_EINVAL, "embed_bwd_sort: 0 <= n_lookups <= n_capacity < 2^31 required");
   if (n_rows <= 0 || n_rows >= 0xffffffffLL)
     return fail(DIR_EINVAL, "embed_bwd_sort: 0 < n_rows < 2^32-1 required");
-  if (n_lookups == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_lookups == 0) {
+    if (workspace && n_capacity > 0) {  // a later reduce over 0 entries must still find zeroed counters
+      BwdWorkspace w0 = carve(workspace, n_capacity, 4);
+      if (workspace_bytes < w0.total) return fail(DIR_ENOMEM, "embed_bwd_sort: workspace too small");
+      cudaMemsetAsync(w0.long_count, 0, 16, st);
+    }
+    return 0;
+  }
   if (!sort_keys || !workspace) return fail(DIR_EINVAL, "embed_bwd_sort: null pointer");
   // K only sizes the tail of the workspace; the sort part does not depend on it
-  BwdWorkspace w = carve(workspace, n_lookups, 4);
+  BwdWorkspace w = carve(workspace, n_capacity, 4);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_sort: workspace too small");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((n_lookups + 255) / 256);
   iota_kernel<<<grid, 256, 0, st>>>(w.pos_in, n_lookups, w.long_count, w.n_unique);
   int rc = launched("embed_bwd_sort/iota");
@@ -899,12 +948,45 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
 
-/* requester side of a row-sharded table: per-unique-row gradient sums -> gu (include/dir_b200.h) */
+/* requester side of a row-sharded table: per-unique-row gradient sums -> gu, or (peer_ptrs != NULL)
+ * straight into the owners' buffers over NVLink (include/dir_b200.h) */
+static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride, const float* feature_value,
+                       const float* g_first, const float* g_fm, const float* S, const float* u,
+                       const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
+                       int64_t gu_stride, int G, const int64_t* seg_start, const int64_t* peer_ptrs,
+                       const int64_t* dst_row_off, void* workspace, size_t workspace_bytes,
+                       dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0) return fail(DIR_EINVAL, "%s: B >= 0, F > 0 required", what);
+  const int64_t n = B * F;
+  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "%s: B*F must be < 2^31", what);
+  if (n == 0) return 0;
+  if (!ubuf || !g_fm || !S || !uidx || !workspace || (!gu && !peer_ptrs))
+    return fail(DIR_EINVAL, "%s: ubuf, g_fm, S, uidx, workspace and a destination are required", what);
+  if (peer_ptrs && (G <= 0 || G > 1024 || !seg_start || !dst_row_off))
+    return fail(DIR_EINVAL, "%s: 0 < G <= 1024, seg_start and dst_row_off are required", what);
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "%s: K must be one of 4, 8, 16, 32, 64", what);
+  if (ubuf_stride < K || (ubuf_stride & 3) || gu_stride < (peer_ptrs ? K + 4 : K + 1) || (gu_stride & 3))
+    return fail(DIR_EINVAL, "%s: strides must be multiples of 4, >= K (ubuf), >= K+1 (gu) / K+4 (peer rows)", what);
+  if (!aligned16(ubuf) || !aligned16(gu) || !aligned16(S) || !aligned16(u))
+    return fail(DIR_EINVAL, "%s: ubuf, gu, S, u must be 16-byte aligned", what);
+  if (n_keys <= 0 || n_keys >= 0xffffffffLL) return fail(DIR_EINVAL, "%s: 0 < n_keys < 2^32-1 required", what);
+  BwdWorkspace w = carve(workspace, n, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "%s: workspace too small", what);
+  BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
+            g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0,
+            seg_start, peer_ptrs, dst_row_off, G, nullptr};
+  set_div(a, F);
+  return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
                                          const float* feature_value, const float* g_first,
                                          const float* g_fm, const float* S, const float* u,
@@ -912,37 +994,32 @@ extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
                                          int64_t n_keys, float* gu, int64_t gu_stride,
                                          void* workspace, size_t workspace_bytes,
                                          dir_stream_t stream) {
-  using namespace dir;
-  if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_emit: B >= 0, F > 0 required");
-  const int64_t n = B * F;
-  if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_emit: B*F must be < 2^31");
-  if (n == 0) return 0;
-  if (!ubuf || !g_fm || !S || !uidx || !gu || !workspace)
-    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: ubuf, g_fm, S, uidx, gu, workspace are required");
-  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
-    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: K must be one of 4, 8, 16, 32, 64");
-  if (ubuf_stride < K || (ubuf_stride & 3) || gu_stride < K + 1 || (gu_stride & 3))
-    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: strides must be multiples of 4, >= K (ubuf), >= K+1 (gu)");
-  if (!aligned16(ubuf) || !aligned16(gu) || !aligned16(S) || !aligned16(u))
-    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: ubuf, gu, S, u must be 16-byte aligned");
-  if (n_keys <= 0 || n_keys >= 0xffffffffLL)
-    return fail(DIR_EINVAL, "embed_bwd_reduce_emit: 0 < n_keys < 2^32-1 required");
-  BwdWorkspace w = carve(workspace, n, K);
-  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_reduce_emit: workspace too small");
-  BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
-            g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0};
-  set_div(a, F);
-  return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
+  if (!gu) return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit: gu is required");
+  return reduce_emit("embed_bwd_reduce_emit", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B, F,
+                     K, n_keys, gu, gu_stride, 0, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stride,
+                                            const float* feature_value, const float* g_first,
+                                            const float* g_fm, const float* S, const float* u,
+                                            const uint32_t* uidx, int64_t B, int F, int K,
+                                            int64_t n_keys, int G, const int64_t* seg_start,
+                                            const int64_t* peer_ptrs, const int64_t* dst_row_off,
+                                            int64_t out_stride, void* workspace,
+                                            size_t workspace_bytes, dir_stream_t stream) {
+  if (!peer_ptrs) return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit_to: peer_ptrs is required");
+  return reduce_emit("embed_bwd_reduce_emit_to", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B,
+                     F, K, n_keys, nullptr, out_stride, G, seg_start, peer_ptrs, dst_row_off, workspace,
+                     workspace_bytes, stream);
 }
 
 /* owner side: per-lookup gradients arrive from the requesters; segmented sum + fused row update */
 extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                                       float* lin_accum, int64_t lin_stride, const float* gbuf,
                                       int64_t gbuf_stride, int64_t n, int K, int64_t n_rows,
-                                      int optimizer, float lr, void* workspace,
-                                      size_t workspace_bytes, int64_t* n_unique_out,
-                                      dir_stream_t stream) {
+                                      int optimizer, float lr, const int64_t* n_device,
+                                      void* workspace, size_t workspace_bytes,
+                                      int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (n < 0 || n >= 0x7fffffffLL) return fail(DIR_EINVAL, "rows_reduce_update: 0 <= n < 2^31 required");
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
@@ -964,7 +1041,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }

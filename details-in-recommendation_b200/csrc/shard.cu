@@ -132,6 +132,10 @@ rows_gather_to_kernel(const float* __restrict__ table, int64_t row_stride, const
                       const int64_t* __restrict__ seg_start, const int64_t* __restrict__ peer_ptrs,
                       const int64_t* __restrict__ dst_row_off, int64_t out_stride) {
   constexpr int TPR = LPR + 1;  // threads per row
+  {  // `n` bounds the launch; the rows really there are seg_start[G] (known on the device alone)
+    const int64_t total = __ldg(seg_start + G);
+    n = total < n ? total : n;
+  }
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i0 = t / TPR;
   const int sub = (int)(t % TPR);

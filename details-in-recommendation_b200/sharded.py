@@ -79,6 +79,20 @@ def exchange(payload: torch.Tensor, send_splits, recv_splits, group=None) -> tor
     return out
 
 
+def exchange_into(out: torch.Tensor, payload: torch.Tensor, send_splits, recv_splits, group=None) -> torch.Tensor:
+    """`exchange` into the head of a caller-owned buffer (fixed address: CUDA-graph replays read it)."""
+    n = int(sum(recv_splits))
+    if n > out.shape[0]:
+        raise ValueError("exchange_into: %d rows received, buffer holds %d" % (n, out.shape[0]))
+    view = out[:n]
+    if not dist.is_initialized():
+        view.copy_(payload)
+        return view
+    dist.all_to_all_single(view, payload.contiguous(), output_split_sizes=list(recv_splits),
+                           input_split_sizes=list(send_splits), group=group)
+    return view
+
+
 class StageTrace:
     """Optional per-stage CUDA-event timing of the sharded step (DIR_B200_TRACE=1): mark(name) closes
     the stage that just ran; report() averages over the steps seen since the last report."""
@@ -142,6 +156,8 @@ class ShardedLookups:
         self.U = self.R = 0
         self.event = None
         self.src = None
+        self.parity = None          # which half of the double-buffered peer memory (None: the layer alternates)
+        self.recv_buf = None        # static mode: fixed-address landing buffer of the ids this rank answers
 
     @staticmethod
     def key_of(feature_index, feature_value):
@@ -160,21 +176,27 @@ class _ShardedFunction(torch.autograd.Function):
         pad = layer.pad_stride
         tr = layer.trace
         tr.mark("start")
-        if h.event is not None:
+        if h.event is not None and not layer.capturing:
             torch.cuda.current_stream().wait_event(h.event)
         U, R = h.U, h.R
+        static = layer.static
         # 4b: the owner answers the ids it received; rows back over NVLink
         G = layer.plan.world_size
-        parity = layer._step_parity
-        layer._step_parity ^= 1
+        if h.parity is not None:
+            parity = h.parity
+        else:
+            parity = layer._step_parity
+            layer._step_parity ^= 1
         if layer.peer is not None:
             if B > layer.max_batch:
                 raise ValueError("batch %d exceeds max_batch=%d the peer buffers were sized for" % (B, layer.max_batch))
             # one kernel gathers the rows and writes them straight into the requesters' buffers
             pb = layer.peer["rows"]
+            # static: launch for the capacity, the kernel stops at recv_off[G] (read on the device)
             check(L.dir_rows_gather_to(ptr(layer.table), layer.row_stride,
                                        ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
-                                       ptr(h.recv_ids), R, K, G, ptr(h.recv_off), ptr(pb.ptrs[parity]),
+                                       ptr(h.recv_buf if static else h.recv_ids), layer.recv_cap if static else R,
+                                       K, G, ptr(h.recv_off), ptr(pb.ptrs[parity]),
                                        ptr(h.fwd_dst_off), pad, st), "dir_rows_gather_to")
             tr.mark("fwd.gather+send")
             pb.barrier(parity)
@@ -199,7 +221,8 @@ class _ShardedFunction(torch.autograd.Function):
         S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
         lin = ubuf[:, K] if layer.first_order else None
         check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
-                                 ptr(h.inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
+                                 ptr(h.inv), ptr(val), ptr(layer.zero_offset), None,
+                                 ubuf.shape[0] if static else max(U, 1), B, F, K,
                                  ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
         tr.mark("fwd.fm")
         if not layer.first_order:
@@ -239,14 +262,29 @@ class _ShardedFunction(torch.autograd.Function):
         with torch.no_grad():
             # 6: per-distinct-row sums on the requester (the sorted list is in the handle's workspace)
             ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
-            gu = torch.empty((max(U, 1), pad), dtype=torch.float32, device=dev)
-            check(L.dir_embed_bwd_reduce_emit(ptr(ubuf), pad, ptr(val), ptr(g_first) if layer.first_order else None,
-                                              ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K,
-                                              layer.plan.cap * layer.plan.world_size, ptr(gu), pad,
-                                              ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
-            tr.mark("bwd.emit")
+            n_keys = layer.plan.cap * layer.plan.world_size
+            gfp = ptr(g_first) if layer.first_order else None
+            if ctx.use_peer and layer.fused_push:
+                # 6+7 in one kernel: each distinct row's sums go straight into its owner's buffer over NVLink
+                pb = layer.peer["grads"]
+                check(L.dir_embed_bwd_reduce_emit_to(
+                    ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K, n_keys,
+                    layer.plan.world_size, ptr(h.owner_off), ptr(pb.ptrs[ctx.parity]), ptr(h.bwd_dst_off), pad,
+                    ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_to")
+                tr.mark("bwd.emit+push")
+                pb.barrier(ctx.parity)
+                tr.mark("bwd.barrier")
+                grecv = pb.bufs[ctx.parity]
+            else:
+                gu = torch.empty((max(U, 1), pad), dtype=torch.float32, device=dev)
+                check(L.dir_embed_bwd_reduce_emit(ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u),
+                                                  ptr(h.uidx), B, F, K, n_keys, ptr(gu), pad,
+                                                  ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
+                tr.mark("bwd.emit")
             # 7: sums to their owners; the owner merges the ranks' contributions and updates
-            if ctx.use_peer:
+            if ctx.use_peer and layer.fused_push:
+                pass
+            elif ctx.use_peer:
                 pb = layer.peer["grads"]
                 check(L.dir_rows_push(ptr(gu), U, pad, layer.plan.world_size, ptr(h.owner_off),
                                       ptr(pb.ptrs[ctx.parity]), ptr(h.bwd_dst_off), st), "dir_rows_push")
@@ -257,14 +295,16 @@ class _ShardedFunction(torch.autograd.Function):
             else:
                 grecv = exchange(gu[:U], h.send_splits, h.recv_splits, layer.group)      # [R, K+4]
                 tr.mark("bwd.a2a_grads")
-            if R > 0:
-                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)      # sorted by presort
+            if R > 0 or layer.static:
+                Rn = layer.recv_cap if layer.static else R        # static: capacity; the count stays on the device
+                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(Rn, K), dev)     # sorted by presort
                 adagrad = layer.optimizer == "adagrad"
+                n_dev = h.recv_off.data_ptr() + 8 * layer.plan.world_size if layer.static else None
                 check(L.dir_rows_reduce_update(
                     ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
                     ptr(layer.w1) if layer.first_order else None,
                     ptr(layer.w1_accum) if (adagrad and layer.first_order) else None, layer.lin_stride,
-                    ptr(grecv), pad, R, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
+                    ptr(grecv), pad, Rn, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr, n_dev,
                     ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
                 tr.mark("bwd.owner_update")
             else:
@@ -333,14 +373,22 @@ class ShardedEmbeddingFM(torch.nn.Module):
         # Payload exchange: NVLink peer memory (symmetric buffers + a device-side barrier) when there is
         # more than one rank and torch's symmetric memory is usable, else NCCL all-to-all.
         self.peer, self._step_parity = None, 0
+        self.static = self.capturing = False
+        self.recv_cap = 0
         self.max_batch = int(max_batch)
         want_peer = os.environ.get("DIR_B200_EXCHANGE", "peer") == "peer"
+        self.fused_push = os.environ.get("DIR_B200_FUSED_PUSH", "1") == "1"   # emit + NVLink push in one kernel
         if want_peer and dist.is_initialized() and world > 1 and dev.type == "cuda" \
                 and dist.get_backend(process_group) == "nccl":
             try:
                 cap = min(self.max_batch * field_size, max(self.plan.cap, 1))       # distinct rows a rank can want
                 self.peer = {"rows": PeerBuffers(process_group, cap, self.pad_stride, dev),         # <- owners
                              "grads": PeerBuffers(process_group, cap * world, self.pad_stride, dev)}  # <- requesters
+                # Static mode: every main-stream launch is sized for these capacities and reads the real counts
+                # on the device, every buffer it touches has a fixed address -- so forward + backward of a step
+                # can be captured in a CUDA graph (the id-only presort stays eager on the side stream).
+                self.recv_cap = cap * world
+                self.static = os.environ.get("DIR_B200_STATIC", "1") == "1"
             except Exception as e:                                              # no IPC / fabric support
                 if rank == 0:
                     print("ShardedEmbeddingFM: symmetric memory unavailable (%s); using NCCL all-to-all" % e,
@@ -430,6 +478,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 h.ulocal = torch.empty(n, dtype=torch.int32, device=dev)
                 h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
                 h.owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
+                h.recv_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+                h.fwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
+                h.bwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
+                if self.static:
+                    h.recv_buf = torch.empty(self.recv_cap, dtype=torch.int32, device=dev)
             check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
                                    self.plan.n_rows, B, F, G, None, F, ptr(h.keys),
                                    ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
@@ -457,19 +510,28 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 dist.all_gather_into_tensor(M, send_counts.contiguous(), group=self.side_group)
                 me = self.plan.rank
                 recv_counts = M[:, me].contiguous()
-                zero = torch.zeros(1, dtype=torch.int64, device=dev)
-                h.recv_off = torch.cat([zero, torch.cumsum(recv_counts, 0)])
-                h.fwd_dst_off = (torch.cumsum(M, 1) - M)[:, me].contiguous()   # my segment inside q's row buffer
-                h.bwd_dst_off = (torch.cumsum(M, 0) - M)[me, :].contiguous()   # my segment inside o's grad buffer
+                # written in place: a captured step reads these at fixed addresses
+                h.recv_off[1:].copy_(torch.cumsum(recv_counts, 0))
+                h.fwd_dst_off.copy_((torch.cumsum(M, 1) - M)[:, me])   # my segment inside q's row buffer
+                h.bwd_dst_off.copy_((torch.cumsum(M, 0) - M)[me, :])   # my segment inside o's grad buffer
             else:
                 recv_counts = exchange_counts(send_counts, self.side_group)
             both = torch.stack([send_counts, recv_counts]).cpu()
             h.send_splits, h.recv_splits = both[0].tolist(), both[1].tolist()
             h.U, h.R = int(sum(h.send_splits)), int(sum(h.recv_splits))
             tr.mark("pre.counts+sync")
-            h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
+            if self.static:
+                if h.R > self.recv_cap:
+                    raise ValueError("%d rows requested from this rank, buffers hold %d" % (h.R, self.recv_cap))
+                h.recv_ids = exchange_into(h.recv_buf, h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
+            else:
+                h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
             tr.mark("pre.a2a_ids")
-            if h.R > 0:                       # the owner's half: arrival order -> local-row order
+            if self.static:                   # laid out for the capacity: the consumer never learns R on the host
+                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(self.recv_cap, K), dev)
+                check(L.dir_embed_bwd_sort_in(ptr(h.recv_ids), h.R, self.recv_cap, self.plan.cap, ptr(ws3),
+                                              ws3.numel(), st), "dir_embed_bwd_sort_in")
+            elif h.R > 0:                     # the owner's half: arrival order -> local-row order
                 ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(h.R, K), dev)
                 check(L.dir_embed_bwd_sort(ptr(h.recv_ids), h.R, self.plan.cap, ptr(ws3), ws3.numel(), st),
                       "dir_embed_bwd_sort")

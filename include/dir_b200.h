@@ -103,6 +103,12 @@ int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, i
 size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K);
 int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
                        void* workspace, size_t workspace_bytes, dir_stream_t stream);
+/* Same sort inside a workspace laid out for n_capacity >= n_lookups entries: the consumer
+ * (dir_rows_reduce_update with n = n_capacity and the real count on the device) then needs no
+ * host-side knowledge of n_lookups -- a step with data-dependent sizes can be replayed from a CUDA graph. */
+int dir_embed_bwd_sort_in(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_capacity,
+                          int64_t n_rows, void* workspace, size_t workspace_bytes,
+                          dir_stream_t stream);
 int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                                 float* lin_accum, int64_t lin_stride, const int64_t* feature_index,
                                 const float* feature_value, const int64_t* field_offset,
@@ -149,6 +155,9 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  * dir_rows_reduce_update: the owner's half.  gbuf[j] = (G[K], g1) received for the j-th id it
  *   answered; dir_embed_bwd_sort(ids, n, n_local_rows) must have run on `workspace`.  Sums the
  *   contributions of each local row in arrival order (source rank major) and applies the update.
+ *   n_device (device int64, may be NULL): the number of entries really received; `n` is then only the
+ *   capacity the launch and the workspace (dir_embed_bwd_sort_in with n_capacity = n) are sized for.
+ * dir_rows_gather_to likewise processes min(n, seg_start[G]) rows: n may be an upper bound.
  */
 int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
                    const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
@@ -181,11 +190,23 @@ int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride, const floa
                               const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
                               int64_t gu_stride, void* workspace, size_t workspace_bytes,
                               dir_stream_t stream);
+/* dir_embed_bwd_reduce_emit with the transfer fused in: each distinct row's (G[K], g1, 0, 0, 0) is
+ * stored straight into its owner's buffer over NVLink as soon as its run is summed -- no gu round
+ * trip through HBM, no separate dir_rows_push, and the NVLink stores overlap the kernel's gathers.
+ * Distinct rows are grouped by owner: seg_start[G+1], peer_ptrs[G], dst_row_off[G] as for
+ * dir_rows_push (all device arrays); out_stride >= K + 4 floats.  Barrier before the owner reads. */
+int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
+                                 const float* g_first, const float* g_fm, const float* S,
+                                 const float* u, const uint32_t* uidx, int64_t B, int F, int K,
+                                 int64_t n_keys, int G, const int64_t* seg_start,
+                                 const int64_t* peer_ptrs, const int64_t* dst_row_off,
+                                 int64_t out_stride, void* workspace, size_t workspace_bytes,
+                                 dir_stream_t stream);
 int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                            float* lin_accum, int64_t lin_stride, const float* gbuf,
                            int64_t gbuf_stride, int64_t n, int K, int64_t n_rows, int optimizer,
-                           float lr, void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
-                           dir_stream_t stream);
+                           float lr, const int64_t* n_device, void* workspace,
+                           size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Column feed -> [B,F] inputs.  The reference's input_fn hands the graph one tensor per column --
