@@ -541,7 +541,7 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
             ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
             layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
             ptr(ups[r]) if emit else None, B, F, K, layer.n_rows, ptr(layer.sorted_fields), n_sel,
-            ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, ptr(ws), ws.numel(), None, st), "update")
+            ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, None, ptr(ws), ws.numel(), None, st), "update")
 
     calls = [("dir_shard_keys", mkkeys, 0),
              ("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),

@@ -11,7 +11,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdir_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-OPT_SGD, OPT_ADAGRAD = 0, 1
+OPT_SGD, OPT_ADAGRAD, OPT_FTRL = 0, 1, 2
+
+
+class LinearOpt(ctypes.Structure):
+    """struct dir_linear_opt (include/dir_b200.h): the linear scope's own optimizer."""
+    _fields_ = [("optimizer", c_int), ("lr", c_float), ("l1", c_float), ("l2", c_float), ("z", c_void_p)]
 _EINVAL, _ENOMEM, _EIO = -22, -12, -5
 
 # name -> (restype, argtypes); must list every symbol include/dir_b200.h declares
@@ -28,7 +33,7 @@ SIGNATURES = {
     "dir_embed_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
-                                            c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                            c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_sorted": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -48,7 +53,7 @@ SIGNATURES = {
                                              c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_rows_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                        c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
-                                       c_size_t, c_void_p, c_void_p]),
+                                       c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_expand_features": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "dir_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

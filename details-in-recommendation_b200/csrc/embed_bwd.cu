@@ -134,6 +134,15 @@ __global__ void iota_kernel(uint32_t* out, int64_t n, uint32_t* zero2, unsigned 
   }
 }
 
+// The linear scope (first-order weights) has an optimizer of its own in the reference
+// (linear_optimizer='Ftrl', models/DeepFM/deepFM.py:58, 236-241).
+struct LinOpt {
+  int opt;      // DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_FTRL
+  float lr;
+  float l1, l2; // Ftrl regularisation strengths
+  float* z;     // Ftrl 'linear' slot, same stride as the weights
+};
+
 struct BwdArgs {
   float* table;
   float* accum;
@@ -180,6 +189,7 @@ struct BwdArgs {
   // entries actually in the sorted list, read on the device (NULL: n).  `n` then only bounds the launch
   // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
   const int64_t* n_dev;
+  LinOpt lo;
 };
 
 __device__ __forceinline__ int64_t entries(const BwdArgs& a) {
@@ -226,6 +236,33 @@ __device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool 
   return __fsub_rn(t, __fmul_rn(lr, g));
 }
 
+// One first-order weight with its de-duplicated gradient g.  Ftrl is [TF] SparseApplyFtrl with
+// learning_rate_power = -0.5 and no l2 shrinkage (tf.train.FtrlOptimizer defaults):
+//   n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma*w
+//   w  = |z| > l1 ? (sign(z)*l1 - z) / (sqrt(n')/lr + 2*l2) : 0
+__device__ __forceinline__ void lin_apply(const LinOpt& o, float* wp, float* np, float* zp, float w,
+                                          float n, float z, float g) {
+  if (o.opt == DIR_OPT_FTRL) {
+    const float nn = __fadd_rn(n, __fmul_rn(g, g));
+    const float rn = __fsqrt_rn(nn);
+    const float sigma = __fdiv_rn(__fsub_rn(rn, __fsqrt_rn(n)), o.lr);
+    z = __fsub_rn(__fadd_rn(z, g), __fmul_rn(sigma, w));
+    const float quad = __fadd_rn(__fdiv_rn(rn, o.lr), __fmul_rn(2.f, o.l2));
+    *wp = fabsf(z) > o.l1 ? __fdiv_rn(__fsub_rn(copysignf(o.l1, z), z), quad) : 0.f;
+    *np = nn;
+    *zp = z;
+    return;
+  }
+  const bool adagrad = o.opt == DIR_OPT_ADAGRAD;
+  *wp = upd(w, g, o.lr, n, adagrad);
+  if (adagrad) *np = n;
+}
+// loads for lin_apply (what each optimizer keeps per weight)
+__device__ __forceinline__ void lin_load(const LinOpt& o, const float* lin_accum, int64_t off, float& n, float& z) {
+  n = o.opt != DIR_OPT_SGD ? lin_accum[off] : 0.f;
+  z = o.opt == DIR_OPT_FTRL ? o.z[off] : 0.f;
+}
+
 template <int LPR>
 __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
                                              float g1) {
@@ -249,21 +286,16 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int
   *trow = T;
   if (adagrad) *arow = A;
   if (a.lin != nullptr && sub == 0) {
-    float* wp = a.lin + (int64_t)key * a.lin_stride;
-    float a1 = 0.f;
-    float* ap = nullptr;
-    if (adagrad) {
-      ap = a.lin_accum + (int64_t)key * a.lin_stride;
-      a1 = *ap;
-    }
-    *wp = upd(*wp, g1, a.lr, a1, adagrad);
-    if (adagrad) *ap = a1;
+    const int64_t off = (int64_t)key * a.lin_stride;
+    float n1, z1;
+    lin_load(a.lo, a.lin_accum, off, n1, z1);
+    lin_apply(a.lo, a.lin + off, a.lin_accum + off, a.lo.z + off, a.lin[off], n1, z1, g1);
   }
 }
 
 // Row update from values already in registers (same arithmetic as apply_update).
 __device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int sub, float4 T,
-                                             float4 A, float4 G, float w, float a1, float g1) {
+                                             float4 A, float4 G, float w, float a1, float z1, float g1) {
   const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
   T.x = upd(T.x, G.x, a.lr, A.x, adagrad);
   T.y = upd(T.y, G.y, a.lr, A.y, adagrad);
@@ -272,8 +304,8 @@ __device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int
   *(reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub) = T;
   if (adagrad) *(reinterpret_cast<float4*>(a.accum + (int64_t)key * a.row_stride) + sub) = A;
   if (a.lin != nullptr && sub == 0) {
-    a.lin[(int64_t)key * a.lin_stride] = upd(w, g1, a.lr, a1, adagrad);
-    if (adagrad) a.lin_accum[(int64_t)key * a.lin_stride] = a1;
+    const int64_t off = (int64_t)key * a.lin_stride;
+    lin_apply(a.lo, a.lin + off, a.lin_accum + off, a.lo.z + off, w, a1, z1, g1);
   }
 }
 
@@ -380,7 +412,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
     for (int j0 = 0; j0 < PASSES; j0 += PB) {
       uint32_t k[PB], rw[PB];
       int ac[PB];
-      float a1[PB], lw[PB];
+      float a1[PB], lw[PB], lz[PB];
       float4 Sb[PB], ub[PB], T[PB], A[PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
@@ -391,7 +423,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
         const uint32_t bb = MODE == kModeGiven ? 0u : __shfl_sync(FULL, b, l);
         ac[j] = __shfl_sync(FULL, act, l);
         Sb[j] = ub[j] = T[j] = A[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        lw[j] = a1[j] = 0.f;
+        lw[j] = a1[j] = lz[j] = 0.f;
         if (k[j] != a.pruned_key) {
           const int64_t ro = (int64_t)rw[j] * a.row_stride;
           if (MODE == kModeGiven) {  // the per-lookup gradient was formed by the requester
@@ -408,7 +440,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
             if (adagrad) A[j] = ld_hint(a.accum + ro + sub * 4, pol_row);
             if (a.lin != nullptr && sub == 0) {
               lw[j] = a.lin[(int64_t)rw[j] * a.lin_stride];
-              if (adagrad) a1[j] = a.lin_accum[(int64_t)rw[j] * a.lin_stride];
+              lin_load(a.lo, a.lin_accum, (int64_t)rw[j] * a.lin_stride, a1[j], lz[j]);
             }
           }
         }
@@ -461,7 +493,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
           if (MODE == kModeEmit) {
             emit_store<LPR>(a, rw[j], sub, d, d1);
           } else {
-            apply_loaded(a, rw[j], sub, T[j], A[j], d, lw[j], a1[j], d1);
+            apply_loaded(a, rw[j], sub, T[j], A[j], d, lw[j], a1[j], lz[j], d1);
           }
         } else if ((ac[j] & 3) >= 2) {
           const int64_t s = chunk * 2 + ((ac[j] & 3) == 2 ? 0 : 1);
@@ -630,6 +662,7 @@ struct OneRowArgs {
   float* part;   // [kOneRowCtas][kOneRowMax][K + 4]
   int* flags;    // [kOneRowMax] some sample had a surviving lookup
   unsigned long long* n_unique;
+  LinOpt lo;
 };
 
 template <int LPR, int P>
@@ -775,15 +808,10 @@ __global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneR
     if (adagrad) *ap = acc;
   } else if (threadIdx.x == K) {
     if (a.lin != nullptr) {
-      float* wp = a.lin + row * a.lin_stride;
-      float a1 = 0.f;
-      float* ap = nullptr;
-      if (adagrad) {
-        ap = a.lin_accum + row * a.lin_stride;
-        a1 = *ap;
-      }
-      *wp = upd(*wp, tot[K], a.lr, a1, adagrad);
-      if (adagrad) *ap = a1;
+      const int64_t off = row * a.lin_stride;
+      float n1, z1;
+      lin_load(a.lo, a.lin_accum, off, n1, z1);
+      lin_apply(a.lo, a.lin + off, a.lin_accum + off, a.lo.z + off, a.lin[off], n1, z1, tot[K]);
     }
     if (a.n_unique) atomicAdd(a.n_unique, 1ull);
   }
@@ -818,6 +846,22 @@ static void set_div(BwdArgs& a, int F) {
   while ((1 << lg) < F) ++lg;
   a.div_shift = 31 + lg;
   a.div_magic = (uint32_t)((((uint64_t)1 << a.div_shift) + (uint64_t)F - 1) / (uint64_t)F);
+}
+
+// The linear scope's optimizer: the caller's dir_linear_opt, or the tables' optimizer and rate.
+static int resolve_lin(const char* what, const dir_linear_opt* in, int optimizer, float lr, const float* lin,
+                       const float* lin_accum, LinOpt& out) {
+  out = LinOpt{optimizer, lr, 0.f, 0.f, nullptr};
+  if (in != nullptr) out = LinOpt{in->optimizer, in->lr, in->l1, in->l2, in->z};
+  if (out.opt != DIR_OPT_SGD && out.opt != DIR_OPT_ADAGRAD && out.opt != DIR_OPT_FTRL)
+    return fail(DIR_EINVAL, "%s: unknown linear optimizer", what);
+  if (lin != nullptr) {
+    if (out.opt != DIR_OPT_SGD && !lin_accum)
+      return fail(DIR_EINVAL, "%s: Adagrad / Ftrl on the linear weights need lin_accum", what);
+    if (out.opt == DIR_OPT_FTRL && (!out.z || !(out.lr > 0.f) || out.l1 < 0.f || out.l2 < 0.f))
+      return fail(DIR_EINVAL, "%s: Ftrl needs z, lr > 0 and l1, l2 >= 0", what);
+  }
+  return 0;
 }
 
 static int dispatch_bwd(const BwdArgs& a, int K, int64_t* n_unique_out, cudaStream_t st) {
@@ -892,8 +936,8 @@ extern "C" int dir_embed_bwd_reduce_update(
     const int64_t* feature_index, const float* feature_value, const int64_t* field_offset,
     const float* g_first, const float* g_fm, const float* S, const float* u, int64_t B, int F, int K,
     int64_t n_rows, const int32_t* field_sel, int n_sel, const int32_t* onerow_fields, int n_onerow,
-    int optimizer, float lr, void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
-    dir_stream_t stream) {
+    int optimizer, float lr, const dir_linear_opt* linear_opt, void* workspace, size_t workspace_bytes,
+    int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B >= 0, F > 0 required");
   if (B * F >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B*F must be < 2^31");
@@ -901,8 +945,10 @@ extern "C" int dir_embed_bwd_reduce_update(
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: unknown optimizer");
   if (!table || !g_fm || !S || !workspace)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: table, g_fm, S, workspace are required");
-  if (optimizer == DIR_OPT_ADAGRAD && (!accum || (lin && !lin_accum)))
-    return fail(DIR_EINVAL, "embed_bwd_reduce_update: Adagrad needs accum (and lin_accum with lin)");
+  if (optimizer == DIR_OPT_ADAGRAD && !accum)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_update: Adagrad needs accum");
+  LinOpt lo;
+  if (int rc = resolve_lin("embed_bwd_reduce_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   if (lin && !g_first) return fail(DIR_EINVAL, "embed_bwd_reduce_update: lin needs g_first");
   if (row_stride < K || (row_stride & 3))
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: row_stride must be >= K, multiple of 4");
@@ -928,7 +974,7 @@ extern "C" int dir_embed_bwd_reduce_update(
     cudaMemsetAsync(w.onerow_flags, 0, kOneRowMax * 4, st);
     OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value,
                  field_offset, g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.onerow_part,
-                 w.onerow_flags, w.n_unique};
+                 w.onerow_flags, w.n_unique, lo};
     int rc;
     switch (K) {
       case 4: rc = launch_onerow<1>(o, n_onerow, st); break;
@@ -948,7 +994,7 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, lo};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -982,7 +1028,7 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
   BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
             (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0,
-            seg_start, peer_ptrs, dst_row_off, G, nullptr};
+            seg_start, peer_ptrs, dst_row_off, G, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}};
   set_div(a, F);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -1017,8 +1063,8 @@ extern "C" int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stri
 extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                                       float* lin_accum, int64_t lin_stride, const float* gbuf,
                                       int64_t gbuf_stride, int64_t n, int K, int64_t n_rows,
-                                      int optimizer, float lr, const int64_t* n_device,
-                                      void* workspace, size_t workspace_bytes,
+                                      int optimizer, float lr, const dir_linear_opt* linear_opt,
+                                      const int64_t* n_device, void* workspace, size_t workspace_bytes,
                                       int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (n < 0 || n >= 0x7fffffffLL) return fail(DIR_EINVAL, "rows_reduce_update: 0 <= n < 2^31 required");
@@ -1027,8 +1073,9 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (n == 0) return 0;
   if (!table || !gbuf || !workspace)
     return fail(DIR_EINVAL, "rows_reduce_update: table, gbuf, workspace are required");
-  if (optimizer == DIR_OPT_ADAGRAD && (!accum || (lin && !lin_accum)))
-    return fail(DIR_EINVAL, "rows_reduce_update: Adagrad needs accum (and lin_accum with lin)");
+  if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "rows_reduce_update: Adagrad needs accum");
+  LinOpt lo;
+  if (int rc = resolve_lin("rows_reduce_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
     return fail(DIR_EINVAL, "rows_reduce_update: K must be one of 4, 8, 16, 32, 64");
   if (row_stride < K || (row_stride & 3) || gbuf_stride < K + 1 || (gbuf_stride & 3))
@@ -1041,7 +1088,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device, lo};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }

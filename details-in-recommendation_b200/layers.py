@@ -23,7 +23,34 @@ from ._lib import check, ptr
 
 _COMBINERS = ("sum", "mean", "sqrtn")
 _OPTIMIZERS = {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD}
+_LINEAR_OPTIMIZERS = dict(_OPTIMIZERS, ftrl=_lib.OPT_FTRL)
 _K_OK = (4, 8, 16, 32, 64)
+
+
+def linear_opt_struct(layer):
+    """The dir_linear_opt the C ABI takes (None: the linear weights follow the tables' optimizer)."""
+    if layer.linear_optimizer is None:
+        return None
+    z = layer.lin_z.data_ptr() if layer.lin_z is not None else None
+    return _lib.ctypes.byref(_lib.LinearOpt(_LINEAR_OPTIMIZERS[layer.linear_optimizer], layer.linear_lr,
+                                            layer.l1, layer.l2, z))
+
+
+def resolve_linear_optimizer(optimizer, lr, linear_optimizer, linear_lr, l1, l2):
+    """-> (linear_optimizer or None, linear_lr, needs_accumulator, needs_z).  None = same rule and rate as the
+    tables (one optimizer over both scopes); the reference's DeepFM default is 'Ftrl' for the linear scope and
+    'Adagrad' for the rest (models/DeepFM/deepFM.py:58-61)."""
+    if linear_optimizer is not None:
+        linear_optimizer = linear_optimizer.lower()
+        if linear_optimizer not in _LINEAR_OPTIMIZERS:
+            raise ValueError("linear_optimizer must be one of %r" % (sorted(_LINEAR_OPTIMIZERS),))
+        if l1 < 0 or l2 < 0:
+            raise ValueError("l1 / l2 regularization strengths must be >= 0")
+    elif linear_lr is not None:
+        linear_optimizer = optimizer
+    eff = linear_optimizer or optimizer
+    return (linear_optimizer, float(lr if linear_lr is None else linear_lr), eff in ("adagrad", "ftrl"),
+            eff == "ftrl")
 
 
 def _stream():
@@ -148,7 +175,10 @@ class EmbeddingFM(torch.nn.Module):
                  rows_per_field: Union[int, Sequence[int]], optimizer: str = "adagrad",
                  lr: float = 0.01, initial_accumulator_value: float = 0.1,
                  combiner: str = "sum", first_order: bool = True, emit_embeddings: bool = True,
-                 check_bounds: bool = False, lin_interleaved: Optional[bool] = None, device="cuda"):
+                 check_bounds: bool = False, lin_interleaved: Optional[bool] = None,
+                 linear_optimizer: Optional[str] = None, linear_lr: Optional[float] = None,
+                 l1_regularization_strength: float = 0.0, l2_regularization_strength: float = 0.0,
+                 device="cuda"):
         super().__init__()
         if lin_interleaved is None:
             lin_interleaved = os.environ.get("DIR_B200_LIN_INTERLEAVED", "0") == "1"
@@ -156,8 +186,12 @@ class EmbeddingFM(torch.nn.Module):
             raise ValueError("empty columns.")                      # deepFM.py:104-105
         if embedding_size not in _K_OK:
             raise ValueError("embedding_size must be one of %r" % (_K_OK,))
+        optimizer = optimizer.lower()
         if optimizer not in _OPTIMIZERS:
             raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
+        self.linear_optimizer, self.linear_lr, lin_needs_acc, lin_needs_z = resolve_linear_optimizer(
+            optimizer, lr, linear_optimizer, linear_lr, self.l1, self.l2)
         if combiner not in _COMBINERS:
             raise ValueError("combiner must be one of %r" % (_COMBINERS,))
         if isinstance(rows_per_field, int):                         # global ids: one shared table
@@ -180,6 +214,8 @@ class EmbeddingFM(torch.nn.Module):
         K = embedding_size
         adagrad = optimizer == "adagrad"
         self.row_stride = 2 * K if adagrad else K
+        if self.linear_optimizer is not None:
+            lin_interleaved = False                 # the interleaved (w, accumulator) pair is the one-optimizer layout
         self.lin_stride = 2 if (adagrad and lin_interleaved) else 1
         dev = torch.device(device)
         self.register_buffer("field_offset", torch.tensor(offsets, dtype=torch.int64, device=dev))
@@ -188,7 +224,9 @@ class EmbeddingFM(torch.nn.Module):
         self.register_buffer("rows", torch.empty((n_rows, self.row_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_rows", torch.zeros((n_rows, self.lin_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_acc", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)
-                             if (adagrad and not lin_interleaved) else None)
+                             if (lin_needs_acc and not (adagrad and lin_interleaved)) else None)
+        self.register_buffer("lin_z", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)    # Ftrl 'linear' slot
+                             if lin_needs_z else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
         # Field plan: a field whose table has ONE row (a numeric feature scaled by feature_value) needs no
         # sort -- every sample hits the same row -- so only the other fields' lookups are sorted.
@@ -210,7 +248,8 @@ class EmbeddingFM(torch.nn.Module):
             torch.nn.init.trunc_normal_(self.table, 0.0, 1.0 / math.sqrt(K), -2.0 / math.sqrt(K), 2.0 / math.sqrt(K))
             if adagrad:
                 self.accum.fill_(initial_accumulator_value)
-                self.w1_accum.fill_(initial_accumulator_value)
+            if self.w1_accum is not None:
+                self.w1_accum.fill_(initial_accumulator_value)     # Adagrad and Ftrl both start at 0.1 in TF
 
     # views into the interleaved storage
     @property
@@ -227,9 +266,9 @@ class EmbeddingFM(torch.nn.Module):
 
     @property
     def w1_accum(self):
-        if self.optimizer != "adagrad":
-            return None
-        return self.lin_rows[:, 1] if self.lin_acc is None else self.lin_acc[:, 0]
+        if self.lin_acc is not None:
+            return self.lin_acc[:, 0]
+        return self.lin_rows[:, 1] if self.lin_stride == 2 else None
 
     @torch.no_grad()
     def load_tables(self, table=None, w1=None, accum=None, w1_accum=None):
@@ -324,11 +363,12 @@ class EmbeddingFM(torch.nn.Module):
         check(L.dir_embed_bwd_reduce_update(
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
             ptr(self.w1) if self.first_order else None,
-            ptr(self.w1_accum) if (adagrad and self.first_order) else None, self.lin_stride,
+            ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
             ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
             ptr(u), B, F, K, self.n_rows, ptr(self.sorted_fields), self.n_sorted_fields,
             ptr(self.onerow_fields), self.n_onerow_fields,
-            _OPTIMIZERS[self.optimizer], self.lr, ptr(ws), ws.numel(), ptr(self.last_n_unique),
+            _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self), ptr(ws), ws.numel(),
+            ptr(self.last_n_unique),
             _stream()), "dir_embed_bwd_reduce_update")
 
 

@@ -24,7 +24,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, ptr
-from .layers import _K_OK, _OPTIMIZERS, _Workspace, _need_cuda, _stream
+from .layers import (_K_OK, _OPTIMIZERS, _Workspace, _need_cuda, _stream, linear_opt_struct,
+                     resolve_linear_optimizer)
 
 
 class ShardPlan:
@@ -303,8 +304,9 @@ class _ShardedFunction(torch.autograd.Function):
                 check(L.dir_rows_reduce_update(
                     ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
                     ptr(layer.w1) if layer.first_order else None,
-                    ptr(layer.w1_accum) if (adagrad and layer.first_order) else None, layer.lin_stride,
-                    ptr(grecv), pad, Rn, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr, n_dev,
+                    ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride,
+                    ptr(grecv), pad, Rn, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
+                    linear_opt_struct(layer), n_dev,
                     ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
                 tr.mark("bwd.owner_update")
             else:
@@ -326,14 +328,20 @@ class ShardedEmbeddingFM(torch.nn.Module):
     def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
                  optimizer: str = "adagrad", lr: float = 0.01, initial_accumulator_value: float = 0.1,
                  first_order: bool = True, emit_embeddings: bool = True, check_bounds: bool = False,
-                 process_group=None, max_batch: int = 65536, device="cuda"):
+                 process_group=None, max_batch: int = 65536, linear_optimizer: Optional[str] = None,
+                 linear_lr: Optional[float] = None, l1_regularization_strength: float = 0.0,
+                 l2_regularization_strength: float = 0.0, device="cuda"):
         super().__init__()
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
         if embedding_size not in _K_OK:
             raise ValueError("embedding_size must be one of %r" % (_K_OK,))
+        optimizer = optimizer.lower()
         if optimizer not in _OPTIMIZERS:
             raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
+        self.linear_optimizer, self.linear_lr, lin_needs_acc, lin_needs_z = resolve_linear_optimizer(
+            optimizer, lr, linear_optimizer, linear_lr, self.l1, self.l2)
         rows = [int(r) for r in rows_per_field]
         if len(rows) != field_size:
             raise ValueError("rows_per_field must have field_size entries")
@@ -357,7 +365,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.register_buffer("zero_offset", torch.zeros(field_size, dtype=torch.int64, device=dev))
         self.register_buffer("rows", torch.empty((cap, self.row_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_rows", torch.zeros((cap, 1), dtype=torch.float32, device=dev))
-        self.register_buffer("lin_acc", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if adagrad else None)
+        self.register_buffer("lin_acc", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if lin_needs_acc else None)
+        self.register_buffer("lin_z", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if lin_needs_z else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
@@ -399,6 +408,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
             torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)
             if adagrad:
                 self.accum.fill_(initial_accumulator_value)
+            if self.lin_acc is not None:
                 self.lin_acc.fill_(initial_accumulator_value)
 
     @property
@@ -415,7 +425,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
 
     @property
     def w1_accum(self):
-        return self.lin_acc[:, 0] if self.optimizer == "adagrad" else None
+        return self.lin_acc[:, 0] if self.lin_acc is not None else None
 
     @torch.no_grad()
     def load_tables(self, table=None, w1=None):

@@ -38,7 +38,24 @@ extern "C" {
 #define DIR_OPT_SGD 0     /* T[r] -= lr*g                         (models/LFM/Biased LFM/train.py:44) */
 #define DIR_OPT_ADAGRAD 1 /* acc[r] += g*g; T[r] -= lr*g/sqrt(acc[r])  (deepFM.py:61 'Adagrad')    */
 
+#define DIR_OPT_FTRL 2    /* linear weights only: [TF] SparseApplyFtrl (deepFM.py:58 'Ftrl')         */
+
 typedef void* dir_stream_t; /* cudaStream_t */
+
+/* Optimizer of the linear scope (first-order weights), which the reference trains separately from
+ * the embedding / DNN scope: linear_optimizer='Ftrl' vs dnn_optimizer='Adagrad'
+ * (models/DeepFM/deepFM.py:58-61, 230-241).  A HOST struct; NULL where it is accepted means "the
+ * tables' optimizer and learning rate".  Ftrl is tf.train.FtrlOptimizer with its defaults
+ * learning_rate_power = -0.5, l2_shrinkage = 0, applied to the de-duplicated gradient g of a weight w:
+ *     n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma * w
+ *     w  = |z| > l1 ? (sign(z) * l1 - z) / (sqrt(n') / lr + 2 * l2) : 0
+ * n is `lin_accum` (initial_accumulator_value 0.1), z the 'linear' slot (zeros). */
+typedef struct dir_linear_opt {
+  int optimizer; /* DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_FTRL */
+  float lr;
+  float l1, l2;  /* Ftrl l1 / l2_regularization_strength */
+  float* z;      /* DEVICE: Ftrl 'linear' slot, lin_stride floats apart like lin (NULL otherwise) */
+} dir_linear_opt;
 
 int dir_version(void);
 const char* dir_last_error(void);
@@ -96,7 +113,8 @@ int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, i
  *   onerow_fields / n_onerow (<= 64): fields whose table has ONE row (a numeric feature scaled by
  *   feature_value).  Every sample hits the same row, so these are left out of the sort and reduced
  *   as a column sum over the batch (fixed order); they need feature_index / field_offset.
- *   accum / lin_accum: Adagrad accumulators with the same strides as table / lin (NULL for SGD).
+ *   accum / lin_accum: accumulators with the same strides as table / lin (NULL for SGD).
+ *   linear_opt (host, may be NULL): the linear scope's own optimizer, see dir_linear_opt.
  *   lin == NULL skips the first-order update.  u == NULL means no upstream embedding gradient.
  *   n_unique_out (device int64, may be NULL) receives the number of distinct rows updated.
  */
@@ -115,7 +133,8 @@ int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, 
                                 const float* g_first, const float* g_fm, const float* S,
                                 const float* u, int64_t B, int F, int K, int64_t n_rows,
                                 const int32_t* field_sel, int n_sel, const int32_t* onerow_fields,
-                                int n_onerow, int optimizer, float lr, void* workspace,
+                                int n_onerow, int optimizer, float lr,
+                                const dir_linear_opt* linear_opt, void* workspace,
                                 size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
 /* Where step 1 left the sorted (row, position) pairs inside its workspace (read-only views). */
@@ -205,8 +224,9 @@ int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stride, const f
 int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                            float* lin_accum, int64_t lin_stride, const float* gbuf,
                            int64_t gbuf_stride, int64_t n, int K, int64_t n_rows, int optimizer,
-                           float lr, const int64_t* n_device, void* workspace,
-                           size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
+                           float lr, const dir_linear_opt* linear_opt, const int64_t* n_device,
+                           void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
+                           dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Column feed -> [B,F] inputs.  The reference's input_fn hands the graph one tensor per column --

@@ -174,6 +174,23 @@ def sparse_adagrad(var, accum, rows, grad, lr):
     var[rows] = var[rows] - dt(lr) * grad / np.sqrt(a)
 
 
+def sparse_ftrl(var, accum, linear, rows, grad, lr, l1=0.0, l2=0.0):
+    """[TF] SparseApplyFtrl after dedupe, tf.train.FtrlOptimizer defaults learning_rate_power = -0.5,
+    l2_shrinkage = 0 (linear_optimizer='Ftrl', models/DeepFM/deepFM.py:58, 236-241):
+        n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma*w
+        w  = |z| > l1 ? (sign(z)*l1 - z) / (sqrt(n')/lr + 2*l2) : 0
+    accum starts at initial_accumulator_value = 0.1, linear at 0.  In place; `rows` unique."""
+    dt = var.dtype.type
+    n, w = accum[rows], var[rows]
+    nn = n + grad * grad
+    sigma = (np.sqrt(nn) - np.sqrt(n)) / dt(lr)
+    z = linear[rows] + grad - sigma * w
+    quad = np.sqrt(nn) / dt(lr) + dt(2.0) * dt(l2)
+    var[rows] = np.where(np.abs(z) > dt(l1), (np.sign(z) * dt(l1) - z) / quad, dt(0))
+    accum[rows] = nn
+    linear[rows] = z
+
+
 def sparse_sgd(var, rows, grad, lr):
     """[TF] ScatterSub of the de-duplicated IndexedSlices: var[r] -= lr*g."""
     var[rows] = var[rows] - var.dtype.type(lr) * grad

@@ -135,12 +135,12 @@ def _rank_main(rank, world, port, out, exchange_mode):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange_mode", ["peer", "nccl"])
-def test_world2_nccl_matches_oracle(pkg, cuda, exchange_mode):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+def test_multi_rank_nccl_matches_oracle(pkg, cuda, exchange_mode, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
@@ -150,4 +150,4 @@ def test_world2_nccl_matches_oracle(pkg, cuda, exchange_mode):
     res = [out.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res

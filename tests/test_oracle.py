@@ -190,3 +190,33 @@ def test_step_fp32_close_to_fp64():
         outs[dt] = (O.deepfm_layer_step(t, acc, w, acc1, 0.0, off, idx, val.astype(dt), labels, 0.05, dtype=dt), t)
     np.testing.assert_allclose(outs[np.float32][0]["logits"], outs[np.float64][0]["logits"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(outs[np.float32][1], outs[np.float64][1], rtol=1e-4, atol=1e-5)
+
+
+def test_kat7_ftrl_closed_forms():
+    """KAT-7: sparse Ftrl (the linear scope's default optimizer, deepFM.py:58).
+    (a) first step from (n, z) = (0.1, 0), l1 = l2 = 0:  w' = w (1 - sqrt(0.1)/sqrt(n')) - lr g / sqrt(n')
+    (b) with l1 = l2 = 0 Ftrl-proximal keeps z = sum_t (g_t - sigma_t w_t) and w = -z lr / sqrt(n)
+    (c) |z| <= l1 snaps the weight to exactly 0; rows not listed are untouched."""
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal(12)
+    n, z = np.full(12, 0.1), np.zeros(12)
+    rows = np.array([1, 4, 5, 9])
+    g = rng.standard_normal(4)
+    w0 = w.copy()
+    O.sparse_ftrl(w, n, z, rows, g, 0.2)
+    nn = 0.1 + g * g
+    assert np.allclose(w[rows], w0[rows] * (1 - np.sqrt(0.1) / np.sqrt(nn)) - 0.2 * g / np.sqrt(nn), rtol=1e-13)
+    assert np.allclose(n[rows], nn)
+    untouched = np.setdiff1d(np.arange(12), rows)
+    assert np.array_equal(w[untouched], w0[untouched]) and np.array_equal(n[untouched], np.full(8, 0.1))
+    g2 = rng.standard_normal(4)
+    O.sparse_ftrl(w, n, z, rows, g2, 0.2)
+    assert np.allclose(w[rows], -z[rows] * 0.2 / np.sqrt(n[rows]), rtol=1e-13)
+    # l1 large enough: exact zeros
+    w3, n3, z3 = w0.copy(), np.full(12, 0.1), np.zeros(12)
+    O.sparse_ftrl(w3, n3, z3, rows, g * 1e-3, 0.2, l1=10.0)
+    assert np.array_equal(w3[rows], np.zeros(4))
+    # l2 only shrinks: same sign, smaller magnitude than the unregularised step
+    w4, n4, z4 = w0.copy(), np.full(12, 0.1), np.zeros(12)
+    O.sparse_ftrl(w4, n4, z4, rows, g, 0.2, l2=0.5)
+    assert np.all(np.abs(w4[rows]) < np.abs(w[rows] * 0 + (w0[rows] * (1 - np.sqrt(0.1) / np.sqrt(nn)) - 0.2 * g / np.sqrt(nn))))
