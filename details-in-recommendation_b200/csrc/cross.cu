@@ -89,18 +89,43 @@ __device__ __forceinline__ void cross_constants(const float* __restrict__ wg,
   __syncthreads();
 }
 
+// w[L][d] -> shared memory as [L][DP], DP = 32 lanes * E columns, zero beyond d: the per-layer loads
+// become unpredicated LDS.128 at lane * 16 + constant offsets (the global loads cost ~7 issue slots each
+// in address arithmetic, predicates and selects: profiles/r01_cross_v4_ncu.txt).  Caller syncs.
+template <int DP>
+__device__ __forceinline__ void stage_w(const float* __restrict__ wg, int d, int L, float* s_w) {
+  for (int t = threadIdx.x; t < L * DP; t += blockDim.x) {
+    const int l = t / DP, c = t - l * DP;
+    s_w[t] = c < d ? __ldg(wg + l * d + c) : 0.f;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> lds_pack(const float* p) {
+  Pack<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+
 // ------------------------------------------------------------------------------ forward
 // One warp per PAIR of samples (the w_l loads are shared by the pair), persistent grid.
 // pg [B,L] (nullable) receives p_l = x0 . w_l for the backward.
-template <int VEC, int NPL>
+template <int VEC, int NPL, bool WSMEM>
 __global__ void __launch_bounds__(kCrossWarps * 32)
 cross_fwd_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
                  const float* __restrict__ bg, int64_t B, int d, int L, float* __restrict__ xLg,
                  float* __restrict__ pg) {
   constexpr int E = VEC * NPL;
+  constexpr int DP = E * 32;
   __shared__ float s_beta[1024];
   __shared__ float s_q[32];
   __shared__ float s_red[kCrossWarps];
+  extern __shared__ __align__(16) float s_w[];  // [L][DP] when WSMEM
+  if (WSMEM) stage_w<DP>(wg, d, L, s_w);
   cross_constants(wg, bg, d, L, s_beta, s_q, s_red);
   const int lane = threadIdx.x & 31;
   const float q_mine = lane < L ? s_q[lane] : 0.f;
@@ -133,14 +158,19 @@ cross_fwd_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
     float ca = 1.f, cb = 1.f;  // c_l = 1 + sum_{j<l} s_j
     for (int l = 0; l < L; ++l) {
       float da = 0.f, db = 0.f;
+      const float* wl = s_w + l * DP + lane * VEC;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int c = (i * 32 + lane) * VEC;
         Pack<VEC> pw{};
-        if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
+        if (WSMEM) {
+          pw = lds_pack<VEC>(wl + i * 32 * VEC);
+        } else if (c < d) {
+          pw = ld_pack<VEC>(wg + l * d + c, false);
+        }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-          const float wv = (c < d) ? pw.v[e] : 0.f;
+          const float wv = (WSMEM || c < d) ? pw.v[e] : 0.f;
           da = fmaf(xa[i * VEC + e], wv, da);
           db = fmaf(xb[i * VEC + e], wv, db);
         }
@@ -456,8 +486,11 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
   float* sD = als + kTS * 8;           // [kCrossWarps][32]
   float* s_q = sD + kCrossWarps * 32;  // [32]
   float* s_red = s_q + 32;             // [kCrossWarps]
+  float* s_w = s_red + kCrossWarps;    // [L][DP] zero-padded copy of w
+  constexpr int DP = E * 32;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
+  stage_w<DP>(wg, d, L, s_w);
   cross_constants(wg, bg, d, L, nullptr, s_q, s_red);
   const float q_mine = lane < L ? s_q[lane] : 0.f;
   float acc[CI][8], accdy[CI];
@@ -514,13 +547,12 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
       } else {
         for (int l = 0; l < L; ++l) {
           float dot = 0.f;
+          const float* wl = s_w + l * DP + lane * VEC;
 #pragma unroll
           for (int i = 0; i < NPL; ++i) {
-            const int c = (i * 32 + lane) * VEC;
-            Pack<VEC> pw{};
-            if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
+            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) dot = fmaf(x0[i * VEC + e], (c < d) ? pw.v[e] : 0.f, dot);
+            for (int e = 0; e < VEC; ++e) dot = fmaf(x0[i * VEC + e], pw.v[e], dot);
           }
           dot = warp_sum(dot);
           if (lane == l) p_mine = dot;
@@ -556,18 +588,16 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
       const float cL = cv[8];
 #pragma unroll
       for (int e = 0; e < E; ++e) dx[e] *= cL;
-      for (int l = 0; l < L; ++l) {
-        float alv = al[0];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) alv = (l == j) ? al[j] : alv;
+      for (int l = 0; l < 8; ++l) {
+        if (l < L) {  // warp-uniform
+          const float* wl = s_w + l * DP + lane * VEC;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int c = (i * 32 + lane) * VEC;
-          Pack<VEC> pw{};
-          if (c < d) pw = ld_pack<VEC>(wg + l * d + c, false);
+          for (int i = 0; i < NPL; ++i) {
+            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            dx[i * VEC + e] = fmaf(alv, (c < d) ? pw.v[e] : 0.f, dx[i * VEC + e]);
+            for (int e = 0; e < VEC; ++e) dx[i * VEC + e] = fmaf(al[l], pw.v[e], dx[i * VEC + e]);
+          }
         }
       }
       if (live) {
@@ -580,15 +610,15 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
     }
     __syncthreads();
     // ---- phase B: thread = column, samples of the tile in order
-#pragma unroll
-    for (int ci = 0; ci < CI; ++ci) {
-      const int c = ci * 256 + threadIdx.x;
-      if (c < d) {
 #pragma unroll 4
-        for (int tb = 0; tb < kTS; ++tb) {
+    for (int tb = 0; tb < kTS; ++tb) {
+      const float4 a0 = *reinterpret_cast<const float4*>(als + tb * 8);  // one broadcast load per sample
+      const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const int c = ci * 256 + threadIdx.x;
+        if (c < d) {
           const float xv = x0s[tb * d + c];
-          const float4 a0 = *reinterpret_cast<const float4*>(als + tb * 8);
-          const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
           acc[ci][0] = fmaf(a0.x, xv, acc[ci][0]);
           acc[ci][1] = fmaf(a0.y, xv, acc[ci][1]);
           acc[ci][2] = fmaf(a0.z, xv, acc[ci][2]);
@@ -741,9 +771,21 @@ extern "C" int dir_cross_fwd(const float* x0, const float* cross_w, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // one warp per pair of samples; persistent beyond 4 CTAs per SM (each CTA recomputes beta_L, q_l)
   const int64_t want = (B + 2 * kCrossWarps - 1) / (2 * kCrossWarps);
-  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 4 ? want : (int64_t)kSMs * 4);
-#define DIR_FWD(V, N) \
-  cross_fwd_kernel<V, N><<<grid, kCrossWarps * 32, 0, st>>>(x0, cross_w, cross_b, B, d, L, xL, s)
+  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 2 ? want : (int64_t)kSMs * 2);
+  // w staged in shared memory when it fits beside two resident CTAs per SM, else read through L1
+#define DIR_FWD(V, N)                                                                               \
+  {                                                                                                 \
+    const size_t wbytes = (size_t)L * (V * N * 32) * 4;                                             \
+    if (wbytes <= 64 * 1024) {                                                                      \
+      cudaFuncSetAttribute(cross_fwd_kernel<V, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)wbytes);                                                            \
+      cross_fwd_kernel<V, N, true><<<grid, kCrossWarps * 32, wbytes, st>>>(x0, cross_w, cross_b, B, d, \
+                                                                           L, xL, s);               \
+    } else {                                                                                        \
+      cross_fwd_kernel<V, N, false><<<grid, kCrossWarps * 32, 0, st>>>(x0, cross_w, cross_b, B, d, L, \
+                                                                       xL, s);                      \
+    }                                                                                               \
+  }
   DIR_CROSS_DISPATCH(DIR_FWD)
 #undef DIR_FWD
   return launched("cross_fwd");
@@ -776,9 +818,10 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
   if (L <= 8) {
-    const size_t smemf = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps) * 4;
+    const size_t smem0 = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps) * 4;
 #define DIR_BWDF(V, N)                                                                          \
   {                                                                                             \
+    const size_t smemf = smem0 + (size_t)L * (V * N * 32) * 4;                                  \
     cudaFuncSetAttribute(cross_bwd_fused_kernel<V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                          (int)smemf);                                                           \
     cross_bwd_fused_kernel<V, N><<<w.G1, kCrossWarps * 32, smemf, st>>>(                        \
