@@ -94,6 +94,22 @@ def exchange_into(out: torch.Tensor, payload: torch.Tensor, send_splits, recv_sp
     return view
 
 
+def peer_offsets(M: torch.Tensor, me: int):
+    """Where the segments of the peer-memory exchange start, from everybody's counts.
+
+    M[q, o] = distinct rows requester q wants from owner o (int64 [G, G], the same on every rank).
+      recv_off[G+1]   owner `me`: its answer list is grouped by requester; group q starts at recv_off[q]
+      fwd_dst_off[G]  owner `me` -> requester q: q's row buffer is grouped by owner, `me`'s group starts here
+      bwd_dst_off[G]  requester `me` -> owner o: o's gradient buffer is grouped by requester (= the order of
+                      its answer list), `me`'s group starts here
+    """
+    recv_counts = M[:, me]
+    recv_off = torch.cat([torch.zeros(1, dtype=M.dtype, device=M.device), torch.cumsum(recv_counts, 0)])
+    fwd_dst_off = (torch.cumsum(M, 1) - M)[:, me].contiguous()
+    bwd_dst_off = (torch.cumsum(M, 0) - M)[me, :].contiguous()
+    return recv_off, fwd_dst_off, bwd_dst_off
+
+
 class StageTrace:
     """Optional per-stage CUDA-event timing of the sharded step (DIR_B200_TRACE=1): mark(name) closes
     the stage that just ran; report() averages over the steps seen since the last report."""
@@ -520,10 +536,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 dist.all_gather_into_tensor(M, send_counts.contiguous(), group=self.side_group)
                 me = self.plan.rank
                 recv_counts = M[:, me].contiguous()
+                recv_off, fwd_dst_off, bwd_dst_off = peer_offsets(M, me)
                 # written in place: a captured step reads these at fixed addresses
-                h.recv_off[1:].copy_(torch.cumsum(recv_counts, 0))
-                h.fwd_dst_off.copy_((torch.cumsum(M, 1) - M)[:, me])   # my segment inside q's row buffer
-                h.bwd_dst_off.copy_((torch.cumsum(M, 0) - M)[me, :])   # my segment inside o's grad buffer
+                h.recv_off.copy_(recv_off)
+                h.fwd_dst_off.copy_(fwd_dst_off)
+                h.bwd_dst_off.copy_(bwd_dst_off)
             else:
                 recv_counts = exchange_counts(send_counts, self.side_group)
             both = torch.stack([send_counts, recv_counts]).cpu()

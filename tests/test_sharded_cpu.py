@@ -51,6 +51,26 @@ def _worker(rank, world, port, out):
         ss, rs = send_counts.tolist(), recv_counts.tolist()
         recv_ids = exchange((ukeys % plan.cap).to(torch.int32), ss, rs)
         assert recv_ids.numel() == 0 or int(recv_ids.max()) < plan.n_local
+        # the fixed-address variant used by the static (CUDA-graph) mode lands the same ids
+        from dir_b200.sharded import exchange_into, peer_offsets
+        landing = torch.full((N,), -1, dtype=torch.int32)
+        view = exchange_into(landing, (ukeys % plan.cap).to(torch.int32), ss, rs)
+        assert torch.equal(view, recv_ids) and view.data_ptr() == landing.data_ptr()
+        with pytest.raises(ValueError):
+            exchange_into(torch.empty(0, dtype=torch.int32), (ukeys % plan.cap).to(torch.int32), ss, rs)
+        # peer-memory segment offsets from everybody's counts: the segments tile each buffer exactly
+        rows_m = [torch.empty_like(send_counts) for _ in range(world)]
+        dist.all_gather(rows_m, send_counts)
+        M = torch.stack(rows_m)                               # M[q, o]
+        recv_off, fwd_dst_off, bwd_dst_off = peer_offsets(M, rank)
+        assert recv_off.tolist() == [0] + torch.cumsum(recv_counts, 0).tolist()
+        offs = [peer_offsets(M, r) for r in range(world)]
+        for q in range(world):                                # requester q's row buffer, grouped by owner
+            starts = [int(offs[o][1][q]) for o in range(world)]
+            assert starts == [int(M[q, :o].sum()) for o in range(world)]
+        for o in range(world):                                # owner o's gradient buffer, grouped by requester
+            starts = [int(offs[q][2][o]) for q in range(world)]
+            assert starts == [int(offs[o][0][q]) for q in range(world)]
         answer = local_table[recv_ids.long()]                 # stand-in for dir_rows_gather
         ubuf = exchange(answer, rs, ss)
         e = ubuf[inv].reshape(B, len(rows), K).numpy()
