@@ -54,6 +54,13 @@ SIGNATURES = {
     "dir_rows_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                        c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dir_embed_bag_fm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dir_embed_bag_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_float, c_void_p,
+                                                c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_expand_features": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "dir_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

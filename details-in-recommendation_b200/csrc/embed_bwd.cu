@@ -190,6 +190,10 @@ struct BwdArgs {
   // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
   const int64_t* n_dev;
   LinOpt lo;
+  // kModeBag (multi-hot bags, embed_bag.cu): sorted payload = entry index j
+  const uint32_t* entry_slot;  // [nnz] slot b*F+f of entry j
+  const float* entry_x;        // [nnz] effective scale w_j / norm(bag)
+  const float* emb;            // [B*F, K] combined embeddings e_s saved by the forward
 };
 
 __device__ __forceinline__ int64_t entries(const BwdArgs& a) {
@@ -223,6 +227,7 @@ __device__ __forceinline__ void emit_store(const BwdArgs& a, uint32_t u, int sub
 constexpr int kModeLocal = 0;  // gradients formed from g, S, u, row; the row is updated in place
 constexpr int kModeEmit = 1;   // requester side of a sharded table: per-row sums go to `emit`
 constexpr int kModeGiven = 2;  // owner side: per-lookup gradients arrive in `gbuf`; update in place
+constexpr int kModeBag = 3;    // multi-hot bags: entry j of slot s contributes x_j (g_fm (S - e_s) + u_s)
 
 // Row update with the de-duplicated gradient: a = acc + g*g; T = T - (lr*g) * rsqrt(a)
 // ([TF] SparseApplyAdagrad, no epsilon; Eigen evaluates it as lr * g * rsqrt(a) as well).  rsqrtf
@@ -377,14 +382,25 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
     last_key = __shfl_sync(FULL, key, 31);
     heads += __popc(__ballot_sync(FULL, valid && key != keyp));
     const unsigned cont = __ballot_sync(FULL, valid && keyn == key);  // run goes on after this lookup
+    float v = 1.f, g2 = 0.f, d1l = 0.f, wraw = 1.f;
+    if (MODE == kModeBag) {  // payload = entry index: fetch its slot, scale and raw weight; pos becomes the slot
+      const uint32_t j = pos;
+      pos = valid ? __ldg(a.entry_slot + j) : 0u;
+      if (valid) {
+        v = __ldg(a.entry_x + j);
+        if (a.val) wraw = __ldg(a.val + j);
+      }
+    }
     // sample of this lookup: entry / (fields per sample in the sorted list)
     const uint32_t b = (uint32_t)(((uint64_t)pos * a.div_magic) >> a.div_shift);
     if (a.field_sel != nullptr)  // compact list of selected fields -> position in the [B, F] inputs
       pos = b * (uint32_t)a.F + (uint32_t)__ldg(a.field_sel + (pos - b * (uint32_t)a.n_sel));
-    float v = 1.f, g2 = 0.f, d1l = 0.f;
     if (valid) {
       if (MODE == kModeGiven) {
         d1l = __ldg(a.gbuf + (int64_t)pos * a.gbuf_stride + K);
+      } else if (MODE == kModeBag) {
+        if (a.g_first) d1l = __fmul_rn(__ldg(a.g_first + b), wraw);   // first order combines with 'sum'
+        g2 = __ldg(a.g_fm + b);
       } else {
         if (a.val) v = __ldg(a.val + pos);
         if (a.g_first) d1l = __ldg(a.g_first + b);
@@ -414,6 +430,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
       int ac[PB];
       float a1[PB], lw[PB], lz[PB];
       float4 Sb[PB], ub[PB], T[PB], A[PB];
+      float4 Rw[MODE == kModeBag ? PB : 1];  // kModeBag: the row itself (T holds the combined e_s)
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int l = (j0 + j) * SLOTS + slot;
@@ -431,12 +448,17 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
           } else {
             if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
             Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
-            // coherent load: this warp may rewrite the row further down
-            T[j] = (tune & 16) ? *(reinterpret_cast<const float4*>(a.table + ro) + sub)
-                               : ld_hint(a.table + ro + sub * 4, pol_row);
+            if (MODE == kModeBag) {
+              T[j] = __ldg(reinterpret_cast<const float4*>(a.emb + (int64_t)p * K) + sub);
+            } else {
+              // coherent load: this warp may rewrite the row further down
+              T[j] = (tune & 16) ? *(reinterpret_cast<const float4*>(a.table + ro) + sub)
+                                 : ld_hint(a.table + ro + sub * 4, pol_row);
+            }
           }
           if (MODE != kModeEmit && (ac[j] & 3) == 1) {
             if (MODE == kModeGiven) T[j] = ld_hint(a.table + ro + sub * 4, pol_row);
+            if (MODE == kModeBag) Rw[j] = ld_hint(a.table + ro + sub * 4, pol_row);
             if (adagrad) A[j] = ld_hint(a.accum + ro + sub * 4, pol_row);
             if (a.lin != nullptr && sub == 0) {
               lw[j] = a.lin[(int64_t)rw[j] * a.lin_stride];
@@ -453,10 +475,12 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
         if (MODE != kModeGiven) {
           // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
           const float x = __shfl_sync(FULL, v, l), gg = __shfl_sync(FULL, g2, l);
-          d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(x, T[j].x))), ub[j].x));
-          d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(x, T[j].y))), ub[j].y));
-          d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(x, T[j].z))), ub[j].z));
-          d.w = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(x, T[j].w))), ub[j].w));
+          // e of this lookup: value * row, or (bags) the combined embedding of its slot
+          const float xe = MODE == kModeBag ? 1.f : x;
+          d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(xe, T[j].x))), ub[j].x));
+          d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(xe, T[j].y))), ub[j].y));
+          d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(xe, T[j].z))), ub[j].z));
+          d.w = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].w, __fmul_rn(xe, T[j].w))), ub[j].w));
         }
         if (k[j] == a.pruned_key) {
           d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -493,7 +517,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
           if (MODE == kModeEmit) {
             emit_store<LPR>(a, rw[j], sub, d, d1);
           } else {
-            apply_loaded(a, rw[j], sub, T[j], A[j], d, lw[j], a1[j], lz[j], d1);
+            apply_loaded(a, rw[j], sub, MODE == kModeBag ? Rw[j] : T[j], A[j], d, lw[j], a1[j], lz[j], d1);
           }
         } else if ((ac[j] & 3) >= 2) {
           const int64_t s = chunk * 2 + ((ac[j] & 3) == 2 ? 0 : 1);
@@ -623,6 +647,8 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
     embed_bwd_reduce_kernel<LPR, kModeEmit><<<rgrid, 256, 0, st>>>(a);
   else if (a.mode == kModeGiven)
     embed_bwd_reduce_kernel<LPR, kModeGiven><<<rgrid, 256, 0, st>>>(a);
+  else if (a.mode == kModeBag)
+    embed_bwd_reduce_kernel<LPR, kModeBag><<<rgrid, 256, 0, st>>>(a);
   else
     embed_bwd_reduce_kernel<LPR, kModeLocal><<<rgrid, 256, 0, st>>>(a);
   constexpr int NG = 256 / LPR;
@@ -994,7 +1020,7 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, lo};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, lo, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -1028,7 +1054,7 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
   BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
             (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0,
-            seg_start, peer_ptrs, dst_row_off, G, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}};
+            seg_start, peer_ptrs, dst_row_off, G, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
   set_div(a, F);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -1088,7 +1114,49 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device, lo};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device, lo, nullptr, nullptr, nullptr};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
+}
+
+/* multi-hot bags: backward + fused update on the sorted (row, entry) list (include/dir_b200.h) */
+extern "C" int dir_embed_bag_bwd_reduce_update(
+    float* table, float* accum, int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
+    const float* bag_weight, const uint32_t* entry_slot, const float* entry_x, int64_t nnz, const float* emb,
+    const float* g_first, const float* g_fm, const float* S, const float* u, int64_t B, int F, int K,
+    int64_t n_rows, int optimizer, float lr, const dir_linear_opt* linear_opt, void* workspace,
+    size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0 || nnz < 0 || nnz >= 0x7fffffffLL || B * F >= 0x7fffffffLL)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: B >= 0, F > 0, 0 <= nnz < 2^31, B*F < 2^31 required");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: unknown optimizer");
+  if (optimizer == DIR_OPT_ADAGRAD && !accum)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: Adagrad needs accum");
+  LinOpt lo;
+  if (int rc = resolve_lin("embed_bag_bwd_reduce_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
+  if (lin && !g_first) return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: lin needs g_first");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: K must be one of 4, 8, 16, 32, 64");
+  if (row_stride < K || (row_stride & 3))
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: row_stride must be >= K, multiple of 4");
+  if (n_rows <= 0 || n_rows >= 0xffffffffLL)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: 0 < n_rows < 2^32-1 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || nnz == 0) {
+    if (n_unique_out) cudaMemsetAsync(n_unique_out, 0, 8, st);
+    return 0;
+  }
+  if (!table || !entry_slot || !entry_x || !emb || !g_fm || !S || !workspace)
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: table, entry_slot, entry_x, emb, g_fm, S, workspace are required");
+  if (!aligned16(table) || !aligned16(accum) || !aligned16(S) || !aligned16(u) || !aligned16(emb))
+    return fail(DIR_EINVAL, "embed_bag_bwd_reduce_update: table, accum, S, u, emb must be 16-byte aligned");
+  BwdWorkspace w = carve(workspace, nnz, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bag_bwd_reduce_update: workspace too small");
+  BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, bag_weight, g_first, g_fm, S,
+            u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, nnz, F,
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeBag, nullptr, nullptr, 0, nullptr, 0,
+            nullptr, nullptr, nullptr, 0, nullptr, lo, entry_slot, entry_x, emb};
+  set_div(a, F);
+  return dispatch_bwd(a, K, n_unique_out, st);
 }

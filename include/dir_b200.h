@@ -229,6 +229,45 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
                            dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-hot / weighted bags: every (sample, field) holds a variable-length list of (id, weight) --
+ * the capability `myself_input_layer` exists for (models/DeepFM/deepFM.py:53, 77, 363-400; the
+ * weighted column of dataset/SequenceTensorFlowDataset/test4.py:50-55, 113-116).  CSR layout:
+ *   bag_offsets [B*F + 1] int64, slot s = b*F + f owns entries bag_offsets[s] .. bag_offsets[s+1]
+ *   bag_index   [nnz] int64 ids local to the slot's field;  bag_weight [nnz] fp32 or NULL (= 1.0)
+ * [TF] _safe_embedding_lookup_sparse: entries with id < 0 or weight <= 0 are pruned, then
+ *   DIR_COMBINER_SUM    e = sum w T[id]
+ *   DIR_COMBINER_MEAN   e = sum w T[id] / sum w        (embedding_column's default)
+ *   DIR_COMBINER_SQRTN  e = sum w T[id] / sqrt(sum w^2)
+ * an empty bag is the zero vector; the first-order term always combines with 'sum'
+ * (linear_model(sparse_combiner='sum'), deepFM.py:255-263).  emb [B,F,K] is required (the backward
+ * reads it); S, first, fm as in dir_embed_fm_fwd.  Per-entry outputs for the backward (all or none):
+ *   sort_keys [nnz]  global row, n_rows when pruned  -> dir_embed_bwd_sort(sort_keys, nnz, n_rows, ...)
+ *   entry_slot [nnz] slot of the entry;  entry_x [nnz] its effective scale w / norm (0 when pruned)
+ * dir_embed_bag_bwd_reduce_update: on the sorted (row, entry) list, per distinct row
+ *     G_r = sum_j x_j (g_fm[b] (S[b] - e_s) + u[s]),   g1_r = sum_j w_j g_first[b]
+ * then the fused update, exactly as dir_embed_bwd_reduce_update (same determinism, same optimizers).
+ */
+#define DIR_COMBINER_SUM 0
+#define DIR_COMBINER_MEAN 1
+#define DIR_COMBINER_SQRTN 2
+int dir_embed_bag_fm_fwd(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
+                         const float* bias, const int64_t* bag_offsets, const int64_t* bag_index,
+                         const float* bag_weight, int64_t nnz, const int64_t* field_offset,
+                         const int64_t* field_rows, int64_t n_rows, int64_t B, int F, int K,
+                         int combiner, float* emb, float* S, float* first, float* fm,
+                         uint32_t* sort_keys, uint32_t* entry_slot, float* entry_x, int* oob_flag,
+                         dir_stream_t stream);
+int dir_embed_bag_bwd_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
+                                    float* lin_accum, int64_t lin_stride, const float* bag_weight,
+                                    const uint32_t* entry_slot, const float* entry_x, int64_t nnz,
+                                    const float* emb, const float* g_first, const float* g_fm,
+                                    const float* S, const float* u, int64_t B, int F, int K,
+                                    int64_t n_rows, int optimizer, float lr,
+                                    const dir_linear_opt* linear_opt, void* workspace,
+                                    size_t workspace_bytes, int64_t* n_unique_out,
+                                    dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Column feed -> [B,F] inputs.  The reference's input_fn hands the graph one tensor per column --
  * ids for categorical columns, floats for numeric ones (models/DeepCrossNetwork/train.py:127-156,
  * columns built at :57-100; DeepFM consumes the same dict, models/DeepFM/deepFM.py:159-177).  The

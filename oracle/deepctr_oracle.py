@@ -225,3 +225,77 @@ def deepfm_layer_step(table, accum, w1, accum1, bias, field_offset, feature_inde
         raise ValueError("optimizer must be 'adagrad' or 'sgd'")
     return dict(first=first, fm=fm, logits=logits, e=e, rows=rows, G=G, g1=g1,
                 dbias=dbias, g=g)
+
+
+# ----------------------------------------------------------------------------
+# multi-hot / weighted bags
+# ----------------------------------------------------------------------------
+def _bag_entries(field_offset, bag_offsets, bag_index, bag_weight, F, dt):
+    """Per entry: slot s = b*F+f, field, global row, weight, keep ([TF] _safe_embedding_lookup_sparse
+    prunes id < 0 and weight <= 0)."""
+    nnz = bag_index.shape[0]
+    n_slots = bag_offsets.shape[0] - 1
+    slot = np.repeat(np.arange(n_slots, dtype=np.int64), np.diff(bag_offsets))
+    field = slot % F
+    w = np.ones(nnz, dtype=dt) if bag_weight is None else bag_weight.astype(dt)
+    keep = (bag_index >= 0) & (w > 0)
+    rows = np.where(keep, bag_index, 0) + np.asarray(field_offset, dtype=np.int64)[field]
+    return slot, rows, w, keep
+
+
+def embedding_bag_lookup(table, w1, bias, field_offset, bag_offsets, bag_index, bag_weight, B, F,
+                         combiner="mean", dtype=np.float32):
+    """myself_input_layer with multi-hot columns (models/DeepFM/deepFM.py:53, 77, 363-400) + the linear
+    model on the same bags (:255-263, sparse_combiner='sum').  [TF] embedding_lookup_sparse:
+    e_s = sum_i w_i T[id_i] / norm, norm = 1 ('sum'), sum w ('mean'), sqrt(sum w^2) ('sqrtn'); entries summed
+    in order; empty bag -> zeros.  -> e[B,F,K], first[B,1], x[nnz] (effective scale w/norm, 0 if pruned)."""
+    dt = np.dtype(dtype).type
+    slot, rows, w, keep = _bag_entries(field_offset, bag_offsets, bag_index, bag_weight, F, dt)
+    K = table.shape[1]
+    wk = np.where(keep, w, dt(0))
+    acc = np.zeros((B * F, K), dtype=dt)
+    np.add.at(acc, slot[keep], wk[keep][:, None] * table[rows[keep]].astype(dt))      # sequential, entry order
+    wsum = np.zeros(B * F, dtype=dt)
+    wsq = np.zeros(B * F, dtype=dt)
+    np.add.at(wsum, slot[keep], wk[keep])
+    np.add.at(wsq, slot[keep], wk[keep] * wk[keep])
+    if combiner == "sum":
+        norm = np.ones(B * F, dtype=dt)
+    elif combiner == "mean":
+        norm = wsum
+    elif combiner == "sqrtn":
+        norm = np.sqrt(wsq)
+    else:
+        raise ValueError("combiner must be 'sum', 'mean' or 'sqrtn'")
+    safe = np.where(wsum > 0, norm, dt(1))
+    e = np.where((wsum > 0)[:, None], acc / safe[:, None], dt(0)).astype(dt)
+    x = np.where(keep, wk / safe[slot], dt(0)).astype(dt)
+    lin = np.zeros(B * F, dtype=dt)
+    np.add.at(lin, slot[keep], wk[keep] * w1[rows[keep]].astype(dt))
+    first = np.zeros(B, dtype=dt)
+    linf = lin.reshape(B, F)
+    for f in range(F):                                       # AddN in column order
+        first = first + linf[:, f]
+    return e.reshape(B, F, K), (first + dt(bias))[:, None], x
+
+
+def embedding_bag_backward(table, field_offset, bag_offsets, bag_index, bag_weight, e, x, g_first, g_fm, u, B, F,
+                           dtype=np.float32):
+    """Backward of the bag lookup + first order + FM (TF autodiff; weights carry no gradient):
+    entry j of slot s=(b,f):  dT[row_j] += x_j * (g_fm[b] (S_b - e_s) + u_s),  dw1[row_j] += w_j * g_first[b].
+    -> (rows[U] sorted unique, G[U,K], g1[U]) with duplicates summed in entry order."""
+    dt = np.dtype(dtype).type
+    slot, rows, w, keep = _bag_entries(field_offset, bag_offsets, bag_index, bag_weight, F, dt)
+    S = np.sum(e, axis=1, dtype=e.dtype)                                     # [B,K]
+    de = g_fm.astype(dt)[:, None, None] * (S[:, None, :] - e)
+    if u is not None:
+        de = de + u.astype(dt)
+    de = de.reshape(B * F, -1)
+    per = x[:, None] * de[slot]                                              # [nnz,K]
+    per1 = g_first.astype(dt)[slot // F] * np.where(keep, w, dt(0))
+    uniq, inv = np.unique(rows[keep], return_inverse=True)
+    G = np.zeros((uniq.shape[0], table.shape[1]), dtype=dt)
+    g1 = np.zeros(uniq.shape[0], dtype=dt)
+    np.add.at(G, inv, per[keep])
+    np.add.at(g1, inv, per1[keep])
+    return uniq, G, g1

@@ -220,3 +220,72 @@ def test_kat7_ftrl_closed_forms():
     w4, n4, z4 = w0.copy(), np.full(12, 0.1), np.zeros(12)
     O.sparse_ftrl(w4, n4, z4, rows, g, 0.2, l2=0.5)
     assert np.all(np.abs(w4[rows]) < np.abs(w[rows] * 0 + (w0[rows] * (1 - np.sqrt(0.1) / np.sqrt(nn)) - 0.2 * g / np.sqrt(nn))))
+
+
+def _random_bags(rng, B, rows, max_len=4, weighted=True, prune=True):
+    F = len(rows)
+    lens = rng.integers(0, max_len + 1, size=B * F)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    field = np.repeat(np.arange(B * F) % F, lens)
+    idx = (rng.random(off[-1]) * np.asarray(rows)[field]).astype(np.int64)
+    w = (rng.random(off[-1]) + 0.25).astype(np.float32) if weighted else None
+    if prune and off[-1] >= 8:
+        idx[rng.integers(0, off[-1], size=max(1, off[-1] // 16))] = -1
+        if weighted:
+            w[rng.integers(0, off[-1], size=max(1, off[-1] // 16))] = 0.0
+    return off, idx, w
+
+
+def test_bags_reduce_to_single_lookups_and_match_autograd():
+    """KAT-8: (a) one-entry bags under 'sum' ARE the one-id-per-field path, bit for bit;
+    (b) 'mean' of k equal ids is that row; (c) gradients of all three combiners against torch autograd (fp64)."""
+    import torch
+    rng = np.random.default_rng(9)
+    rows = [7, 1, 30, 4]
+    B, F, K = 12, 4, 4
+    off_f = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64)
+    N = sum(rows)
+    table = rng.standard_normal((N, K)).astype(np.float32)
+    w1 = rng.standard_normal(N).astype(np.float32)
+    # (a)
+    idx = np.stack([rng.integers(0, r, size=B) for r in rows], 1).astype(np.int64)
+    val = (rng.random((B, F)) + 0.5).astype(np.float32)
+    e1, _ = O.embedding_lookup(table, off_f, idx, val)
+    f1 = O.first_order(w1, 0.25, off_f, idx, val)
+    eb, fb, xb = O.embedding_bag_lookup(table, w1, 0.25, off_f, np.arange(B * F + 1, dtype=np.int64), idx.reshape(-1),
+                                        val.reshape(-1), B, F, "sum")
+    assert np.array_equal(eb, e1) and np.array_equal(fb, f1) and np.array_equal(xb, val.reshape(-1))
+    # (b)
+    off = np.arange(0, 3 * B * F + 1, 3, dtype=np.int64)
+    rep = np.repeat(idx.reshape(-1), 3)
+    em, _, xm = O.embedding_bag_lookup(table, w1, 0.0, off_f, off, rep, None, B, F, "mean")
+    assert np.allclose(em, table[idx + off_f[None, :]], rtol=1e-6) and np.allclose(xm, 1 / 3)
+    # (c)
+    off, bidx, bw = _random_bags(rng, B, rows)
+    g_first, g_fm = rng.standard_normal(B), rng.standard_normal(B)
+    u = rng.standard_normal((B, F, K))
+    for comb in ("sum", "mean", "sqrtn"):
+        t64, w64 = table.astype(np.float64), w1.astype(np.float64)
+        e, first, x = O.embedding_bag_lookup(t64, w64, 0.0, off_f, off, bidx, bw, B, F, comb, np.float64)
+        rows_u, G, g1 = O.embedding_bag_backward(t64, off_f, off, bidx, bw, e, x, g_first, g_fm, u, B, F, np.float64)
+        T = torch.tensor(t64, requires_grad=True)
+        W = torch.tensor(w64, requires_grad=True)
+        slot = np.repeat(np.arange(B * F), np.diff(off))
+        keep = (bidx >= 0) & (bw > 0)
+        grow = np.where(keep, bidx, 0) + off_f[slot % F]
+        wt = torch.tensor(np.where(keep, bw, 0.0).astype(np.float64))
+        acc = torch.zeros((B * F, K), dtype=torch.float64).index_add(0, torch.tensor(slot), wt[:, None] * T[torch.tensor(grow)])
+        wsum = torch.zeros(B * F, dtype=torch.float64).index_add(0, torch.tensor(slot), wt)
+        wsq = torch.zeros(B * F, dtype=torch.float64).index_add(0, torch.tensor(slot), wt * wt)
+        norm = {"sum": torch.ones_like(wsum), "mean": wsum, "sqrtn": wsq.sqrt()}[comb]
+        norm = torch.where(wsum > 0, norm, torch.ones_like(norm))
+        et = (acc / norm[:, None]).reshape(B, F, K)
+        assert np.allclose(et.detach().numpy(), e, rtol=1e-12, atol=1e-12)
+        lin = torch.zeros(B * F, dtype=torch.float64).index_add(0, torch.tensor(slot), wt * W[torch.tensor(grow)])
+        fm = 0.5 * ((et.sum(1)) ** 2 - (et ** 2).sum(1)).sum(-1)
+        loss = (lin.reshape(B, F).sum(1) * torch.tensor(g_first)).sum() + (fm * torch.tensor(g_fm)).sum() + (et * torch.tensor(u)).sum()
+        loss.backward()
+        assert np.allclose(T.grad.numpy()[rows_u], G, rtol=1e-10, atol=1e-12)
+        assert np.allclose(W.grad.numpy()[rows_u], g1, rtol=1e-10, atol=1e-12)
+        rest = np.setdiff1d(np.arange(N), rows_u)
+        assert np.all(T.grad.numpy()[rest] == 0)
