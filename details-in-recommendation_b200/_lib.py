@@ -63,6 +63,9 @@ SIGNATURES = {
                                                 c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_expand_features": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
+    "dir_input_layer_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_int64, c_int, c_void_p, c_void_p]),
+    "dir_input_layer_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "dir_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                               c_void_p, c_void_p]),
     "dir_cross_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),

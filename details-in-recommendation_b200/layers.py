@@ -432,3 +432,107 @@ class CrossNetwork(torch.nn.Module):
         if x0.dim() != 2 or x0.shape[1] != self.input_dim:
             raise ValueError("x0 must be [B, input_dim=%d]" % self.input_dim)
         return _CrossFunction.apply(x0.contiguous().float(), self.cross_w, self.cross_b, self)
+
+
+class _InputLayerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, numeric, ind, layer):
+        B = layer._batch(numeric, ind, emb)
+        dev = layer.col_kind.device
+        x0 = torch.empty((B, layer.output_dim), dtype=torch.float32, device=dev)
+        check(_lib.lib().dir_input_layer_fwd(
+            ptr(numeric), layer.n_numeric, ptr(ind), layer.n_indicator, ptr(emb), layer.emb_width,
+            ptr(layer.col_kind), ptr(layer.col_src), ptr(layer.col_arg), B, layer.output_dim, ptr(x0), _stream()),
+            "dir_input_layer_fwd")
+        ctx.layer, ctx.B = layer, B
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        layer, B = ctx.layer, ctx.B
+        if layer.emb_width == 0:
+            return None, None, None, None
+        dx0 = dx0.contiguous().float()
+        u = torch.empty((B, layer.emb_width), dtype=torch.float32, device=dx0.device)
+        check(_lib.lib().dir_input_layer_bwd(ptr(dx0), ptr(layer.emb_col), B, layer.output_dim, layer.emb_width,
+                                             ptr(u), _stream()), "dir_input_layer_bwd")
+        return u, None, None, None
+
+
+class InputLayer(torch.nn.Module):
+    """`tf.feature_column.input_layer(features, feature_columns)` in the reference's own DCN convention
+    (models/DeepCrossNetwork/DeepCrossNetwork.py:126 over the columns of train.py:88-100): all dense columns
+    side by side, **sorted by column name** -- numeric columns pass through 1-wide, indicator columns are one-hot
+    vectors of their id, embedding columns are the K-wide rows of `EmbeddingFM` (census: d = 51).
+
+    columns: [(name, kind, size)], kind 'numeric' (size 1), 'indicator' (size = vocabulary size) or
+    'embedding' (size = K).  Inputs follow the LISTING order of each kind:
+        forward(numeric[B, n_numeric] fp32 | None, indicator_ids[B, n_indicator] int64 | None,
+                embeddings[B, sum K] | None)  ->  x0[B, output_dim]
+    The backward returns the embedding columns' slice of dL/dx0 -- the upstream gradient the fused embedding
+    backward takes; numeric and indicator columns carry no parameters.
+    """
+
+    def __init__(self, columns, device="cuda"):
+        super().__init__()
+        if not columns:
+            raise ValueError("empty columns.")
+        names = [c[0] for c in columns]
+        if len(set(names)) != len(names):
+            raise ValueError("column names must be unique")
+        n_num = n_ind = emb_w = 0
+        src = {}
+        for name, kind, size in columns:
+            size = int(size)
+            if kind == "numeric":
+                if size != 1:
+                    raise ValueError("numeric column %r must have size 1" % name)
+                src[name] = (0, n_num, size)
+                n_num += 1
+            elif kind == "indicator":
+                if size <= 0:
+                    raise ValueError("indicator column %r needs a positive vocabulary size" % name)
+                src[name] = (1, n_ind, size)
+                n_ind += 1
+            elif kind == "embedding":
+                if size <= 0:
+                    raise ValueError("embedding column %r needs a positive dimension" % name)
+                src[name] = (2, emb_w, size)
+                emb_w += size
+            else:
+                raise ValueError("column kind must be 'numeric', 'indicator' or 'embedding', got %r" % (kind,))
+        kind_l, src_l, arg_l, emb_col = [], [], [], [-1] * emb_w
+        for name in sorted(names):                      # [TF] input_layer orders columns by name
+            k, s, size = src[name]
+            for t in range(size):
+                if k == 2:
+                    emb_col[s + t] = len(kind_l)
+                kind_l.append(k)
+                src_l.append(s + t if k == 2 else s)
+                arg_l.append(t if k == 1 else 0)
+        self.n_numeric, self.n_indicator, self.emb_width, self.output_dim = n_num, n_ind, emb_w, len(kind_l)
+        dev = torch.device(device)
+        self.register_buffer("col_kind", torch.tensor(kind_l, dtype=torch.int32, device=dev))
+        self.register_buffer("col_src", torch.tensor(src_l, dtype=torch.int32, device=dev))
+        self.register_buffer("col_arg", torch.tensor(arg_l, dtype=torch.int32, device=dev))
+        self.register_buffer("emb_col", torch.tensor(emb_col or [-1], dtype=torch.int32, device=dev))
+
+    def _batch(self, numeric, ind, emb):
+        sizes = {t.shape[0] for t in (numeric, ind, emb) if t is not None}
+        if len(sizes) != 1:
+            raise ValueError("inputs must share one batch size")
+        return sizes.pop()
+
+    def forward(self, numeric=None, indicator_ids=None, embeddings=None):
+        for t, n, w, dt in ((numeric, "numeric", self.n_numeric, torch.float32),
+                            (indicator_ids, "indicator_ids", self.n_indicator, torch.int64),
+                            (embeddings, "embeddings", self.emb_width, torch.float32)):
+            if w == 0:
+                continue
+            if t is None or t.dim() != 2 or t.shape[1] != w or t.dtype != dt:
+                raise ValueError("%s must be a [B, %d] %s tensor" % (n, w, dt))
+            _need_cuda(t, n)
+        numeric = numeric.contiguous() if self.n_numeric else None
+        indicator_ids = indicator_ids.contiguous() if self.n_indicator else None
+        embeddings = embeddings.contiguous() if self.emb_width else None
+        return _InputLayerFunction.apply(embeddings, numeric, indicator_ids, self)

@@ -284,6 +284,26 @@ int dir_expand_features(const void* sparse_index, int index_bytes, const float* 
                         int64_t* feature_index, float* feature_value, dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * tf.feature_column.input_layer in the reference's own DCN convention
+ * (models/DeepCrossNetwork/DeepCrossNetwork.py:126 over the columns of train.py:88-100): all dense
+ * columns side by side, sorted by column name -- numeric columns 1-wide, indicator columns one-hot,
+ * embedding columns K-wide (the rows dir_embed_fm_fwd gathered).  The host lays the d output columns
+ * out in three int32[d] maps:
+ *   col_kind 0 numeric    col_src = column of numeric[B, n_numeric]
+ *            1 indicator  col_src = column of indicator_ids[B, n_indicator] (int64), col_arg = class:
+ *                         1.0 where the id equals the class, else 0.0 (ids < 0 / out of vocabulary: zeros)
+ *            2 embedding  col_src = component of emb[B, emb_width]
+ * dir_input_layer_bwd returns the embedding columns' slice of dL/dx0 as u[B, emb_width], the upstream
+ * gradient of dir_embed_bwd_reduce_update; emb_col[emb_width] = the x0 column of each component (-1: unused).
+ */
+int dir_input_layer_fwd(const float* numeric, int n_numeric, const int64_t* indicator_ids,
+                        int n_indicator, const float* emb, int emb_width, const int32_t* col_kind,
+                        const int32_t* col_src, const int32_t* col_arg, int64_t B, int d, float* x0,
+                        dir_stream_t stream);
+int dir_input_layer_bwd(const float* dx0, const int32_t* emb_col, int64_t B, int d, int emb_width,
+                        float* u, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DCN cross network, all L layers in one pass.  Replaces _cross_architecture / _cross_op
  * (models/DeepCrossNetwork/DeepCrossNetwork.py:336-367): x_{l+1} = (x0 * (x_l . w_l) + b_l) + x_l.
  *   x0 [B,d], cross_w / cross_b [L,d] (names as DeepCrossNetwork.py:329-332), xL [B,d],

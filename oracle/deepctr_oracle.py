@@ -299,3 +299,35 @@ def embedding_bag_backward(table, field_offset, bag_offsets, bag_index, bag_weig
     np.add.at(G, inv, per[keep])
     np.add.at(g1, inv, per1[keep])
     return uniq, G, g1
+
+
+# ----------------------------------------------------------------------------
+# tf.feature_column.input_layer in the reference's DCN convention
+# ----------------------------------------------------------------------------
+def input_layer(columns, numeric, indicator_ids, emb):
+    """models/DeepCrossNetwork/DeepCrossNetwork.py:126 over the columns of train.py:88-100.
+    columns: [(name, kind, size)]; inputs in the listing order of each kind; output = the dense columns
+    concatenated in NAME order ([TF] input_layer sorts by name): numeric 1-wide, indicator one-hot
+    (id outside [0, size) -> zeros), embedding K-wide.  -> x0[B, d] and the list of (name, start, stop)."""
+    B = next(a.shape[0] for a in (numeric, indicator_ids, emb) if a is not None)
+    pieces, where = {}, {}
+    i_num = i_ind = i_emb = 0
+    for name, kind, size in columns:
+        if kind == "numeric":
+            pieces[name] = numeric[:, i_num:i_num + 1].astype(np.float32)
+            i_num += 1
+        elif kind == "indicator":
+            ids = indicator_ids[:, i_ind]
+            pieces[name] = (ids[:, None] == np.arange(size)[None, :]).astype(np.float32)
+            i_ind += 1
+        elif kind == "embedding":
+            pieces[name] = emb[:, i_emb:i_emb + size].astype(np.float32)
+            i_emb += size
+        else:
+            raise ValueError(kind)
+    out, c = [], 0
+    for name in sorted(pieces):
+        out.append(pieces[name])
+        where[name] = (c, c + pieces[name].shape[1])
+        c += pieces[name].shape[1]
+    return np.concatenate(out, axis=1) if out else np.zeros((B, 0), np.float32), where
