@@ -276,6 +276,72 @@ class EmbeddingFM(torch.nn.Module):
             if src is not None:
                 dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(dst.device))
 
+    # -- checkpoint / warm start (the reference's `warm_start_from`, models/DeepFM/deepFM.py:71, and the
+    #    per-column variables a TF checkpoint of it holds: one `embedding_weights` [N_f, K] and one linear
+    #    `weights` [N_f, 1] per column, deepFM.py:385-390, :258-263).  The concatenated, accumulator-interleaved
+    #    storage is this layer's business; what crosses the boundary is the reference's shape.
+    @torch.no_grad()
+    def export_columns(self, column_names=None, with_slots=False):
+        """-> {name + '/embedding_weights': [N_f, K], name + '/weights': [N_f, 1]} on the CPU, one pair per field
+        (plus '/embedding_weights/Adagrad', '/weights/Adagrad' / '/weights/Ftrl', '/weights/Ftrl_1' with
+        `with_slots`).  column_names defaults to field_0 .. field_{F-1}."""
+        if self.shared_table:
+            raise ValueError("export_columns needs per-field tables (rows_per_field given as a list)")
+        names = list(column_names) if column_names is not None else ["field_%d" % f for f in range(self.field_size)]
+        if len(names) != self.field_size or len(set(names)) != len(names):
+            raise ValueError("column_names must be field_size distinct names")
+        off = self.field_offset.tolist()
+        rows = self.field_rows.tolist()
+        out = {}
+        table, w1, acc, acc1 = self.table.cpu(), self.w1.cpu(), self.accum, self.w1_accum
+        acc = None if acc is None else acc.cpu()
+        acc1 = None if acc1 is None else acc1.cpu()
+        z = None if self.lin_z is None else self.lin_z[:, 0].cpu()
+        lin_slot = "Ftrl" if (self.linear_optimizer or self.optimizer) == "ftrl" else "Adagrad"
+        for f, name in enumerate(names):
+            sl = slice(off[f], off[f] + rows[f])
+            out[name + "/embedding_weights"] = table[sl].clone()
+            out[name + "/weights"] = w1[sl].clone().reshape(-1, 1)
+            if with_slots:
+                if acc is not None:
+                    out[name + "/embedding_weights/Adagrad"] = acc[sl].clone()
+                if acc1 is not None:
+                    out[name + "/weights/" + lin_slot] = acc1[sl].clone().reshape(-1, 1)
+                if z is not None:
+                    out[name + "/weights/Ftrl_1"] = z[sl].clone().reshape(-1, 1)
+        return out
+
+    @torch.no_grad()
+    def import_columns(self, columns, column_names=None, strict=True):
+        """Warm start from per-column arrays shaped as `export_columns` writes them (slots optional).
+        strict=False skips columns that are absent (WarmStartSettings' vars_to_warm_start subset)."""
+        if self.shared_table:
+            raise ValueError("import_columns needs per-field tables (rows_per_field given as a list)")
+        names = list(column_names) if column_names is not None else ["field_%d" % f for f in range(self.field_size)]
+        if len(names) != self.field_size:
+            raise ValueError("column_names must have field_size entries")
+        off, rows, K = self.field_offset.tolist(), self.field_rows.tolist(), self.embedding_size
+        lin_slot = "Ftrl" if (self.linear_optimizer or self.optimizer) == "ftrl" else "Adagrad"
+        targets = [("/embedding_weights", self.table, K), ("/weights", self.w1, None),
+                   ("/embedding_weights/Adagrad", self.accum, K), ("/weights/" + lin_slot, self.w1_accum, None),
+                   ("/weights/Ftrl_1", None if self.lin_z is None else self.lin_z[:, 0], None)]
+        for f, name in enumerate(names):
+            sl = slice(off[f], off[f] + rows[f])
+            for suffix, dst, width in targets:
+                src = columns.get(name + suffix)
+                if src is None:
+                    if strict and suffix in ("/embedding_weights", "/weights"):
+                        raise KeyError("missing %s" % (name + suffix))
+                    continue
+                if dst is None:
+                    raise ValueError("%s given but this layer keeps no such slot" % (name + suffix))
+                src = torch.as_tensor(src, dtype=torch.float32)
+                want = (rows[f], width) if width else (rows[f],)
+                src = src.reshape(want) if src.numel() == rows[f] * (width or 1) else src
+                if tuple(src.shape) != want:
+                    raise ValueError("%s: expected shape %r, got %r" % (name + suffix, want, tuple(src.shape)))
+                dst[sl].copy_(src.to(dst.device))
+
     def _prepare(self, feature_index, feature_value):
         if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
             raise ValueError("feature_index must be [B, field_size=%d]" % self.field_size)

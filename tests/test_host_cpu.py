@@ -1,0 +1,77 @@
+"""Host-side logic that needs no GPU: checkpoint export / import in the reference's per-column shape,
+state_dict round trips, the roofline byte model against SURVEY.md's worked numbers, the InputLayer column map."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_export_import_columns_round_trip(pkg):
+    rows, K = [5, 1, 7], 8
+    a = pkg.EmbeddingFM(3, K, rows, optimizer="adagrad", linear_optimizer="ftrl", device="cpu")
+    with torch.no_grad():
+        a.w1.normal_()
+        a.accum.uniform_(0.1, 1.0)
+        a.w1_accum.uniform_(0.1, 1.0)
+        a.lin_z.normal_()
+    names = ["C1_embedding", "I1", "C2_embedding"]
+    ck = a.export_columns(names, with_slots=True)
+    assert ck["C1_embedding/embedding_weights"].shape == (5, K) and ck["I1/weights"].shape == (1, 1)
+    assert "C2_embedding/embedding_weights/Adagrad" in ck and "C2_embedding/weights/Ftrl" in ck and "I1/weights/Ftrl_1" in ck
+    assert torch.equal(ck["C2_embedding/embedding_weights"], a.table[6:13])
+    b = pkg.EmbeddingFM(3, K, rows, optimizer="adagrad", linear_optimizer="ftrl", device="cpu")
+    b.import_columns(ck, names)
+    for x, y in ((a.table, b.table), (a.w1, b.w1), (a.accum, b.accum), (a.w1_accum, b.w1_accum), (a.lin_z, b.lin_z)):
+        assert torch.equal(x, y)
+    # weights only (a TF checkpoint without optimizer slots): accumulators keep their initial value
+    c = pkg.EmbeddingFM(3, K, rows, optimizer="adagrad", device="cpu")
+    c.import_columns(a.export_columns(names), names)
+    assert torch.equal(c.table, a.table) and float(c.accum.min()) == float(c.accum.max()) == pytest.approx(0.1)
+    # partial warm start and error behaviour
+    d = pkg.EmbeddingFM(3, K, rows, device="cpu")
+    before = d.table.clone()
+    d.import_columns({k: v for k, v in ck.items() if k.startswith("I1/") and "Ftrl" not in k}, names, strict=False)
+    assert torch.equal(d.table[5:6], a.table[5:6]) and torch.equal(d.table[:5], before[:5])
+    with pytest.raises(KeyError):
+        d.import_columns({}, names)
+    with pytest.raises(ValueError):
+        d.import_columns({"C1_embedding/embedding_weights": torch.zeros(4, K), "C1_embedding/weights": torch.zeros(5, 1)},
+                         names, strict=False)
+    with pytest.raises(ValueError):
+        pkg.EmbeddingFM(3, K, 13, device="cpu").export_columns()
+
+
+def test_state_dict_round_trip(pkg):
+    a = pkg.DeepFM(3, 8, [5, 1, 7], dnn_hidden_units=(16, 8), linear_optimizer="ftrl", device="cpu")
+    b = pkg.DeepFM(3, 8, [5, 1, 7], dnn_hidden_units=(16, 8), linear_optimizer="ftrl", device="cpu")
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(a.embedding.rows, b.embedding.rows) and torch.equal(a.embedding.lin_z, b.embedding.lin_z)
+    assert torch.equal(a.dnn.final.weight, b.dnn.final.weight)
+
+
+def test_roofline_bytes_match_the_survey(pkg):
+    """SURVEY.md section 8d worked numbers (K = 16, F = 39, weighted): 3 128 B / sample forward (+2 496 with E),
+    4 + 39*76 + u*39*272 backward, 4 992 / 7 488 B per sample for the 6-layer cross on d = 624."""
+    R = pkg.roofline
+    B, F, K = 65536, 39, 16
+    assert R.embed_fwd_bytes(B, F, K, True, False) == B * 3128
+    assert R.embed_fwd_bytes(B, F, K, True, True) == B * (3128 + 2496)
+    U = 1_566_675
+    assert R.embed_bwd_bytes(B, F, K, U, True, True, "adagrad") == 4 * B + B * F * 64 + B * F * 76 + U * 272
+    assert R.embed_bwd_bytes(B, F, K, U, True, False, "sgd") == 4 * B + B * F * 76 + U * 136
+    assert R.cross_fwd_bytes(B, 624, 6) == B * 4992 + 2 * 6 * 624 * 4
+    assert R.cross_bwd_bytes(B, 624, 6) == B * 7488 + 4 * 6 * 624 * 4
+    peak, src = R.measured_peaks()
+    assert peak > 1000 and src in ("measured", "fallback")
+
+
+def test_input_layer_column_map(pkg):
+    cols = [("z", "embedding", 4), ("a", "indicator", 3), ("m", "embedding", 2), ("b", "numeric", 1)]
+    layer = pkg.InputLayer(cols, device="cpu")
+    # name order: a(3) b(1) m(2) z(4)
+    assert layer.output_dim == 10
+    assert layer.col_kind.tolist() == [1, 1, 1, 0, 2, 2, 2, 2, 2, 2]
+    assert layer.col_arg.tolist()[:3] == [0, 1, 2]
+    assert layer.col_src.tolist()[4:] == [4, 5, 0, 1, 2, 3]        # m is the second embedding column: components 4, 5
+    assert layer.emb_col.tolist() == [6, 7, 8, 9, 4, 5]
+    with pytest.raises(ValueError, match="no CPU path"):
+        layer(torch.zeros((2, 1)), torch.zeros((2, 1), dtype=torch.int64), torch.zeros((2, 6)))
