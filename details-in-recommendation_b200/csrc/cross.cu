@@ -654,6 +654,265 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------ fused backward, TMA-fed
+// Same arithmetic as cross_bwd_fused_kernel, but the x0 / dy tiles ([kTS][d] each, contiguous in HBM) are
+// brought into a two-stage shared-memory ring by bulk asynchronous copies (cp.async.bulk, the 1-D TMA path,
+// completion counted on an mbarrier): the next tile is in flight while the current one is being consumed, so
+// HBM stays busy through phase B and through the barriers, and phase A reads its rows with LDS instead of
+// LDG + STS.  One CTA per SM (the ring takes 4 * kTS * d * 4 bytes).  d % 4 == 0 only.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// NS = samples a warp works on at once (1 or 2): with one CTA per SM registers are plentiful, and two
+// independent samples double the ILP of the shuffle / recurrence chains and share the w loads.
+template <int NPL, int NS>
+__global__ void __launch_bounds__(kCrossWarps * 32, 1)
+cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
+                     const float* __restrict__ bg, const float* __restrict__ dyg,
+                     const float* __restrict__ pg, int64_t B, int d, int L,
+                     float* __restrict__ dx0g, float* __restrict__ Dpart,
+                     float* __restrict__ dypart, float* __restrict__ dwpart) {
+  constexpr int VEC = 4;
+  constexpr int E = VEC * NPL;
+  constexpr int DP = E * 32;
+  constexpr int CI = (E * 32 + 255) / 256;
+  extern __shared__ __align__(128) float smem[];
+  float* ring = smem;                          // [2 stages][x0 tile | dy tile], each tile [kTS][d]
+  const int tile_f = kTS * d;                  // floats per tile
+  float* als = ring + 4 * tile_f;              // [kTS][8]
+  float* sD = als + kTS * 8;                   // [kCrossWarps][32]
+  float* s_q = sD + kCrossWarps * 32;          // [32]
+  float* s_red = s_q + 32;                     // [kCrossWarps]
+  float* s_w = s_red + kCrossWarps;            // [L][DP]
+  __shared__ __align__(8) uint64_t full[2];    // one mbarrier per stage
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t ntiles = (B + kTS - 1) / kTS;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t tile, int stage) {  // thread 0 only
+    const int64_t b0 = tile * kTS;
+    const int rows = (int)(B - b0 < kTS ? B - b0 : kTS);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
+    float* dst = ring + (size_t)stage * 2 * tile_f;
+    mbar_expect_tx(&full[stage], 2u * bytes);
+    bulk_g2s(dst, x0g + b0 * d, bytes, &full[stage]);
+    bulk_g2s(dst + tile_f, dyg + b0 * d, bytes, &full[stage]);
+  };
+  if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+
+  stage_w<DP>(wg, d, L, s_w);
+  cross_constants(wg, bg, d, L, nullptr, s_q, s_red);
+  const float q_mine = lane < L ? s_q[lane] : 0.f;
+  float acc[CI][8], accdy[CI];
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) {
+    accdy[ci] = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[ci][l] = 0.f;
+  }
+  float Dacc = 0.f;
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int64_t b0 = tile * kTS;
+    const int nv = (int)(B - b0 < kTS ? B - b0 : kTS);  // samples in this tile
+    // the other stage was released by the barrier that closed the previous iteration: refill it now
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&full[stage], (uint32_t)((it >> 1) & 1));
+    const float* x0s = ring + (size_t)stage * 2 * tile_f;
+    const float* dys = x0s + tile_f;
+    // ---- phase A: one warp per NS samples, rows read from the ring
+#pragma unroll 1
+    for (int h = 0; h < kTS / kCrossWarps; h += NS) {
+      float x0[NS][E], dx[NS][E], a[NS], p_mine[NS];
+      int tbs[NS];
+      bool live[NS];
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        tbs[s2] = (h + s2) * kCrossWarps + wib;
+        live[s2] = tbs[s2] < nv;
+        a[s2] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int c = (i * 32 + lane) * VEC;
+          float4 px = make_float4(0.f, 0.f, 0.f, 0.f), pd = px;
+          if (live[s2] && c < d) {
+            px = *reinterpret_cast<const float4*>(x0s + tbs[s2] * d + c);
+            pd = *reinterpret_cast<const float4*>(dys + tbs[s2] * d + c);
+          }
+          x0[s2][i * 4] = px.x; x0[s2][i * 4 + 1] = px.y; x0[s2][i * 4 + 2] = px.z; x0[s2][i * 4 + 3] = px.w;
+          dx[s2][i * 4] = pd.x; dx[s2][i * 4 + 1] = pd.y; dx[s2][i * 4 + 2] = pd.z; dx[s2][i * 4 + 3] = pd.w;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) a[s2] = fmaf(dx[s2][i * VEC + e], x0[s2][i * VEC + e], a[s2]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) a[s2] += __shfl_xor_sync(0xffffffffu, a[s2], o);
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) p_mine[s2] = 0.f;
+      if (pg) {
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2)
+          if (live[s2] && lane < L) p_mine[s2] = __ldg(pg + (b0 + tbs[s2]) * L + lane);
+      } else {
+        for (int l = 0; l < L; ++l) {
+          float dot[NS];
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) dot[s2] = 0.f;
+          const float* wl = s_w + l * DP + lane * VEC;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+#pragma unroll
+              for (int s2 = 0; s2 < NS; ++s2) dot[s2] = fmaf(x0[s2][i * VEC + e], pw.v[e], dot[s2]);
+          }
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) {
+            dot[s2] = warp_sum(dot[s2]);
+            if (lane == l) p_mine[s2] = dot[s2];
+          }
+        }
+      }
+      float al[NS][8];
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        float pv[8], cv[9];
+        cv[0] = 1.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          pv[l] = __shfl_sync(0xffffffffu, p_mine[s2], l);
+          const float q = __shfl_sync(0xffffffffu, q_mine, l);
+          cv[l + 1] = cv[l] + fmaf(cv[l], pv[l], q);
+        }
+        float t = 0.f, ds_mine = 0.f, al_mine = 0.f;
+#pragma unroll
+        for (int l = 7; l >= 0; --l) {
+          float ds = 0.f;
+          if (l < L) {
+            ds = a[s2] + t;
+            t = fmaf(ds, pv[l], t);
+          }
+          al[s2][l] = ds * cv[l];
+          if (lane == l) {
+            ds_mine = ds;
+            al_mine = al[s2][l];
+          }
+        }
+        Dacc += ds_mine;
+        if (lane < 8) als[tbs[s2] * 8 + lane] = al_mine;
+        const float cL = cv[8];
+#pragma unroll
+        for (int e = 0; e < E; ++e) dx[s2][e] *= cL;
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        if (l < L) {
+          const float* wl = s_w + l * DP + lane * VEC;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+#pragma unroll
+              for (int s2 = 0; s2 < NS; ++s2) dx[s2][i * VEC + e] = fmaf(al[s2][l], pw.v[e], dx[s2][i * VEC + e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        if (live[s2]) {
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int c = (i * 32 + lane) * VEC;
+            if (c < d) st_pack<VEC>(dx0g + (b0 + tbs[s2]) * d + c, &dx[s2][i * VEC]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: thread = column, the tile's samples in order (only the nv live ones: the rest of the
+    // ring slot holds whatever an earlier tile left there)
+    for (int tb = 0; tb < nv; ++tb) {
+      const float4 a0 = *reinterpret_cast<const float4*>(als + tb * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const int c = ci * 256 + threadIdx.x;
+        if (c < d) {
+          const float xv = x0s[tb * d + c];
+          acc[ci][0] = fmaf(a0.x, xv, acc[ci][0]);
+          acc[ci][1] = fmaf(a0.y, xv, acc[ci][1]);
+          acc[ci][2] = fmaf(a0.z, xv, acc[ci][2]);
+          acc[ci][3] = fmaf(a0.w, xv, acc[ci][3]);
+          acc[ci][4] = fmaf(a1.x, xv, acc[ci][4]);
+          acc[ci][5] = fmaf(a1.y, xv, acc[ci][5]);
+          acc[ci][6] = fmaf(a1.z, xv, acc[ci][6]);
+          acc[ci][7] = fmaf(a1.w, xv, acc[ci][7]);
+          accdy[ci] += dys[tb * d + c];
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with this stage and with als: the stage may be refilled
+  }
+#pragma unroll
+  for (int ci = 0; ci < CI; ++ci) {
+    const int c = ci * 256 + threadIdx.x;
+    if (c < d) {
+      dypart[(int64_t)blockIdx.x * d + c] = accdy[ci];
+#pragma unroll
+      for (int l = 0; l < 8; ++l)
+        if (l < L) dwpart[((int64_t)blockIdx.x * L + l) * d + c] = acc[ci][l];
+    }
+  }
+  sD[wib * 32 + lane] = Dacc;
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) t += sD[w * 32 + threadIdx.x];
+    Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+  }
+}
+
 // Fixed-order combine of per-CTA partials: a CTA owns 8 columns; 32 "g-lanes" per column each sum
 // every 32nd partial in order, then the 32 sums are added in lane order.
 __global__ void __launch_bounds__(256)
@@ -817,6 +1076,36 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
     return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
+  if (L <= 8 && (tune() & 128) && sh.vec == 4) {
+    // TMA-fed variant (experiment bit 128): one CTA per SM, two-stage ring of x0 / dy tiles
+    const size_t ring = (size_t)4 * kTS * d * 4;
+    const size_t smemt = ring + ((size_t)kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps + (size_t)L * (4 * sh.npl * 32)) * 4;
+    if (smemt <= 220 * 1024 && w.G1 <= kSMs * 2) {
+#define DIR_BWDT1(N, S)                                                                               \
+  {                                                                                                  \
+    cudaFuncSetAttribute(cross_bwd_tma_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt); \
+    cross_bwd_tma_kernel<N, S><<<w.G1, kCrossWarps * 32, smemt, st>>>(x0, cross_w, cross_b, dy, s, B, d, L, dx0, \
+                                                                       w.Dpart, w.dypart, w.dwpart);  \
+  }
+#define DIR_BWDT(N)                 \
+  if (tune() & 256) DIR_BWDT1(N, 2) \
+  else DIR_BWDT1(N, 1)
+      switch (sh.npl) {
+        case 1: DIR_BWDT(1) break;
+        case 2: DIR_BWDT(2) break;
+        case 3: DIR_BWDT(3) break;
+        case 4: DIR_BWDT(4) break;
+        case 5: DIR_BWDT(5) break;
+        case 6: DIR_BWDT(6) break;
+        default: DIR_BWDT(8) break;
+      }
+#undef DIR_BWDT
+#undef DIR_BWDT1
+      cross_bwd_finish2_kernel<<<(d + 7) / 8, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
+                                                             w.G1, w.G2, d, L, dw, db);
+      return launched("cross_bwd", 2);
+    }
+  }
   if (L <= 8) {
     const size_t smem0 = ((size_t)2 * kTS * d + kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps) * 4;
 #define DIR_BWDF(V, N)                                                                          \
