@@ -13,7 +13,6 @@ Embedding tables and first-order weights are optimizer-owned state of the layer 
 `.backward()`); everything else is an ordinary Parameter stepped by `dense_optimizer()`, the dense
 counterpart of the same rule ([TF] ApplyAdagrad: accumulator 0.1, no epsilon).
 """
-import math
 from typing import Optional, Sequence
 
 import torch

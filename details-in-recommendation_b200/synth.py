@@ -7,8 +7,8 @@ weighted-column / 'sum' semantics of dataset/SequenceTensorFlowDataset/test4.py:
 Seeds follow SURVEY.md section 8d: ids 1234, values 1235, tables 1236, labels 1237,
 upstream grads 1238.
 """
-from dataclasses import dataclass, field
-from typing import List, Optional
+from dataclasses import dataclass
+from typing import Optional
 
 import numpy as np
 

@@ -12,7 +12,6 @@ Only tests/ and bench.py's cpu_baseline / --impl reference legs may import it.
 """
 import time
 
-import numpy as np
 import torch
 import torch.nn.functional as Fn
 
