@@ -56,3 +56,39 @@ def oracle_forward(case, bias=0.0, dtype=np.float32):
     first = O.first_order(case["w1"].astype(dtype), bias, case["off"], case["idx"], case["val"], dtype)
     fm = O.fm_second_order(e)
     return e, first, fm, keep
+
+
+def torch_embedding_reference(T0, w1_0, bias, field_offset, idx, val, g_first=None, g_fm=None, u=None):
+    """The layer's forward / backward in fp64 with torch indexing and index_add_, on whatever device the tensors live:
+    an independent implementation fast enough for BASELINE.json's full sizes (the numpy oracle is not).  It is itself
+    checked against the oracle on a small case (tests/test_host_cpu.py).
+    -> dict(e[B,F,K] fp64 from fp32 rows, S, fm[B], first[B], and with gradients given: G[N,K], Gfloor[N,K] (the
+    cancellation-aware magnitude sum |x| (|g_fm| sum_f |e_f| + |u|)), g1[N], g1abs[N], touched[N] bool)."""
+    B, F = idx.shape
+    N, K = T0.shape
+    rows = idx + field_offset[None, :]
+    keep = (idx >= 0) & (val > 0)
+    rows = torch.where(keep, rows, torch.zeros_like(rows))
+    x = torch.where(keep, val, torch.zeros_like(val)).double()
+    e = T0[rows].double() * x[..., None]
+    S = e.sum(1)
+    out = dict(e=e, S=S, fm=0.5 * ((S * S) - (e * e).sum(1)).sum(-1),
+               first=(w1_0[rows].double() * x).sum(1) + float(bias), keep=keep, rows=rows,
+               first_abs=(w1_0[rows].double().abs() * x).sum(1))
+    if g_fm is None:
+        return out
+    gfm = g_fm.double()
+    uu = u.reshape(B, F, K).double() if u is not None else torch.zeros_like(e)
+    per = x[..., None] * (gfm[:, None, None] * (S[:, None, :] - e) + uu)
+    A = e.abs().sum(1)
+    per_floor = x[..., None] * (gfm.abs()[:, None, None] * A[:, None, :] + uu.abs())
+    flat = rows.reshape(-1)
+    G = torch.zeros((N, K), dtype=torch.float64, device=T0.device).index_add_(0, flat, per.reshape(-1, K))
+    Gfloor = torch.zeros((N, K), dtype=torch.float64, device=T0.device).index_add_(0, flat, per_floor.reshape(-1, K))
+    t1 = (x * g_first.double()[:, None]).reshape(-1)
+    g1 = torch.zeros(N, dtype=torch.float64, device=T0.device).index_add_(0, flat, t1)
+    g1abs = torch.zeros(N, dtype=torch.float64, device=T0.device).index_add_(0, flat, t1.abs())
+    touched = torch.zeros(N, dtype=torch.bool, device=T0.device)
+    touched[flat[keep.reshape(-1)]] = True
+    out.update(G=G, Gfloor=Gfloor, g1=g1, g1abs=g1abs, touched=touched)
+    return out

@@ -75,3 +75,32 @@ def test_input_layer_column_map(pkg):
     assert layer.emb_col.tolist() == [6, 7, 8, 9, 4, 5]
     with pytest.raises(ValueError, match="no CPU path"):
         layer(torch.zeros((2, 1)), torch.zeros((2, 1), dtype=torch.int64), torch.zeros((2, 6)))
+
+
+def test_torch_reference_of_the_full_size_tests_matches_the_oracle():
+    """tests/test_gpu_zz_fullsize.py checks the kernels at BASELINE sizes against `torch_embedding_reference`
+    (the numpy oracle is too slow there); here that reference is itself pinned to the oracle on a small case."""
+    from oracle import deepctr_oracle as O
+    from tests._util import make_case, torch_embedding_reference
+    case = make_case(21, 150, [9, 1, 40, 3, 1], 8, weighted=True, prune=True, skew=2.0)
+    rng, B, F, K = case["rng"], case["B"], case["F"], case["K"]
+    g_first, g_fm = rng.standard_normal(B).astype(np.float32), rng.standard_normal(B).astype(np.float32)
+    u = rng.standard_normal((B, F, K)).astype(np.float32)
+    ref = torch_embedding_reference(torch.as_tensor(case["table"]), torch.as_tensor(case["w1"]), 0.25,
+                                    torch.as_tensor(case["off"]), torch.as_tensor(case["idx"]), torch.as_tensor(case["val"]),
+                                    torch.as_tensor(g_first), torch.as_tensor(g_fm), torch.as_tensor(u))
+    t64, w64 = case["table"].astype(np.float64), case["w1"].astype(np.float64)
+    e, keep = O.embedding_lookup(t64, case["off"], case["idx"], case["val"], "sum", np.float64)
+    assert np.allclose(ref["e"].numpy(), e, rtol=0, atol=0)
+    assert np.allclose(ref["fm"].numpy(), O.fm_second_order(e)[:, 0], rtol=1e-12, atol=1e-12)
+    assert np.allclose(ref["first"].numpy(), O.first_order(w64, 0.25, case["off"], case["idx"], case["val"], np.float64)[:, 0],
+                       rtol=1e-12, atol=1e-12)
+    rows, G, g1, _, Gabs, g1abs = O.embedding_backward(t64, case["off"], case["idx"], case["val"], g_first, g_fm, u,
+                                                        "sum", np.float64, return_abs=True)
+    assert np.array_equal(np.flatnonzero(ref["touched"].numpy()), rows)
+    assert np.allclose(ref["G"].numpy()[rows], G, rtol=1e-11, atol=1e-12)
+    assert np.allclose(ref["g1"].numpy()[rows], g1, rtol=1e-11, atol=1e-12)
+    assert np.allclose(ref["g1abs"].numpy()[rows], g1abs, rtol=1e-11, atol=1e-12)
+    assert np.all(ref["Gfloor"].numpy()[rows] >= Gabs * (1 - 1e-12))        # the cancellation-aware floor dominates
+    untouched = np.setdiff1d(np.arange(case["N"]), rows)
+    assert np.all(ref["G"].numpy()[untouched] == 0)

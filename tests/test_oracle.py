@@ -289,3 +289,43 @@ def test_bags_reduce_to_single_lookups_and_match_autograd():
         assert np.allclose(W.grad.numpy()[rows_u], g1, rtol=1e-10, atol=1e-12)
         rest = np.setdiff1d(np.arange(N), rows_u)
         assert np.all(T.grad.numpy()[rest] == 0)
+
+
+def test_cross_rank1_algebra_of_the_kernels():
+    """The CUDA cross kernels do not sweep layer by layer: they use x_l = x0 c_l + beta_l (cross.cu header).
+    This restates that algebra in numpy (fp64) and checks it against the layer-by-layer oracle and its backward,
+    for random shapes -- the identities the kernels rely on, independent of any GPU."""
+    rng = np.random.default_rng(11)
+    for B, d, L in [(1, 1, 1), (7, 5, 3), (33, 51, 2), (20, 64, 8), (5, 9, 32)]:
+        x0 = rng.standard_normal((B, d)) * 0.5
+        w = rng.standard_normal((L, d)) * 0.2
+        b = rng.standard_normal((L, d)) * 0.2
+        dy = rng.standard_normal((B, d))
+        # forward: p_l = x0 . w_l, beta_l = sum_{j<l} b_j, q_l = beta_l . w_l, c_{l+1} = c_l + c_l p_l + q_l
+        p = x0 @ w.T                                            # [B, L]
+        beta = np.concatenate([np.zeros((1, d)), np.cumsum(b, axis=0)])      # beta[l], l = 0..L
+        q = np.einsum("ld,ld->l", beta[:L], w)
+        c = np.ones((B, L + 1))
+        for l in range(L):
+            c[:, l + 1] = c[:, l] + c[:, l] * p[:, l] + q[l]
+        xL = x0 * c[:, L:L + 1] + beta[L][None, :]
+        want, s = O.cross_forward(x0, w, b)
+        assert np.allclose(xL, want, rtol=1e-11, atol=1e-12)
+        assert np.allclose(c[:, :L] * p + q[None, :], s, rtol=1e-11, atol=1e-12)      # s_l = c_l p_l + q_l
+        # backward: a = dy . x0, ds_l = a + sum_{j>l} ds_j p_j, alpha_l = ds_l c_l
+        a = np.sum(dy * x0, axis=1)
+        ds = np.zeros((B, L))
+        t = np.zeros(B)
+        for l in range(L - 1, -1, -1):
+            ds[:, l] = a + t
+            t = t + ds[:, l] * p[:, l]
+        alpha = ds * c[:, :L]
+        dx0 = c[:, L:L + 1] * dy + alpha @ w
+        D = ds.sum(axis=0)                                      # sum_b ds_l
+        dw = alpha.T @ x0 + beta[:L] * D[:, None]
+        tail = np.concatenate([np.cumsum((w * D[:, None])[::-1], axis=0)[::-1][1:], np.zeros((1, d))])   # sum_{j>l} w_j D_j
+        db = dy.sum(axis=0)[None, :] + tail
+        wdx0, wdw, wdb = O.cross_backward(x0, w, b, dy)
+        assert np.allclose(dx0, wdx0, rtol=1e-10, atol=1e-11)
+        assert np.allclose(dw, wdw, rtol=1e-10, atol=1e-11)
+        assert np.allclose(db, wdb, rtol=1e-10, atol=1e-11)
