@@ -472,18 +472,45 @@ def run_b200(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": r["sample"] + "; PyTorch-CPU restatement of the reference's TF 1.x graph"}
 
-    if world > 1 and getattr(layer, "trace", None) is not None and layer.trace.on:
+    stages, nvlink = None, None
+    if world > 1 and getattr(layer, "trace", None) is not None:
+        # Stage times of the sharded step: a diagnostic pass AFTER the timed regions.  Eager launches, every stage
+        # bracketed by CUDA events on its stream, one device sync per step.  Every rank takes part (the steps
+        # contain the cross-rank barriers); rank 0 reports.
+        layer.trace.on = layer.trace_pre.on = True
         layer.trace.report()
         layer.trace_pre.report()
-        t0 = time.perf_counter()
-        for s_ in range(20):
-            run(s_ % R)
+        sharded_id_work(0)
+        for s_ in range(8):
+            step(*devs[s_ % R], ups[s_ % R], slot=s_ % R)
         torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) / 20 * 1e6
+        stages = (layer.trace.report(), layer.trace_pre.report())
+        layer.trace.on = layer.trace_pre.on = False
         if rank == 0:
-            print("stage trace (us/step, rank 0; wall %.0f us/step): %s | side stream: %s" % (wall, json.dumps(
-                {k: round(v, 1) for k, v in layer.trace.report().items()}), json.dumps(
-                {k: round(v, 1) for k, v in layer.trace_pre.report().items()})), file=sys.stderr)
+            try:
+                main = stages[0]
+                U = int(layer.last_exchange.get("unique_sent", 0))
+                row_bytes = (K + 4) * 4                                   # (row | first-order weight | pad) per distinct row
+                key = "bwd.emit+push" if "bwd.emit+push" in main else "bwd.emit"
+                # requester half of the backward: g, upstream u, per lookup id + value + one K-vector, per distinct
+                # row the (G[K], g1) sums written to its owner
+                nbytes = 4 * B + (B * d * 4 if emit else 0) + B * F * (8 + 4 + 4 * K) + U * row_bytes
+                peak, src = RL.measured_peaks()
+                gbs = nbytes / main[key] * 1e-3
+                roof = {"bound": "hbm", "kernel": "dir_embed_bwd_reduce_emit_to" if key.endswith("push") else
+                        "dir_embed_bwd_reduce_emit", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src if src == "measured"
+                        else "fallback (B200_PROFILING.md)", "traffic": None, "algorithmic_bytes_per_launch": int(nbytes),
+                        "us_per_launch": main[key],
+                        "how": "stage time (CUDA events, rank 0) from an eager traced pass after the timed regions"}
+                link = U * row_bytes * (world - 1) / world                 # bytes that leave / reach this rank, each way
+                t_fwd = main.get("fwd.gather+send")
+                nvlink = {"bytes_per_direction_per_rank": int(link), "peak": 770.0, "unit": "GB/s",
+                          "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
+                          "rows_gather_to_gbs": link / t_fwd * 1e-3 if t_fwd else None,
+                          "frac": link / t_fwd * 1e-3 / 770.0 if t_fwd else None}
+            except Exception as e:                                         # diagnostics must never cost the bench line
+                print("bench.py: stage roofline skipped (%s)" % e, file=sys.stderr)
     if rank == 0:
         cfg = workload_config(w, args, world)
         cfg.update({"l2_policy": "%d rotating input sets (%.0f MB of ids/values/upstream each) + a %.2f GB table: "
@@ -497,6 +524,10 @@ def run_b200(args):
                 "config": cfg, "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "roofline": roof, "kernels": kernels,
                 "cpu_baseline": cpu}
+        if stages is not None:
+            line["stages_us"] = {"main_stream": {k: round(v, 1) for k, v in stages[0].items()},
+                                 "side_stream": {k: round(v, 1) for k, v in stages[1].items()}}
+            line["nvlink"] = nvlink
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
