@@ -104,3 +104,30 @@ def test_torch_reference_of_the_full_size_tests_matches_the_oracle():
     assert np.all(ref["Gfloor"].numpy()[rows] >= Gabs * (1 - 1e-12))        # the cancellation-aware floor dominates
     untouched = np.setdiff1d(np.arange(case["N"]), rows)
     assert np.all(ref["G"].numpy()[untouched] == 0)
+
+
+def test_shard_plan_at_terabyte_scale(pkg):
+    """cfg4 (BASELINE.json configs[3]): ~880 M rows over 2 / 4 / 8 ranks.  The composite sort key
+    owner * cap + local row must stay below 2^32 - 1 (it travels as uint32), and owner / local / global
+    must round-trip at the far end of the row range."""
+    w = pkg.synth.cfg("cfg4")
+    assert w.n_rows == 880_000_013 and w.field_size == 39
+    rng = np.random.default_rng(1)
+    for G in (2, 4, 8):
+        for rank in (0, G - 1):
+            plan = pkg.ShardPlan(list(w.rows_per_field), G, rank)
+            assert plan.cap * G < 2 ** 32 - 1 and plan.cap * G >= w.n_rows
+            assert sum(pkg.ShardPlan(list(w.rows_per_field), G, r).n_local for r in range(G)) == w.n_rows
+            rows = torch.as_tensor(np.concatenate([rng.integers(0, w.n_rows, size=1000),
+                                                   [0, w.n_rows - 1, w.n_rows - G, 291_999_999, 292_000_000]]))
+            owner, local = plan.owner(rows), plan.local_row(rows)
+            assert int(owner.max()) < G and int(local.max()) < plan.cap
+            assert torch.equal(plan.global_row(local, owner), rows)
+            key = owner * plan.cap + local
+            assert int(key.max()) < plan.cap * G            # < the pruned key G * cap, itself < 2^32 - 1
+    # one rank more than the uint32 key space allows is refused
+    with pytest.raises(ValueError):
+        pkg.ShardPlan([2 ** 32], 2, 0)
+    # memory per rank: rows + accumulators interleaved (128 B per row at K = 16) must fit 180 GB from G = 2 on
+    for G in (2, 4, 8):
+        assert pkg.ShardPlan(list(w.rows_per_field), G, 0).cap * 128 < 100e9
