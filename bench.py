@@ -477,16 +477,21 @@ def run_b200(args):
         # Stage times of the sharded step: a diagnostic pass AFTER the timed regions.  Eager launches, every stage
         # bracketed by CUDA events on its stream, one device sync per step.  Every rank takes part (the steps
         # contain the cross-rank barriers); rank 0 reports.
-        layer.trace.on = layer.trace_pre.on = True
-        layer.trace.report()
-        layer.trace_pre.report()
-        sharded_id_work(0)
-        for s_ in range(8):
-            step(*devs[s_ % R], ups[s_ % R], slot=s_ % R)
-        torch.cuda.synchronize()
-        stages = (layer.trace.report(), layer.trace_pre.report())
+        try:                                  # the same code on every rank: a failure here is symmetric
+            layer.trace.on = layer.trace_pre.on = True
+            layer.trace.report()
+            layer.trace_pre.report()
+            sharded_id_work(0)
+            for s_ in range(8):
+                step(*devs[s_ % R], ups[s_ % R], slot=s_ % R)
+            torch.cuda.synchronize()
+            stages = (layer.trace.report(), layer.trace_pre.report())
+        except Exception as e:
+            stages = None
+            if rank == 0:
+                print("bench.py: stage trace skipped (%s)" % e, file=sys.stderr)
         layer.trace.on = layer.trace_pre.on = False
-        if rank == 0:
+        if rank == 0 and stages is not None:
             try:
                 main = stages[0]
                 U = int(layer.last_exchange.get("unique_sent", 0))
