@@ -690,10 +690,46 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// cross_constants for a CTA of WARPS warps (the default kernels keep the 8-warp original).
+template <int WARPS>
+__device__ __forceinline__ void cross_constants_t(const float* __restrict__ wg, const float* __restrict__ bg,
+                                                  int d, int L, float* s_q, float* s_red) {
+  constexpr int NT = WARPS * 32;
+  constexpr int CPT = (1024 + NT - 1) / NT;  // columns per thread, d <= 1024
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float beta[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) beta[j] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int c = threadIdx.x + j * NT;
+      if (c < d) {
+        part = fmaf(beta[j], __ldg(wg + l * d + c), part);
+        beta[j] += __ldg(bg + l * d + c);
+      }
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_red[wib] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) t += s_red[w];
+      s_q[l] = t;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
 // NS = samples a warp works on at once (1 or 2): with one CTA per SM registers are plentiful, and two
 // independent samples double the ILP of the shuffle / recurrence chains and share the w loads.
-template <int NPL, int NS>
-__global__ void __launch_bounds__(kCrossWarps * 32, 1)
+// WARPS = warps per CTA (8 or 16): sixteen warps walk a whole tile in one phase-A round and give phase B
+// 512 column threads.
+template <int NPL, int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
                      const float* __restrict__ bg, const float* __restrict__ dyg,
                      const float* __restrict__ pg, int64_t B, int d, int L,
@@ -702,15 +738,16 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
   constexpr int VEC = 4;
   constexpr int E = VEC * NPL;
   constexpr int DP = E * 32;
-  constexpr int CI = (E * 32 + 255) / 256;
+  constexpr int NT = WARPS * 32;
+  constexpr int CI = (E * 32 + NT - 1) / NT;
   extern __shared__ __align__(128) float smem[];
   float* ring = smem;                          // [2 stages][x0 tile | dy tile], each tile [kTS][d]
   const int tile_f = kTS * d;                  // floats per tile
   float* als = ring + 4 * tile_f;              // [kTS][8]
-  float* sD = als + kTS * 8;                   // [kCrossWarps][32]
-  float* s_q = sD + kCrossWarps * 32;          // [32]
-  float* s_red = s_q + 32;                     // [kCrossWarps]
-  float* s_w = s_red + kCrossWarps;            // [L][DP]
+  float* sD = als + kTS * 8;                   // [WARPS][32]
+  float* s_q = sD + WARPS * 32;                // [32]
+  float* s_red = s_q + 32;                     // [WARPS]
+  float* s_w = s_red + WARPS;                  // [L][DP]
   __shared__ __align__(8) uint64_t full[2];    // one mbarrier per stage
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -734,7 +771,7 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
   if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
 
   stage_w<DP>(wg, d, L, s_w);
-  cross_constants(wg, bg, d, L, nullptr, s_q, s_red);
+  cross_constants_t<WARPS>(wg, bg, d, L, s_q, s_red);
   const float q_mine = lane < L ? s_q[lane] : 0.f;
   float acc[CI][8], accdy[CI];
 #pragma unroll
@@ -757,13 +794,13 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
     const float* dys = x0s + tile_f;
     // ---- phase A: one warp per NS samples, rows read from the ring
 #pragma unroll 1
-    for (int h = 0; h < kTS / kCrossWarps; h += NS) {
+    for (int h = 0; h < kTS / WARPS; h += NS) {
       float x0[NS][E], dx[NS][E], a[NS], p_mine[NS];
       int tbs[NS];
       bool live[NS];
 #pragma unroll
       for (int s2 = 0; s2 < NS; ++s2) {
-        tbs[s2] = (h + s2) * kCrossWarps + wib;
+        tbs[s2] = (h + s2) * WARPS + wib;
         live[s2] = tbs[s2] < nv;
         a[s2] = 0.f;
 #pragma unroll
@@ -876,7 +913,7 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
       const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
 #pragma unroll
       for (int ci = 0; ci < CI; ++ci) {
-        const int c = ci * 256 + threadIdx.x;
+        const int c = ci * NT + threadIdx.x;
         if (c < d) {
           const float xv = x0s[tb * d + c];
           acc[ci][0] = fmaf(a0.x, xv, acc[ci][0]);
@@ -895,7 +932,7 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
   }
 #pragma unroll
   for (int ci = 0; ci < CI; ++ci) {
-    const int c = ci * 256 + threadIdx.x;
+    const int c = ci * NT + threadIdx.x;
     if (c < d) {
       dypart[(int64_t)blockIdx.x * d + c] = accdy[ci];
 #pragma unroll
@@ -908,7 +945,7 @@ cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg
   if (threadIdx.x < L) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < kCrossWarps; ++w) t += sD[w * 32 + threadIdx.x];
+    for (int w = 0; w < WARPS; ++w) t += sD[w * 32 + threadIdx.x];
     Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = t;
   }
 }
@@ -1079,17 +1116,21 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
   if (L <= 8 && (tune() & 128) && sh.vec == 4) {
     // TMA-fed variant (experiment bit 128): one CTA per SM, two-stage ring of x0 / dy tiles
     const size_t ring = (size_t)4 * kTS * d * 4;
-    const size_t smemt = ring + ((size_t)kTS * 8 + kCrossWarps * 32 + 32 + kCrossWarps + (size_t)L * (4 * sh.npl * 32)) * 4;
+    const int tw = (tune() & 512) ? 16 : kCrossWarps;
+    const size_t smemt = ring + ((size_t)kTS * 8 + tw * 32 + 32 + tw + (size_t)L * (4 * sh.npl * 32)) * 4;
     if (smemt <= 220 * 1024 && w.G1 <= kSMs * 2) {
-#define DIR_BWDT1(N, S)                                                                               \
+#define DIR_BWDT1(N, S, W)                                                                            \
   {                                                                                                  \
-    cudaFuncSetAttribute(cross_bwd_tma_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt); \
-    cross_bwd_tma_kernel<N, S><<<w.G1, kCrossWarps * 32, smemt, st>>>(x0, cross_w, cross_b, dy, s, B, d, L, dx0, \
-                                                                       w.Dpart, w.dypart, w.dwpart);  \
+    cudaFuncSetAttribute(cross_bwd_tma_kernel<N, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smemt);                                                                \
+    cross_bwd_tma_kernel<N, S, W><<<w.G1, W * 32, smemt, st>>>(x0, cross_w, cross_b, dy, s, B, d, L, dx0, \
+                                                               w.Dpart, w.dypart, w.dwpart);          \
   }
-#define DIR_BWDT(N)                 \
-  if (tune() & 256) DIR_BWDT1(N, 2) \
-  else DIR_BWDT1(N, 1)
+  // +256: two samples per warp (8 warps); +512: sixteen warps per CTA, one sample each
+#define DIR_BWDT(N)                         \
+  if (tune() & 512) DIR_BWDT1(N, 1, 16)     \
+  else if (tune() & 256) DIR_BWDT1(N, 2, 8) \
+  else DIR_BWDT1(N, 1, 8)
       switch (sh.npl) {
         case 1: DIR_BWDT(1) break;
         case 2: DIR_BWDT(2) break;

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Parity tests of the cross kernels, then CUDA-event timing of dir_cross_fwd / dir_cross_bwd at the cfg3 shape,
-in one process (the DIR_B200_TUNE experiment bits are read once at load): `DIR_B200_TUNE=384 python tools/time_cross.py`."""
+in one process (the DIR_B200_TUNE experiment bits are read once at load):
+    DIR_B200_TUNE=128 | 384 | 640 python tools/time_cross.py     # TMA ring: 8 warps, +2 samples per warp, 16 warps
+"""
 import os
 import sys
 
