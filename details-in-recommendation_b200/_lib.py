@@ -44,6 +44,7 @@ SIGNATURES = {
                                 c_int64, c_void_p]),
     "dir_rows_gather_to": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dir_ids_push": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_rows_push": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int64,

@@ -195,6 +195,21 @@ rows_push_kernel(const float* __restrict__ src, int64_t n, int stride4, int G,
   }
 }
 
+// requester side, ids: ship the distinct local rows [n] (int32) to their owners' landing buffers.  Same segment
+// arithmetic as rows_push_kernel with 4-byte elements; n bounds the launch, seg_start[G] is the real count.
+__global__ void __launch_bounds__(256)
+ids_push_kernel(const int32_t* __restrict__ src, int64_t n, int G, const int64_t* __restrict__ seg_start,
+                const int64_t* __restrict__ peer_ptrs, const int64_t* __restrict__ dst_off) {
+  const int64_t total = __ldg(seg_start + G);
+  n = total < n ? total : n;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const int q = segment_of(seg_start, G, i);
+    int32_t* dst = reinterpret_cast<int32_t*>(__ldg(peer_ptrs + q)) + (__ldg(dst_off + q) + i - __ldg(seg_start + q));
+    *dst = __ldg(src + i);
+  }
+}
+
 struct UniqueWs {
   uint32_t* incl;
   void* cub_temp;
@@ -351,4 +366,16 @@ extern "C" int dir_rows_push(const float* src, int64_t n, int64_t stride, int G,
   rows_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, stride4, G, seg_start, peer_ptrs,
                                                                          dst_row_off);
   return launched("rows_push");
+}
+
+extern "C" int dir_ids_push(const int32_t* src, int64_t n, int G, const int64_t* seg_start,
+                            const int64_t* peer_ptrs, const int64_t* dst_off, dir_stream_t stream) {
+  using namespace dir;
+  if (n < 0 || G <= 0) return fail(DIR_EINVAL, "ids_push: n >= 0, G > 0 required");
+  if (n == 0) return 0;
+  if (!src || !seg_start || !peer_ptrs || !dst_off) return fail(DIR_EINVAL, "ids_push: null pointer");
+  const int64_t want = (n + 255) / 256;
+  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
+  ids_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, G, seg_start, peer_ptrs, dst_off);
+  return launched("ids_push");
 }

@@ -174,6 +174,7 @@ class ShardedLookups:
         self.event = None
         self.src = None
         self.parity = None          # which half of the double-buffered peer memory (None: the layer alternates)
+        self.recv_handle = self.recv_ptrs = None   # DIR_B200_IDS=peer: symmetric-memory handle / peer addresses of recv_buf
         self.recv_buf = None        # static mode: fixed-address landing buffer of the ids this rank answers
 
     @staticmethod
@@ -398,7 +399,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         # Payload exchange: NVLink peer memory (symmetric buffers + a device-side barrier) when there is
         # more than one rank and torch's symmetric memory is usable, else NCCL all-to-all.
         self.peer, self._step_parity = None, 0
-        self.static = self.capturing = False
+        self.static = self.capturing = self.ids_peer = False
         self.recv_cap = 0
         self.max_batch = int(max_batch)
         want_peer = os.environ.get("DIR_B200_EXCHANGE", "peer") == "peer"
@@ -414,6 +415,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 # can be captured in a CUDA graph (the id-only presort stays eager on the side stream).
                 self.recv_cap = cap * world
                 self.static = os.environ.get("DIR_B200_STATIC", "1") == "1"
+                # experiment (not yet run on a GPU): ids through peer memory instead of the NCCL all-to-all
+                self.ids_peer = self.static and os.environ.get("DIR_B200_IDS", "nccl") == "peer"
             except Exception as e:                                              # no IPC / fabric support
                 if rank == 0:
                     print("ShardedEmbeddingFM: symmetric memory unavailable (%s); using NCCL all-to-all" % e,
@@ -507,7 +510,15 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 h.recv_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
                 h.fwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
                 h.bwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
-                if self.static:
+                if self.static and self.ids_peer:
+                    # the landing buffer of the ids is symmetric memory too: requesters store into it directly
+                    # (collective: every rank reaches this line for the same handle, in the same order)
+                    import torch.distributed._symmetric_memory as symm_mem
+                    h.recv_buf = symm_mem.empty(self.recv_cap, dtype=torch.int32, device=dev)
+                    h.recv_handle = symm_mem.rendezvous(h.recv_buf, self.group if self.group is not None
+                                                        else dist.group.WORLD)
+                    h.recv_ptrs = torch.tensor(list(h.recv_handle.buffer_ptrs), dtype=torch.int64, device=dev)
+                elif self.static:
                     h.recv_buf = torch.empty(self.recv_cap, dtype=torch.int32, device=dev)
             check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
                                    self.plan.n_rows, B, F, G, None, F, ptr(h.keys),
@@ -550,6 +561,14 @@ class ShardedEmbeddingFM(torch.nn.Module):
             if self.static:
                 if h.R > self.recv_cap:
                     raise ValueError("%d rows requested from this rank, buffers hold %d" % (h.R, self.recv_cap))
+            if self.static and self.ids_peer:
+                # ids over NVLink peer memory: my segment for owner o starts where my gradient segment will
+                # (bwd_dst_off[o]); a device-side barrier on this handle's own signal pad closes the exchange
+                check(L.dir_ids_push(ptr(h.ulocal), n, G, ptr(h.owner_off), ptr(h.recv_ptrs), ptr(h.bwd_dst_off), st),
+                      "dir_ids_push")
+                h.recv_handle.barrier(channel=0)
+                h.recv_ids = h.recv_buf[:h.R]
+            elif self.static:
                 h.recv_ids = exchange_into(h.recv_buf, h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
             else:
                 h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)

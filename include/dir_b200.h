@@ -204,6 +204,11 @@ int dir_rows_gather_to(const float* table, int64_t row_stride, const float* lin,
                        dir_stream_t stream);
 int dir_rows_push(const float* src, int64_t n, int64_t stride, int G, const int64_t* seg_start,
                   const int64_t* peer_ptrs, const int64_t* dst_row_off, dir_stream_t stream);
+/* The id exchange over peer memory as well (instead of an NCCL all-to-all): distinct local rows [n] int32,
+ * grouped by owner (seg_start[G+1]), stored into each owner's landing buffer (peer_ptrs[q]) at element
+ * dst_off[q].  n bounds the launch; min(n, seg_start[G]) ids are sent.  Barrier before the owner reads. */
+int dir_ids_push(const int32_t* src, int64_t n, int G, const int64_t* seg_start,
+                 const int64_t* peer_ptrs, const int64_t* dst_off, dir_stream_t stream);
 int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
                               const float* g_first, const float* g_fm, const float* S, const float* u,
                               const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
