@@ -70,3 +70,37 @@ def test_synth_workloads(pkg):
     assert ((val[:, :26] == 1).all() and (val[:, 26:] < 1).all())
     idx2, _, _ = s.make_inputs(w5)
     assert np.array_equal(idx, idx2)    # seeded
+
+
+def test_argument_validation_of_the_widened_entry_points(pkg):
+    """Every new entry point validates before it launches (so this runs without a GPU): -EINVAL and a message."""
+    import ctypes
+    from dir_b200 import _lib
+    lib = _lib.lib()
+    P = 16                                    # any non-NULL, 16-byte aligned "pointer": nothing dereferences it
+    # bags: combiner out of range, then K unsupported
+    rc = lib.dir_embed_bag_fm_fwd(P, 16, None, 1, None, P, P, None, 4, P, None, 10, 2, 2, 16, 7, P, None, None, P,
+                                  None, None, None, None, None)
+    assert rc == -22 and b"combiner" in lib.dir_last_error()
+    rc = lib.dir_embed_bag_fm_fwd(P, 16, None, 1, None, P, P, None, 4, P, None, 10, 2, 2, 12, 1, P, None, None, P,
+                                  None, None, None, None, None)
+    assert rc == -22 and b"K must be" in lib.dir_last_error()
+    assert lib.dir_embed_bag_fm_fwd(None, 16, None, 1, None, None, None, None, 0, None, None, 10, 0, 2, 16, 1, None,
+                                    None, None, None, None, None, None, None, None) == 0           # empty batch
+    # the linear scope's optimizer: Ftrl without its z slot, an unknown optimizer code
+    bad = _lib.LinearOpt(_lib.OPT_FTRL, 0.2, 0.0, 0.0, None)
+    rc = lib.dir_embed_bwd_reduce_update(P, P, 32, P, P, 1, P, None, P, P, P, P, None, 4, 2, 16, 10, None, 0, None, 0,
+                                         1, 0.05, ctypes.byref(bad), P, 1 << 20, None, None)
+    assert rc == -22 and b"Ftrl needs z" in lib.dir_last_error()
+    bad = _lib.LinearOpt(9, 0.2, 0.0, 0.0, None)
+    rc = lib.dir_embed_bwd_reduce_update(P, P, 32, P, P, 1, P, None, P, P, P, P, None, 4, 2, 16, 10, None, 0, None, 0,
+                                         1, 0.05, ctypes.byref(bad), P, 1 << 20, None, None)
+    assert rc == -22 and b"unknown linear optimizer" in lib.dir_last_error()
+    # input layer, column feed, id push, capacity sort
+    assert lib.dir_input_layer_fwd(None, 0, None, 0, P, 8, P, P, P, 4, 0, P, None) == -22
+    assert lib.dir_input_layer_bwd(None, None, 0, 8, 8, None, None) == 0
+    assert lib.dir_ids_push(P, 4, 0, P, P, P, None) == -22
+    assert lib.dir_embed_bwd_sort_in(P, 8, 4, 10, P, 1 << 20, None) == -22          # capacity below the count
+    with pytest.raises(ValueError):
+        _lib.check(lib.dir_embed_bwd_reduce_emit_to(P, 20, None, None, P, P, None, P, 4, 2, 16, 100, 2, P, None, P, 20,
+                                                    P, 1 << 20, None), "emit_to")      # peer_ptrs missing
