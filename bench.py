@@ -71,6 +71,43 @@ def workload_config(w, args, n_gpus):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the PyTorch-CPU restatement of the reference graph on host cores
 # ------------------------------------------------------------------------------------------------
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_cfg1(budget_s=6.0):
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable case (B = 1 024, 39 fields, K = 8) -- on the
+    restatement: 20 warm-up steps, then timed steps for about `budget_s` (at most 200); median step time."""
+    import torch
+    from oracle import torch_restatement as TR
+    import dir_b200
+    w = dir_b200.synth.cfg("cfg1")
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = TR.DeepFMLayerCPU(w.rows_per_field, w.embedding_size, lr=LR)
+    i, v, y = dir_b200.synth.make_inputs(w)
+    b = (torch.as_tensor(i), torch.as_tensor(v), torch.as_tensor(y),
+         torch.randn((w.batch, w.field_size * w.embedding_size)) * 1e-2)
+    for _ in range(20):
+        model.step(*b)
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < 200 and time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        model.step(*b)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": w.batch / med, "unit": UNIT, "ms_per_step": med * 1e3,
+            "p10_ms": times[len(times) // 10] * 1e3, "p90_ms": times[(len(times) * 9) // 10] * 1e3,
+            "sample": "cfg1: B=1024, F=39, K=8, 26 x 10 000 + 13 x 1 rows; %d timed steps, median" % len(times)}
+
+
 def cpu_restatement(w, steps, warmup, budget_s, full_batch):
     """Times oracle/torch_restatement.DeepFMLayerCPU (one variable per column, separate materialising
     ops, sparse Adagrad) on a bounded sample: the per-step batch is cut so that (steps + warmup)
@@ -124,7 +161,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(w, args, 1),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": r["sample"] + "; PyTorch-CPU restatement of the TF 1.x graph (TF not installable)"},
+                         "sample": r["sample"] + "; PyTorch-CPU restatement of the TF 1.x graph (TF not installable)",
+                         "cpu_model": cpu_model_name()},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -470,7 +508,12 @@ def run_b200(args):
         wc = dir_b200.synth.cfg("cfg2") if w.name == "cfg3" else w
         r = cpu_restatement(wc, 3, 1, args.cpu_seconds, B)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": r["sample"] + "; PyTorch-CPU restatement of the reference's TF 1.x graph"}
+               "sample": r["sample"] + "; PyTorch-CPU restatement of the reference's TF 1.x graph",
+               "cpu_model": cpu_model_name()}
+        try:
+            cpu["cfg1"] = cpu_cfg1()
+        except Exception as e:                                   # an extra, never worth the bench line
+            print("bench.py: cfg1 CPU timing skipped (%s)" % e, file=sys.stderr)
 
     stages, nvlink = None, None
     if world > 1 and getattr(layer, "trace", None) is not None:
@@ -624,7 +667,7 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
         except Exception:
             traffic = None
     roof = {"bound": "hbm", "kernel": top["call"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": top["achieved_gbs"] / peak, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
+            "frac": top["achieved_gbs"] / peak, "frac_of_nominal_8000": top["achieved_gbs"] / 8000.0, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
             if src == "measured" else "fallback (B200_PROFILING.md)", "traffic": traffic,
             "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "us_per_launch": top["us"]}
     return roof, table
