@@ -104,3 +104,29 @@ def test_argument_validation_of_the_widened_entry_points(pkg):
     with pytest.raises(ValueError):
         _lib.check(lib.dir_embed_bwd_reduce_emit_to(P, 20, None, None, P, P, None, P, 4, 2, 16, 100, 2, P, None, P, 20,
                                                     P, 1 << 20, None), "emit_to")      # peer_ptrs missing
+
+
+def test_integration_md_stub_matches_the_library(pkg):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would paste) must bind:
+    execute it against the built library and compare every argtypes list it declares with _lib.SIGNATURES."""
+    import ctypes
+    from dir_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text.split("```python\n# dir_b200_binding.py", 1)[1].split("```", 1)[0]
+    block = "# dir_b200_binding.py" + block
+    block = block.replace('C.CDLL("details-in-recommendation_b200/libdir_b200.so")', "C.CDLL(%r)" % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    lib = ns["lib"]
+    declared = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        declared += 1
+        assert len(fn.argtypes) == len(args), "%s: INTEGRATION.md lists %d arguments, the library takes %d" % (
+            name, len(fn.argtypes), len(args))
+        for a, b in zip(fn.argtypes, args):
+            assert ctypes.sizeof(a) == ctypes.sizeof(b), "%s: argument width differs" % name
+    assert declared >= 8
+    assert ctypes.sizeof(ns["LinearOpt"]) == ctypes.sizeof(_lib.LinearOpt)
