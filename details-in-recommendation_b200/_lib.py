@@ -44,6 +44,16 @@ SIGNATURES = {
                                 c_int64, c_void_p]),
     "dir_rows_gather_to": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dir_onerow_workspace_bytes": (c_size_t, [c_int]),
+    "dir_embed_bwd_reduce_emit_fields_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                    c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_int,
+                                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "dir_embed_bwd_onerow_emit_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "dir_dense_rows_apply": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                     c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dir_ids_push": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_rows_push": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1032,10 +1032,12 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
                        const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
                        int64_t gu_stride, int G, const int64_t* seg_start, const int64_t* peer_ptrs,
                        const int64_t* dst_row_off, void* workspace, size_t workspace_bytes,
-                       dir_stream_t stream) {
+                       dir_stream_t stream, const int32_t* field_sel = nullptr, int n_sel = 0) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "%s: B >= 0, F > 0 required", what);
-  const int64_t n = B * F;
+  if (field_sel == nullptr) n_sel = F;      // the sorted list covers every field
+  if (n_sel <= 0 || n_sel > F) return fail(DIR_EINVAL, "%s: 0 < n_sel <= F required", what);
+  const int64_t n = B * n_sel;
   if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "%s: B*F must be < 2^31", what);
   if (n == 0) return 0;
   if (!ubuf || !g_fm || !S || !uidx || !workspace || (!gu && !peer_ptrs))
@@ -1053,9 +1055,10 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "%s: workspace too small", what);
   BwdArgs a{const_cast<float*>(ubuf), nullptr, ubuf_stride, nullptr, nullptr, 0, feature_value, g_first,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeEmit, uidx, gu, gu_stride, nullptr, 0,
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), field_sel, field_sel ? n_sel : 0, kModeEmit, uidx, gu,
+            gu_stride, nullptr, 0,
             seg_start, peer_ptrs, dst_row_off, G, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
-  set_div(a, F);
+  set_div(a, n_sel);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
 
@@ -1083,6 +1086,23 @@ extern "C" int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stri
   return reduce_emit("embed_bwd_reduce_emit_to", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B,
                      F, K, n_keys, nullptr, out_stride, G, seg_start, peer_ptrs, dst_row_off, workspace,
                      workspace_bytes, stream);
+}
+
+/* EXPERIMENT (see the end of this file): emit_to over a sorted list that covers only the fields field_sel[n_sel] */
+extern "C" int dir_embed_bwd_reduce_emit_fields_to(const float* ubuf, int64_t ubuf_stride,
+                                                   const float* feature_value, const float* g_first,
+                                                   const float* g_fm, const float* S, const float* u,
+                                                   const uint32_t* uidx, int64_t B, int F, int K,
+                                                   int64_t n_keys, const int32_t* field_sel, int n_sel, int G,
+                                                   const int64_t* seg_start, const int64_t* peer_ptrs,
+                                                   const int64_t* dst_row_off, int64_t out_stride,
+                                                   void* workspace, size_t workspace_bytes,
+                                                   dir_stream_t stream) {
+  if (!peer_ptrs || !field_sel)
+    return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit_fields_to: peer_ptrs and field_sel are required");
+  return reduce_emit("embed_bwd_reduce_emit_fields_to", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx,
+                     B, F, K, n_keys, nullptr, out_stride, G, seg_start, peer_ptrs, dst_row_off, workspace,
+                     workspace_bytes, stream, field_sel, n_sel);
 }
 
 /* owner side: per-lookup gradients arrive from the requesters; segmented sum + fused row update */
@@ -1159,4 +1179,240 @@ extern "C" int dir_embed_bag_bwd_reduce_update(
             nullptr, nullptr, nullptr, 0, nullptr, lo, entry_slot, entry_x, emb};
   set_div(a, F);
   return dispatch_bwd(a, K, n_unique_out, st);
+}
+
+// =================================================================================================
+// EXPERIMENT (written after this round's GPU budget was spent; reached only through
+// ShardedEmbeddingFM(DIR_B200_SHARD_ONEROW=1), off by default): one-row (numeric) fields of a
+// row-sharded table kept as REPLICATED parameters.  Every sample of every rank hits the same row,
+// so sorting / exchanging those lookups (a third of cfg2's) buys nothing: each rank forms the
+// field's gradient over its own samples (the column-sum kernel above), the G partial sums meet in
+// every rank's peer buffer, and after the step's barrier every rank adds them in rank order and
+// applies the same update to its replica.  Nothing above this line is changed by it.
+// =================================================================================================
+namespace dir {
+
+struct OneRowWs {
+  int* flags;   // [kOneRowMax]
+  float* part;  // [kOneRowCtas][kOneRowMax][K + 4]
+  size_t total;
+};
+static OneRowWs onerow_carve(void* base, int K) {
+  OneRowWs w;
+  char* p = static_cast<char*>(base);
+  w.flags = reinterpret_cast<int*>(p);
+  const size_t off = align_up((size_t)kOneRowMax * 4, 256);
+  w.part = reinterpret_cast<float*>(p ? p + off : nullptr);
+  w.total = off + align_up((size_t)kOneRowCtas * kOneRowMax * (K + 4) * 4, 256);
+  return w;
+}
+
+template <int LPR>
+static int launch_onerow_partials(const OneRowArgs& a, int n_fields, cudaStream_t st, int* ctas) {
+  constexpr int PER = kOneRowPasses * (32 / LPR);
+  constexpr int SLOTS = 32 / LPR;
+  const int64_t want = (a.B + 7) / 8;
+  const int G = (int)(want < kOneRowCtas ? want : kOneRowCtas);
+  int n = 0;
+  for (int f0 = 0; f0 < n_fields; f0 += PER, ++n) {
+    const int nf = n_fields - f0 < PER ? n_fields - f0 : PER;
+    switch ((nf + SLOTS - 1) / SLOTS) {
+      case 1: embed_bwd_onerow_kernel<LPR, 1><<<G, 256, 0, st>>>(a, f0, nf); break;
+      case 2: embed_bwd_onerow_kernel<LPR, 2><<<G, 256, 0, st>>>(a, f0, nf); break;
+      case 3: embed_bwd_onerow_kernel<LPR, 3><<<G, 256, 0, st>>>(a, f0, nf); break;
+      default: embed_bwd_onerow_kernel<LPR, 4><<<G, 256, 0, st>>>(a, f0, nf); break;
+    }
+  }
+  *ctas = G;
+  return launched("embed_bwd_onerow_partials", n);
+}
+
+// one CTA per one-row field: the CTA partials summed exactly as embed_bwd_onerow_finish_kernel sums them, then
+// the field's (G[K], g1, touched, 0, 0) is stored into slot dst_row_base + rank * n_fields + j of EVERY rank's buffer
+template <int LPR>
+__global__ void __launch_bounds__(256)
+onerow_emit_to_kernel(const OneRowArgs a, int ctas, int n_fields, int G, int rank,
+                      const int64_t* __restrict__ peer_ptrs, int64_t dst_row_base, int64_t out_stride) {
+  constexpr int K = LPR * 4;
+  __shared__ float red[8][33];
+  __shared__ __align__(16) float tot[K + 4];
+  const int j = blockIdx.x;
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  for (int c0 = 0; c0 <= K; c0 += 32) {
+    const int c = c0 + cx;
+    float t = 0.f;
+    if (c <= K)
+#pragma unroll 8
+      for (int g = gy; g < ctas; g += 8) t += __ldg(a.part + ((int64_t)g * kOneRowMax + j) * (K + 4) + c);
+    red[gy][cx] = t;
+    __syncthreads();
+    if (gy == 0 && c <= K) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += red[k][cx];
+      tot[c] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tot[K + 1] = a.flags[j] != 0 ? 1.f : 0.f;  // some sample of this rank had a surviving lookup
+    tot[K + 2] = tot[K + 3] = 0.f;
+  }
+  __syncthreads();
+  constexpr int NV = LPR + 1;  // float4s per row
+  const int64_t row = dst_row_base + (int64_t)rank * n_fields + j;
+  for (int t = threadIdx.x; t < G * NV; t += blockDim.x) {
+    const int q = t / NV, v = t % NV;
+    float4* dst = reinterpret_cast<float4*>(__ldg(peer_ptrs + q)) + (row * out_stride) / 4 + v;
+    *dst = *reinterpret_cast<const float4*>(tot + 4 * v);
+  }
+}
+
+struct DenseApplyArgs {
+  float* table;  // replica: [n_fields] rows, row_stride apart (row | accumulator when Adagrad)
+  float* accum;
+  int64_t row_stride;
+  float* lin;        // [n_fields]
+  float* lin_accum;  // [n_fields]
+  LinOpt lo;         // lo.z: [n_fields]
+  const float* gbuf;  // this rank's peer buffer
+  int64_t gbuf_stride;
+  int64_t dst_row_base;
+  int n_fields, G, opt;
+  float lr;
+  // the sharded table's copy of the row (written by the rank that owns it; shard_row[j] < 0 elsewhere)
+  float* s_table;
+  float* s_accum;
+  int64_t s_row_stride;
+  float* s_lin;
+  float* s_lin_accum;
+  float* s_lin_z;
+  int64_t s_lin_stride;
+  const int64_t* shard_row;
+  unsigned long long* n_unique;  // += touched fields (pass it on one rank only)
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(128) dense_rows_apply_kernel(const DenseApplyArgs a) {
+  constexpr int K = LPR * 4;
+  const int j = blockIdx.x, c = threadIdx.x;
+  if (c > K) return;
+  float g = 0.f, touched = 0.f;
+  for (int q = 0; q < a.G; ++q) {  // rank order: the same sum on every rank
+    const float* src = a.gbuf + (a.dst_row_base + (int64_t)q * a.n_fields + j) * a.gbuf_stride;
+    g += src[c];
+    touched += src[K + 1];
+  }
+  if (touched == 0.f) return;  // no rank had a surviving lookup: the row is not touched
+  const int64_t sr = __ldg(a.shard_row + j);
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  if (c < K) {
+    float* tp = a.table + (int64_t)j * a.row_stride + c;
+    float acc = 0.f;
+    if (adagrad) acc = a.accum[(int64_t)j * a.row_stride + c];
+    const float t = upd(*tp, g, a.lr, acc, adagrad);
+    *tp = t;
+    if (adagrad) a.accum[(int64_t)j * a.row_stride + c] = acc;
+    if (sr >= 0) {
+      a.s_table[sr * a.s_row_stride + c] = t;
+      if (adagrad) a.s_accum[sr * a.s_row_stride + c] = acc;
+    }
+  } else {
+    if (a.lin != nullptr) {
+      float n1, z1;
+      lin_load(a.lo, a.lin_accum, j, n1, z1);
+      lin_apply(a.lo, a.lin + j, a.lin_accum + j, a.lo.z + j, a.lin[j], n1, z1, g);
+      if (sr >= 0) {
+        a.s_lin[sr * a.s_lin_stride] = a.lin[j];
+        if (a.lo.opt != DIR_OPT_SGD) a.s_lin_accum[sr * a.s_lin_stride] = a.lin_accum[j];
+        if (a.lo.opt == DIR_OPT_FTRL) a.s_lin_z[sr * a.s_lin_stride] = a.lo.z[j];
+      }
+    }
+    if (a.n_unique) atomicAdd(a.n_unique, 1ull);
+  }
+}
+
+}  // namespace dir
+
+extern "C" size_t dir_onerow_workspace_bytes(int K) {
+  if (K <= 0) return 0;
+  return dir::onerow_carve(nullptr, K).total;
+}
+
+extern "C" int dir_embed_bwd_onerow_emit_to(const float* dense_table, int64_t row_stride,
+                                            const int64_t* feature_index, const float* feature_value,
+                                            const int64_t* dense_field_offset, const float* g_first,
+                                            const float* g_fm, const float* S, const float* u,
+                                            const int32_t* onerow_fields, int n_onerow, int64_t B, int F,
+                                            int K, int G, int rank, const int64_t* peer_ptrs,
+                                            int64_t dst_row_base, int64_t out_stride, void* workspace,
+                                            size_t workspace_bytes, dir_stream_t stream) {
+  using namespace dir;
+  if (B <= 0 || F <= 0 || n_onerow <= 0 || n_onerow > kOneRowMax || G <= 0 || rank < 0 || rank >= G)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: B, F > 0, 0 < n_onerow <= 64, 0 <= rank < G required");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: K must be one of 4, 8, 16, 32, 64");
+  if (!dense_table || !dense_field_offset || !g_fm || !S || !onerow_fields || !peer_ptrs || !workspace)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: null pointer");
+  if (row_stride < K || (row_stride & 3) || out_stride < K + 4 || (out_stride & 3) || dst_row_base < 0)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: strides must be multiples of 4, >= K (rows), >= K+4 (out)");
+  if (!aligned16(dense_table) || !aligned16(S) || !aligned16(u))
+    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: dense_table, S, u must be 16-byte aligned");
+  OneRowWs w = onerow_carve(workspace, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_onerow_emit_to: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(w.flags, 0, kOneRowMax * 4, st);
+  OneRowArgs o{const_cast<float*>(dense_table), nullptr, row_stride, nullptr, nullptr, 0, feature_index,
+               feature_value, dense_field_offset, g_first, g_fm, S, u, onerow_fields, B, F, DIR_OPT_SGD, 0.f,
+               w.part, w.flags, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}};
+  int ctas = 0, rc;
+#define DIR_ORE(L)                                                                                   \
+  rc = launch_onerow_partials<L>(o, n_onerow, st, &ctas);                                            \
+  if (rc) return rc;                                                                                 \
+  onerow_emit_to_kernel<L><<<n_onerow, 256, 0, st>>>(o, ctas, n_onerow, G, rank, peer_ptrs, dst_row_base, \
+                                                     out_stride);
+  switch (K) {
+    case 4: DIR_ORE(1) break;
+    case 8: DIR_ORE(2) break;
+    case 16: DIR_ORE(4) break;
+    case 32: DIR_ORE(8) break;
+    default: DIR_ORE(16) break;
+  }
+#undef DIR_ORE
+  return launched("embed_bwd_onerow_emit_to");
+}
+
+extern "C" int dir_dense_rows_apply(float* dense_table, float* dense_accum, int64_t row_stride, float* dense_lin,
+                                    float* dense_lin_accum, const float* gbuf, int64_t gbuf_stride,
+                                    int64_t dst_row_base, int n_onerow, int K, int G, int optimizer, float lr,
+                                    const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
+                                    int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
+                                    float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
+                                    int64_t* n_unique_out, dir_stream_t stream) {
+  using namespace dir;
+  if (n_onerow <= 0 || n_onerow > kOneRowMax || G <= 0)
+    return fail(DIR_EINVAL, "dense_rows_apply: 0 < n_onerow <= 64, G > 0 required");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "dense_rows_apply: K must be one of 4, 8, 16, 32, 64");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD) return fail(DIR_EINVAL, "dense_rows_apply: unknown optimizer");
+  if (!dense_table || !gbuf || !shard_row || !shard_table) return fail(DIR_EINVAL, "dense_rows_apply: null pointer");
+  if (optimizer == DIR_OPT_ADAGRAD && (!dense_accum || !shard_accum))
+    return fail(DIR_EINVAL, "dense_rows_apply: Adagrad needs the accumulators");
+  LinOpt lo;
+  if (int rc = resolve_lin("dense_rows_apply", linear_opt, optimizer, lr, dense_lin, dense_lin_accum, lo)) return rc;
+  if (dense_lin && (!shard_lin || (lo.opt != DIR_OPT_SGD && !shard_lin_accum) || (lo.opt == DIR_OPT_FTRL && !shard_lin_z)))
+    return fail(DIR_EINVAL, "dense_rows_apply: the sharded copies of the linear state are required");
+  DenseApplyArgs a{dense_table, dense_accum, row_stride, dense_lin, dense_lin_accum, lo, gbuf, gbuf_stride,
+                   dst_row_base, n_onerow, G, optimizer, lr, shard_table, shard_accum, shard_row_stride, shard_lin,
+                   shard_lin_accum, shard_lin_z, shard_lin_stride, shard_row,
+                   reinterpret_cast<unsigned long long*>(n_unique_out)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (K) {
+    case 4: dense_rows_apply_kernel<1><<<n_onerow, 128, 0, st>>>(a); break;
+    case 8: dense_rows_apply_kernel<2><<<n_onerow, 128, 0, st>>>(a); break;
+    case 16: dense_rows_apply_kernel<4><<<n_onerow, 128, 0, st>>>(a); break;
+    case 32: dense_rows_apply_kernel<8><<<n_onerow, 128, 0, st>>>(a); break;
+    default: dense_rows_apply_kernel<16><<<n_onerow, 128, 0, st>>>(a); break;
+  }
+  return launched("dense_rows_apply");
 }

@@ -175,6 +175,7 @@ class ShardedLookups:
         self.src = None
         self.parity = None          # which half of the double-buffered peer memory (None: the layer alternates)
         self.recv_handle = self.recv_ptrs = None   # DIR_B200_IDS=peer: symmetric-memory handle / peer addresses of recv_buf
+        self.inv_c = None                          # DIR_B200_SHARD_ONEROW=1: compact [B, n_sel] row indices
         self.recv_buf = None        # static mode: fixed-address landing buffer of the ids this rank answers
 
     @staticmethod
@@ -217,6 +218,12 @@ class _ShardedFunction(torch.autograd.Function):
                                        K, G, ptr(h.recv_off), ptr(pb.ptrs[parity]),
                                        ptr(h.fwd_dst_off), pad, st), "dir_rows_gather_to")
             tr.mark("fwd.gather+send")
+            if layer.onerow_rep:
+                # EXPERIMENT: the replicated one-row fields' rows sit behind the exchanged ones (inv points there)
+                tail = pb.bufs[parity][layer.rows_cap:]
+                check(L.dir_rows_gather(ptr(layer.dense_table), layer.row_stride,
+                                        ptr(layer.dense_lin) if layer.first_order else None, 1,
+                                        ptr(layer.dense_ids), layer.n_onerow, K, ptr(tail), pad, st), "dir_rows_gather")
             pb.barrier(parity)
             tr.mark("fwd.barrier")
             ubuf = pb.bufs[parity]
@@ -248,6 +255,7 @@ class _ShardedFunction(torch.autograd.Function):
         layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": B * F}
         ctx.layer, ctx.train, ctx.shape, ctx.h = layer, train, (B, F, K), h
         ctx.use_peer, ctx.parity = use_peer, parity
+        ctx.idx = idx if layer.onerow_rep else None
         ctx.set_materialize_grads(False)
         if train:
             ctx.save_for_backward(val, S, ubuf)
@@ -282,7 +290,27 @@ class _ShardedFunction(torch.autograd.Function):
             ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
             n_keys = layer.plan.cap * layer.plan.world_size
             gfp = ptr(g_first) if layer.first_order else None
-            if ctx.use_peer and layer.fused_push:
+            if ctx.use_peer and layer.onerow_rep:
+                # EXPERIMENT: the sorted list covers the multi-row fields only; the one-row fields' gradients over this
+                # rank's samples go to every rank's buffer (behind the exchanged rows) from a column-sum kernel
+                pb = layer.peer["grads"]
+                G_ = layer.plan.world_size
+                ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * layer.n_sel, 1), K), dev)
+                check(L.dir_embed_bwd_reduce_emit_fields_to(
+                    ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K, n_keys,
+                    ptr(layer.sparse_fields), layer.n_sel, G_, ptr(h.owner_off), ptr(pb.ptrs[ctx.parity]),
+                    ptr(h.bwd_dst_off), pad, ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_fields_to")
+                ows = layer._onerow_ws.get(L.dir_onerow_workspace_bytes(K), dev)
+                check(L.dir_embed_bwd_onerow_emit_to(
+                    ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val), ptr(layer.dense_field_offset), gfp,
+                    ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), layer.n_onerow, B, F, K, G_, layer.plan.rank,
+                    ptr(pb.ptrs[ctx.parity]), layer.recv_cap, pad, ptr(ows), ows.numel(), st),
+                    "dir_embed_bwd_onerow_emit_to")
+                tr.mark("bwd.emit+push")
+                pb.barrier(ctx.parity)
+                tr.mark("bwd.barrier")
+                grecv = pb.bufs[ctx.parity]
+            elif ctx.use_peer and layer.fused_push:
                 # 6+7 in one kernel: each distinct row's sums go straight into its owner's buffer over NVLink
                 pb = layer.peer["grads"]
                 check(L.dir_embed_bwd_reduce_emit_to(
@@ -300,7 +328,7 @@ class _ShardedFunction(torch.autograd.Function):
                                                   ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
                 tr.mark("bwd.emit")
             # 7: sums to their owners; the owner merges the ranks' contributions and updates
-            if ctx.use_peer and layer.fused_push:
+            if ctx.use_peer and (layer.fused_push or layer.onerow_rep):
                 pass
             elif ctx.use_peer:
                 pb = layer.peer["grads"]
@@ -328,6 +356,21 @@ class _ShardedFunction(torch.autograd.Function):
                 tr.mark("bwd.owner_update")
             else:
                 layer.last_n_unique.zero_()
+            if ctx.use_peer and layer.onerow_rep:
+                adagrad = layer.optimizer == "adagrad"
+                lo = layer.dense_linear_opt()
+                check(L.dir_dense_rows_apply(
+                    ptr(layer.dense_table), ptr(layer.dense_accum) if adagrad else None, layer.row_stride,
+                    ptr(layer.dense_lin) if layer.first_order else None,
+                    ptr(layer.dense_lin_acc) if layer.first_order else None, ptr(grecv), pad, layer.recv_cap,
+                    layer.n_onerow, K, layer.plan.world_size, _OPTIMIZERS[layer.optimizer], layer.lr, lo,
+                    ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
+                    ptr(layer.w1) if layer.first_order else None,
+                    ptr(layer.w1_accum) if layer.first_order else None,
+                    ptr(layer.lin_z) if (layer.first_order and layer.lin_z is not None) else None, layer.lin_stride,
+                    ptr(layer.dense_shard_row), ptr(layer.last_n_unique) if layer.plan.rank == 0 else None, st),
+                    "dir_dense_rows_apply")
+                tr.mark("bwd.dense_apply")
             tr.close_step()
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None, None
@@ -399,7 +442,13 @@ class ShardedEmbeddingFM(torch.nn.Module):
         # Payload exchange: NVLink peer memory (symmetric buffers + a device-side barrier) when there is
         # more than one rank and torch's symmetric memory is usable, else NCCL all-to-all.
         self.peer, self._step_parity = None, 0
-        self.static = self.capturing = self.ids_peer = False
+        self.static = self.capturing = self.ids_peer = self.onerow_rep = False
+        # EXPERIMENT (DIR_B200_SHARD_ONEROW=1, needs the peer exchange): one-row fields as replicated parameters
+        onerow = [f for f, r in enumerate(rows) if r == 1][:64]
+        want_rep = os.environ.get("DIR_B200_SHARD_ONEROW", "0") == "1" and 0 < len(onerow) < field_size
+        self.n_onerow = len(onerow) if want_rep else 0
+        sparse = [f for f in range(field_size) if not (want_rep and f in set(onerow))]
+        self.n_sel = len(sparse)
         self.recv_cap = 0
         self.max_batch = int(max_batch)
         want_peer = os.environ.get("DIR_B200_EXCHANGE", "peer") == "peer"
@@ -408,8 +457,10 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 and dist.get_backend(process_group) == "nccl":
             try:
                 cap = min(self.max_batch * field_size, max(self.plan.cap, 1))       # distinct rows a rank can want
-                self.peer = {"rows": PeerBuffers(process_group, cap, self.pad_stride, dev),         # <- owners
-                             "grads": PeerBuffers(process_group, cap * world, self.pad_stride, dev)}  # <- requesters
+                n1 = self.n_onerow                                                  # replicated rows ride behind them
+                self.peer = {"rows": PeerBuffers(process_group, cap + n1, self.pad_stride, dev),         # <- owners
+                             "grads": PeerBuffers(process_group, cap * world + n1 * world, self.pad_stride, dev)}  # <- requesters
+                self.rows_cap = cap
                 # Static mode: every main-stream launch is sized for these capacities and reads the real counts
                 # on the device, every buffer it touches has a fixed address -- so forward + backward of a step
                 # can be captured in a CUDA graph (the id-only presort stays eager on the side stream).
@@ -417,6 +468,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 self.static = os.environ.get("DIR_B200_STATIC", "1") == "1"
                 # experiment (not yet run on a GPU): ids through peer memory instead of the NCCL all-to-all
                 self.ids_peer = self.static and os.environ.get("DIR_B200_IDS", "nccl") == "peer"
+                self.onerow_rep = self.static and want_rep
             except Exception as e:                                              # no IPC / fabric support
                 if rank == 0:
                     print("ShardedEmbeddingFM: symmetric memory unavailable (%s); using NCCL all-to-all" % e,
@@ -429,6 +481,10 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 self.accum.fill_(initial_accumulator_value)
             if self.lin_acc is not None:
                 self.lin_acc.fill_(initial_accumulator_value)
+        if not self.onerow_rep:
+            self.n_onerow, self.n_sel = 0, field_size
+        else:
+            self._init_onerow_replicas(onerow, sparse, dev, initial_accumulator_value)
 
     @property
     def table(self):
@@ -446,6 +502,70 @@ class ShardedEmbeddingFM(torch.nn.Module):
     def w1_accum(self):
         return self.lin_acc[:, 0] if self.lin_acc is not None else None
 
+    # -- EXPERIMENT: replicated one-row fields ------------------------------------------------------------------
+    @torch.no_grad()
+    def _init_onerow_replicas(self, onerow, sparse, dev, acc0):
+        K, G, rank = self.embedding_size, self.plan.world_size, self.plan.rank
+        n1 = len(onerow)
+        self.register_buffer("onerow_fields", torch.tensor(onerow, dtype=torch.int32, device=dev))
+        self.register_buffer("sparse_fields", torch.tensor(sparse, dtype=torch.int32, device=dev))
+        self.register_buffer("dense_ids", torch.arange(n1, dtype=torch.int32, device=dev))
+        dfo = [0] * self.field_size
+        for j, f in enumerate(onerow):
+            dfo[f] = j
+        self.register_buffer("dense_field_offset", torch.tensor(dfo, dtype=torch.int64, device=dev))
+        grow = [self.plan.field_offset[f] for f in onerow]                     # the fields' rows in the full table
+        self.dense_global_rows = grow
+        self.register_buffer("dense_shard_row", torch.tensor([g // G if g % G == rank else -1 for g in grow],
+                                                             dtype=torch.int64, device=dev))
+        self.register_buffer("dense_rows", torch.zeros((n1, self.row_stride), dtype=torch.float32, device=dev))
+        self.register_buffer("dense_lin", torch.zeros(n1, dtype=torch.float32, device=dev))
+        self.register_buffer("dense_lin_acc", torch.full((n1,), float(acc0), dtype=torch.float32, device=dev)
+                             if self.lin_acc is not None else None)
+        self.register_buffer("dense_lin_z", torch.zeros(n1, dtype=torch.float32, device=dev)
+                             if self.lin_z is not None else None)
+        self._onerow_ws = _Workspace()
+        self._sync_onerow_replicas()
+
+    @torch.no_grad()
+    def _sync_onerow_replicas(self):
+        """Replicas <- the owners' rows of the sharded table (all-reduce of rows that are zero off their owner)."""
+        K = self.embedding_size
+        buf = torch.zeros((self.n_onerow, self.row_stride + 3), dtype=torch.float32, device=self.rows.device)
+        mine = self.dense_shard_row >= 0
+        sr = self.dense_shard_row[mine]
+        buf[mine, :self.row_stride] = self.rows[sr]
+        buf[mine, self.row_stride] = self.lin_rows[sr, 0]
+        if self.lin_acc is not None:
+            buf[mine, self.row_stride + 1] = self.lin_acc[sr, 0]
+        if self.lin_z is not None:
+            buf[mine, self.row_stride + 2] = self.lin_z[sr, 0]
+        if dist.is_initialized() and self.plan.world_size > 1:
+            dist.all_reduce(buf, group=self.group)
+        self.dense_rows.copy_(buf[:, :self.row_stride])
+        self.dense_lin.copy_(buf[:, self.row_stride])
+        if self.dense_lin_acc is not None:
+            self.dense_lin_acc.copy_(buf[:, self.row_stride + 1])
+        if self.dense_lin_z is not None:
+            self.dense_lin_z.copy_(buf[:, self.row_stride + 2])
+
+    @property
+    def dense_table(self):
+        return self.dense_rows[:, :self.embedding_size]
+
+    @property
+    def dense_accum(self):
+        return self.dense_rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+
+    def dense_linear_opt(self):
+        """dir_linear_opt for the replicas (same rule as the sharded weights, the replicas' own Ftrl slot)."""
+        if self.linear_optimizer is None:
+            return None
+        from .layers import _LINEAR_OPTIMIZERS
+        z = self.dense_lin_z.data_ptr() if self.dense_lin_z is not None else None
+        return _lib.ctypes.byref(_lib.LinearOpt(_LINEAR_OPTIMIZERS[self.linear_optimizer], self.linear_lr,
+                                                self.l1, self.l2, z))
+
     @torch.no_grad()
     def load_tables(self, table=None, w1=None):
         """Takes the FULL [n_rows, K] table / [n_rows] first-order weights and keeps this rank's rows."""
@@ -453,6 +573,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
             if src is not None:
                 mine = torch.as_tensor(self.plan.shard_of(src), dtype=torch.float32)
                 dst[:mine.shape[0]].copy_(mine.to(dst.device))
+        if self.onerow_rep:
+            self._sync_onerow_replicas()
 
     def _prepare(self, feature_index, feature_value):
         if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
@@ -488,7 +610,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
         K, G = self.embedding_size, self.plan.world_size
         dev = idx.device
         L = _lib.lib()
-        n = B * F
+        n_full = B * F
+        n = B * self.n_sel if self.onerow_rep else n_full      # EXPERIMENT: one-row fields stay out of the sorted list
         h = handle if handle is not None else ShardedLookups()
         main, side = torch.cuda.current_stream(), self.side_stream(dev)
         if fork:        # order after whatever the current stream has queued (it may be producing the ids)
@@ -506,6 +629,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 h.uidx = torch.empty(n, dtype=torch.int32, device=dev)
                 h.ulocal = torch.empty(n, dtype=torch.int32, device=dev)
                 h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
+                if self.onerow_rep:
+                    h.inv_c = torch.empty((B, self.n_sel), dtype=torch.int64, device=dev)
                 h.owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
                 h.recv_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
                 h.fwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
@@ -521,10 +646,12 @@ class ShardedEmbeddingFM(torch.nn.Module):
                 elif self.static:
                     h.recv_buf = torch.empty(self.recv_cap, dtype=torch.int32, device=dev)
             check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
-                                   self.plan.n_rows, B, F, G, None, F, ptr(h.keys),
+                                   self.plan.n_rows, B, F, G, ptr(self.sparse_fields) if self.onerow_rep else None,
+                                   self.n_sel if self.onerow_rep else F, ptr(h.keys),
                                    ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
             tr.mark("pre.keys")
-            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n, 1), K), dev)
+            # sized for all B * F lookups whatever the list holds, so that nobody re-allocates it later
+            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n_full, 1), K), dev)
             check(L.dir_embed_bwd_sort(ptr(h.keys), n, self.plan.cap * G, ptr(ws), ws.numel(), st),
                   "dir_embed_bwd_sort")
             tr.mark("pre.sort")
@@ -535,8 +662,16 @@ class ShardedEmbeddingFM(torch.nn.Module):
             else:
                 skeys = spos = None
             ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(n), 1), dev)
-            check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, ptr(h.uidx), ptr(h.ulocal), ptr(h.inv),
+            check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, ptr(h.uidx), ptr(h.ulocal),
+                                     ptr(h.inv_c if self.onerow_rep else h.inv),
                                      ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+            if self.onerow_rep:              # compact [B, n_sel] indices -> their columns of the [B, F] index
+                h.inv.index_copy_(1, self.sparse_fields.long(), h.inv_c)
+                # the replicated rows sit behind the exchanged ones in the row buffer; an id other than 0 is pruned
+                one = self.onerow_fields.long()
+                tail = self.rows_cap + torch.arange(self.n_onerow, dtype=torch.int64, device=dev)[None, :]
+                h.inv.index_copy_(1, one, torch.where(idx.index_select(1, one) == 0, tail.expand(B, -1),
+                                                      torch.full_like(tail, -1).expand(B, -1)))
             tr.mark("pre.unique")
             # counts: the one host read per step (NCCL needs the split sizes); it waits on the side stream only
             send_counts = h.owner_off[1:] - h.owner_off[:-1]

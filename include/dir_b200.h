@@ -234,6 +234,41 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
                            dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * EXPERIMENT, off by default (ShardedEmbeddingFM with DIR_B200_SHARD_ONEROW=1; written after round 1's
+ * GPU budget was spent, not yet run): one-row (numeric) fields of a row-sharded table kept as
+ * replicated parameters instead of being sorted and exchanged like every other lookup.
+ *   dir_embed_bwd_reduce_emit_fields_to  dir_embed_bwd_reduce_emit_to over a sorted list that covers
+ *       only the fields field_sel[n_sel] (keys from dir_shard_keys with the same list)
+ *   dir_embed_bwd_onerow_emit_to  each one-row field's gradient over THIS rank's samples (fixed-order
+ *       column sums) -> row dst_row_base + rank * n_onerow + j of every rank's buffer, as
+ *       (G[K], g1, touched, 0, 0); dense_field_offset[F] maps a field to its row of dense_table
+ *   dir_dense_rows_apply  after the barrier: the G ranks' sums added in rank order, the same update
+ *       applied to every replica; shard_row[j] >= 0 names the row of the sharded table to mirror into
+ *       (on the rank that owns it), so the table stays a faithful view
+ */
+size_t dir_onerow_workspace_bytes(int K);
+int dir_embed_bwd_reduce_emit_fields_to(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
+                                        const float* g_first, const float* g_fm, const float* S,
+                                        const float* u, const uint32_t* uidx, int64_t B, int F, int K,
+                                        int64_t n_keys, const int32_t* field_sel, int n_sel, int G,
+                                        const int64_t* seg_start, const int64_t* peer_ptrs,
+                                        const int64_t* dst_row_off, int64_t out_stride, void* workspace,
+                                        size_t workspace_bytes, dir_stream_t stream);
+int dir_embed_bwd_onerow_emit_to(const float* dense_table, int64_t row_stride, const int64_t* feature_index,
+                                 const float* feature_value, const int64_t* dense_field_offset,
+                                 const float* g_first, const float* g_fm, const float* S, const float* u,
+                                 const int32_t* onerow_fields, int n_onerow, int64_t B, int F, int K, int G,
+                                 int rank, const int64_t* peer_ptrs, int64_t dst_row_base, int64_t out_stride,
+                                 void* workspace, size_t workspace_bytes, dir_stream_t stream);
+int dir_dense_rows_apply(float* dense_table, float* dense_accum, int64_t row_stride, float* dense_lin,
+                         float* dense_lin_accum, const float* gbuf, int64_t gbuf_stride, int64_t dst_row_base,
+                         int n_onerow, int K, int G, int optimizer, float lr,
+                         const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
+                         int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
+                         float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
+                         int64_t* n_unique_out, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-hot / weighted bags: every (sample, field) holds a variable-length list of (id, weight) --
  * the capability `myself_input_layer` exists for (models/DeepFM/deepFM.py:53, 77, 363-400; the
  * weighted column of dataset/SequenceTensorFlowDataset/test4.py:50-55, 113-116).  CSR layout:
