@@ -40,7 +40,7 @@ struct BwdWorkspace {
   uint32_t* long_count;
   unsigned long long* n_unique;
   int* onerow_flags;   // [64]
-  float* onerow_part;  // [296][64][K + 4]
+  double* onerow_part; // [296][64][K + 4] fp64 partial column sums
   size_t total;
 };
 
@@ -120,7 +120,7 @@ static BwdWorkspace carve(void* base, int64_t n, int K) {
   w.onerow_flags = reinterpret_cast<int*>(take(64 * 4));
   w.part1 = reinterpret_cast<float*>(take((size_t)nchunks * 2 * 4));
   w.part = reinterpret_cast<float*>(take((size_t)nchunks * 2 * K * 4));
-  w.onerow_part = reinterpret_cast<float*>(take((size_t)296 * 64 * (K + 4) * 4));
+  w.onerow_part = reinterpret_cast<double*>(take((size_t)296 * 64 * (K + 4) * 8));
   w.total = off;
   return w;
 }
@@ -662,6 +662,10 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
 // every sample looks up the same row: no sort is needed, the row's gradient is a column sum over
 // the batch.  Warps stride over samples and keep one accumulator per field (LPR lanes per field);
 // warps, then CTAs, are combined in a fixed order and the finish kernel applies the update.
+// Each term is formed in fp32 in the oracle's evaluation order; the B-term column sum is carried in
+// fp64 (thread -> warp -> CTA -> grid, fixed order) and rounded to fp32 once: a 65 536-term fp32 sum
+// whose result lands near zero otherwise leaves ~3e-5 absolute on G, which Adagrad's lr/sqrt(0.1)
+// slope turns into > 5e-6 on the row (round-1 full-size parity failure).
 constexpr int kOneRowPasses = 4;   // fields per launch = kOneRowPasses * 32 / LPR
 constexpr int kOneRowCtas = 296;   // two per SM
 constexpr int kOneRowMax = 64;     // one-row fields per call
@@ -685,7 +689,7 @@ struct OneRowArgs {
   int F;
   int opt;
   float lr;
-  float* part;   // [kOneRowCtas][kOneRowMax][K + 4]
+  double* part;  // [kOneRowCtas][kOneRowMax][K + 4]
   int* flags;    // [kOneRowMax] some sample had a surviving lookup
   unsigned long long* n_unique;
   LinOpt lo;
@@ -697,20 +701,21 @@ embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
   constexpr int K = LPR * 4;
   constexpr int SLOTS = 32 / LPR;
   constexpr int UN = 4;  // samples whose loads are in flight together
-  __shared__ float4 sm4[8][P][32];
-  __shared__ float sm1[8][P][32];
+  __shared__ double sm4[8][P][32][4];
+  __shared__ double sm1[8][P][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sub = lane % LPR, slot = lane / LPR;
-  float4 T[P], acc[P];
-  float acc1[P];
+  float4 T[P];
+  double acc[P][4], acc1[P];
   int fld[P];
   bool any[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const int j = p * SLOTS + slot;
     fld[p] = j < nf ? __ldg(a.fields + f0 + j) : -1;
-    acc[p] = T[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc1[p] = 0.f;
+    T[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
+    acc1[p] = 0.0;
     any[p] = false;
     if (fld[p] >= 0)
       T[p] = *(reinterpret_cast<const float4*>(a.table + __ldg(a.field_offset + fld[p]) * a.row_stride) + sub);
@@ -760,18 +765,19 @@ embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
       for (int p = 0; p < P; ++p) {
         if (!ok[s][p]) continue;
         const float x = v[s][p], gg = g2[s];
-        acc[p].x = __fadd_rn(acc[p].x, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].x, __fmul_rn(x, T[p].x))), ub[s][p].x)));
-        acc[p].y = __fadd_rn(acc[p].y, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].y, __fmul_rn(x, T[p].y))), ub[s][p].y)));
-        acc[p].z = __fadd_rn(acc[p].z, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].z, __fmul_rn(x, T[p].z))), ub[s][p].z)));
-        acc[p].w = __fadd_rn(acc[p].w, __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].w, __fmul_rn(x, T[p].w))), ub[s][p].w)));
-        acc1[p] = __fadd_rn(acc1[p], __fmul_rn(g1[s], x));
+        acc[p][0] += (double)__fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].x, __fmul_rn(x, T[p].x))), ub[s][p].x));
+        acc[p][1] += (double)__fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].y, __fmul_rn(x, T[p].y))), ub[s][p].y));
+        acc[p][2] += (double)__fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].z, __fmul_rn(x, T[p].z))), ub[s][p].z));
+        acc[p][3] += (double)__fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[s].w, __fmul_rn(x, T[p].w))), ub[s][p].w));
+        acc1[p] += (double)__fmul_rn(g1[s], x);
         any[p] = true;
       }
     }
   }
 #pragma unroll
   for (int p = 0; p < P; ++p) {
-    sm4[wib][p][lane] = acc[p];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sm4[wib][p][lane][c] = acc[p][c];
     sm1[wib][p][lane] = acc1[p];
     if (any[p] && sub == 0) a.flags[f0 + p * SLOTS + slot] = 1;  // benign race: everyone writes 1
   }
@@ -780,16 +786,17 @@ embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
     const int p = wib;
     const int j = p * SLOTS + slot;
     if (j < nf) {
-      float4 t = sm4[0][p][lane];
-      float t1 = sm1[0][p][lane];
+      double t[4] = {sm4[0][p][lane][0], sm4[0][p][lane][1], sm4[0][p][lane][2], sm4[0][p][lane][3]};
+      double t1 = sm1[0][p][lane];
 #pragma unroll
       for (int w = 1; w < 8; ++w) {
-        const float4 o = sm4[w][p][lane];
-        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] += sm4[w][p][lane][c];
         t1 += sm1[w][p][lane];
       }
-      float* dst = a.part + ((int64_t)blockIdx.x * kOneRowMax + f0 + j) * (K + 4);
-      *(reinterpret_cast<float4*>(dst) + sub) = t;
+      double* dst = a.part + ((int64_t)blockIdx.x * kOneRowMax + f0 + j) * (K + 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[sub * 4 + c] = t[c];
       if (sub == 0) dst[K] = t1;
     }
   }
@@ -799,24 +806,24 @@ embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
 template <int LPR>
 __global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneRowArgs a, int G) {
   constexpr int K = LPR * 4;
-  __shared__ float red[8][33];
+  __shared__ double red[8][33];
   __shared__ float tot[K + 1];
   const int j = blockIdx.x;
   if (a.flags[j] == 0) return;  // no surviving lookup: the row is not touched
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   for (int c0 = 0; c0 <= K; c0 += 32) {
     const int c = c0 + cx;
-    float t = 0.f;
+    double t = 0.0;
     if (c <= K)
 #pragma unroll 8
       for (int g = gy; g < G; g += 8) t += __ldg(a.part + ((int64_t)g * kOneRowMax + j) * (K + 4) + c);
     red[gy][cx] = t;
     __syncthreads();
     if (gy == 0 && c <= K) {
-      float v = 0.f;
+      double v = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) v += red[k][cx];
-      tot[c] = v;
+      tot[c] = (float)v;  // the one rounding of the column sum
     }
     __syncthreads();
   }
@@ -1194,7 +1201,7 @@ namespace dir {
 
 struct OneRowWs {
   int* flags;   // [kOneRowMax]
-  float* part;  // [kOneRowCtas][kOneRowMax][K + 4]
+  double* part;  // [kOneRowCtas][kOneRowMax][K + 4]
   size_t total;
 };
 static OneRowWs onerow_carve(void* base, int K) {
@@ -1202,8 +1209,8 @@ static OneRowWs onerow_carve(void* base, int K) {
   char* p = static_cast<char*>(base);
   w.flags = reinterpret_cast<int*>(p);
   const size_t off = align_up((size_t)kOneRowMax * 4, 256);
-  w.part = reinterpret_cast<float*>(p ? p + off : nullptr);
-  w.total = off + align_up((size_t)kOneRowCtas * kOneRowMax * (K + 4) * 4, 256);
+  w.part = reinterpret_cast<double*>(p ? p + off : nullptr);
+  w.total = off + align_up((size_t)kOneRowCtas * kOneRowMax * (K + 4) * 8, 256);
   return w;
 }
 
@@ -1234,23 +1241,23 @@ __global__ void __launch_bounds__(256)
 onerow_emit_to_kernel(const OneRowArgs a, int ctas, int n_fields, int G, int rank,
                       const int64_t* __restrict__ peer_ptrs, int64_t dst_row_base, int64_t out_stride) {
   constexpr int K = LPR * 4;
-  __shared__ float red[8][33];
+  __shared__ double red[8][33];
   __shared__ __align__(16) float tot[K + 4];
   const int j = blockIdx.x;
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   for (int c0 = 0; c0 <= K; c0 += 32) {
     const int c = c0 + cx;
-    float t = 0.f;
+    double t = 0.0;
     if (c <= K)
 #pragma unroll 8
       for (int g = gy; g < ctas; g += 8) t += __ldg(a.part + ((int64_t)g * kOneRowMax + j) * (K + 4) + c);
     red[gy][cx] = t;
     __syncthreads();
     if (gy == 0 && c <= K) {
-      float v = 0.f;
+      double v = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) v += red[k][cx];
-      tot[c] = v;
+      tot[c] = (float)v;
     }
     __syncthreads();
   }

@@ -83,15 +83,35 @@ def test_backward_update_full_size(pkg, cuda, name, optimizer, lr):
         err1 = (got_w - (w64 - g1)).abs()
         assert bool((err1 <= REL * g1abs + 2.0 ** -23 * (w64.abs() + g1.abs())).all())
     else:
+        # Adagrad: T' = T - lr f(G), f(G) = G / sqrt(0.1 + G^2), monotone with slope 0.1 / (0.1 + G^2)^1.5 <= 1/sqrt(0.1).
+        # The gradient sum is allowed the same cancellation-aware band as in the SGD branch (REL * Gfloor);
+        # what reaches the row is that band pushed through f -- exactly, since f is monotone -- plus the rounding of
+        # rsqrt / multiply / subtract (a few ulp of the step and of T).  A flat REL * max|T| ignores the conditioning:
+        # it is too loose where |G| is large and too tight where a 65 536-term sum lands near zero.
+        def f(g):
+            return g / (0.1 + g * g).sqrt()
+
+        def band(g, d, t64):
+            step = lr * torch.maximum((f(g + d) - f(g)).abs(), (f(g - d) - f(g)).abs())
+            return step + 2.0 ** -21 * lr * f(g).abs() + 2.0 ** -23 * (t64.abs() + lr)
+
         acc64 = 0.1 + G * G
-        want_T = torch.where(touched[:, None], T64 - lr * G / acc64.sqrt(), T64)
-        assert float((got_T - want_T).abs().max()) <= REL * float(T64.abs().max())
+        want_T = torch.where(touched[:, None], T64 - lr * f(G), T64)
+        err = (got_T - want_T).abs()
+        bound = band(G, REL * Gfloor, T64)
+        assert bool((err <= bound).all()), (float((err - bound).max()), int((err > bound).sum()))
+        # and the kernel sits far inside that band where the band is widest: one-row fields (B-term column sums, carried
+        # in fp64 by the kernel; what is left is the fp32 rounding of the B terms themselves, ~2e-6 on the row at G ~ 0)
+        one = [int(layer.field_offset[f]) for f in range(F) if w.rows_per_field[f] == 1]
+        if one:
+            assert float(err[one].max()) <= 4 * REL * float(T64.abs().max()), float(err[one].max())
         got_acc = after[:, K:].double()
         want_acc = torch.where(touched[:, None], acc64, torch.full_like(acc64, 0.1))
         assert bool(((got_acc - want_acc).abs() <= REL * (0.1 + 2 * G.abs() * Gfloor)).all())
         n64 = 0.1 + g1 * g1
-        want_w = torch.where(touched, w64 - lr * g1 / n64.sqrt(), w64)
-        assert float((got_w - want_w).abs().max()) <= REL * (float(w64.abs().max()) + lr)
+        want_w = torch.where(touched, w64 - lr * f(g1), w64)
+        err1 = (got_w - want_w).abs()
+        assert bool((err1 <= band(g1, REL * g1abs, w64)).all()), float(err1.max())
         got_n = layer.lin_acc[:, 0].double()
         want_n = torch.where(touched, n64, torch.full_like(n64, 0.1))
         assert bool(((got_n - want_n).abs() <= REL * (0.1 + 2 * g1.abs() * g1abs)).all())
