@@ -240,10 +240,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "DIR_B200_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["DIR_B200_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)                   # its banner would share stdout with the JSON line
+        if "NCCL_DEBUG" in os.environ:                          # keep NCCL's banner: it goes to stderr, the JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # owns stdout
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
@@ -260,9 +258,13 @@ def run_b200(args):
         layer = dir_b200.EmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
                                      emit_embeddings=emit, device=dev).train()
     else:
+        # cfg4's 880 M rows are filled on the device from a counter hash (no 56 GB host table, no fp32 temporaries)
         layer = dir_b200.ShardedEmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
-                                            emit_embeddings=emit, max_batch=B, device=dev).train()
+                                            emit_embeddings=emit, max_batch=B, device=dev,
+                                            init="counter" if w.name == "cfg4" else "trunc_normal").train()
     layer.w1.normal_(0.0, 0.01)            # TF's zero init would make the first-order path trivial
+    if getattr(layer, "n_dense", 0):
+        layer._sync_dense_replicas()
     cross = dir_b200.CrossNetwork(d, L, device=dev).train() if L else None
 
     # R rotating input sets: pinned host copies (for e2e) and device-resident copies (for value)
@@ -275,25 +277,33 @@ def run_b200(args):
         ups.append(torch.randn((B, d), device=dev) * 1e-2 if emit else None)
     n_rows_touched = []
 
-    # The sort of a batch needs its ids only, so the sort for batch i+1 is issued (side stream) at the
-    # start of step i and runs underneath it: every step still performs exactly one sort.
-    pipelined = True
-    ready_events = {}          # e2e: slot -> event of its H2D copy (the sharded presort waits for it)
+    # The id-only work of a batch (keys, sort; sharded: distinct-row numbering and the id exchange) needs its ids
+    # only, so the work for batch i+1 is issued at the start of step i and runs underneath it on the side stream:
+    # every step still performs exactly one sort.  A running cursor keeps the rotation (and, sharded, the
+    # one-batch-ahead id phase) consistent across the warm-up, timed, e2e and trace loops.
+    ready_events = {}          # e2e: slot -> event of its H2D copy (the id work of that batch waits for it)
     handles = [dir_b200.SortedLookups() if world == 1 else dir_b200.ShardedLookups() for _ in range(R)]
+    cursor = [0]
+    side = layer.side_stream(dev)
 
-    def step(idx, val, y, up, slot=None, events=True, id_work=True):
-        """One step on resident inputs.  id_work=False leaves the sharded layer's id-only work for the next
-        batch (NCCL + one host read: not capturable) to the caller."""
-        pre = None
-        if slot is not None:
-            nxt = (slot + 1) % R
-            if world == 1:
-                layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=events)
-            pre = handles[slot]
-        first, fm, emb = layer(idx, val, presorted=pre)
+    def id_work(nxt, phase="both", inline=False):
+        if world == 1:
+            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=not inline)
+        elif inline:
+            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], inline=True, phase=phase)
+        else:
+            layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False, after=ready_events.get(nxt))
+
+    def model(slot):
+        idx, val, y = devs[slot]
+        up = ups[slot]
+        first, fm, emb = layer(idx, val, presorted=handles[slot])
         with torch.no_grad():
             logits = first + fm
             g = torch.sigmoid(logits).sub_(y.unsqueeze(1))          # SUM-reduced CE: no 1/B (deepFM.py:72)
+        return first, fm, emb, g, up, logits
+
+    def backward(first, fm, emb, g, up):
         if cross is not None:
             xL = cross(emb)
             torch.autograd.backward((first, fm, xL), (g, g, up))
@@ -301,97 +311,101 @@ def run_b200(args):
             torch.autograd.backward((first, fm, emb), (g, g, up))
         else:
             torch.autograd.backward((first, fm), (g, g))
-        if world == 1 and slot is not None and not events:     # captured: join the side branch ourselves
-            torch.cuda.current_stream().wait_stream(layer.side_stream(dev))
-        if world > 1 and slot is not None and id_work:
-            sharded_id_work(nxt)
+
+    def step(slot, captured=False):
+        """One step on resident inputs of `slot` plus the id-only work of the next slot."""
+        nxt = (slot + 1) % R
+        main = torch.cuda.current_stream()
+        if world == 1:
+            id_work(nxt, inline=captured)          # forks onto the side stream itself
+            first, fm, emb, g, up, logits = model(slot)
+            backward(first, fm, emb, g, up)
+            if captured:                           # join the side branch inside the graph
+                main.wait_stream(side)
+            return logits
+        if not captured:
+            first, fm, emb, g, up, logits = model(slot)
+            backward(first, fm, emb, g, up)
+            # issued AFTER this step's kernels are queued; it waits (on the device) for this step's rows barrier
+            id_work(nxt)
+            return logits
+        # captured, sharded: the id phase of the next batch is a branch of the same graph.  Its local half (keys,
+        # sort, numbering) starts with the step; its exchange half starts once this step's rows barrier has
+        # passed -- every rank is then done with the previous step, whose buffers the exchange overwrites.
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            id_work(nxt, phase="local", inline=True)
+        first, fm, emb, g, up, logits = model(slot)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            id_work(nxt, phase="exchange", inline=True)
+        backward(first, fm, emb, g, up)
+        main.wait_stream(side)
         return logits
 
-    def sharded_id_work(nxt):
-        # sharded: the next batch's id-only work (incl. the one host read of the split sizes) is issued
-        # AFTER this step's kernels are queued, so the host wait does not starve the main stream
-        layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False, after=ready_events.get(nxt))
-
     # warm every slot eagerly (allocates workspaces), note U per slot
-    out = None
-    if pipelined:
-        layer.presort(devs[0][0], devs[0][1], handle=handles[0])
+    id_work(0)
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)
     for r in range(R):
-        out = step(*devs[r], ups[r], slot=r)
+        step(r)
         n_rows_touched.append(int(layer.last_n_unique.item()))
     torch.cuda.synchronize()
+    if world > 1:
+        layer.check_errors()
+    cursor[0] = 0                                  # the last step left slot 0's id work ready
 
     graphs, graph_out = [None] * R, [None] * R
-    # Sharded: the main-stream half of a step (rows over NVLink, FM, gradient sums over NVLink, owner update) has
-    # device-side sizes and fixed addresses in the layer's static mode, so it is captured too; the id-only half
-    # (sort, NCCL id exchange, the one host read of the split sizes) stays eager on the side stream.
-    sharded_graph = (world > 1 and getattr(layer, "static", False) and R % 2 == 0
-                     and os.environ.get("DIR_B200_SHARDED_GRAPH", "1") == "1")
-    use_graph = not args.no_graph and (world == 1 or sharded_graph)
-    if use_graph and world > 1:
+    use_graph = not args.no_graph and (world == 1 or (layer.px is not None and R % 2 == 0))
+    if use_graph:
         try:
-            for r in range(R):
-                handles[r].parity = r % 2          # captured: the half of the peer buffers is baked in
-            for r in range(R):                      # every slot once more, eagerly, with its fixed parity
-                step(*devs[r], ups[r], slot=r)
-            torch.cuda.synchronize()
-            dist.barrier()
-            layer.capturing = True                 # the wait for the side stream happens outside the graph
-            pool = None
-            for r in range(R):
-                # handle r holds batch r's id work at fixed addresses (the eager pass above left it there)
-                g_ = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_, pool=pool, capture_error_mode="thread_local"):
-                    graph_out[r] = step(*devs[r], ups[r], slot=r, id_work=False)
-                pool = g_.pool()
-                graphs[r] = g_
-            layer.capturing = False
-            torch.cuda.synchronize()
-            dist.barrier()
-        except Exception as e:
-            layer.capturing = False
-            if rank == 0:
-                print("bench.py: CUDA graph capture of the sharded step failed (%s); launching eagerly" % e,
-                      file=sys.stderr)
-            use_graph = False
-            for r in range(R):
-                handles[r].parity = None
-            torch.cuda.synchronize()
-    elif use_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
+            if world > 1:
                 for r in range(R):
-                    step(*devs[r], ups[r], slot=r, events=False)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            pool = None
-            for r in range(R):
-                g_ = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_, pool=pool):
-                    graph_out[r] = step(*devs[r], ups[r], slot=r, events=False)
-                pool = g_.pool()
-                graphs[r] = g_
-            if pipelined:                       # slot 0's list for the first replay
-                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
+                    handles[r].parity = r % 2      # captured: the exchange buffer of a slot is baked in
+                    assert handles[r].parity is not None
+                # one more eager round so that every slot has run with exactly the parity it is captured with
+                for r in range(R):
+                    step(r)
                 torch.cuda.synchronize()
+                assert [h.parity for h in handles] == [r % 2 for r in range(R)], "parity drifted"
+                dist.barrier()
+            cap_stream = torch.cuda.Stream()
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            layer.capturing = True
+            pool = None
+            with torch.cuda.stream(cap_stream):
+                for r in range(R):
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_, pool=pool, stream=cap_stream, capture_error_mode="thread_local"):
+                        graph_out[r] = step(r, captured=True)
+                    pool = g_.pool()
+                    graphs[r] = g_
+            layer.capturing = False
+            torch.cuda.current_stream().wait_stream(cap_stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
         except Exception as e:                                       # eager launches are still our kernels
+            layer.capturing = False
             if rank == 0:
                 print("bench.py: CUDA graph capture failed (%s); launching eagerly" % e, file=sys.stderr)
             use_graph = False
             torch.cuda.synchronize()
+    if world == 1:
+        id_work(0)                                 # slot 0's list for the first step
+        torch.cuda.synchronize()
 
-    def run(slot):
-        if use_graph and world > 1:
-            torch.cuda.current_stream().wait_event(handles[slot].event)    # this batch's id work (side stream)
-            graphs[slot].replay()
-            sharded_id_work((slot + 1) % R)
-            return graph_out[slot]
+    def run():
+        slot = cursor[0] % R
+        cursor[0] += 1
         if use_graph:
+            if world > 1:
+                ev = ready_events.get((slot + 1) % R)
+                if ev is not None:                 # e2e: the graph's id branch reads the next batch
+                    torch.cuda.current_stream().wait_event(ev)
             graphs[slot].replay()
-            return graph_out[slot]
-        return step(*devs[slot], ups[slot], slot=slot)
+            return slot, graph_out[slot]
+        return slot, step(slot)
 
     def barrier():
         if world > 1:
@@ -401,21 +415,21 @@ def run_b200(args):
     lib = dir_b200._lib.lib()
     # per-step launch count of OUR kernels (graph replays do not pass through the library's counter)
     n0 = lib.dir_launch_count()
-    step(*devs[0], ups[0], slot=0)
+    s0 = cursor[0] % R
+    step(s0)
+    cursor[0] += 1
     launches_per_step = int(lib.dir_launch_count() - n0)
-    if pipelined:                               # that step presorted slot 1; slot 0 runs next
-        layer.presort(devs[0][0], devs[0][1], handle=handles[0])
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
 
     # ---------------- value: device-resident inputs -------------------------------------------
     for s in range(args.warmup):
-        run(s % R)
+        run()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record()
         for s in range(args.steps):
-            run(s % R)
+            run()
         ev1.record()
         clocks.sample()
         torch.cuda.synchronize()
@@ -430,8 +444,8 @@ def run_b200(args):
 
     # ---------------- e2e: pinned host inputs, H2D + D2H inside the timed region ---------------
     e2e = None
-    if not args.no_e2e:
-        # R device slots form a ring: while step s computes on slot s%R, the sort of batch s+1 (already on
+    if not args.no_e2e and R >= 3:
+        # R device slots form a ring: while step s computes on its slot, the id work of batch s+1 (already on
         # the device) runs on the side stream and batch s+2 lands through the copy stream.
         # The host ships what the reference's input_fn yields -- one column per feature: int32 ids of the
         # categorical fields, floats of the numeric ones, labels -- and dir_expand_features widens them into
@@ -447,55 +461,52 @@ def run_b200(args):
         out_host = [torch.empty((B, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         d2h = out_host[0].numel() * 4
-        ahead = 2 if R >= 3 else 1
+        ahead = 2
 
         def e2e_loop(n):
+            # Slot cursor % R holds the batch whose id work the previous step already did from the RESIDENT copy
+            # of that slot; the feeder ships the same batch again, so the first step stays consistent.
+            c0 = cursor[0]
             for s in range(min(ahead, n)):
-                feeder.prefetch(s % R, host[s % R])
-            if pipelined:                                    # batch 0's list; later ones are sorted a step ahead
-                feeder.wait(0)
-                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
+                feeder.prefetch((c0 + s) % R, host[(c0 + s) % R])
             for s in range(n):
-                cur = s % R
+                cur = (c0 + s) % R
                 if s + ahead < n:
-                    feeder.prefetch((s + ahead) % R, host[(s + ahead) % R])
+                    feeder.prefetch((c0 + s + ahead) % R, host[(c0 + s + ahead) % R])
                 feeder.wait(cur)
-                if pipelined and s + 1 < n:
-                    if world == 1:
-                        feeder.wait((s + 1) % R)             # this step presorts the next batch
+                if s + 1 < n:
+                    if world == 1 and not use_graph:
+                        feeder.wait((c0 + s + 1) % R)        # this step presorts the next batch
                     else:
-                        ready_events[(s + 1) % R] = feeder.ready[(s + 1) % R]
-                o = run(cur)
+                        ready_events[(c0 + s + 1) % R] = feeder.ready[(c0 + s + 1) % R]
+                else:
+                    ready_events.pop((c0 + s + 1) % R, None)   # the batch after the last one is the resident copy
+                if world == 1 and use_graph and s + 1 < n:
+                    torch.cuda.current_stream().wait_event(feeder.ready[(c0 + s + 1) % R])
+                _, o = run()
                 feeder.release(cur)
                 out_host[s & 1].copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-
-        if R >= 3 or not pipelined:
-            e2e_loop(max(3, args.warmup))
-            barrier()
-            ev0.record()
-            e2e_loop(args.steps)
-            ev1.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "feed": "columns: int32 ids [B,%d] + fp32 values [B,%d] + labels [B], widened on the device by "
-                           "dir_expand_features" % (len(sp_f), len(de_f)) if args.feed == "columns"
-                           else "resolved: feature_index [B,F] int64 + feature_value [B,F] fp32 + labels [B]",
-                   "how": "EmbeddingFM.presort/forward/backward fed by %s from pinned host memory "
-                          "(ring of %d device slots, H2D on a copy stream), logits read back each step" % (
-                              type(feeder).__name__, R)}
             ready_events.clear()
-            # the feeder overwrote the slots: restore the resident sets
-            for r in range(R):
-                feeder.prefetch(r, host[r])
-                feeder.wait(r)
-            if pipelined:
-                layer.presort(devs[0][0], devs[0][1], handle=handles[0])
-            torch.cuda.synchronize()
+
+        e2e_loop(max(4, args.warmup))
+        barrier()
+        ev0.record()
+        e2e_loop(args.steps)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "feed": "columns: int32 ids [B,%d] + fp32 values [B,%d] + labels [B], widened on the device by "
+                       "dir_expand_features" % (len(sp_f), len(de_f)) if args.feed == "columns"
+                       else "resolved: feature_index [B,F] int64 + feature_value [B,F] fp32 + labels [B]",
+               "how": "%s.presort/forward/backward fed by %s from pinned host memory "
+                      "(ring of %d device slots, H2D on a copy stream), logits read back each step" % (
+                          type(layer).__name__, type(feeder).__name__, R)}
+        torch.cuda.synchronize()
 
     # ---------------- roofline: each C-ABI call timed on its own (rank 0's GPU) ---------------
     roof, kernels = None, []
@@ -524,9 +535,9 @@ def run_b200(args):
             layer.trace.on = layer.trace_pre.on = True
             layer.trace.report()
             layer.trace_pre.report()
-            sharded_id_work(0)
             for s_ in range(8):
-                step(*devs[s_ % R], ups[s_ % R], slot=s_ % R)
+                step(cursor[0] % R)
+                cursor[0] += 1
             torch.cuda.synchronize()
             stages = (layer.trace.report(), layer.trace_pre.report())
         except Exception as e:
@@ -538,7 +549,7 @@ def run_b200(args):
             try:
                 main = stages[0]
                 U = int(layer.last_exchange.get("unique_sent", 0))
-                row_bytes = (K + 4) * 4                                   # (row | first-order weight | pad) per distinct row
+                row_bytes = (K + 1) * 4                                   # (row, first-order weight) per distinct row
                 key = "bwd.emit+push" if "bwd.emit+push" in main else "bwd.emit"
                 # requester half of the backward: g, upstream u, per lookup id + value + one K-vector, per distinct
                 # row the (G[K], g1) sums written to its owner
@@ -673,8 +684,21 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     return roof, table
 
 
+def watchdog(seconds):
+    """A lost cross-rank barrier traps on the device after 20 s (sharded.BARRIER_TIMEOUT_MS); anything else that
+    wedges the process is ended here rather than at the driver's limit."""
+    def fire():
+        print("bench.py: watchdog: no result after %d s, aborting" % seconds, file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     args = parse_args()
+    watchdog(float(os.environ.get("DIR_B200_WATCHDOG_S", "600")))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -17,6 +17,17 @@ OPT_SGD, OPT_ADAGRAD, OPT_FTRL = 0, 1, 2
 class LinearOpt(ctypes.Structure):
     """struct dir_linear_opt (include/dir_b200.h): the linear scope's own optimizer."""
     _fields_ = [("optimizer", c_int), ("lr", c_float), ("l1", c_float), ("l2", c_float), ("z", c_void_p)]
+
+
+class PeerLayout(ctypes.Structure):
+    """struct dir_peer_layout (include/dir_b200.h): the exchange buffer every rank owns, per parity."""
+    _fields_ = [("G", c_int), ("rank", c_int), ("K", c_int), ("n_dense", c_int),
+                ("seg_cap", c_int64), ("u_cap", c_int64),
+                ("off_hdr", c_int64), ("off_ids", c_int64), ("off_rows", c_int64), ("off_w", c_int64),
+                ("off_g", c_int64), ("off_g1", c_int64), ("off_dense", c_int64), ("total_bytes", c_int64),
+                ("peer_base", c_void_p), ("local", c_void_p)]
+
+
 _EINVAL, _ENOMEM, _EIO = -22, -12, -5
 
 # name -> (restype, argtypes); must list every symbol include/dir_b200.h declares
@@ -29,7 +40,6 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dir_embed_bwd_sort": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
-    "dir_embed_bwd_sort_in": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_embed_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
@@ -38,30 +48,34 @@ SIGNATURES = {
     "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dir_shard_unique_workspace_bytes": (c_size_t, [c_int64]),
-    "dir_shard_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dir_shard_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dir_shard_dense_inv": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p,
+                                    c_void_p]),
+    "dir_peer_layout_init": (c_int, [c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "dir_shard_ids_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dir_shard_slots": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "dir_shard_gather_send": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                      c_void_p]),
+    "dir_embed_bwd_reduce_emit_to": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]),
+    "dir_shard_g1_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dir_shard_dense_workspace_bytes": (c_size_t, [c_int]),
+    "dir_shard_dense_emit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "dir_shard_owner_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                       c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dir_shard_dense_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float,
+                                      c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_void_p, c_void_p]),
+    "dir_table_init_counter": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_uint64, c_float,
+                                       c_void_p]),
     "dir_rows_gather": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                 c_int64, c_void_p]),
-    "dir_rows_gather_to": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "dir_onerow_workspace_bytes": (c_size_t, [c_int]),
-    "dir_embed_bwd_reduce_emit_fields_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                    c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_int,
-                                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
-    "dir_embed_bwd_onerow_emit_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                             c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int,
-                                             c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
-    "dir_dense_rows_apply": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                     c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int64,
-                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "dir_ids_push": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dir_rows_push": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_reduce_emit": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int64,
                                           c_void_p, c_size_t, c_void_p]),
-    "dir_embed_bwd_reduce_emit_to": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                             c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_void_p, c_void_p,
-                                             c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "dir_rows_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                        c_int64, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p, c_void_p]),

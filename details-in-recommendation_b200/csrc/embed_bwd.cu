@@ -20,6 +20,7 @@
 #include <cub/device/dispatch/dispatch_radix_sort.cuh>
 
 #include "common.cuh"
+#include "update.cuh"
 
 namespace dir {
 
@@ -134,15 +135,6 @@ __global__ void iota_kernel(uint32_t* out, int64_t n, uint32_t* zero2, unsigned 
   }
 }
 
-// The linear scope (first-order weights) has an optimizer of its own in the reference
-// (linear_optimizer='Ftrl', models/DeepFM/deepFM.py:58, 236-241).
-struct LinOpt {
-  int opt;      // DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_FTRL
-  float lr;
-  float l1, l2; // Ftrl regularisation strengths
-  float* z;     // Ftrl 'linear' slot, same stride as the weights
-};
-
 struct BwdArgs {
   float* table;
   float* accum;
@@ -179,12 +171,15 @@ struct BwdArgs {
   int64_t emit_stride;
   const float* gbuf;       // kModeGiven: [n, gbuf_stride] per-lookup (G[K], g1), indexed by position
   int64_t gbuf_stride;
-  // kModeEmit straight into the owners' buffers over NVLink (NULL: rows go to `emit`): distinct row u
-  // of segment q (emit_seg[q] <= u < emit_seg[q+1]) is row emit_dst_off[q] + u - emit_seg[q] of the
-  // buffer at the peer-mapped address emit_peers[q]
+  // kModeEmit straight into the owners' buffers over NVLink (emit_peers != NULL; csrc/shard_peer.cu): distinct
+  // row u of segment q (emit_seg[q] <= u < emit_seg[q+1]) is row emit_dst_row + u - emit_seg[q] of the gradient
+  // region (emit_byte_off) of the buffer at the peer-mapped address emit_peers[q]; its g1 goes to emit_g1[u]
   const int64_t* emit_seg;
   const int64_t* emit_peers;
-  const int64_t* emit_dst_off;
+  int64_t emit_byte_off;
+  int64_t emit_dst_row;
+  int64_t emit_seg_cap;
+  float* emit_g1;
   int emit_G;
   // entries actually in the sorted list, read on the device (NULL: n).  `n` then only bounds the launch
   // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
@@ -202,71 +197,30 @@ __device__ __forceinline__ int64_t entries(const BwdArgs& a) {
   return m < a.n ? m : a.n;
 }
 
-// where distinct row u's (G[K], g1) goes
-__device__ __forceinline__ float* emit_row(const BwdArgs& a, uint32_t u) {
-  if (a.emit_peers == nullptr) return a.emit + (int64_t)u * a.emit_stride;
-  int q = 0;
-  for (int g = 1; g < a.emit_G; ++g) q += ((int64_t)u >= __ldg(a.emit_seg + g)) ? 1 : 0;
-  float* base = reinterpret_cast<float*>(__ldg(a.emit_peers + q));
-  return base + (__ldg(a.emit_dst_off + q) + (int64_t)u - __ldg(a.emit_seg + q)) * a.emit_stride;
-}
-// one distinct row's sums: LPR lanes store the K-vector, lane 0 of the group the 16-byte tail (g1, 0, 0, 0)
-// when the rows cross NVLink (whole 16-byte stores only), the bare g1 otherwise
+// one distinct row's sums: LPR lanes store the K-vector; g1 follows it in a local emit row, or goes to emit_g1[u]
+// when the rows cross NVLink (64-byte rows there: whole 16-byte stores only, g1 is shipped in bulk afterwards)
 template <int LPR>
 __device__ __forceinline__ void emit_store(const BwdArgs& a, uint32_t u, int sub, float4 G, float g1) {
-  float* e = emit_row(a, u);
-  *(reinterpret_cast<float4*>(e) + sub) = G;
-  if (sub == 0) {
-    if (a.emit_peers != nullptr)
-      *(reinterpret_cast<float4*>(e) + LPR) = make_float4(g1, 0.f, 0.f, 0.f);
-    else
-      e[LPR * 4] = g1;
+  if (a.emit_peers == nullptr) {
+    float* e = a.emit + (int64_t)u * a.emit_stride;
+    *(reinterpret_cast<float4*>(e) + sub) = G;
+    if (sub == 0) e[LPR * 4] = g1;
+    return;
   }
+  int q = 0;
+  for (int g = 1; g < a.emit_G; ++g) q += ((int64_t)u >= __ldg(a.emit_seg + g)) ? 1 : 0;
+  const int64_t j = (int64_t)u - __ldg(a.emit_seg + q);
+  if (j < a.emit_seg_cap) {  // (the id push flagged the overflow; never store out of bounds)
+    float4* base = reinterpret_cast<float4*>(__ldg(a.emit_peers + q) + a.emit_byte_off);
+    base[(a.emit_dst_row + j) * LPR + sub] = G;
+  }
+  if (sub == 0) a.emit_g1[u] = g1;
 }
 
 constexpr int kModeLocal = 0;  // gradients formed from g, S, u, row; the row is updated in place
 constexpr int kModeEmit = 1;   // requester side of a sharded table: per-row sums go to `emit`
 constexpr int kModeGiven = 2;  // owner side: per-lookup gradients arrive in `gbuf`; update in place
 constexpr int kModeBag = 3;    // multi-hot bags: entry j of slot s contributes x_j (g_fm (S - e_s) + u_s)
-
-// Row update with the de-duplicated gradient: a = acc + g*g; T = T - (lr*g) * rsqrt(a)
-// ([TF] SparseApplyAdagrad, no epsilon; Eigen evaluates it as lr * g * rsqrt(a) as well).  rsqrtf
-// is MUFU.RSQ (<= 2 ulp): an IEEE divide + square root per component made this line a quarter of
-// all instructions the kernel issued (profiles/r01_reduce_v1_source.txt).
-__device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool adagrad) {
-  if (adagrad) {
-    a = __fadd_rn(a, __fmul_rn(g, g));
-    return __fsub_rn(t, __fmul_rn(__fmul_rn(lr, g), rsqrtf(a)));
-  }
-  return __fsub_rn(t, __fmul_rn(lr, g));
-}
-
-// One first-order weight with its de-duplicated gradient g.  Ftrl is [TF] SparseApplyFtrl with
-// learning_rate_power = -0.5 and no l2 shrinkage (tf.train.FtrlOptimizer defaults):
-//   n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma*w
-//   w  = |z| > l1 ? (sign(z)*l1 - z) / (sqrt(n')/lr + 2*l2) : 0
-__device__ __forceinline__ void lin_apply(const LinOpt& o, float* wp, float* np, float* zp, float w,
-                                          float n, float z, float g) {
-  if (o.opt == DIR_OPT_FTRL) {
-    const float nn = __fadd_rn(n, __fmul_rn(g, g));
-    const float rn = __fsqrt_rn(nn);
-    const float sigma = __fdiv_rn(__fsub_rn(rn, __fsqrt_rn(n)), o.lr);
-    z = __fsub_rn(__fadd_rn(z, g), __fmul_rn(sigma, w));
-    const float quad = __fadd_rn(__fdiv_rn(rn, o.lr), __fmul_rn(2.f, o.l2));
-    *wp = fabsf(z) > o.l1 ? __fdiv_rn(__fsub_rn(copysignf(o.l1, z), z), quad) : 0.f;
-    *np = nn;
-    *zp = z;
-    return;
-  }
-  const bool adagrad = o.opt == DIR_OPT_ADAGRAD;
-  *wp = upd(w, g, o.lr, n, adagrad);
-  if (adagrad) *np = n;
-}
-// loads for lin_apply (what each optimizer keeps per weight)
-__device__ __forceinline__ void lin_load(const LinOpt& o, const float* lin_accum, int64_t off, float& n, float& z) {
-  n = o.opt != DIR_OPT_SGD ? lin_accum[off] : 0.f;
-  z = o.opt == DIR_OPT_FTRL ? o.z[off] : 0.f;
-}
 
 template <int LPR>
 __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
@@ -881,22 +835,6 @@ static void set_div(BwdArgs& a, int F) {
   a.div_magic = (uint32_t)((((uint64_t)1 << a.div_shift) + (uint64_t)F - 1) / (uint64_t)F);
 }
 
-// The linear scope's optimizer: the caller's dir_linear_opt, or the tables' optimizer and rate.
-static int resolve_lin(const char* what, const dir_linear_opt* in, int optimizer, float lr, const float* lin,
-                       const float* lin_accum, LinOpt& out) {
-  out = LinOpt{optimizer, lr, 0.f, 0.f, nullptr};
-  if (in != nullptr) out = LinOpt{in->optimizer, in->lr, in->l1, in->l2, in->z};
-  if (out.opt != DIR_OPT_SGD && out.opt != DIR_OPT_ADAGRAD && out.opt != DIR_OPT_FTRL)
-    return fail(DIR_EINVAL, "%s: unknown linear optimizer", what);
-  if (lin != nullptr) {
-    if (out.opt != DIR_OPT_SGD && !lin_accum)
-      return fail(DIR_EINVAL, "%s: Adagrad / Ftrl on the linear weights need lin_accum", what);
-    if (out.opt == DIR_OPT_FTRL && (!out.z || !(out.lr > 0.f) || out.l1 < 0.f || out.l2 < 0.f))
-      return fail(DIR_EINVAL, "%s: Ftrl needs z, lr > 0 and l1, l2 >= 0", what);
-  }
-  return 0;
-}
-
 static int dispatch_bwd(const BwdArgs& a, int K, int64_t* n_unique_out, cudaStream_t st) {
   switch (K) {
     case 4: return launch_bwd<1>(a, n_unique_out, st);
@@ -927,12 +865,7 @@ extern "C" int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups,
 
 extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
                                   void* workspace, size_t workspace_bytes, dir_stream_t stream) {
-  return dir_embed_bwd_sort_in(sort_keys, n_lookups, n_lookups, n_rows, workspace, workspace_bytes, stream);
-}
-
-extern "C" int dir_embed_bwd_sort_in(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_capacity,
-                                     int64_t n_rows, void* workspace, size_t workspace_bytes,
-                                     dir_stream_t stream) {
+  const int64_t n_capacity = n_lookups;
   using namespace dir;
   if (n_lookups < 0 || n_lookups >= 0x7fffffffLL || n_capacity < n_lookups || n_capacity >= 0x7fffffffLL)
     return fail(DIR_EINVAL, "embed_bwd_sort: 0 <= n_lookups <= n_capacity < 2^31 required");
@@ -1027,34 +960,33 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr, lo, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
 
-/* requester side of a row-sharded table: per-unique-row gradient sums -> gu, or (peer_ptrs != NULL)
- * straight into the owners' buffers over NVLink (include/dir_b200.h) */
+/* requester side of a row-sharded table: per-unique-row gradient sums -> gu, or (layout != NULL) straight
+ * into the owners' buffers over NVLink (include/dir_b200.h) */
 static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride, const float* feature_value,
                        const float* g_first, const float* g_fm, const float* S, const float* u,
                        const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
-                       int64_t gu_stride, int G, const int64_t* seg_start, const int64_t* peer_ptrs,
-                       const int64_t* dst_row_off, void* workspace, size_t workspace_bytes,
-                       dir_stream_t stream, const int32_t* field_sel = nullptr, int n_sel = 0) {
+                       int64_t gu_stride, const dir_peer_layout* layout, const int64_t* owner_off, float* g1_local,
+                       void* workspace, size_t workspace_bytes, dir_stream_t stream, const int32_t* field_sel,
+                       int n_sel) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "%s: B >= 0, F > 0 required", what);
   if (field_sel == nullptr) n_sel = F;      // the sorted list covers every field
-  if (n_sel <= 0 || n_sel > F) return fail(DIR_EINVAL, "%s: 0 < n_sel <= F required", what);
+  if (n_sel < 0 || n_sel > F) return fail(DIR_EINVAL, "%s: 0 <= n_sel <= F required", what);
   const int64_t n = B * n_sel;
   if (n >= 0x7fffffffLL) return fail(DIR_EINVAL, "%s: B*F must be < 2^31", what);
   if (n == 0) return 0;
-  if (!ubuf || !g_fm || !S || !uidx || !workspace || (!gu && !peer_ptrs))
+  if (!ubuf || !g_fm || !S || !uidx || !workspace || (!gu && !layout))
     return fail(DIR_EINVAL, "%s: ubuf, g_fm, S, uidx, workspace and a destination are required", what);
-  if (peer_ptrs && (G <= 0 || G > 1024 || !seg_start || !dst_row_off))
-    return fail(DIR_EINVAL, "%s: 0 < G <= 1024, seg_start and dst_row_off are required", what);
+  if (layout && (!owner_off || !g1_local)) return fail(DIR_EINVAL, "%s: owner_off and g1_local are required", what);
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
     return fail(DIR_EINVAL, "%s: K must be one of 4, 8, 16, 32, 64", what);
-  if (ubuf_stride < K || (ubuf_stride & 3) || gu_stride < (peer_ptrs ? K + 4 : K + 1) || (gu_stride & 3))
-    return fail(DIR_EINVAL, "%s: strides must be multiples of 4, >= K (ubuf), >= K+1 (gu) / K+4 (peer rows)", what);
+  if (ubuf_stride < K || (ubuf_stride & 3) || (gu && (gu_stride < K + 1 || (gu_stride & 3))))
+    return fail(DIR_EINVAL, "%s: strides must be multiples of 4, >= K (ubuf), >= K+1 (gu)", what);
   if (!aligned16(ubuf) || !aligned16(gu) || !aligned16(S) || !aligned16(u))
     return fail(DIR_EINVAL, "%s: ubuf, gu, S, u must be 16-byte aligned", what);
   if (n_keys <= 0 || n_keys >= 0xffffffffLL) return fail(DIR_EINVAL, "%s: 0 < n_keys < 2^32-1 required", what);
@@ -1064,7 +996,9 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
             g_fm, S, u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
             (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), field_sel, field_sel ? n_sel : 0, kModeEmit, uidx, gu,
             gu_stride, nullptr, 0,
-            seg_start, peer_ptrs, dst_row_off, G, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
+            owner_off, layout ? layout->peer_base : nullptr, layout ? layout->off_g : 0,
+            layout ? (int64_t)layout->rank * layout->seg_cap : 0, layout ? layout->seg_cap : 0, g1_local,
+            layout ? layout->G : 0, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -1078,38 +1012,23 @@ extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
                                          dir_stream_t stream) {
   if (!gu) return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit: gu is required");
   return reduce_emit("embed_bwd_reduce_emit", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B, F,
-                     K, n_keys, gu, gu_stride, 0, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+                     K, n_keys, gu, gu_stride, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream,
+                     nullptr, 0);
 }
 
-extern "C" int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stride,
-                                            const float* feature_value, const float* g_first,
-                                            const float* g_fm, const float* S, const float* u,
-                                            const uint32_t* uidx, int64_t B, int F, int K,
-                                            int64_t n_keys, int G, const int64_t* seg_start,
-                                            const int64_t* peer_ptrs, const int64_t* dst_row_off,
-                                            int64_t out_stride, void* workspace,
+extern "C" int dir_embed_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* feature_value,
+                                            const float* g_first, const float* g_fm, const float* S,
+                                            const float* u, const uint32_t* uidx, const int64_t* owner_off,
+                                            int64_t B, int F, int64_t n_keys, const int32_t* field_sel,
+                                            int n_sel, float* g1_local, void* workspace,
                                             size_t workspace_bytes, dir_stream_t stream) {
-  if (!peer_ptrs) return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit_to: peer_ptrs is required");
-  return reduce_emit("embed_bwd_reduce_emit_to", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B,
-                     F, K, n_keys, nullptr, out_stride, G, seg_start, peer_ptrs, dst_row_off, workspace,
-                     workspace_bytes, stream);
-}
-
-/* EXPERIMENT (see the end of this file): emit_to over a sorted list that covers only the fields field_sel[n_sel] */
-extern "C" int dir_embed_bwd_reduce_emit_fields_to(const float* ubuf, int64_t ubuf_stride,
-                                                   const float* feature_value, const float* g_first,
-                                                   const float* g_fm, const float* S, const float* u,
-                                                   const uint32_t* uidx, int64_t B, int F, int K,
-                                                   int64_t n_keys, const int32_t* field_sel, int n_sel, int G,
-                                                   const int64_t* seg_start, const int64_t* peer_ptrs,
-                                                   const int64_t* dst_row_off, int64_t out_stride,
-                                                   void* workspace, size_t workspace_bytes,
-                                                   dir_stream_t stream) {
-  if (!peer_ptrs || !field_sel)
-    return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit_fields_to: peer_ptrs and field_sel are required");
-  return reduce_emit("embed_bwd_reduce_emit_fields_to", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx,
-                     B, F, K, n_keys, nullptr, out_stride, G, seg_start, peer_ptrs, dst_row_off, workspace,
-                     workspace_bytes, stream, field_sel, n_sel);
+  using namespace dir;
+  if (!layout || !layout->peer_base || !layout->local || layout->G <= 0 || layout->G > 64)
+    return fail(DIR_EINVAL, "embed_bwd_reduce_emit_to: a filled dir_peer_layout is required");
+  const float* rows = reinterpret_cast<const float*>(layout->local + layout->off_rows);
+  return reduce_emit("embed_bwd_reduce_emit_to", rows, layout->K, feature_value, g_first, g_fm, S, u, uidx, B, F,
+                     layout->K, n_keys, nullptr, 0, layout, owner_off, g1_local, workspace, workspace_bytes, stream,
+                     field_sel, n_sel);
 }
 
 /* owner side: per-lookup gradients arrive from the requesters; segmented sum + fused row update */
@@ -1141,7 +1060,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, nullptr, 0, n_device, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, 0, 0, 0, nullptr, 0, n_device, lo, nullptr, nullptr, nullptr};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }
@@ -1183,24 +1102,21 @@ extern "C" int dir_embed_bag_bwd_reduce_update(
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, bag_weight, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, nnz, F,
             (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeBag, nullptr, nullptr, 0, nullptr, 0,
-            nullptr, nullptr, nullptr, 0, nullptr, lo, entry_slot, entry_x, emb};
+            nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr, lo, entry_slot, entry_x, emb};
   set_div(a, F);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
 
-// =================================================================================================
-// EXPERIMENT (written after this round's GPU budget was spent; reached only through
-// ShardedEmbeddingFM(DIR_B200_SHARD_ONEROW=1), off by default): one-row (numeric) fields of a
-// row-sharded table kept as REPLICATED parameters.  Every sample of every rank hits the same row,
-// so sorting / exchanging those lookups (a third of cfg2's) buys nothing: each rank forms the
-// field's gradient over its own samples (the column-sum kernel above), the G partial sums meet in
-// every rank's peer buffer, and after the step's barrier every rank adds them in rank order and
-// applies the same update to its replica.  Nothing above this line is changed by it.
-// =================================================================================================
+// ------------------------------------------------------------------------------------------
+// Row-sharded tables: one-row (numeric) fields are REPLICATED parameters.  Every sample of every rank
+// hits the same row, so sorting / exchanging those lookups (a third of cfg2's) buys nothing: each rank
+// forms the field's gradient over its own samples (the column-sum kernel above), the G partial sums meet
+// in every rank's exchange buffer, and after the step's barrier every rank adds them in rank order and
+// applies the same update to its replica (csrc/shard_peer.cu: dir_shard_dense_apply).
 namespace dir {
 
 struct OneRowWs {
-  int* flags;   // [kOneRowMax]
+  int* flags;    // [kOneRowMax]
   double* part;  // [kOneRowCtas][kOneRowMax][K + 4]
   size_t total;
 };
@@ -1221,6 +1137,8 @@ static int launch_onerow_partials(const OneRowArgs& a, int n_fields, cudaStream_
   const int64_t want = (a.B + 7) / 8;
   const int G = (int)(want < kOneRowCtas ? want : kOneRowCtas);
   int n = 0;
+  *ctas = G;
+  if (G == 0) return 0;  // an empty batch on this rank: the emit kernel ships zeros, `touched` = 0
   for (int f0 = 0; f0 < n_fields; f0 += PER, ++n) {
     const int nf = n_fields - f0 < PER ? n_fields - f0 : PER;
     switch ((nf + SLOTS - 1) / SLOTS) {
@@ -1230,16 +1148,14 @@ static int launch_onerow_partials(const OneRowArgs& a, int n_fields, cudaStream_
       default: embed_bwd_onerow_kernel<LPR, 4><<<G, 256, 0, st>>>(a, f0, nf); break;
     }
   }
-  *ctas = G;
   return launched("embed_bwd_onerow_partials", n);
 }
 
 // one CTA per one-row field: the CTA partials summed exactly as embed_bwd_onerow_finish_kernel sums them, then
-// the field's (G[K], g1, touched, 0, 0) is stored into slot dst_row_base + rank * n_fields + j of EVERY rank's buffer
+// the field's (G[K], g1, touched, 0, 0) is stored into dense[rank][j] of EVERY rank's exchange buffer
 template <int LPR>
 __global__ void __launch_bounds__(256)
-onerow_emit_to_kernel(const OneRowArgs a, int ctas, int n_fields, int G, int rank,
-                      const int64_t* __restrict__ peer_ptrs, int64_t dst_row_base, int64_t out_stride) {
+onerow_emit_to_kernel(const OneRowArgs a, int ctas, const dir_peer_layout L) {
   constexpr int K = LPR * 4;
   __shared__ double red[8][33];
   __shared__ __align__(16) float tot[K + 4];
@@ -1267,117 +1183,52 @@ onerow_emit_to_kernel(const OneRowArgs a, int ctas, int n_fields, int G, int ran
   }
   __syncthreads();
   constexpr int NV = LPR + 1;  // float4s per row
-  const int64_t row = dst_row_base + (int64_t)rank * n_fields + j;
-  for (int t = threadIdx.x; t < G * NV; t += blockDim.x) {
+  const int64_t row = (int64_t)L.rank * L.n_dense + j;
+  for (int t = threadIdx.x; t < L.G * NV; t += blockDim.x) {
     const int q = t / NV, v = t % NV;
-    float4* dst = reinterpret_cast<float4*>(__ldg(peer_ptrs + q)) + (row * out_stride) / 4 + v;
+    float4* dst = reinterpret_cast<float4*>(__ldg(L.peer_base + q) + L.off_dense) + row * NV + v;
     *dst = *reinterpret_cast<const float4*>(tot + 4 * v);
-  }
-}
-
-struct DenseApplyArgs {
-  float* table;  // replica: [n_fields] rows, row_stride apart (row | accumulator when Adagrad)
-  float* accum;
-  int64_t row_stride;
-  float* lin;        // [n_fields]
-  float* lin_accum;  // [n_fields]
-  LinOpt lo;         // lo.z: [n_fields]
-  const float* gbuf;  // this rank's peer buffer
-  int64_t gbuf_stride;
-  int64_t dst_row_base;
-  int n_fields, G, opt;
-  float lr;
-  // the sharded table's copy of the row (written by the rank that owns it; shard_row[j] < 0 elsewhere)
-  float* s_table;
-  float* s_accum;
-  int64_t s_row_stride;
-  float* s_lin;
-  float* s_lin_accum;
-  float* s_lin_z;
-  int64_t s_lin_stride;
-  const int64_t* shard_row;
-  unsigned long long* n_unique;  // += touched fields (pass it on one rank only)
-};
-
-template <int LPR>
-__global__ void __launch_bounds__(128) dense_rows_apply_kernel(const DenseApplyArgs a) {
-  constexpr int K = LPR * 4;
-  const int j = blockIdx.x, c = threadIdx.x;
-  if (c > K) return;
-  float g = 0.f, touched = 0.f;
-  for (int q = 0; q < a.G; ++q) {  // rank order: the same sum on every rank
-    const float* src = a.gbuf + (a.dst_row_base + (int64_t)q * a.n_fields + j) * a.gbuf_stride;
-    g += src[c];
-    touched += src[K + 1];
-  }
-  if (touched == 0.f) return;  // no rank had a surviving lookup: the row is not touched
-  const int64_t sr = __ldg(a.shard_row + j);
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
-  if (c < K) {
-    float* tp = a.table + (int64_t)j * a.row_stride + c;
-    float acc = 0.f;
-    if (adagrad) acc = a.accum[(int64_t)j * a.row_stride + c];
-    const float t = upd(*tp, g, a.lr, acc, adagrad);
-    *tp = t;
-    if (adagrad) a.accum[(int64_t)j * a.row_stride + c] = acc;
-    if (sr >= 0) {
-      a.s_table[sr * a.s_row_stride + c] = t;
-      if (adagrad) a.s_accum[sr * a.s_row_stride + c] = acc;
-    }
-  } else {
-    if (a.lin != nullptr) {
-      float n1, z1;
-      lin_load(a.lo, a.lin_accum, j, n1, z1);
-      lin_apply(a.lo, a.lin + j, a.lin_accum + j, a.lo.z + j, a.lin[j], n1, z1, g);
-      if (sr >= 0) {
-        a.s_lin[sr * a.s_lin_stride] = a.lin[j];
-        if (a.lo.opt != DIR_OPT_SGD) a.s_lin_accum[sr * a.s_lin_stride] = a.lin_accum[j];
-        if (a.lo.opt == DIR_OPT_FTRL) a.s_lin_z[sr * a.s_lin_stride] = a.lo.z[j];
-      }
-    }
-    if (a.n_unique) atomicAdd(a.n_unique, 1ull);
   }
 }
 
 }  // namespace dir
 
-extern "C" size_t dir_onerow_workspace_bytes(int K) {
+extern "C" size_t dir_shard_dense_workspace_bytes(int K) {
   if (K <= 0) return 0;
   return dir::onerow_carve(nullptr, K).total;
 }
 
-extern "C" int dir_embed_bwd_onerow_emit_to(const float* dense_table, int64_t row_stride,
-                                            const int64_t* feature_index, const float* feature_value,
-                                            const int64_t* dense_field_offset, const float* g_first,
-                                            const float* g_fm, const float* S, const float* u,
-                                            const int32_t* onerow_fields, int n_onerow, int64_t B, int F,
-                                            int K, int G, int rank, const int64_t* peer_ptrs,
-                                            int64_t dst_row_base, int64_t out_stride, void* workspace,
-                                            size_t workspace_bytes, dir_stream_t stream) {
+extern "C" int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table, int64_t row_stride,
+                                    const int64_t* feature_index, const float* feature_value,
+                                    const int64_t* dense_field_offset, const float* g_first, const float* g_fm,
+                                    const float* S, const float* u, const int32_t* onerow_fields, int64_t B, int F,
+                                    void* workspace, size_t workspace_bytes, dir_stream_t stream) {
   using namespace dir;
-  if (B <= 0 || F <= 0 || n_onerow <= 0 || n_onerow > kOneRowMax || G <= 0 || rank < 0 || rank >= G)
-    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: B, F > 0, 0 < n_onerow <= 64, 0 <= rank < G required");
+  if (!layout || !layout->peer_base || layout->G <= 0 || layout->G > 64 || layout->rank < 0 || layout->rank >= layout->G)
+    return fail(DIR_EINVAL, "shard_dense_emit: a filled dir_peer_layout is required");
+  const int K = layout->K, n_onerow = layout->n_dense;
+  if (n_onerow == 0) return 0;
+  if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > kOneRowMax)
+    return fail(DIR_EINVAL, "shard_dense_emit: B >= 0, F > 0, 0 <= n_dense <= 64 required");
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
-    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: K must be one of 4, 8, 16, 32, 64");
-  if (!dense_table || !dense_field_offset || !g_fm || !S || !onerow_fields || !peer_ptrs || !workspace)
-    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: null pointer");
-  if (row_stride < K || (row_stride & 3) || out_stride < K + 4 || (out_stride & 3) || dst_row_base < 0)
-    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: strides must be multiples of 4, >= K (rows), >= K+4 (out)");
+    return fail(DIR_EINVAL, "shard_dense_emit: K must be one of 4, 8, 16, 32, 64");
+  if (!dense_table || !dense_field_offset || (B > 0 && (!g_fm || !S)) || !onerow_fields || !workspace)
+    return fail(DIR_EINVAL, "shard_dense_emit: null pointer");
+  if (row_stride < K || (row_stride & 3)) return fail(DIR_EINVAL, "shard_dense_emit: row_stride must be >= K, multiple of 4");
   if (!aligned16(dense_table) || !aligned16(S) || !aligned16(u))
-    return fail(DIR_EINVAL, "embed_bwd_onerow_emit_to: dense_table, S, u must be 16-byte aligned");
+    return fail(DIR_EINVAL, "shard_dense_emit: dense_table, S, u must be 16-byte aligned");
   OneRowWs w = onerow_carve(workspace, K);
-  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_onerow_emit_to: workspace too small");
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "shard_dense_emit: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaMemsetAsync(w.flags, 0, kOneRowMax * 4, st);
   OneRowArgs o{const_cast<float*>(dense_table), nullptr, row_stride, nullptr, nullptr, 0, feature_index,
                feature_value, dense_field_offset, g_first, g_fm, S, u, onerow_fields, B, F, DIR_OPT_SGD, 0.f,
                w.part, w.flags, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}};
   int ctas = 0, rc;
-#define DIR_ORE(L)                                                                                   \
-  rc = launch_onerow_partials<L>(o, n_onerow, st, &ctas);                                            \
-  if (rc) return rc;                                                                                 \
-  onerow_emit_to_kernel<L><<<n_onerow, 256, 0, st>>>(o, ctas, n_onerow, G, rank, peer_ptrs, dst_row_base, \
-                                                     out_stride);
+#define DIR_ORE(LP)                                          \
+  rc = launch_onerow_partials<LP>(o, n_onerow, st, &ctas); \
+  if (rc) return rc;                                         \
+  onerow_emit_to_kernel<LP><<<n_onerow, 256, 0, st>>>(o, ctas, *layout);
   switch (K) {
     case 4: DIR_ORE(1) break;
     case 8: DIR_ORE(2) break;
@@ -1386,40 +1237,5 @@ extern "C" int dir_embed_bwd_onerow_emit_to(const float* dense_table, int64_t ro
     default: DIR_ORE(16) break;
   }
 #undef DIR_ORE
-  return launched("embed_bwd_onerow_emit_to");
-}
-
-extern "C" int dir_dense_rows_apply(float* dense_table, float* dense_accum, int64_t row_stride, float* dense_lin,
-                                    float* dense_lin_accum, const float* gbuf, int64_t gbuf_stride,
-                                    int64_t dst_row_base, int n_onerow, int K, int G, int optimizer, float lr,
-                                    const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
-                                    int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
-                                    float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
-                                    int64_t* n_unique_out, dir_stream_t stream) {
-  using namespace dir;
-  if (n_onerow <= 0 || n_onerow > kOneRowMax || G <= 0)
-    return fail(DIR_EINVAL, "dense_rows_apply: 0 < n_onerow <= 64, G > 0 required");
-  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
-    return fail(DIR_EINVAL, "dense_rows_apply: K must be one of 4, 8, 16, 32, 64");
-  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD) return fail(DIR_EINVAL, "dense_rows_apply: unknown optimizer");
-  if (!dense_table || !gbuf || !shard_row || !shard_table) return fail(DIR_EINVAL, "dense_rows_apply: null pointer");
-  if (optimizer == DIR_OPT_ADAGRAD && (!dense_accum || !shard_accum))
-    return fail(DIR_EINVAL, "dense_rows_apply: Adagrad needs the accumulators");
-  LinOpt lo;
-  if (int rc = resolve_lin("dense_rows_apply", linear_opt, optimizer, lr, dense_lin, dense_lin_accum, lo)) return rc;
-  if (dense_lin && (!shard_lin || (lo.opt != DIR_OPT_SGD && !shard_lin_accum) || (lo.opt == DIR_OPT_FTRL && !shard_lin_z)))
-    return fail(DIR_EINVAL, "dense_rows_apply: the sharded copies of the linear state are required");
-  DenseApplyArgs a{dense_table, dense_accum, row_stride, dense_lin, dense_lin_accum, lo, gbuf, gbuf_stride,
-                   dst_row_base, n_onerow, G, optimizer, lr, shard_table, shard_accum, shard_row_stride, shard_lin,
-                   shard_lin_accum, shard_lin_z, shard_lin_stride, shard_row,
-                   reinterpret_cast<unsigned long long*>(n_unique_out)};
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (K) {
-    case 4: dense_rows_apply_kernel<1><<<n_onerow, 128, 0, st>>>(a); break;
-    case 8: dense_rows_apply_kernel<2><<<n_onerow, 128, 0, st>>>(a); break;
-    case 16: dense_rows_apply_kernel<4><<<n_onerow, 128, 0, st>>>(a); break;
-    case 32: dense_rows_apply_kernel<8><<<n_onerow, 128, 0, st>>>(a); break;
-    default: dense_rows_apply_kernel<16><<<n_onerow, 128, 0, st>>>(a); break;
-  }
-  return launched("dense_rows_apply");
+  return launched("shard_dense_emit");
 }

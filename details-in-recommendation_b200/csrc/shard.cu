@@ -62,12 +62,17 @@ struct HeadFlag {
 __global__ void __launch_bounds__(256)
 shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ pos,
                     const uint32_t* __restrict__ incl, int64_t n, uint32_t pruned, uint32_t cap,
+                    const int32_t* __restrict__ field_sel, int n_sel, int F,
                     uint32_t* __restrict__ uidx, int32_t* __restrict__ ulocal,
                     int64_t* __restrict__ inv) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = __ldg(keys + i);
-  const uint32_t p = __ldg(pos + i);
+  uint32_t p = __ldg(pos + i);
+  if (field_sel != nullptr) {  // entry of the compact [B, n_sel] list -> position in the [B, F] inputs
+    const uint32_t b = p / (uint32_t)n_sel;
+    p = b * (uint32_t)F + (uint32_t)__ldg(field_sel + (p - b * (uint32_t)n_sel));
+  }
   if (k == pruned) {
     uidx[i] = 0u;
     inv[p] = -1;  // pruned by the forward kernel (id < 0)
@@ -108,106 +113,6 @@ rows_gather_kernel(const float* __restrict__ table, int64_t row_stride, const fl
   const float4 v = __ldg(reinterpret_cast<const float4*>(table + r * row_stride) + sub);
   stg_stream(out + i * out_stride + sub * 4, v);
   if (sub == 0) out[i * out_stride + K] = lin ? __ldg(lin + r * lin_stride) : 0.f;
-}
-
-// ---- exchange over NVLink peer memory (no NCCL on the payload path) ---------------------------------
-// The n rows are grouped into G segments (seg_start[G+1]); segment q goes to rank q's buffer
-// (peer_ptrs[q], a peer-mapped device pointer from symmetric memory) starting at row dst_row_off[q].
-// Stores to a peer pointer travel over NVLink; the caller runs a cross-rank barrier afterwards.
-__device__ __forceinline__ int segment_of(const int64_t* __restrict__ seg_start, int G, int64_t i) {
-  int q = 0;
-  while (q + 1 < G && i >= __ldg(seg_start + q + 1)) ++q;
-  return q;
-}
-
-// owner side, fused gather + send: LPR lanes carry the row, one more lane carries (w, 0, 0, 0).
-// A thread handles kRowsPerThread rows a grid-stride apart, loads first, so several 128-byte lines
-// per thread are in flight before the first NVLink store.
-constexpr int kRowsPerThread = 4;
-
-template <int LPR>
-__global__ void __launch_bounds__(256)
-rows_gather_to_kernel(const float* __restrict__ table, int64_t row_stride, const float* __restrict__ lin,
-                      int64_t lin_stride, const int32_t* __restrict__ ids, int64_t n, int G,
-                      const int64_t* __restrict__ seg_start, const int64_t* __restrict__ peer_ptrs,
-                      const int64_t* __restrict__ dst_row_off, int64_t out_stride) {
-  constexpr int TPR = LPR + 1;  // threads per row
-  {  // `n` bounds the launch; the rows really there are seg_start[G] (known on the device alone)
-    const int64_t total = __ldg(seg_start + G);
-    n = total < n ? total : n;
-  }
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i0 = t / TPR;
-  const int sub = (int)(t % TPR);
-  const int64_t step = ((int64_t)gridDim.x * blockDim.x) / TPR;
-  float4 v[kRowsPerThread];
-  int64_t r[kRowsPerThread];
-#pragma unroll
-  for (int k = 0; k < kRowsPerThread; ++k) {
-    const int64_t i = i0 + k * step;
-    r[k] = i < n ? (int64_t)__ldg(ids + i) : -1;
-  }
-#pragma unroll
-  for (int k = 0; k < kRowsPerThread; ++k) {
-    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r[k] >= 0) {
-      if (sub < LPR)
-        v[k] = __ldg(reinterpret_cast<const float4*>(table + r[k] * row_stride) + sub);
-      else if (lin)
-        v[k].x = __ldg(lin + r[k] * lin_stride);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kRowsPerThread; ++k) {
-    const int64_t i = i0 + k * step;
-    if (r[k] < 0) continue;
-    const int q = segment_of(seg_start, G, i);
-    float* dst = reinterpret_cast<float*>(__ldg(peer_ptrs + q)) +
-                 (__ldg(dst_row_off + q) + i - __ldg(seg_start + q)) * out_stride;
-    *(reinterpret_cast<float4*>(dst) + sub) = v[k];
-  }
-}
-
-// requester side: ship rows [n, stride] to their owners' buffers
-__global__ void __launch_bounds__(256)
-rows_push_kernel(const float* __restrict__ src, int64_t n, int stride4, int G,
-                 const int64_t* __restrict__ seg_start, const int64_t* __restrict__ peer_ptrs,
-                 const int64_t* __restrict__ dst_row_off) {
-  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  const int64_t total = n * stride4;
-  float4 v[kRowsPerThread];
-#pragma unroll
-  for (int k = 0; k < kRowsPerThread; ++k) {
-    const int64_t t = t0 + k * step;
-    v[k] = t < total ? ldg_stream(src + t * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int k = 0; k < kRowsPerThread; ++k) {
-    const int64_t t = t0 + k * step;
-    if (t >= total) continue;
-    const int64_t i = t / stride4;
-    const int c = (int)(t % stride4);
-    const int q = segment_of(seg_start, G, i);
-    float4* dst = reinterpret_cast<float4*>(__ldg(peer_ptrs + q)) +
-                  (__ldg(dst_row_off + q) + i - __ldg(seg_start + q)) * stride4 + c;
-    *dst = v[k];
-  }
-}
-
-// requester side, ids: ship the distinct local rows [n] (int32) to their owners' landing buffers.  Same segment
-// arithmetic as rows_push_kernel with 4-byte elements; n bounds the launch, seg_start[G] is the real count.
-__global__ void __launch_bounds__(256)
-ids_push_kernel(const int32_t* __restrict__ src, int64_t n, int G, const int64_t* __restrict__ seg_start,
-                const int64_t* __restrict__ peer_ptrs, const int64_t* __restrict__ dst_off) {
-  const int64_t total = __ldg(seg_start + G);
-  n = total < n ? total : n;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-    const int q = segment_of(seg_start, G, i);
-    int32_t* dst = reinterpret_cast<int32_t*>(__ldg(peer_ptrs + q)) + (__ldg(dst_off + q) + i - __ldg(seg_start + q));
-    *dst = __ldg(src + i);
-  }
 }
 
 struct UniqueWs {
@@ -269,9 +174,10 @@ extern "C" size_t dir_shard_unique_workspace_bytes(int64_t n_lookups) {
 }
 
 extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos,
-                                int64_t n_lookups, int64_t n_rows, int G, uint32_t* uidx,
-                                int32_t* unique_local_rows, int64_t* inv, int64_t* owner_off,
-                                void* workspace, size_t workspace_bytes, dir_stream_t stream) {
+                                int64_t n_lookups, int64_t n_rows, int G, const int32_t* field_sel, int n_sel,
+                                int F, uint32_t* uidx, int32_t* unique_local_rows, int64_t* inv,
+                                int64_t* owner_off, void* workspace, size_t workspace_bytes,
+                                dir_stream_t stream) {
   using namespace dir;
   if (n_lookups < 0 || n_lookups >= 0x7fffffffLL || G <= 0 || G > 1023 || n_rows <= 0)
     return fail(DIR_EINVAL, "shard_unique: 0 <= n_lookups < 2^31, 0 < G <= 1023, n_rows > 0 required");
@@ -283,6 +189,8 @@ extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sor
   }
   if (!sorted_keys || !sorted_pos || !uidx || !unique_local_rows || !inv || !workspace)
     return fail(DIR_EINVAL, "shard_unique: null pointer");
+  if (field_sel != nullptr && (n_sel <= 0 || n_sel > F || n_lookups % n_sel != 0))
+    return fail(DIR_EINVAL, "shard_unique: with field_sel, 0 < n_sel <= F and n_lookups = B * n_sel are required");
   const int64_t cap = (n_rows + G - 1) / G;
   const uint32_t pruned = (uint32_t)(cap * G);
   UniqueWs w = unique_carve(workspace, n_lookups);
@@ -294,7 +202,8 @@ extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sor
   cudaError_t e = cub::DeviceScan::InclusiveSum(w.cub_temp, bytes, flags, w.incl, (int)n_lookups, st);
   if (e != cudaSuccess) return fail(DIR_EIO, "shard_unique: %s", cudaGetErrorString(e));
   shard_number_kernel<<<(unsigned)((n_lookups + 255) / 256), 256, 0, st>>>(
-      sorted_keys, sorted_pos, w.incl, n_lookups, pruned, (uint32_t)cap, uidx, unique_local_rows, inv);
+      sorted_keys, sorted_pos, w.incl, n_lookups, pruned, (uint32_t)cap, field_sel, n_sel, F, uidx, unique_local_rows,
+      inv);
   shard_bounds_kernel<<<1, 1024, 0, st>>>(sorted_keys, w.incl, n_lookups, G, (uint32_t)cap, owner_off);
   return launched("shard_unique", 4);
 }
@@ -324,58 +233,47 @@ extern "C" int dir_rows_gather(const float* table, int64_t row_stride, const flo
   return launched("rows_gather");
 }
 
-extern "C" int dir_rows_gather_to(const float* table, int64_t row_stride, const float* lin,
-                                  int64_t lin_stride, const int32_t* local_rows, int64_t n, int K, int G,
-                                  const int64_t* seg_start, const int64_t* peer_ptrs,
-                                  const int64_t* dst_row_off, int64_t out_stride, dir_stream_t stream) {
-  using namespace dir;
-  if (n < 0 || G <= 0) return fail(DIR_EINVAL, "rows_gather_to: n >= 0, G > 0 required");
-  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
-    return fail(DIR_EINVAL, "rows_gather_to: K must be one of 4, 8, 16, 32, 64");
-  if (n == 0) return 0;
-  if (!table || !local_rows || !seg_start || !peer_ptrs || !dst_row_off)
-    return fail(DIR_EINVAL, "rows_gather_to: null pointer");
-  if (row_stride < K || (row_stride & 3) || out_stride < K + 4 || (out_stride & 3))
-    return fail(DIR_EINVAL, "rows_gather_to: strides must be multiples of 4, >= K (rows), >= K+4 (out)");
-  if (!aligned16(table)) return fail(DIR_EINVAL, "rows_gather_to: 16-byte alignment required");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int lpr = K / 4;
-  const unsigned grid = (unsigned)((n * (lpr + 1) + 256 * kRowsPerThread - 1) / (256 * kRowsPerThread));
-#define DIR_GT(L) rows_gather_to_kernel<L><<<grid, 256, 0, st>>>(table, row_stride, lin, lin_stride, local_rows, n, G, seg_start, peer_ptrs, dst_row_off, out_stride)
-  switch (lpr) {
-    case 1: DIR_GT(1); break;
-    case 2: DIR_GT(2); break;
-    case 4: DIR_GT(4); break;
-    case 8: DIR_GT(8); break;
-    default: DIR_GT(16); break;
+// ------------------------------------------------------------------------------------------------
+// Tables too large to come from the host (cfg4: 880 M rows) are filled on the device from a counter hash,
+// so that any row can be reproduced without the table (oracle/deepctr_oracle.py: counter_rows).
+namespace dir {
+__host__ __device__ inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+table_init_counter_kernel(float* __restrict__ table, int64_t row_stride, int64_t n_local, int K, int G, int rank,
+                          int64_t n_rows, uint64_t seed, float scale) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / K;
+  const int k = (int)(t % K);
+  if (i >= n_local) return;
+  const int64_t row = i * G + rank;
+  float v = 0.f;
+  if (row < n_rows) {
+    const uint64_t h = mix64(seed ^ mix64((uint64_t)row * 64ull + (uint64_t)k));
+    // four 16-bit uniforms: the sum is an integer in [0, 4 * 65535], centred exactly, scaled by one multiply
+    const int sum = (int)(h & 0xffff) + (int)((h >> 16) & 0xffff) + (int)((h >> 32) & 0xffff) + (int)(h >> 48);
+    v = __fmul_rn((float)(sum - 131070), scale);
   }
-#undef DIR_GT
-  return launched("rows_gather_to");
+  table[i * row_stride + k] = v;
 }
+}  // namespace dir
 
-extern "C" int dir_rows_push(const float* src, int64_t n, int64_t stride, int G, const int64_t* seg_start,
-                             const int64_t* peer_ptrs, const int64_t* dst_row_off, dir_stream_t stream) {
+extern "C" int dir_table_init_counter(float* table, int64_t row_stride, int64_t n_local_rows, int K, int G,
+                                      int rank, int64_t n_rows, uint64_t seed, float sd, dir_stream_t stream) {
   using namespace dir;
-  if (n < 0 || G <= 0 || stride <= 0 || (stride & 3))
-    return fail(DIR_EINVAL, "rows_push: n >= 0, G > 0, stride a positive multiple of 4 required");
-  if (n == 0) return 0;
-  if (!src || !seg_start || !peer_ptrs || !dst_row_off) return fail(DIR_EINVAL, "rows_push: null pointer");
-  if (!aligned16(src)) return fail(DIR_EINVAL, "rows_push: 16-byte alignment required");
-  const int stride4 = (int)(stride / 4);
-  const unsigned grid = (unsigned)((n * stride4 + 256 * kRowsPerThread - 1) / (256 * kRowsPerThread));
-  rows_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, stride4, G, seg_start, peer_ptrs,
-                                                                         dst_row_off);
-  return launched("rows_push");
-}
-
-extern "C" int dir_ids_push(const int32_t* src, int64_t n, int G, const int64_t* seg_start,
-                            const int64_t* peer_ptrs, const int64_t* dst_off, dir_stream_t stream) {
-  using namespace dir;
-  if (n < 0 || G <= 0) return fail(DIR_EINVAL, "ids_push: n >= 0, G > 0 required");
-  if (n == 0) return 0;
-  if (!src || !seg_start || !peer_ptrs || !dst_off) return fail(DIR_EINVAL, "ids_push: null pointer");
-  const int64_t want = (n + 255) / 256;
-  const unsigned grid = (unsigned)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
-  ids_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, G, seg_start, peer_ptrs, dst_off);
-  return launched("ids_push");
+  if (!table || n_local_rows <= 0 || K <= 0 || K > 64 || G <= 0 || rank < 0 || rank >= G || row_stride < K)
+    return fail(DIR_EINVAL, "table_init_counter: table, n_local_rows > 0, 0 < K <= 64 <= row_stride, 0 <= rank < G required");
+  // a 16-bit uniform has variance (65536^2 - 1) / 12; four of them: sd_sum = sqrt((65536^2 - 1) / 3)
+  const float scale = sd / 37837.2272f;
+  const int64_t n = n_local_rows * K;
+  const int64_t grid = (n + 255) / 256;
+  if (grid > 0x7fffffffLL) return fail(DIR_EINVAL, "table_init_counter: table too large for one launch");
+  table_init_counter_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, row_stride, n_local_rows, K, G, rank, n_rows, seed, scale);
+  return launched("table_init_counter");
 }

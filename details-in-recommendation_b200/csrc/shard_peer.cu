@@ -1,0 +1,539 @@
+// Row-sharded tables, device-driven exchange over NVLink peer memory (no NCCL, no host read on the step).
+//
+// Every rank owns one exchange buffer per parity with the same layout (dir_peer_layout); peers store
+// straight into it through peer-mapped addresses.  Sizes that depend on the data travel as headers and are
+// read on the device, so every launch of a step is sized by capacities known up front and the whole step --
+// id phase included -- can be replayed from a CUDA graph:
+//
+//   requester q                                         owner o
+//   dir_shard_keys / sort / dir_shard_unique  (ids only)
+//   dir_shard_ids_push    hdr[q] = (count, base_u), ids[q][0..count)  -->  o's buffer
+//   ---- barrier (ids) ----
+//                                                       dir_shard_slots      slot[row][q] = i + 1
+//                                                       dir_shard_gather_send  T[row] -> q's rows[base_u + i],
+//                                                                              w[row] -> q's w[base_u + i]
+//   ---- barrier (rows) ----
+//   dir_embed_fm_fwd on rows / w, indexed by inv
+//   dir_embed_bwd_reduce_emit_to   per-distinct-row sums  -->  o's g[q][i]       (embed_bwd.cu)
+//   dir_shard_g1_push              first-order sums       -->  o's g1[q][i]
+//   dir_shard_dense_emit           one-row fields' sums   -->  everybody's dense[q][j]
+//   ---- barrier (grads) ----
+//                                                       dir_shard_owner_update  per local row: the requesters'
+//                                                         sums added in rank order, fused row update
+//                                                       dir_shard_slots(clear)
+//   dir_shard_dense_apply   replicated one-row fields: ranks' sums added in rank order, same update everywhere
+//
+// The owner never sorts: a requester sends each row at most once, so slot[row][q] (one cell per local row and
+// requester, written without atomics) tells an arrival whether an earlier rank asked for the same row; the first
+// one merges.  Deterministic: no floating-point atomics, sums in rank order.
+//
+// Reference: the partitioner hook around the embedding variables, models/DeepFM/deepFM.py:163-175 (under a TF
+// parameter-server cluster the variables are sharded by row and ids / IndexedSlices travel over gRPC).
+#include "common.cuh"
+#include "update.cuh"
+
+namespace dir {
+
+constexpr int kMaxG = 64;
+constexpr int kPeerCtas = kSMs * 8;  // grid-stride launches: the real counts are known on the device only
+
+__device__ __forceinline__ char* peer_buf(const dir_peer_layout& L, int q) {
+  return reinterpret_cast<char*>(__ldg(L.peer_base + q));
+}
+__device__ __forceinline__ int seg_of(const int64_t* s, int G, int64_t i) {  // s[G+1] ascending, in shared memory
+  int q = 0;
+  while (q + 1 < G && i >= s[q + 1]) ++q;
+  return q;
+}
+
+// requester: header + distinct local rows to every owner
+__global__ void __launch_bounds__(256)
+peer_ids_push_kernel(const dir_peer_layout L, const int32_t* __restrict__ ulocal,
+                     const int64_t* __restrict__ owner_off, int64_t n_cap, int* err) {
+  __shared__ int64_t s_off[kMaxG + 1];
+  if (threadIdx.x <= L.G) s_off[threadIdx.x] = owner_off[threadIdx.x];
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < L.G) {
+    const int o = threadIdx.x;
+    int64_t cnt = s_off[o + 1] - s_off[o];
+    if (cnt > L.seg_cap || s_off[L.G] > L.u_cap) {
+      *err = 1;  // more distinct rows than the buffers were sized for: nothing is written out of bounds
+      cnt = cnt > L.seg_cap ? L.seg_cap : cnt;
+    }
+    int64_t* hdr = reinterpret_cast<int64_t*>(peer_buf(L, o) + L.off_hdr) + (int64_t)L.rank * 4;
+    hdr[0] = cnt;
+    hdr[1] = s_off[o];
+  }
+  int64_t total = s_off[L.G];
+  total = total < n_cap ? total : n_cap;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int o = seg_of(s_off, L.G, i);
+    const int64_t j = i - s_off[o];
+    if (j < L.seg_cap)
+      reinterpret_cast<int32_t*>(peer_buf(L, o) + L.off_ids)[(int64_t)L.rank * L.seg_cap + j] = __ldg(ulocal + i);
+  }
+}
+
+// owner: what arrived.  pre[q] = arrivals from requesters < q; base[q] = where q keeps my rows.
+struct Arrivals {
+  int64_t pre[kMaxG + 1];
+  int64_t base[kMaxG];
+};
+__device__ __forceinline__ void load_arrivals(const dir_peer_layout& L, Arrivals& s) {
+  if (threadIdx.x == 0) {
+    const int64_t* hdr = reinterpret_cast<const int64_t*>(L.local + L.off_hdr);
+    int64_t pre = 0;
+    for (int q = 0; q < L.G; ++q) {
+      s.pre[q] = pre;
+      int64_t c = hdr[q * 4];
+      c = c < 0 ? 0 : (c > L.seg_cap ? L.seg_cap : c);
+      pre += c;
+      s.base[q] = hdr[q * 4 + 1];
+    }
+    s.pre[L.G] = pre;
+  }
+  __syncthreads();
+}
+
+// owner: slot[row * G + q] = i + 1 for arrival i of requester q (set = 1), or 0 again (set = 0)
+__global__ void __launch_bounds__(256)
+peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t n_local, int set, int* err) {
+  __shared__ Arrivals s;
+  load_arrivals(L, s);
+  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
+  const int64_t total = s.pre[L.G];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < total; a += step) {
+    const int q = seg_of(s.pre, L.G, a);
+    const int64_t i = a - s.pre[q];
+    const int64_t r = __ldg(ids + (int64_t)q * L.seg_cap + i);
+    if (r < 0 || r >= n_local) {
+      *err = 2;
+      continue;
+    }
+    slot[r * L.G + q] = set ? (uint32_t)(i + 1) : 0u;
+  }
+}
+
+// owner: fused gather + send.  LPR lanes carry one row (16 bytes each) into the requester's rows[base_u + i];
+// a thread handles kRows rows a grid-stride apart, loads first, so several lines per thread are in flight
+// before the first NVLink store.  The first-order weights go out from a lane-per-arrival loop (128-byte
+// contiguous stores per warp).  CTA 0 also refreshes the replicated one-row fields' rows behind my own rows.
+constexpr int kRows = 4;
+template <int LPR>
+__global__ void __launch_bounds__(256)
+peer_gather_send_kernel(const dir_peer_layout L, const float* __restrict__ table, int64_t row_stride,
+                        const float* __restrict__ lin, int64_t lin_stride,
+                        const float* __restrict__ dense_table, int64_t dense_stride,
+                        const float* __restrict__ dense_lin) {
+  constexpr int K = LPR * 4;
+  __shared__ Arrivals s;
+  __shared__ char* s_peer[kMaxG];
+  if (threadIdx.x < L.G) s_peer[threadIdx.x] = peer_buf(L, threadIdx.x);
+  load_arrivals(L, s);
+  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
+  const int64_t total = s.pre[L.G];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = (int)(t % LPR);
+  const int64_t step = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  for (int64_t a0 = t / LPR; a0 < total; a0 += step * kRows) {
+    int64_t r[kRows], dst[kRows];
+    int q[kRows];
+    float4 v[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int64_t a = a0 + k * step;
+      r[k] = -1;
+      if (a < total) {
+        q[k] = seg_of(s.pre, L.G, a);
+        const int64_t i = a - s.pre[q[k]];
+        r[k] = __ldg(ids + (int64_t)q[k] * L.seg_cap + i);
+        dst[k] = s.base[q[k]] + i;
+        if (dst[k] < 0 || dst[k] >= L.u_cap) r[k] = -1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k)
+      if (r[k] >= 0) v[k] = __ldg(reinterpret_cast<const float4*>(table + r[k] * row_stride) + sub);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k)
+      if (r[k] >= 0)
+        *(reinterpret_cast<float4*>(s_peer[q[k]] + L.off_rows) + dst[k] * LPR + sub) = v[k];
+  }
+  if (lin != nullptr) {
+    const int64_t step1 = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t a = t; a < total; a += step1) {
+      const int q = seg_of(s.pre, L.G, a);
+      const int64_t i = a - s.pre[q];
+      const int64_t r = __ldg(ids + (int64_t)q * L.seg_cap + i);
+      const int64_t d = s.base[q] + i;
+      if (d >= 0 && d < L.u_cap) reinterpret_cast<float*>(s_peer[q] + L.off_w)[d] = __ldg(lin + r * lin_stride);
+    }
+  }
+  if (blockIdx.x == 0 && L.n_dense > 0 && dense_table != nullptr) {
+    float* rows = reinterpret_cast<float*>(L.local + L.off_rows) + L.u_cap * K;
+    float* w = reinterpret_cast<float*>(L.local + L.off_w) + L.u_cap;
+    for (int e = threadIdx.x; e < L.n_dense * K; e += blockDim.x)
+      rows[e] = dense_table[(int64_t)(e / K) * dense_stride + (e % K)];
+    for (int j = threadIdx.x; j < L.n_dense; j += blockDim.x) w[j] = dense_lin ? dense_lin[j] : 0.f;
+  }
+}
+
+// requester: first-order gradient sums of the distinct rows (g1_local[u], grouped by owner) -> owners
+__global__ void __launch_bounds__(256)
+peer_g1_push_kernel(const dir_peer_layout L, const float* __restrict__ g1_local,
+                    const int64_t* __restrict__ owner_off, int64_t n_cap) {
+  __shared__ int64_t s_off[kMaxG + 1];
+  if (threadIdx.x <= L.G) s_off[threadIdx.x] = owner_off[threadIdx.x];
+  __syncthreads();
+  int64_t total = s_off[L.G];
+  total = total < n_cap ? total : n_cap;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int o = seg_of(s_off, L.G, i);
+    const int64_t j = i - s_off[o];
+    if (j < L.seg_cap)
+      reinterpret_cast<float*>(peer_buf(L, o) + L.off_g1)[(int64_t)L.rank * L.seg_cap + j] = __ldg(g1_local + i);
+  }
+}
+
+// owner: merge + fused update.  LPR lanes per arrival; the arrival of the lowest rank that asked for a row
+// adds the other ranks' sums in rank order and updates the row (row and accumulator share a 128-byte line).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ slot, float* table, float* accum,
+                         int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
+                         int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
+  constexpr int SLOTS = 32 / LPR;
+  __shared__ Arrivals s;
+  load_arrivals(L, s);
+  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
+  const float* gbuf = reinterpret_cast<const float*>(L.local + L.off_g);
+  const float* g1buf = reinterpret_cast<const float*>(L.local + L.off_g1);
+  const int64_t total = s.pre[L.G];
+  const bool adagrad = opt == DIR_OPT_ADAGRAD;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t pol_row = policy_evict_first();
+  unsigned leaders = 0;
+  for (int64_t a0 = warp * SLOTS; a0 < total; a0 += nwarps * SLOTS) {  // warp-uniform trip count
+    const int64_t a = a0 + lane / LPR;
+    bool lead = false;
+    int q = 0;
+    int64_t i = 0, r = 0;
+    if (a < total) {
+      q = seg_of(s.pre, L.G, a);
+      i = a - s.pre[q];
+      r = __ldg(ids + (int64_t)q * L.seg_cap + i);
+      lead = r >= 0 && r < n_local;
+      const uint32_t* sl = slot + r * L.G;
+      for (int p = 0; lead && p < q; ++p) lead = __ldg(sl + p) == 0u;  // an earlier rank merges this row
+    }
+    if (lead) {
+      const int64_t ro = r * row_stride;
+      float4 T = ld_hint(table + ro + sub * 4, pol_row);
+      float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (adagrad) A = ld_hint(accum + ro + sub * 4, pol_row);
+      const int64_t e = (int64_t)q * L.seg_cap + i;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gbuf) + e * LPR + sub);
+      float g1 = sub == 0 ? __ldg(g1buf + e) : 0.f;
+      const uint32_t* sl = slot + r * L.G;
+      for (int p = q + 1; p < L.G; ++p) {  // rank order
+        const uint32_t sp = __ldg(sl + p);
+        if (sp != 0u) {
+          const int64_t e2 = (int64_t)p * L.seg_cap + (sp - 1u);
+          const float4 o = __ldg(reinterpret_cast<const float4*>(gbuf) + e2 * LPR + sub);
+          g.x = __fadd_rn(g.x, o.x);
+          g.y = __fadd_rn(g.y, o.y);
+          g.z = __fadd_rn(g.z, o.z);
+          g.w = __fadd_rn(g.w, o.w);
+          if (sub == 0) g1 = __fadd_rn(g1, __ldg(g1buf + e2));
+        }
+      }
+      T.x = upd(T.x, g.x, lr, A.x, adagrad);
+      T.y = upd(T.y, g.y, lr, A.y, adagrad);
+      T.z = upd(T.z, g.z, lr, A.z, adagrad);
+      T.w = upd(T.w, g.w, lr, A.w, adagrad);
+      *(reinterpret_cast<float4*>(table + ro) + sub) = T;
+      if (adagrad) *(reinterpret_cast<float4*>(accum + ro) + sub) = A;
+      if (lin != nullptr && sub == 0) {
+        const int64_t off = r * lin_stride;
+        float n1, z1;
+        lin_load(lo, lin_accum, off, n1, z1);
+        lin_apply(lo, lin + off, lin_accum + off, lo.z + off, lin[off], n1, z1, g1);
+      }
+    }
+    leaders += __popc(__ballot_sync(0xffffffffu, lead && sub == 0));
+  }
+  if (lane == 0 && leaders && n_unique) atomicAdd(n_unique, (unsigned long long)leaders);
+}
+
+// replicated one-row fields: the G ranks' sums added in rank order, the same update applied to every replica;
+// shard_row[j] >= 0 names the row of the sharded table to mirror into (on the rank that owns it)
+struct DenseApplyArgs {
+  float* table;  // replica: [n_dense] rows, row_stride apart (row | accumulator when Adagrad)
+  float* accum;
+  int64_t row_stride;
+  float* lin;
+  float* lin_accum;
+  LinOpt lo;  // lo.z: [n_dense]
+  int opt;
+  float lr;
+  float* s_table;  // the sharded table's copy of the row
+  float* s_accum;
+  int64_t s_row_stride;
+  float* s_lin;
+  float* s_lin_accum;
+  float* s_lin_z;
+  int64_t s_lin_stride;
+  const int64_t* shard_row;
+  unsigned long long* n_unique;
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(128) peer_dense_apply_kernel(const dir_peer_layout L, const DenseApplyArgs a) {
+  constexpr int K = LPR * 4;
+  const int j = blockIdx.x, c = threadIdx.x;
+  if (c > K) return;
+  const float* gbuf = reinterpret_cast<const float*>(L.local + L.off_dense);
+  float g = 0.f, touched = 0.f;
+  for (int q = 0; q < L.G; ++q) {  // rank order: the same sum on every rank
+    const float* src = gbuf + ((int64_t)q * L.n_dense + j) * (K + 4);
+    g = q == 0 ? src[c] : __fadd_rn(g, src[c]);
+    touched += src[K + 1];
+  }
+  if (touched == 0.f) return;  // no rank had a surviving lookup: the row is not touched
+  const int64_t sr = __ldg(a.shard_row + j);
+  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  if (c < K) {
+    float* tp = a.table + (int64_t)j * a.row_stride + c;
+    float acc = 0.f;
+    if (adagrad) acc = a.accum[(int64_t)j * a.row_stride + c];
+    const float t = upd(*tp, g, a.lr, acc, adagrad);
+    *tp = t;
+    if (adagrad) a.accum[(int64_t)j * a.row_stride + c] = acc;
+    if (sr >= 0) {
+      a.s_table[sr * a.s_row_stride + c] = t;
+      if (adagrad) a.s_accum[sr * a.s_row_stride + c] = acc;
+    }
+  } else {
+    if (a.lin != nullptr) {
+      float n1, z1;
+      lin_load(a.lo, a.lin_accum, j, n1, z1);
+      lin_apply(a.lo, a.lin + j, a.lin_accum + j, a.lo.z + j, a.lin[j], n1, z1, g);
+      if (sr >= 0) {
+        a.s_lin[sr * a.s_lin_stride] = a.lin[j];
+        if (a.lo.opt != DIR_OPT_SGD) a.s_lin_accum[sr * a.s_lin_stride] = a.lin_accum[j];
+        if (a.lo.opt == DIR_OPT_FTRL) a.s_lin_z[sr * a.s_lin_stride] = a.lo.z[j];
+      }
+    }
+    if (a.n_unique) atomicAdd(a.n_unique, 1ull);
+  }
+}
+
+// inv[b, f] of the replicated one-row fields: their rows sit behind the exchanged ones (u_cap + j); an id other
+// than 0 or a value <= 0 prunes the lookup ([TF] _safe_embedding_lookup_sparse)
+__global__ void __launch_bounds__(256)
+dense_inv_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val,
+                 const int32_t* __restrict__ fields, int n_fields, int64_t B, int F, int64_t tail,
+                 int64_t* __restrict__ inv, int* oob_flag) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n_fields) return;
+  const int64_t b = t / n_fields;
+  const int j = (int)(t % n_fields);
+  const int64_t p = b * F + __ldg(fields + j);
+  const int64_t id = __ldg(idx + p);
+  const float v = val ? __ldg(val + p) : 1.f;
+  if (id > 0 && v > 0.f && oob_flag) *oob_flag = 1;
+  inv[p] = (id == 0 && v > 0.f) ? tail + j : -1;
+}
+
+static int check_layout(const char* what, const dir_peer_layout* L) {
+  if (!L) return fail(DIR_EINVAL, "%s: layout is required", what);
+  if (L->G <= 0 || L->G > kMaxG || L->rank < 0 || L->rank >= L->G)
+    return fail(DIR_EINVAL, "%s: need 0 <= rank < G <= 64", what);
+  if (L->K != 4 && L->K != 8 && L->K != 16 && L->K != 32 && L->K != 64)
+    return fail(DIR_EINVAL, "%s: K must be one of 4, 8, 16, 32, 64", what);
+  if (L->seg_cap <= 0 || L->u_cap <= 0 || L->n_dense < 0 || L->n_dense > 64)
+    return fail(DIR_EINVAL, "%s: seg_cap, u_cap > 0 and 0 <= n_dense <= 64 required", what);
+  if (!L->peer_base || !L->local) return fail(DIR_EINVAL, "%s: peer_base and local are required", what);
+  if ((reinterpret_cast<uintptr_t>(L->local) & 255u) != 0)
+    return fail(DIR_EINVAL, "%s: the exchange buffer must be 256-byte aligned", what);
+  return 0;
+}
+
+}  // namespace dir
+
+extern "C" int dir_peer_layout_init(int G, int rank, int K, int n_dense, int64_t seg_cap, int64_t u_cap,
+                                    dir_peer_layout* out) {
+  using namespace dir;
+  if (!out) return fail(DIR_EINVAL, "peer_layout_init: out is required");
+  if (G <= 0 || G > kMaxG || rank < 0 || rank >= G) return fail(DIR_EINVAL, "peer_layout_init: need 0 <= rank < G <= 64");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "peer_layout_init: K must be one of 4, 8, 16, 32, 64");
+  if (seg_cap <= 0 || u_cap <= 0 || n_dense < 0 || n_dense > 64)
+    return fail(DIR_EINVAL, "peer_layout_init: seg_cap, u_cap > 0 and 0 <= n_dense <= 64 required");
+  out->G = G;
+  out->rank = rank;
+  out->K = K;
+  out->n_dense = n_dense;
+  out->seg_cap = seg_cap;
+  out->u_cap = u_cap;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += align_up(bytes, 256);
+    return (int64_t)at;
+  };
+  out->off_hdr = take((size_t)G * 4 * 8);
+  out->off_ids = take((size_t)G * seg_cap * 4);
+  out->off_rows = take((size_t)(u_cap + n_dense) * K * 4);
+  out->off_w = take((size_t)(u_cap + n_dense) * 4);
+  out->off_g = take((size_t)G * seg_cap * K * 4);
+  out->off_g1 = take((size_t)G * seg_cap * 4);
+  out->off_dense = take((size_t)G * (n_dense > 0 ? n_dense : 1) * (K + 4) * 4);
+  out->total_bytes = (int64_t)off;
+  out->peer_base = nullptr;
+  out->local = nullptr;
+  return 0;
+}
+
+extern "C" int dir_shard_dense_inv(const int64_t* feature_index, const float* feature_value,
+                                   const int32_t* onerow_fields, int n_onerow, int64_t B, int F, int64_t tail_row,
+                                   int64_t* inv, int* oob_flag, dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > F) return fail(DIR_EINVAL, "shard_dense_inv: bad sizes");
+  if (B == 0 || n_onerow == 0) return 0;
+  if (!feature_index || !onerow_fields || !inv) return fail(DIR_EINVAL, "shard_dense_inv: null pointer");
+  const int64_t n = B * n_onerow;
+  dense_inv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      feature_index, feature_value, onerow_fields, n_onerow, B, F, tail_row, inv, oob_flag);
+  return launched("shard_dense_inv");
+}
+
+extern "C" int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_local_rows,
+                                  const int64_t* owner_off, int64_t n_capacity, int* err_flag,
+                                  dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_ids_push", layout)) return rc;
+  if (!owner_off || !err_flag || n_capacity < 0 || (n_capacity > 0 && !unique_local_rows))
+    return fail(DIR_EINVAL, "shard_ids_push: owner_off, err_flag and the id list are required");
+  const int64_t want = (n_capacity + 255) / 256;
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want < kPeerCtas ? want : kPeerCtas));
+  peer_ids_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, unique_local_rows, owner_off,
+                                                                           n_capacity, err_flag);
+  return launched("shard_ids_push");
+}
+
+extern "C" int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
+                               int* err_flag, dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_slots", layout)) return rc;
+  if (!slot || !err_flag || n_local_rows <= 0) return fail(DIR_EINVAL, "shard_slots: slot, err_flag, n_local_rows > 0 required");
+  peer_slots_kernel<<<kPeerCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, slot, n_local_rows, set, err_flag);
+  return launched("shard_slots");
+}
+
+extern "C" int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
+                                     const float* lin, int64_t lin_stride, const float* dense_table,
+                                     int64_t dense_row_stride, const float* dense_lin, dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_gather_send", layout)) return rc;
+  const int K = layout->K;
+  if (!table || row_stride < K || (row_stride & 3) || !aligned16(table))
+    return fail(DIR_EINVAL, "shard_gather_send: table (16-byte aligned), row_stride >= K and a multiple of 4 required");
+  if (layout->n_dense > 0 && (!dense_table || dense_row_stride < K))
+    return fail(DIR_EINVAL, "shard_gather_send: the replicated rows are required when n_dense > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define DIR_GS(LP) \
+  peer_gather_send_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, table, row_stride, lin, lin_stride, dense_table, \
+                                                         dense_row_stride, dense_lin)
+  switch (K / 4) {
+    case 1: DIR_GS(1); break;
+    case 2: DIR_GS(2); break;
+    case 4: DIR_GS(4); break;
+    case 8: DIR_GS(8); break;
+    default: DIR_GS(16); break;
+  }
+#undef DIR_GS
+  return launched("shard_gather_send");
+}
+
+extern "C" int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_local, const int64_t* owner_off,
+                                 int64_t n_capacity, dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_g1_push", layout)) return rc;
+  if (!owner_off || n_capacity < 0 || (n_capacity > 0 && !g1_local))
+    return fail(DIR_EINVAL, "shard_g1_push: owner_off and g1_local are required");
+  const int64_t want = (n_capacity + 255) / 256;
+  const unsigned grid = (unsigned)(want < 1 ? 1 : (want < kPeerCtas ? want : kPeerCtas));
+  peer_g1_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, g1_local, owner_off, n_capacity);
+  return launched("shard_g1_push");
+}
+
+extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
+                                      int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
+                                      int64_t n_local_rows, int optimizer, float lr,
+                                      const dir_linear_opt* linear_opt, int64_t* n_unique_out, dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_owner_update", layout)) return rc;
+  const int K = layout->K;
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+    return fail(DIR_EINVAL, "shard_owner_update: unknown optimizer");
+  if (!slot || !table || n_local_rows <= 0) return fail(DIR_EINVAL, "shard_owner_update: slot, table, n_local_rows > 0 required");
+  if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "shard_owner_update: Adagrad needs accum");
+  if (row_stride < K || (row_stride & 3) || !aligned16(table) || !aligned16(accum))
+    return fail(DIR_EINVAL, "shard_owner_update: rows must be 16-byte aligned, row_stride >= K and a multiple of 4");
+  LinOpt lo;
+  if (int rc = resolve_lin("shard_owner_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_unique_out) cudaMemsetAsync(n_unique_out, 0, 8, st);
+  unsigned long long* nu = reinterpret_cast<unsigned long long*>(n_unique_out);
+#define DIR_OU(LP) \
+  peer_owner_update_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, slot, table, accum, row_stride, lin, lin_accum, \
+                                                          lin_stride, lo, optimizer, lr, n_local_rows, nu)
+  switch (K / 4) {
+    case 1: DIR_OU(1); break;
+    case 2: DIR_OU(2); break;
+    case 4: DIR_OU(4); break;
+    case 8: DIR_OU(8); break;
+    default: DIR_OU(16); break;
+  }
+#undef DIR_OU
+  return launched("shard_owner_update");
+}
+
+extern "C" int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
+                                     int64_t row_stride, float* dense_lin, float* dense_lin_accum, int optimizer,
+                                     float lr, const dir_linear_opt* linear_opt, float* shard_table,
+                                     float* shard_accum, int64_t shard_row_stride, float* shard_lin,
+                                     float* shard_lin_accum, float* shard_lin_z, int64_t shard_lin_stride,
+                                     const int64_t* shard_row, int64_t* n_unique_inout, dir_stream_t stream) {
+  using namespace dir;
+  if (int rc = check_layout("shard_dense_apply", layout)) return rc;
+  if (layout->n_dense == 0) return 0;
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD) return fail(DIR_EINVAL, "shard_dense_apply: unknown optimizer");
+  if (!dense_table || !shard_row || !shard_table) return fail(DIR_EINVAL, "shard_dense_apply: null pointer");
+  if (optimizer == DIR_OPT_ADAGRAD && (!dense_accum || !shard_accum))
+    return fail(DIR_EINVAL, "shard_dense_apply: Adagrad needs the accumulators");
+  LinOpt lo;
+  if (int rc = resolve_lin("shard_dense_apply", linear_opt, optimizer, lr, dense_lin, dense_lin_accum, lo)) return rc;
+  if (dense_lin && (!shard_lin || (lo.opt != DIR_OPT_SGD && !shard_lin_accum) || (lo.opt == DIR_OPT_FTRL && !shard_lin_z)))
+    return fail(DIR_EINVAL, "shard_dense_apply: the sharded copies of the linear state are required");
+  DenseApplyArgs a{dense_table, dense_accum, row_stride, dense_lin, dense_lin_accum, lo, optimizer, lr,
+                   shard_table, shard_accum, shard_row_stride, shard_lin, shard_lin_accum, shard_lin_z,
+                   shard_lin_stride, shard_row, reinterpret_cast<unsigned long long*>(n_unique_inout)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = layout->n_dense;
+  switch (layout->K / 4) {
+    case 1: peer_dense_apply_kernel<1><<<n, 128, 0, st>>>(*layout, a); break;
+    case 2: peer_dense_apply_kernel<2><<<n, 128, 0, st>>>(*layout, a); break;
+    case 4: peer_dense_apply_kernel<4><<<n, 128, 0, st>>>(*layout, a); break;
+    case 8: peer_dense_apply_kernel<8><<<n, 128, 0, st>>>(*layout, a); break;
+    default: peer_dense_apply_kernel<16><<<n, 128, 0, st>>>(*layout, a); break;
+  }
+  return launched("shard_dense_apply");
+}

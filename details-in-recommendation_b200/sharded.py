@@ -1,15 +1,21 @@
 """Row-sharded embedding + FM layer: one process per GPU, tables sharded by row over the ranks of a
-process group, NCCL all-to-all for the lookup and the gradient exchange, the FM / first-order /
-cross interaction data-parallel on the requesting rank.
+process group, the FM / first-order / cross interaction data-parallel on the requesting rank
+(SURVEY.md section 8e).
 
 The reference's only hook for this is the partitioner around its embedding variables
 (`input_layer_partitioner`, models/DeepFM/deepFM.py:163-175): with a TF parameter-server cluster
-the variables are split by row and ids / IndexedSlices travel over gRPC.  Here the exchange is two
-all-to-alls per direction (counts, then payload) over NVLink, and only DISTINCT rows travel:
-the requester sorts its lookups by (owner, local row), numbers the distinct ones, and after the
-owner answered runs the ordinary forward kernel on the received buffer; in the backward it sums
-the gradients of each distinct row before shipping them, so a one-row "dense" field or a Zipf-hot
-row costs one row of traffic per rank and step instead of one per sample.
+the variables are split by row and ids / IndexedSlices travel over gRPC.  Here only DISTINCT rows
+travel: the requester sorts its lookups by (owner, local row), numbers the distinct ones, and after
+the owner answered runs the ordinary forward kernel on the received rows; in the backward it sums
+the gradients of each distinct row before shipping them, so a Zipf-hot row costs one row of traffic
+per rank and step instead of one per lookup.  One-row (numeric) fields are replicated parameters.
+
+Two exchange flavours (DIR_B200_EXCHANGE):
+  peer  (default) NVLink peer memory, driven from the device: kernels store straight into the peers'
+        exchange buffers (symmetric memory), counts travel as headers read on the device, a
+        device-side barrier separates the phases.  No NCCL, no host read: the whole step replays
+        from a CUDA graph (csrc/shard_peer.cu).  With one process the buffers are plain local memory.
+  nccl  the baseline: counts and payload through `all_to_all_single`, one host read per step.
 
 `ShardPlan` (pure index arithmetic) and `exchange` / `exchange_counts` (the collectives) carry no
 CUDA-only code: tests run them under gloo with world_size 2 on CPU.
@@ -80,36 +86,6 @@ def exchange(payload: torch.Tensor, send_splits, recv_splits, group=None) -> tor
     return out
 
 
-def exchange_into(out: torch.Tensor, payload: torch.Tensor, send_splits, recv_splits, group=None) -> torch.Tensor:
-    """`exchange` into the head of a caller-owned buffer (fixed address: CUDA-graph replays read it)."""
-    n = int(sum(recv_splits))
-    if n > out.shape[0]:
-        raise ValueError("exchange_into: %d rows received, buffer holds %d" % (n, out.shape[0]))
-    view = out[:n]
-    if not dist.is_initialized():
-        view.copy_(payload)
-        return view
-    dist.all_to_all_single(view, payload.contiguous(), output_split_sizes=list(recv_splits),
-                           input_split_sizes=list(send_splits), group=group)
-    return view
-
-
-def peer_offsets(M: torch.Tensor, me: int):
-    """Where the segments of the peer-memory exchange start, from everybody's counts.
-
-    M[q, o] = distinct rows requester q wants from owner o (int64 [G, G], the same on every rank).
-      recv_off[G+1]   owner `me`: its answer list is grouped by requester; group q starts at recv_off[q]
-      fwd_dst_off[G]  owner `me` -> requester q: q's row buffer is grouped by owner, `me`'s group starts here
-      bwd_dst_off[G]  requester `me` -> owner o: o's gradient buffer is grouped by requester (= the order of
-                      its answer list), `me`'s group starts here
-    """
-    recv_counts = M[:, me]
-    recv_off = torch.cat([torch.zeros(1, dtype=M.dtype, device=M.device), torch.cumsum(recv_counts, 0)])
-    fwd_dst_off = (torch.cumsum(M, 1) - M)[:, me].contiguous()
-    bwd_dst_off = (torch.cumsum(M, 0) - M)[me, :].contiguous()
-    return recv_off, fwd_dst_off, bwd_dst_off
-
-
 class StageTrace:
     """Optional per-stage CUDA-event timing of the sharded step (DIR_B200_TRACE=1): mark(name) closes
     the stage that just ran; report() averages over the steps seen since the last report."""
@@ -138,45 +114,77 @@ class StageTrace:
         return out
 
 
-class PeerBuffers:
-    """Double-buffered symmetric memory for the payload exchange: every rank allocates the same buffers and
-    maps its peers' copies (torch.distributed._symmetric_memory, CUDA IPC over NVLink).  `ptrs[p]` is a
-    device int64[G] of peer-mapped addresses of buffer p; `barrier(p)` is a device-side cross-rank barrier
-    on the current stream (no host involvement)."""
+BARRIER_TIMEOUT_MS = int(os.environ.get("DIR_B200_BARRIER_TIMEOUT_MS", "20000"))
 
-    def __init__(self, group, rows_cap, stride, device):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.bufs, self.handles, self.ptrs = [], [], []
-        name = group if group is not None else dist.group.WORLD
+
+class PeerExchange:
+    """The exchange buffers of the device-driven path: one per parity (consecutive steps alternate), laid out by
+    `dir_peer_layout_init`, allocated as symmetric memory (torch.distributed._symmetric_memory: CUDA IPC mappings
+    over NVLink + a device-side barrier) and mapped by every peer.  With one process they are plain local memory
+    and the barrier is a no-op: the same kernels run.  `barrier(p, channel)` is a device-side cross-rank barrier on
+    the current stream; a lost barrier traps after BARRIER_TIMEOUT_MS instead of spinning forever."""
+
+    def __init__(self, group, world, rank, K, n_dense, seg_cap, u_cap, device):
+        L = _lib.lib()
+        self.world, self.rank, self.K, self.n_dense = world, rank, K, n_dense
+        self.seg_cap, self.u_cap = int(seg_cap), int(u_cap)
+        self.layouts, self.bufs, self.handles, self.peer_base = [], [], [], []
         for _ in range(2):
-            t = symm_mem.empty((rows_cap, stride), dtype=torch.float32, device=device)
-            h = symm_mem.rendezvous(t, name)
-            self.bufs.append(t)
+            lay = _lib.PeerLayout()
+            check(L.dir_peer_layout_init(world, rank, K, n_dense, self.seg_cap, self.u_cap, _lib.ctypes.byref(lay)),
+                  "dir_peer_layout_init")
+            nbytes = int(lay.total_bytes)
+            if world > 1:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+                h = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                base = torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=device)
+            else:
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                h = None
+                base = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=device)
+            buf.zero_()
+            lay.peer_base, lay.local = base.data_ptr(), buf.data_ptr()
+            self.layouts.append(lay)
+            self.bufs.append(buf)
             self.handles.append(h)
-            self.ptrs.append(torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=device))
-        self.rows_cap = rows_cap
+            self.peer_base.append(base)
+        if world > 1:
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                      # nobody stores into a buffer its owner is still zeroing
+
+    def ref(self, p):
+        return _lib.ctypes.byref(self.layouts[p])
+
+    def rows(self, p):
+        lay = self.layouts[p]
+        n = self.u_cap + self.n_dense
+        return self.bufs[p][lay.off_rows: lay.off_rows + n * self.K * 4].view(torch.float32).view(n, self.K)
+
+    def w(self, p):
+        lay = self.layouts[p]
+        n = self.u_cap + self.n_dense
+        return self.bufs[p][lay.off_w: lay.off_w + n * 4].view(torch.float32)
 
     def barrier(self, p, channel=0):
-        self.handles[p].barrier(channel=channel)
+        if self.handles[p] is not None:
+            self.handles[p].barrier(channel=channel, timeout_ms=BARRIER_TIMEOUT_MS)
 
 
 class ShardedLookups:
     """What `ShardedEmbeddingFM.presort` leaves behind for one batch -- everything that depends on the
     ids only: this rank's lookups sorted by (owner, local row), the distinct rows numbered, the ids
-    already exchanged, and the owner's half (the ids it received, sorted for the gradient merge)."""
+    already at their owners (and, NCCL flavour, the owner's list sorted for the gradient merge)."""
 
     def __init__(self):
         self.ws, self.ws2, self.ws3 = _Workspace(), _Workspace(), _Workspace()
-        self.keys = self.uidx = self.ulocal = self.inv = self.owner_off = self.recv_ids = None
-        self.send_splits = self.recv_splits = None
-        self.recv_off = self.fwd_dst_off = self.bwd_dst_off = None     # device offsets of the peer exchange
+        self.keys = self.uidx = self.ulocal = self.inv = self.owner_off = self.g1_local = None
+        self.send_splits = self.recv_splits = self.recv_ids = None      # NCCL flavour
         self.U = self.R = 0
         self.event = None
         self.src = None
-        self.parity = None          # which half of the double-buffered peer memory (None: the layer alternates)
-        self.recv_handle = self.recv_ptrs = None   # DIR_B200_IDS=peer: symmetric-memory handle / peer addresses of recv_buf
-        self.inv_c = None                          # DIR_B200_SHARD_ONEROW=1: compact [B, n_sel] row indices
-        self.recv_buf = None        # static mode: fixed-address landing buffer of the ids this rank answers
+        self.parity = None          # which exchange buffer this batch uses (peer flavour; set by presort)
+        self.shape = None
 
     @staticmethod
     def key_of(feature_index, feature_value):
@@ -192,43 +200,36 @@ class _ShardedFunction(torch.autograd.Function):
         dev = idx.device
         L = _lib.lib()
         st = _stream()
-        pad = layer.pad_stride
         tr = layer.trace
         tr.mark("start")
         if h.event is not None and not layer.capturing:
             torch.cuda.current_stream().wait_event(h.event)
-        U, R = h.U, h.R
-        static = layer.static
-        # 4b: the owner answers the ids it received; rows back over NVLink
-        G = layer.plan.world_size
-        if h.parity is not None:
-            parity = h.parity
-        else:
-            parity = layer._step_parity
-            layer._step_parity ^= 1
-        if layer.peer is not None:
-            if B > layer.max_batch:
-                raise ValueError("batch %d exceeds max_batch=%d the peer buffers were sized for" % (B, layer.max_batch))
-            # one kernel gathers the rows and writes them straight into the requesters' buffers
-            pb = layer.peer["rows"]
-            # static: launch for the capacity, the kernel stops at recv_off[G] (read on the device)
-            check(L.dir_rows_gather_to(ptr(layer.table), layer.row_stride,
-                                       ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
-                                       ptr(h.recv_buf if static else h.recv_ids), layer.recv_cap if static else R,
-                                       K, G, ptr(h.recv_off), ptr(pb.ptrs[parity]),
-                                       ptr(h.fwd_dst_off), pad, st), "dir_rows_gather_to")
+        emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
+        fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        first = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
+        ubuf = None
+        if layer.px is not None:
+            # the owner answers the ids it received: one kernel gathers the rows and stores them straight
+            # into the requesters' buffers over NVLink
+            px, p = layer.px, h.parity
+            check(L.dir_shard_gather_send(px.ref(p), ptr(layer.table), layer.row_stride,
+                                          ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
+                                          ptr(layer.dense_table) if layer.n_dense else None, layer.row_stride,
+                                          ptr(layer.dense_lin) if (layer.n_dense and layer.first_order) else None, st),
+                  "dir_shard_gather_send")
             tr.mark("fwd.gather+send")
-            if layer.onerow_rep:
-                # EXPERIMENT: the replicated one-row fields' rows sit behind the exchanged ones (inv points there)
-                tail = pb.bufs[parity][layer.rows_cap:]
-                check(L.dir_rows_gather(ptr(layer.dense_table), layer.row_stride,
-                                        ptr(layer.dense_lin) if layer.first_order else None, 1,
-                                        ptr(layer.dense_ids), layer.n_onerow, K, ptr(tail), pad, st), "dir_rows_gather")
-            pb.barrier(parity)
+            px.barrier(p, 0)
+            layer._note_forward()
             tr.mark("fwd.barrier")
-            ubuf = pb.bufs[parity]
-            use_peer = True
+            rows, lin = px.rows(p), px.w(p) if layer.first_order else None
+            check(L.dir_embed_fm_fwd(ptr(rows), K, ptr(lin), 1, ptr(bias) if layer.first_order else None,
+                                     ptr(h.inv), ptr(val), ptr(layer.zero_offset), None, rows.shape[0], B, F, K,
+                                     ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
+            tr.mark("fwd.fm")
         else:
+            U, R = h.U, h.R
+            pad = layer.pad_stride
             answer = torch.empty((R, pad), dtype=torch.float32, device=dev)
             check(L.dir_rows_gather(ptr(layer.table), layer.row_stride,
                                     ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
@@ -238,27 +239,21 @@ class _ShardedFunction(torch.autograd.Function):
             tr.mark("fwd.a2a_rows")
             if U == 0:
                 ubuf = torch.zeros((1, pad), dtype=torch.float32, device=dev)
-            use_peer = False
-        # 5: the ordinary forward on the received rows
-        emb = torch.empty((B, F * K), dtype=torch.float32, device=dev) if layer.emit_embeddings else None
-        fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
-        first = torch.empty((B, 1), dtype=torch.float32, device=dev)
-        S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
-        lin = ubuf[:, K] if layer.first_order else None
-        check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
-                                 ptr(h.inv), ptr(val), ptr(layer.zero_offset), None,
-                                 ubuf.shape[0] if static else max(U, 1), B, F, K,
-                                 ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
-        tr.mark("fwd.fm")
+            lin = ubuf[:, K] if layer.first_order else None
+            check(L.dir_embed_fm_fwd(ptr(ubuf), pad, ptr(lin), pad, ptr(bias) if layer.first_order else None,
+                                     ptr(h.inv), ptr(val), ptr(layer.zero_offset), None, max(U, 1), B, F, K,
+                                     ptr(emb), ptr(S), ptr(first), ptr(fm), None, None, st), "dir_embed_fm_fwd")
+            tr.mark("fwd.fm")
         if not layer.first_order:
             first.zero_()
-        layer.last_exchange = {"unique_sent": U, "unique_received": R, "lookups": B * F}
         ctx.layer, ctx.train, ctx.shape, ctx.h = layer, train, (B, F, K), h
-        ctx.use_peer, ctx.parity = use_peer, parity
-        ctx.idx = idx if layer.onerow_rep else None
+        ctx.idx = idx
         ctx.set_materialize_grads(False)
         if train:
-            ctx.save_for_backward(val, S, ubuf)
+            if ubuf is None:
+                ctx.save_for_backward(val, S)
+            else:
+                ctx.save_for_backward(val, S, ubuf)
         if emb is None:
             emb = torch.empty((B, 0), dtype=torch.float32, device=dev)
             ctx.mark_non_differentiable(emb)
@@ -269,14 +264,15 @@ class _ShardedFunction(torch.autograd.Function):
         if not ctx.train:
             raise RuntimeError("ShardedEmbeddingFM.backward: forward ran without gradient tracking")
         layer, h = ctx.layer, ctx.h
-        val, S, ubuf = ctx.saved_tensors
         B, F, K = ctx.shape
-        U, R = h.U, h.R
-        dev = S.device
         L = _lib.lib()
         st = _stream()
-        pad = layer.pad_stride
-        n = B * F
+        if layer.px is not None:
+            val, S = ctx.saved_tensors
+            ubuf = None
+        else:
+            val, S, ubuf = ctx.saved_tensors
+        dev = S.device
         g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
                    else g_first.reshape(B).contiguous().float())
         g_fm = (torch.zeros(B, dtype=torch.float32, device=dev) if g_fm is None
@@ -285,92 +281,79 @@ class _ShardedFunction(torch.autograd.Function):
             u = u.contiguous().float()
         tr = layer.trace
         tr.mark("between")
+        adagrad = layer.optimizer == "adagrad"
+        gfp = ptr(g_first) if layer.first_order else None
+        n_keys = layer.plan.cap * layer.plan.world_size
         with torch.no_grad():
-            # 6: per-distinct-row sums on the requester (the sorted list is in the handle's workspace)
-            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
-            n_keys = layer.plan.cap * layer.plan.world_size
-            gfp = ptr(g_first) if layer.first_order else None
-            if ctx.use_peer and layer.onerow_rep:
-                # EXPERIMENT: the sorted list covers the multi-row fields only; the one-row fields' gradients over this
-                # rank's samples go to every rank's buffer (behind the exchanged rows) from a column-sum kernel
-                pb = layer.peer["grads"]
-                G_ = layer.plan.world_size
-                ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * layer.n_sel, 1), K), dev)
-                check(L.dir_embed_bwd_reduce_emit_fields_to(
-                    ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K, n_keys,
-                    ptr(layer.sparse_fields), layer.n_sel, G_, ptr(h.owner_off), ptr(pb.ptrs[ctx.parity]),
-                    ptr(h.bwd_dst_off), pad, ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_fields_to")
-                ows = layer._onerow_ws.get(L.dir_onerow_workspace_bytes(K), dev)
-                check(L.dir_embed_bwd_onerow_emit_to(
-                    ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val), ptr(layer.dense_field_offset), gfp,
-                    ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), layer.n_onerow, B, F, K, G_, layer.plan.rank,
-                    ptr(pb.ptrs[ctx.parity]), layer.recv_cap, pad, ptr(ows), ows.numel(), st),
-                    "dir_embed_bwd_onerow_emit_to")
-                tr.mark("bwd.emit+push")
-                pb.barrier(ctx.parity)
-                tr.mark("bwd.barrier")
-                grecv = pb.bufs[ctx.parity]
-            elif ctx.use_peer and layer.fused_push:
-                # 6+7 in one kernel: each distinct row's sums go straight into its owner's buffer over NVLink
-                pb = layer.peer["grads"]
+            if layer.px is not None:
+                px, p = layer.px, h.parity
+                n = B * layer.n_sel
+                # per-distinct-row sums on the requester (the sorted list is in the handle's workspace), each
+                # stored straight into its owner's buffer over NVLink as soon as its run is summed
+                ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n, 1), K), dev)
                 check(L.dir_embed_bwd_reduce_emit_to(
-                    ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), B, F, K, n_keys,
-                    layer.plan.world_size, ptr(h.owner_off), ptr(pb.ptrs[ctx.parity]), ptr(h.bwd_dst_off), pad,
+                    px.ref(p), ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), ptr(h.owner_off), B, F, n_keys,
+                    ptr(layer.sparse_fields) if layer.n_sel < F else None, layer.n_sel, ptr(h.g1_local),
                     ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_to")
+                check(L.dir_shard_g1_push(px.ref(p), ptr(h.g1_local), ptr(h.owner_off), n, st), "dir_shard_g1_push")
                 tr.mark("bwd.emit+push")
-                pb.barrier(ctx.parity)
+                if layer.n_dense:
+                    # replicated one-row fields: this rank's column sums -> every rank's buffer
+                    ows = layer._dense_ws.get(L.dir_shard_dense_workspace_bytes(K), dev)
+                    check(L.dir_shard_dense_emit(
+                        px.ref(p), ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val),
+                        ptr(layer.dense_field_offset), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), B, F,
+                        ptr(ows), ows.numel(), st), "dir_shard_dense_emit")
+                    tr.mark("bwd.dense_emit")
+                px.barrier(p, 0)
                 tr.mark("bwd.barrier")
-                grecv = pb.bufs[ctx.parity]
+                # the owner merges the ranks' contributions (rank order) and updates its rows
+                check(L.dir_shard_owner_update(
+                    px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
+                    layer.row_stride, ptr(layer.w1) if layer.first_order else None,
+                    ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
+                    _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer), ptr(layer.last_n_unique), st),
+                    "dir_shard_owner_update")
+                check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, 0, ptr(layer.err_flag), st),
+                      "dir_shard_slots")
+                layer._slots_set[p] = False
+                tr.mark("bwd.owner_update")
+                if layer.n_dense:
+                    check(L.dir_shard_dense_apply(
+                        px.ref(p), ptr(layer.dense_table), ptr(layer.dense_accum) if adagrad else None,
+                        layer.row_stride, ptr(layer.dense_lin) if layer.first_order else None,
+                        ptr(layer.dense_lin_acc) if layer.first_order else None, _OPTIMIZERS[layer.optimizer],
+                        layer.lr, layer.dense_linear_opt(), ptr(layer.table), ptr(layer.accum) if adagrad else None,
+                        layer.row_stride, ptr(layer.w1) if layer.first_order else None,
+                        ptr(layer.w1_accum) if layer.first_order else None,
+                        ptr(layer.lin_z) if (layer.first_order and layer.lin_z is not None) else None,
+                        layer.lin_stride, ptr(layer.dense_shard_row),
+                        ptr(layer.last_n_unique) if layer.plan.rank == 0 else None, st), "dir_shard_dense_apply")
+                    tr.mark("bwd.dense_apply")
             else:
+                U, R = h.U, h.R
+                pad = layer.pad_stride
+                n = B * F
+                ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(n, K), dev)
                 gu = torch.empty((max(U, 1), pad), dtype=torch.float32, device=dev)
                 check(L.dir_embed_bwd_reduce_emit(ptr(ubuf), pad, ptr(val), gfp, ptr(g_fm), ptr(S), ptr(u),
                                                   ptr(h.uidx), B, F, K, n_keys, ptr(gu), pad,
                                                   ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit")
                 tr.mark("bwd.emit")
-            # 7: sums to their owners; the owner merges the ranks' contributions and updates
-            if ctx.use_peer and (layer.fused_push or layer.onerow_rep):
-                pass
-            elif ctx.use_peer:
-                pb = layer.peer["grads"]
-                check(L.dir_rows_push(ptr(gu), U, pad, layer.plan.world_size, ptr(h.owner_off),
-                                      ptr(pb.ptrs[ctx.parity]), ptr(h.bwd_dst_off), st), "dir_rows_push")
-                tr.mark("bwd.push")
-                pb.barrier(ctx.parity)
-                tr.mark("bwd.barrier")
-                grecv = pb.bufs[ctx.parity]
-            else:
                 grecv = exchange(gu[:U], h.send_splits, h.recv_splits, layer.group)      # [R, K+4]
                 tr.mark("bwd.a2a_grads")
-            if R > 0 or layer.static:
-                Rn = layer.recv_cap if layer.static else R        # static: capacity; the count stays on the device
-                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(Rn, K), dev)     # sorted by presort
-                adagrad = layer.optimizer == "adagrad"
-                n_dev = h.recv_off.data_ptr() + 8 * layer.plan.world_size if layer.static else None
-                check(L.dir_rows_reduce_update(
-                    ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
-                    ptr(layer.w1) if layer.first_order else None,
-                    ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride,
-                    ptr(grecv), pad, Rn, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
-                    linear_opt_struct(layer), n_dev,
-                    ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
-                tr.mark("bwd.owner_update")
-            else:
-                layer.last_n_unique.zero_()
-            if ctx.use_peer and layer.onerow_rep:
-                adagrad = layer.optimizer == "adagrad"
-                lo = layer.dense_linear_opt()
-                check(L.dir_dense_rows_apply(
-                    ptr(layer.dense_table), ptr(layer.dense_accum) if adagrad else None, layer.row_stride,
-                    ptr(layer.dense_lin) if layer.first_order else None,
-                    ptr(layer.dense_lin_acc) if layer.first_order else None, ptr(grecv), pad, layer.recv_cap,
-                    layer.n_onerow, K, layer.plan.world_size, _OPTIMIZERS[layer.optimizer], layer.lr, lo,
-                    ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
-                    ptr(layer.w1) if layer.first_order else None,
-                    ptr(layer.w1_accum) if layer.first_order else None,
-                    ptr(layer.lin_z) if (layer.first_order and layer.lin_z is not None) else None, layer.lin_stride,
-                    ptr(layer.dense_shard_row), ptr(layer.last_n_unique) if layer.plan.rank == 0 else None, st),
-                    "dir_dense_rows_apply")
-                tr.mark("bwd.dense_apply")
+                if R > 0:
+                    ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(R, K), dev)     # sorted by presort
+                    check(L.dir_rows_reduce_update(
+                        ptr(layer.table), ptr(layer.accum) if adagrad else None, layer.row_stride,
+                        ptr(layer.w1) if layer.first_order else None,
+                        ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride,
+                        ptr(grecv), pad, R, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
+                        linear_opt_struct(layer), None,
+                        ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
+                    tr.mark("bwd.owner_update")
+                else:
+                    layer.last_n_unique.zero_()
             tr.close_step()
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None, None
@@ -383,6 +366,9 @@ class ShardedEmbeddingFM(torch.nn.Module):
     (first_order, fm_second_order, embeddings) for THIS rank's samples; `.backward()` updates the
     rows this rank owns with the gradients of every rank's samples.  `bias` is an ordinary
     replicated parameter: all-reduce its gradient like any dense parameter.
+
+    `max_batch` sizes the exchange buffers (peer flavour).  `presort` may run at most one batch ahead
+    of `forward`; every presorted batch must be run.
     """
 
     def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
@@ -390,7 +376,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
                  first_order: bool = True, emit_embeddings: bool = True, check_bounds: bool = False,
                  process_group=None, max_batch: int = 65536, linear_optimizer: Optional[str] = None,
                  linear_lr: Optional[float] = None, l1_regularization_strength: float = 0.0,
-                 l2_regularization_strength: float = 0.0, device="cuda"):
+                 l2_regularization_strength: float = 0.0, init: str = "trunc_normal", device="cuda"):
         super().__init__()
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
@@ -399,6 +385,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
         optimizer = optimizer.lower()
         if optimizer not in _OPTIMIZERS:
             raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        if init not in ("trunc_normal", "counter", "none"):
+            raise ValueError("init must be 'trunc_normal', 'counter' or 'none'")
         self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
         self.linear_optimizer, self.linear_lr, lin_needs_acc, lin_needs_z = resolve_linear_optimizer(
             optimizer, lr, linear_optimizer, linear_lr, self.l1, self.l2)
@@ -416,10 +404,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
         adagrad = optimizer == "adagrad"
         self.row_stride = 2 * K if adagrad else K
         self.lin_stride = 1
-        self.pad_stride = K + 4                                     # (row[K], first-order weight, 3 pad)
-        self.n_rows = self.plan.cap                                 # local rows allocated
+        self.pad_stride = K + 4                                     # NCCL flavour: (row[K], first-order weight, 3 pad)
+        self.n_rows = max(self.plan.cap, 1)                         # local rows allocated
+        self.max_batch = int(max_batch)
         dev = torch.device(device)
-        cap = max(self.plan.cap, 1)
+        cap = self.n_rows
         self.register_buffer("field_offset", torch.tensor(self.plan.field_offset, dtype=torch.int64, device=dev))
         self.register_buffer("field_rows", torch.tensor(rows, dtype=torch.int64, device=dev))
         self.register_buffer("zero_offset", torch.zeros(field_size, dtype=torch.int64, device=dev))
@@ -428,63 +417,54 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.register_buffer("lin_acc", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if lin_needs_acc else None)
         self.register_buffer("lin_z", torch.zeros((cap, 1), dtype=torch.float32, device=dev) if lin_needs_z else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
+        self.register_buffer("err_flag", torch.zeros(1, dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.last_exchange = {}
         self._side = None
         self._inline = ShardedLookups()
-        # the id exchange of the NEXT batch runs concurrently with this batch's row / gradient exchange:
-        # give it a communicator of its own so the two never queue behind each other
-        self.side_group = (dist.new_group(ranks=dist.get_process_group_ranks(process_group or dist.group.WORLD))
-                           if dist.is_initialized() and dist.get_backend(process_group) == "nccl" else process_group)
         self.trace, self.trace_pre = StageTrace(), StageTrace()
-        # Payload exchange: NVLink peer memory (symmetric buffers + a device-side barrier) when there is
-        # more than one rank and torch's symmetric memory is usable, else NCCL all-to-all.
-        self.peer, self._step_parity = None, 0
-        self.static = self.capturing = self.ids_peer = self.onerow_rep = False
-        # EXPERIMENT (DIR_B200_SHARD_ONEROW=1, needs the peer exchange): one-row fields as replicated parameters
-        onerow = [f for f, r in enumerate(rows) if r == 1][:64]
-        want_rep = os.environ.get("DIR_B200_SHARD_ONEROW", "0") == "1" and 0 < len(onerow) < field_size
-        self.n_onerow = len(onerow) if want_rep else 0
-        sparse = [f for f in range(field_size) if not (want_rep and f in set(onerow))]
-        self.n_sel = len(sparse)
-        self.recv_cap = 0
-        self.max_batch = int(max_batch)
-        want_peer = os.environ.get("DIR_B200_EXCHANGE", "peer") == "peer"
-        self.fused_push = os.environ.get("DIR_B200_FUSED_PUSH", "1") == "1"   # emit + NVLink push in one kernel
-        if want_peer and dist.is_initialized() and world > 1 and dev.type == "cuda" \
-                and dist.get_backend(process_group) == "nccl":
-            try:
-                cap = min(self.max_batch * field_size, max(self.plan.cap, 1))       # distinct rows a rank can want
-                n1 = self.n_onerow                                                  # replicated rows ride behind them
-                self.peer = {"rows": PeerBuffers(process_group, cap + n1, self.pad_stride, dev),         # <- owners
-                             "grads": PeerBuffers(process_group, cap * world + n1 * world, self.pad_stride, dev)}  # <- requesters
-                self.rows_cap = cap
-                # Static mode: every main-stream launch is sized for these capacities and reads the real counts
-                # on the device, every buffer it touches has a fixed address -- so forward + backward of a step
-                # can be captured in a CUDA graph (the id-only presort stays eager on the side stream).
-                self.recv_cap = cap * world
-                self.static = os.environ.get("DIR_B200_STATIC", "1") == "1"
-                # experiment (not yet run on a GPU): ids through peer memory instead of the NCCL all-to-all
-                self.ids_peer = self.static and os.environ.get("DIR_B200_IDS", "nccl") == "peer"
-                self.onerow_rep = self.static and want_rep
-            except Exception as e:                                              # no IPC / fabric support
-                if rank == 0:
-                    print("ShardedEmbeddingFM: symmetric memory unavailable (%s); using NCCL all-to-all" % e,
-                          file=sys.stderr)
-                self.peer = None
+        self.capturing = False
+        self.exchange_mode = os.environ.get("DIR_B200_EXCHANGE", "peer")
+        if self.exchange_mode not in ("peer", "nccl"):
+            raise ValueError("DIR_B200_EXCHANGE must be 'peer' or 'nccl'")
+        if dev.type != "cuda":
+            raise ValueError("ShardedEmbeddingFM needs a CUDA device: this layer has no CPU path")
+        if self.exchange_mode == "peer" and world > 1 and dist.get_backend(process_group) != "nccl":
+            raise ValueError("the peer-memory exchange needs the nccl backend (one process per GPU)")
+        # One-row (numeric) fields are replicated parameters in the peer flavour: every sample of every rank hits
+        # the same row, so they stay out of the sort and the exchange; their gradients are column sums.
+        onerow = [f for f, r in enumerate(rows) if r == 1][:64] if self.exchange_mode == "peer" else []
+        sparse = [f for f in range(field_size) if f not in set(onerow)]
+        self.n_dense, self.n_sel = len(onerow), len(sparse)
+        self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
+        self.register_buffer("sparse_fields", torch.tensor(sparse or [0], dtype=torch.int32, device=dev))
+        self.px, self.slot = None, None
+        self._slots_set = [False, False]
+        self._ids_issued = self._fwd_issued = 0
+        self._fwd_event = None
+        # the id exchange of the NEXT batch runs concurrently with this batch's row / gradient exchange: the NCCL
+        # flavour gives it a communicator of its own so the two never queue behind each other
+        self.side_group = process_group
+        if self.exchange_mode == "peer":
+            seg_cap = max(1, min(self.max_batch * max(self.n_sel, 1), cap))   # rows one requester can ask of one owner
+            u_cap = max(1, self.max_batch * max(self.n_sel, 1))               # distinct rows a requester can ask for
+            self.px = PeerExchange(process_group, world, rank, K, self.n_dense, seg_cap, u_cap, dev)
+            self.slot = [torch.zeros(cap * world, dtype=torch.int32, device=dev) for _ in range(2)]
+        elif dist.is_initialized() and dist.get_backend(process_group) == "nccl":
+            self.side_group = dist.new_group(ranks=dist.get_process_group_ranks(process_group or dist.group.WORLD))
         with torch.no_grad():
             sd = 1.0 / math.sqrt(K)
-            torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)
+            if init == "trunc_normal":
+                torch.nn.init.trunc_normal_(self.table, 0.0, sd, -2.0 * sd, 2.0 * sd)
+            elif init == "counter":
+                self.init_counter(seed=1236, sd=sd)
             if adagrad:
                 self.accum.fill_(initial_accumulator_value)
             if self.lin_acc is not None:
                 self.lin_acc.fill_(initial_accumulator_value)
-        if not self.onerow_rep:
-            self.n_onerow, self.n_sel = 0, field_size
-        else:
-            self._init_onerow_replicas(onerow, sparse, dev, initial_accumulator_value)
+        if self.n_dense:
+            self._init_dense_replicas(onerow, dev, initial_accumulator_value)
 
     @property
     def table(self):
@@ -502,14 +482,22 @@ class ShardedEmbeddingFM(torch.nn.Module):
     def w1_accum(self):
         return self.lin_acc[:, 0] if self.lin_acc is not None else None
 
-    # -- EXPERIMENT: replicated one-row fields ------------------------------------------------------------------
     @torch.no_grad()
-    def _init_onerow_replicas(self, onerow, sparse, dev, acc0):
-        K, G, rank = self.embedding_size, self.plan.world_size, self.plan.rank
+    def init_counter(self, seed=1236, sd=None):
+        """Fill this rank's rows on the device from the counter hash of (seed, global row, component): tables too
+        large to come from the host (cfg4), reproducible row by row (oracle.deepctr_oracle.counter_rows)."""
+        sd = 1.0 / math.sqrt(self.embedding_size) if sd is None else float(sd)
+        check(_lib.lib().dir_table_init_counter(ptr(self.table), self.row_stride, self.n_rows, self.embedding_size,
+                                                self.plan.world_size, self.plan.rank, self.plan.n_rows, int(seed), sd,
+                                                _stream()), "dir_table_init_counter")
+        if self.n_dense:
+            self._sync_dense_replicas()
+
+    # -- replicated one-row fields ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def _init_dense_replicas(self, onerow, dev, acc0):
+        G, rank = self.plan.world_size, self.plan.rank
         n1 = len(onerow)
-        self.register_buffer("onerow_fields", torch.tensor(onerow, dtype=torch.int32, device=dev))
-        self.register_buffer("sparse_fields", torch.tensor(sparse, dtype=torch.int32, device=dev))
-        self.register_buffer("dense_ids", torch.arange(n1, dtype=torch.int32, device=dev))
         dfo = [0] * self.field_size
         for j, f in enumerate(onerow):
             dfo[f] = j
@@ -524,14 +512,13 @@ class ShardedEmbeddingFM(torch.nn.Module):
                              if self.lin_acc is not None else None)
         self.register_buffer("dense_lin_z", torch.zeros(n1, dtype=torch.float32, device=dev)
                              if self.lin_z is not None else None)
-        self._onerow_ws = _Workspace()
-        self._sync_onerow_replicas()
+        self._dense_ws = _Workspace()
+        self._sync_dense_replicas()
 
     @torch.no_grad()
-    def _sync_onerow_replicas(self):
+    def _sync_dense_replicas(self):
         """Replicas <- the owners' rows of the sharded table (all-reduce of rows that are zero off their owner)."""
-        K = self.embedding_size
-        buf = torch.zeros((self.n_onerow, self.row_stride + 3), dtype=torch.float32, device=self.rows.device)
+        buf = torch.zeros((self.n_dense, self.row_stride + 3), dtype=torch.float32, device=self.rows.device)
         mine = self.dense_shard_row >= 0
         sr = self.dense_shard_row[mine]
         buf[mine, :self.row_stride] = self.rows[sr]
@@ -573,8 +560,27 @@ class ShardedEmbeddingFM(torch.nn.Module):
             if src is not None:
                 mine = torch.as_tensor(self.plan.shard_of(src), dtype=torch.float32)
                 dst[:mine.shape[0]].copy_(mine.to(dst.device))
-        if self.onerow_rep:
-            self._sync_onerow_replicas()
+        if self.n_dense:
+            self._sync_dense_replicas()
+
+    def check_errors(self):
+        """Raise if a kernel of the device-driven exchange flagged an overflow (one host read)."""
+        code = int(self.err_flag.item())
+        if code:
+            self.err_flag.zero_()
+            raise RuntimeError("sharded exchange: " + ("more distinct rows than the exchange buffers hold "
+                               "(raise max_batch)" if code == 1 else "a received local row is out of range"))
+
+    @property
+    def last_exchange(self):
+        """Sizes of the last inline step (host reads: diagnostics only)."""
+        h = self._inline if self._last_handle is None else self._last_handle
+        if h.owner_off is None:
+            return {}
+        off = h.owner_off.tolist()
+        return {"unique_sent": int(off[-1]), "lookups": int(h.shape[0] * h.shape[1]) if h.shape else 0}
+
+    _last_handle = None
 
     def _prepare(self, feature_index, feature_value):
         if feature_index.dim() != 2 or feature_index.shape[1] != self.field_size:
@@ -596,130 +602,143 @@ class ShardedEmbeddingFM(torch.nn.Module):
             self._side = torch.cuda.Stream(device=device, priority=-1)
         return self._side
 
+    def _note_forward(self):
+        """Bookkeeping after the rows barrier of a step: every rank has finished the previous step, so the id
+        exchange of the next batch may now overwrite the other parity's buffers."""
+        self._fwd_issued += 1
+        if not self.capturing:
+            self._fwd_event = torch.cuda.Event()
+            self._fwd_event.record()
+
+    # ---- id phase ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def presort(self, feature_index, feature_value=None, handle=None, after=None, fork=True):
-        """Everything of a step that depends on the ids only, on the side stream and on a process group of
-        its own: composite keys, sort, distinct-row numbering, the counts / ids all-to-all, and the owner's
-        sort of the ids it received.  Issue it for batch i+1 right after enqueueing step i: it then runs
-        underneath step i, and the one host read of the split sizes waits on the side stream only.
-        `fork=False`: do not order the side stream after the work already queued on the current stream (the
-        ids are already on the device, or `after` marks their arrival) -- this is what lets it overlap.
-        """
-        idx, val = self._prepare(feature_index, feature_value)
+    def id_local(self, h, idx, val):
+        """Keys, sort, distinct-row numbering on the current stream: needs the ids only, touches no peer."""
         B, F = idx.shape
         K, G = self.embedding_size, self.plan.world_size
         dev = idx.device
         L = _lib.lib()
-        n_full = B * F
-        n = B * self.n_sel if self.onerow_rep else n_full      # EXPERIMENT: one-row fields stay out of the sorted list
-        h = handle if handle is not None else ShardedLookups()
-        main, side = torch.cuda.current_stream(), self.side_stream(dev)
-        if fork:        # order after whatever the current stream has queued (it may be producing the ids)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            side.wait_event(ev)
-        if after is not None:
-            side.wait_event(after)
+        st = _stream()
+        peer = self.px is not None
+        n_sel = self.n_sel if peer else F
+        n = B * n_sel
         tr = self.trace_pre
-        with torch.cuda.stream(side):
-            st = side.cuda_stream
-            tr.mark("pre.start")
-            if h.keys is None or h.keys.numel() != n or h.keys.device != dev:
-                h.keys = torch.empty(n, dtype=torch.int32, device=dev)
-                h.uidx = torch.empty(n, dtype=torch.int32, device=dev)
-                h.ulocal = torch.empty(n, dtype=torch.int32, device=dev)
-                h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
-                if self.onerow_rep:
-                    h.inv_c = torch.empty((B, self.n_sel), dtype=torch.int64, device=dev)
-                h.owner_off = torch.empty(G + 1, dtype=torch.int64, device=dev)
-                h.recv_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
-                h.fwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
-                h.bwd_dst_off = torch.zeros(G, dtype=torch.int64, device=dev)
-                if self.static and self.ids_peer:
-                    # the landing buffer of the ids is symmetric memory too: requesters store into it directly
-                    # (collective: every rank reaches this line for the same handle, in the same order)
-                    import torch.distributed._symmetric_memory as symm_mem
-                    h.recv_buf = symm_mem.empty(self.recv_cap, dtype=torch.int32, device=dev)
-                    h.recv_handle = symm_mem.rendezvous(h.recv_buf, self.group if self.group is not None
-                                                        else dist.group.WORLD)
-                    h.recv_ptrs = torch.tensor(list(h.recv_handle.buffer_ptrs), dtype=torch.int64, device=dev)
-                elif self.static:
-                    h.recv_buf = torch.empty(self.recv_cap, dtype=torch.int32, device=dev)
-            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
-                                   self.plan.n_rows, B, F, G, ptr(self.sparse_fields) if self.onerow_rep else None,
-                                   self.n_sel if self.onerow_rep else F, ptr(h.keys),
-                                   ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
-            tr.mark("pre.keys")
-            # sized for all B * F lookups whatever the list holds, so that nobody re-allocates it later
-            ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n_full, 1), K), dev)
-            check(L.dir_embed_bwd_sort(ptr(h.keys), n, self.plan.cap * G, ptr(ws), ws.numel(), st),
+        tr.mark("pre.start")
+        if h.shape != (B, F) or h.keys is None or h.keys.device != dev:
+            h.keys = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            h.uidx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            h.ulocal = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            h.g1_local = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+            h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
+            h.owner_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+            h.shape = (B, F)
+        sel = ptr(self.sparse_fields) if (peer and n_sel < F) else None
+        check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
+                               self.plan.n_rows, B, F, G, sel, n_sel, ptr(h.keys),
+                               ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
+        tr.mark("pre.keys")
+        ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), dev)
+        check(L.dir_embed_bwd_sort(ptr(h.keys), n, self.plan.cap * G, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
+        tr.mark("pre.sort")
+        if n > 0:
+            skeys, spos = _lib.c_void_p(), _lib.c_void_p()
+            check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
+                  "dir_embed_bwd_sorted")
+        else:
+            skeys = spos = None
+        ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(n), 1), dev)
+        check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, sel, n_sel, F, ptr(h.uidx), ptr(h.ulocal),
+                                 ptr(h.inv), ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+        if peer and self.n_dense:
+            check(L.dir_shard_dense_inv(ptr(idx), ptr(val), ptr(self.onerow_fields), self.n_dense, B, F,
+                                        self.px.u_cap, ptr(h.inv),
+                                        ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_dense_inv")
+        tr.mark("pre.unique")
+
+    @torch.no_grad()
+    def id_exchange(self, h):
+        """Ships the distinct ids to their owners (current stream).  Peer flavour: header + ids stored into the
+        owners' buffers, a device-side barrier, then the owner marks who asked for which row.  NCCL flavour: counts
+        and ids through all-to-all, one host read, then the owner's sort for the gradient merge."""
+        L = _lib.lib()
+        st = _stream()
+        tr = self.trace_pre
+        B, F = h.shape
+        K = self.embedding_size
+        dev = h.keys.device
+        if self.px is not None:
+            if self._ids_issued - self._fwd_issued >= 2 and not self.capturing:
+                raise RuntimeError("ShardedEmbeddingFM.presort may run at most one batch ahead of forward")
+            if h.parity is None or not self.capturing:
+                h.parity = self._ids_issued % 2
+            self._ids_issued += 1
+            p, px = h.parity, self.px
+            if self._fwd_event is not None and not self.capturing:
+                torch.cuda.current_stream().wait_event(self._fwd_event)     # every rank is done with parity p
+            if self._slots_set[p]:      # a presorted batch was never run: take its marks back before re-using ids[p]
+                check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag), st),
+                      "dir_shard_slots")
+            check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), B * self.n_sel,
+                                       ptr(self.err_flag), st), "dir_shard_ids_push")
+            tr.mark("pre.ids_push")
+            px.barrier(p, 1)
+            tr.mark("pre.barrier")
+            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 1, ptr(self.err_flag), st),
+                  "dir_shard_slots")
+            self._slots_set[p] = True
+            tr.mark("pre.slots")
+            return
+        send_counts = h.owner_off[1:] - h.owner_off[:-1]
+        recv_counts = exchange_counts(send_counts, self.side_group)
+        both = torch.stack([send_counts, recv_counts]).cpu()        # the one host read of a step
+        h.send_splits, h.recv_splits = both[0].tolist(), both[1].tolist()
+        h.U, h.R = int(sum(h.send_splits)), int(sum(h.recv_splits))
+        tr.mark("pre.counts+sync")
+        h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
+        tr.mark("pre.a2a_ids")
+        if h.R > 0:                     # the owner's half: arrival order -> local-row order
+            ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(h.R, K), dev)
+            check(L.dir_embed_bwd_sort(ptr(h.recv_ids), h.R, self.plan.cap, ptr(ws3), ws3.numel(), st),
                   "dir_embed_bwd_sort")
-            tr.mark("pre.sort")
-            if n > 0:
-                skeys, spos = _lib.c_void_p(), _lib.c_void_p()
-                check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
-                      "dir_embed_bwd_sorted")
-            else:
-                skeys = spos = None
-            ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(n), 1), dev)
-            check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, ptr(h.uidx), ptr(h.ulocal),
-                                     ptr(h.inv_c if self.onerow_rep else h.inv),
-                                     ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
-            if self.onerow_rep:              # compact [B, n_sel] indices -> their columns of the [B, F] index
-                h.inv.index_copy_(1, self.sparse_fields.long(), h.inv_c)
-                # the replicated rows sit behind the exchanged ones in the row buffer; an id other than 0 is pruned
-                one = self.onerow_fields.long()
-                tail = self.rows_cap + torch.arange(self.n_onerow, dtype=torch.int64, device=dev)[None, :]
-                h.inv.index_copy_(1, one, torch.where(idx.index_select(1, one) == 0, tail.expand(B, -1),
-                                                      torch.full_like(tail, -1).expand(B, -1)))
-            tr.mark("pre.unique")
-            # counts: the one host read per step (NCCL needs the split sizes); it waits on the side stream only
-            send_counts = h.owner_off[1:] - h.owner_off[:-1]
-            if self.peer is not None:
-                # everybody's counts: M[q, o] = distinct rows q wants from o.  From it, on the device, where
-                # each rank's segment starts inside its peers' exchange buffers.
-                M = torch.empty((G, G), dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(M, send_counts.contiguous(), group=self.side_group)
-                me = self.plan.rank
-                recv_counts = M[:, me].contiguous()
-                recv_off, fwd_dst_off, bwd_dst_off = peer_offsets(M, me)
-                # written in place: a captured step reads these at fixed addresses
-                h.recv_off.copy_(recv_off)
-                h.fwd_dst_off.copy_(fwd_dst_off)
-                h.bwd_dst_off.copy_(bwd_dst_off)
-            else:
-                recv_counts = exchange_counts(send_counts, self.side_group)
-            both = torch.stack([send_counts, recv_counts]).cpu()
-            h.send_splits, h.recv_splits = both[0].tolist(), both[1].tolist()
-            h.U, h.R = int(sum(h.send_splits)), int(sum(h.recv_splits))
-            tr.mark("pre.counts+sync")
-            if self.static:
-                if h.R > self.recv_cap:
-                    raise ValueError("%d rows requested from this rank, buffers hold %d" % (h.R, self.recv_cap))
-            if self.static and self.ids_peer:
-                # ids over NVLink peer memory: my segment for owner o starts where my gradient segment will
-                # (bwd_dst_off[o]); a device-side barrier on this handle's own signal pad closes the exchange
-                check(L.dir_ids_push(ptr(h.ulocal), n, G, ptr(h.owner_off), ptr(h.recv_ptrs), ptr(h.bwd_dst_off), st),
-                      "dir_ids_push")
-                h.recv_handle.barrier(channel=0)
-                h.recv_ids = h.recv_buf[:h.R]
-            elif self.static:
-                h.recv_ids = exchange_into(h.recv_buf, h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
-            else:
-                h.recv_ids = exchange(h.ulocal[:h.U], h.send_splits, h.recv_splits, self.side_group)
-            tr.mark("pre.a2a_ids")
-            if self.static:                   # laid out for the capacity: the consumer never learns R on the host
-                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(self.recv_cap, K), dev)
-                check(L.dir_embed_bwd_sort_in(ptr(h.recv_ids), h.R, self.recv_cap, self.plan.cap, ptr(ws3),
-                                              ws3.numel(), st), "dir_embed_bwd_sort_in")
-            elif h.R > 0:                     # the owner's half: arrival order -> local-row order
-                ws3 = h.ws3.get(L.dir_embed_bwd_workspace_bytes(h.R, K), dev)
-                check(L.dir_embed_bwd_sort(ptr(h.recv_ids), h.R, self.plan.cap, ptr(ws3), ws3.numel(), st),
-                      "dir_embed_bwd_sort")
-            tr.mark("pre.owner_sort")
-            h.event = torch.cuda.Event()
-            h.event.record(side)
-            tr.close_step()
+        tr.mark("pre.owner_sort")
+
+    @torch.no_grad()
+    def presort(self, feature_index, feature_value=None, handle=None, after=None, fork=True, inline=False,
+                phase="both"):
+        """Everything of a step that depends on the ids only: composite keys, sort, distinct-row numbering
+        (phase "local": touches no peer), then the id exchange and the owner's bookkeeping (phase "exchange").
+        By default on the side stream, so that issued for batch i+1 right after enqueueing step i it runs underneath
+        step i.  `fork=False`: do not order the side stream after the work already queued on the current stream (the
+        ids are already on the device, or `after` marks their arrival).  `inline=True`: on the current stream (a
+        caller that captures CUDA graphs places the two phases itself).  At most one batch ahead of `forward`."""
+        idx, val = self._prepare(feature_index, feature_value)
+        if self.px is not None and idx.shape[0] > self.max_batch:
+            raise ValueError("batch %d exceeds max_batch=%d the exchange buffers were sized for" % (
+                idx.shape[0], self.max_batch))
+        if phase not in ("both", "local", "exchange"):
+            raise ValueError("phase must be 'both', 'local' or 'exchange'")
+        h = handle if handle is not None else ShardedLookups()
+        if inline:
+            if phase != "exchange":
+                self.id_local(h, idx, val)
+            if phase != "local":
+                self.id_exchange(h)
+                self.trace_pre.close_step()
+            h.event = None
+        else:
+            main, side = torch.cuda.current_stream(), self.side_stream(idx.device)
+            if fork:        # order after whatever the current stream has queued (it may be producing the ids)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+            if after is not None:
+                side.wait_event(after)
+            with torch.cuda.stream(side):
+                self.id_local(h, idx, val)
+                self.id_exchange(h)
+                h.event = torch.cuda.Event()
+                h.event.record(side)
+                self.trace_pre.close_step()
         h.src = ShardedLookups.key_of(feature_index, feature_value)
         return h
 
@@ -727,11 +746,20 @@ class ShardedEmbeddingFM(torch.nn.Module):
         idx, val = self._prepare(feature_index, feature_value)
         train = self.training and torch.is_grad_enabled()
         if presorted is None:
-            presorted = self.presort(feature_index, feature_value, handle=self._inline)
+            presorted = self.presort(feature_index, feature_value, handle=self._inline, inline=True)
         elif presorted.src != ShardedLookups.key_of(feature_index, feature_value):
             raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
+        self._last_handle = presorted
         first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
-        if self.check_bounds and int(self.oob_flag.item()) != 0:
-            self.oob_flag.zero_()
-            raise IndexError("feature_index out of range for its field")
+        if self.px is not None and not train:
+            # no backward will come: release the owner's marks of this batch
+            p = presorted.parity
+            check(_lib.lib().dir_shard_slots(self.px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag),
+                                             _stream()), "dir_shard_slots")
+            self._slots_set[p] = False
+        if self.check_bounds:
+            if int(self.oob_flag.item()) != 0:
+                self.oob_flag.zero_()
+                raise IndexError("feature_index out of range for its field")
+            self.check_errors()
         return first, fm, emb

@@ -121,12 +121,6 @@ int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, i
 size_t dir_embed_bwd_workspace_bytes(int64_t n_lookups, int K);
 int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_rows,
                        void* workspace, size_t workspace_bytes, dir_stream_t stream);
-/* Same sort inside a workspace laid out for n_capacity >= n_lookups entries: the consumer
- * (dir_rows_reduce_update with n = n_capacity and the real count on the device) then needs no
- * host-side knowledge of n_lookups -- a step with data-dependent sizes can be replayed from a CUDA graph. */
-int dir_embed_bwd_sort_in(const uint32_t* sort_keys, int64_t n_lookups, int64_t n_capacity,
-                          int64_t n_rows, void* workspace, size_t workspace_bytes,
-                          dir_stream_t stream);
 int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                                 float* lin_accum, int64_t lin_stride, const int64_t* feature_index,
                                 const float* feature_value, const int64_t* field_offset,
@@ -146,26 +140,41 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  * global row div G, every rank keeps ceil(n_rows / G) rows; the batch stays data-parallel.
  * The reference has no counterpart beyond the partitioner hook around its embedding variables
  * (models/DeepFM/deepFM.py:163-175: under a TF parameter-server cluster the variables are
- * sharded by row and ids / IndexedSlices travel over gRPC).  Here only DISTINCT rows cross
- * NVLink, once per step in each direction (NCCL all-to-all, issued by the host layer):
+ * sharded by row and ids / IndexedSlices travel over gRPC).  Here only DISTINCT rows travel,
+ * once per step in each direction.
  *
- *   requester                                          owner
- *   dir_shard_keys      (owner, local row) per lookup
- *   dir_embed_bwd_sort  sort (key, position)
- *   dir_shard_unique    number distinct keys  --ids-->  dir_rows_gather  (row | first-order weight)
- *   dir_embed_fm_fwd    on the returned buffer <-rows--
- *   dir_embed_bwd_reduce_emit  per-row sums   --grads-> dir_embed_bwd_sort + dir_rows_reduce_update
- *
- * dir_shard_keys: keys[b*F+f] = owner * cap + local row, cap = ceil(n_rows / G); pruned lookups
- *   (id < 0, value <= 0, id beyond its field) get G * cap, the `n_rows` to pass to dir_embed_bwd_sort.
- *   With G = 1 the key is the global row: this is also how the single-GPU layer forms its sort keys.
- *   field_sel / n_sel restrict the list to some fields: keys[b*n_sel + j] for field field_sel[j].
+ * Id-only part (both exchange flavours):
+ * dir_shard_keys: keys[b*n_sel + j] = owner * cap + local row of field field_sel[j], cap = ceil(n_rows / G);
+ *   pruned lookups (id < 0, value <= 0, id beyond its field) get G * cap, the `n_rows` to pass to
+ *   dir_embed_bwd_sort.  With G = 1 the key is the global row: this is also how the single-GPU layer forms
+ *   its sort keys.  field_sel == NULL: all F fields.
  * dir_shard_unique, on the sorted list:
  *   uidx[i]               index of sorted entry i's key among the distinct keys
  *   unique_local_rows[u]  local row (at its owner) of distinct key u; grouped by owner, ascending
- *   inv[b*F+f]            int64 index of that lookup's row in the exchanged buffer, -1 if pruned:
- *                         the feature_index to hand to dir_embed_fm_fwd
+ *   inv[b*F + f]          int64 index of that lookup's row in the exchanged buffer, -1 if pruned: the
+ *                         feature_index to hand to dir_embed_fm_fwd (f = field_sel[j] of the sorted entry)
  *   owner_off[g], g = 0..G   distinct keys owned by ranks < g (owner_off[G] = their total)
+ * dir_shard_dense_inv: one-row (numeric) fields are replicated parameters, not exchanged: inv[b, f] =
+ *   tail_row + j where the lookup survives (id == 0, value > 0), else -1.
+ */
+int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
+                   const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
+                   int F, int G, const int32_t* field_sel, int n_sel, uint32_t* keys, int* oob_flag,
+                   dir_stream_t stream);
+size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
+int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
+                     int64_t n_rows, int G, const int32_t* field_sel, int n_sel, int F, uint32_t* uidx,
+                     int32_t* unique_local_rows, int64_t* inv, int64_t* owner_off, void* workspace,
+                     size_t workspace_bytes, dir_stream_t stream);
+int dir_shard_dense_inv(const int64_t* feature_index, const float* feature_value,
+                        const int32_t* onerow_fields, int n_onerow, int64_t B, int F, int64_t tail_row,
+                        int64_t* inv, int* oob_flag, dir_stream_t stream);
+
+/* Exchange over NCCL all-to-all, issued by the host layer (DIR_B200_EXCHANGE=nccl; the baseline):
+ *   requester                                          owner
+ *   dir_shard_keys / dir_embed_bwd_sort / dir_shard_unique  --ids-->  dir_rows_gather  (row | first-order weight)
+ *   dir_embed_fm_fwd    on the returned buffer <-rows--
+ *   dir_embed_bwd_reduce_emit  per-row sums   --grads-> dir_embed_bwd_sort + dir_rows_reduce_update
  * dir_rows_gather: out[i, 0:K] = table[local_rows[i]], out[i, K] = lin[local_rows[i]] (0 if lin is
  *   NULL); out rows are out_stride floats apart (multiple of 4, >= K + 1).
  * dir_embed_bwd_reduce_emit: as dir_embed_bwd_reduce_update, but rows are read from the exchanged
@@ -174,58 +183,16 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  * dir_rows_reduce_update: the owner's half.  gbuf[j] = (G[K], g1) received for the j-th id it
  *   answered; dir_embed_bwd_sort(ids, n, n_local_rows) must have run on `workspace`.  Sums the
  *   contributions of each local row in arrival order (source rank major) and applies the update.
- *   n_device (device int64, may be NULL): the number of entries really received; `n` is then only the
- *   capacity the launch and the workspace (dir_embed_bwd_sort_in with n_capacity = n) are sized for.
- * dir_rows_gather_to likewise processes min(n, seg_start[G]) rows: n may be an upper bound.
+ *   n_device (device int64, may be NULL): the number of entries really in the list when `n` is only a bound.
  */
-int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
-                   const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
-                   int F, int G, const int32_t* field_sel, int n_sel, uint32_t* keys, int* oob_flag,
-                   dir_stream_t stream);
-size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
-int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
-                     int64_t n_rows, int G, uint32_t* uidx, int32_t* unique_local_rows, int64_t* inv,
-                     int64_t* owner_off, void* workspace, size_t workspace_bytes, dir_stream_t stream);
 int dir_rows_gather(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
                     const int32_t* local_rows, int64_t n, int K, float* out, int64_t out_stride,
                     dir_stream_t stream);
-/* Payload exchange over NVLink peer memory instead of an NCCL all-to-all (one kernel does the
- * gather AND the transfer).  The n rows are grouped into G segments, seg_start[G+1] (device);
- * segment q is written into rank q's buffer: peer_ptrs[q] is that buffer's peer-mapped device
- * address (symmetric memory), dst_row_off[q] the row at which this rank's segment starts there
- * (both device arrays).  The caller runs a cross-rank barrier before the buffer is read.
- *   dir_rows_gather_to  owner side: row q-segment j = (table[local_rows[j]] | lin | 0 0 0),
- *                       out_stride >= K + 4 floats
- *   dir_rows_push       requester side: ships rows [n, stride] (per-row gradient sums) as they are
- */
-int dir_rows_gather_to(const float* table, int64_t row_stride, const float* lin, int64_t lin_stride,
-                       const int32_t* local_rows, int64_t n, int K, int G, const int64_t* seg_start,
-                       const int64_t* peer_ptrs, const int64_t* dst_row_off, int64_t out_stride,
-                       dir_stream_t stream);
-int dir_rows_push(const float* src, int64_t n, int64_t stride, int G, const int64_t* seg_start,
-                  const int64_t* peer_ptrs, const int64_t* dst_row_off, dir_stream_t stream);
-/* The id exchange over peer memory as well (instead of an NCCL all-to-all): distinct local rows [n] int32,
- * grouped by owner (seg_start[G+1]), stored into each owner's landing buffer (peer_ptrs[q]) at element
- * dst_off[q].  n bounds the launch; min(n, seg_start[G]) ids are sent.  Barrier before the owner reads. */
-int dir_ids_push(const int32_t* src, int64_t n, int G, const int64_t* seg_start,
-                 const int64_t* peer_ptrs, const int64_t* dst_off, dir_stream_t stream);
 int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
                               const float* g_first, const float* g_fm, const float* S, const float* u,
                               const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
                               int64_t gu_stride, void* workspace, size_t workspace_bytes,
                               dir_stream_t stream);
-/* dir_embed_bwd_reduce_emit with the transfer fused in: each distinct row's (G[K], g1, 0, 0, 0) is
- * stored straight into its owner's buffer over NVLink as soon as its run is summed -- no gu round
- * trip through HBM, no separate dir_rows_push, and the NVLink stores overlap the kernel's gathers.
- * Distinct rows are grouped by owner: seg_start[G+1], peer_ptrs[G], dst_row_off[G] as for
- * dir_rows_push (all device arrays); out_stride >= K + 4 floats.  Barrier before the owner reads. */
-int dir_embed_bwd_reduce_emit_to(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
-                                 const float* g_first, const float* g_fm, const float* S,
-                                 const float* u, const uint32_t* uidx, int64_t B, int F, int K,
-                                 int64_t n_keys, int G, const int64_t* seg_start,
-                                 const int64_t* peer_ptrs, const int64_t* dst_row_off,
-                                 int64_t out_stride, void* workspace, size_t workspace_bytes,
-                                 dir_stream_t stream);
 int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float* lin,
                            float* lin_accum, int64_t lin_stride, const float* gbuf,
                            int64_t gbuf_stride, int64_t n, int K, int64_t n_rows, int optimizer,
@@ -233,40 +200,100 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
                            void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
                            dir_stream_t stream);
 
-/* ---------------------------------------------------------------------------------------------
- * EXPERIMENT, off by default (ShardedEmbeddingFM with DIR_B200_SHARD_ONEROW=1; written after round 1's
- * GPU budget was spent, not yet run): one-row (numeric) fields of a row-sharded table kept as
- * replicated parameters instead of being sorted and exchanged like every other lookup.
- *   dir_embed_bwd_reduce_emit_fields_to  dir_embed_bwd_reduce_emit_to over a sorted list that covers
- *       only the fields field_sel[n_sel] (keys from dir_shard_keys with the same list)
- *   dir_embed_bwd_onerow_emit_to  each one-row field's gradient over THIS rank's samples (fixed-order
- *       column sums) -> row dst_row_base + rank * n_onerow + j of every rank's buffer, as
- *       (G[K], g1, touched, 0, 0); dense_field_offset[F] maps a field to its row of dense_table
- *   dir_dense_rows_apply  after the barrier: the G ranks' sums added in rank order, the same update
- *       applied to every replica; shard_row[j] >= 0 names the row of the sharded table to mirror into
- *       (on the rank that owns it), so the table stays a faithful view
+/* Exchange over NVLink peer memory, driven from the device (the default; csrc/shard_peer.cu).  No NCCL and
+ * no host read on the step: data-dependent counts travel as headers and are read by the kernels, every
+ * launch is sized by capacities, so the whole step -- id phase included -- replays from a CUDA graph.
+ * Every rank allocates one exchange buffer per parity (consecutive steps alternate) with the layout below
+ * and maps its peers' buffers (symmetric memory); the host layer runs a device-side cross-rank barrier
+ * where marked.  One-row fields are replicated parameters: their gradient partial sums meet in every rank's
+ * buffer and are applied by every rank in rank order.
+ *
+ *   requester q                                         owner o
+ *   dir_shard_ids_push     hdr[q] = (count, base_u), ids[q][0..count)  -->  o's buffer
+ *   ---- barrier ----
+ *                                                       dir_shard_slots(set)    slot[row * G + q] = i + 1
+ *                                                       dir_shard_gather_send   T[row] -> q's rows[base_u + i],
+ *                                                                               w[row] -> q's w[base_u + i]
+ *   ---- barrier ----
+ *   dir_embed_fm_fwd(rows, w, inv)
+ *   dir_embed_bwd_reduce_emit_to   per-distinct-row sums -->  o's g[q][i]
+ *   dir_shard_g1_push              first-order sums      -->  o's g1[q][i]
+ *   dir_shard_dense_emit           one-row fields        -->  every rank's dense[q][j]
+ *   ---- barrier ----
+ *                                                       dir_shard_owner_update  ranks' sums added in rank
+ *                                                         order (slot tells who else asked), fused update
+ *                                                       dir_shard_slots(clear)
+ *   dir_shard_dense_apply  (every rank)
+ *
+ * slot: uint32 [n_local_rows * G], zero before the first step (the owner never sorts: a requester sends a
+ * row at most once, so a cell is written by one thread).  err_flag (device int, zero-initialised): 1 = a
+ * requester had more distinct rows than seg_cap / u_cap, 2 = a received local row is out of range; nothing is
+ * written out of bounds in either case, the host layer raises.
  */
-size_t dir_onerow_workspace_bytes(int K);
-int dir_embed_bwd_reduce_emit_fields_to(const float* ubuf, int64_t ubuf_stride, const float* feature_value,
-                                        const float* g_first, const float* g_fm, const float* S,
-                                        const float* u, const uint32_t* uidx, int64_t B, int F, int K,
-                                        int64_t n_keys, const int32_t* field_sel, int n_sel, int G,
-                                        const int64_t* seg_start, const int64_t* peer_ptrs,
-                                        const int64_t* dst_row_off, int64_t out_stride, void* workspace,
-                                        size_t workspace_bytes, dir_stream_t stream);
-int dir_embed_bwd_onerow_emit_to(const float* dense_table, int64_t row_stride, const int64_t* feature_index,
-                                 const float* feature_value, const int64_t* dense_field_offset,
+typedef struct dir_peer_layout {
+  int G, rank, K, n_dense;   /* ranks, this rank, embedding size, replicated one-row fields (<= 64)     */
+  int64_t seg_cap;           /* rows one requester may ask of one owner in a step                         */
+  int64_t u_cap;             /* distinct rows one requester may ask for in total                          */
+  /* byte offsets inside every rank's exchange buffer (filled by dir_peer_layout_init)                    */
+  int64_t off_hdr;           /* int64 [G][4]              owner <- requester q: (count, base_u, -, -)      */
+  int64_t off_ids;           /* int32 [G][seg_cap]        owner <- requesters: local rows asked for        */
+  int64_t off_rows;          /* float [u_cap + n_dense][K]  requester <- owners; replicated rows behind   */
+  int64_t off_w;             /* float [u_cap + n_dense]     requester <- owners: first-order weights      */
+  int64_t off_g;             /* float [G][seg_cap][K]     owner <- requesters: per-row gradient sums       */
+  int64_t off_g1;            /* float [G][seg_cap]        owner <- requesters: first-order gradient sums   */
+  int64_t off_dense;         /* float [G][n_dense][K+4]   every rank <- every rank: (G[K], g1, touched, 0, 0) */
+  int64_t total_bytes;       /* size of the buffer                                                        */
+  const int64_t* peer_base;  /* DEVICE int64 [G]: peer-mapped address of each rank's buffer               */
+  char* local;               /* DEVICE: this rank's own buffer (256-byte aligned)                         */
+} dir_peer_layout;
+int dir_peer_layout_init(int G, int rank, int K, int n_dense, int64_t seg_cap, int64_t u_cap,
+                         dir_peer_layout* out);
+int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_local_rows,
+                       const int64_t* owner_off, int64_t n_capacity, int* err_flag, dir_stream_t stream);
+int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
+                    int* err_flag, dir_stream_t stream);
+/* dense_table / dense_lin: the replicated one-row fields' rows [n_dense] (copied behind this rank's own
+ * exchanged rows so that dir_embed_fm_fwd finds them at u_cap + j); NULL when n_dense == 0 */
+int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
+                          const float* lin, int64_t lin_stride, const float* dense_table,
+                          int64_t dense_row_stride, const float* dense_lin, dir_stream_t stream);
+/* dir_embed_bwd_reduce_emit with the transfer fused in: each distinct row's G[K] is stored straight into its
+ * owner's buffer over NVLink as soon as its run is summed (no round trip through HBM, the NVLink stores overlap
+ * the kernel's gathers); g1 goes to g1_local[u] and is shipped by dir_shard_g1_push.  The sorted list covers
+ * the fields field_sel[n_sel] (NULL: all); owner_off[G+1] as written by dir_shard_unique. */
+int dir_embed_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* feature_value,
                                  const float* g_first, const float* g_fm, const float* S, const float* u,
-                                 const int32_t* onerow_fields, int n_onerow, int64_t B, int F, int K, int G,
-                                 int rank, const int64_t* peer_ptrs, int64_t dst_row_base, int64_t out_stride,
+                                 const uint32_t* uidx, const int64_t* owner_off, int64_t B, int F,
+                                 int64_t n_keys, const int32_t* field_sel, int n_sel, float* g1_local,
                                  void* workspace, size_t workspace_bytes, dir_stream_t stream);
-int dir_dense_rows_apply(float* dense_table, float* dense_accum, int64_t row_stride, float* dense_lin,
-                         float* dense_lin_accum, const float* gbuf, int64_t gbuf_stride, int64_t dst_row_base,
-                         int n_onerow, int K, int G, int optimizer, float lr,
-                         const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
-                         int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
-                         float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
-                         int64_t* n_unique_out, dir_stream_t stream);
+int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_local, const int64_t* owner_off,
+                      int64_t n_capacity, dir_stream_t stream);
+/* one-row fields: each field's gradient over THIS rank's samples (fixed-order fp64-carried column sums) ->
+ * dense[rank][j] of every rank's buffer.  dense_field_offset[F] maps a field to its row of dense_table. */
+size_t dir_shard_dense_workspace_bytes(int K);
+int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table, int64_t row_stride,
+                         const int64_t* feature_index, const float* feature_value,
+                         const int64_t* dense_field_offset, const float* g_first, const float* g_fm,
+                         const float* S, const float* u, const int32_t* onerow_fields, int64_t B, int F,
+                         void* workspace, size_t workspace_bytes, dir_stream_t stream);
+int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
+                           int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
+                           int64_t n_local_rows, int optimizer, float lr, const dir_linear_opt* linear_opt,
+                           int64_t* n_unique_out, dir_stream_t stream);
+/* shard_row[j] >= 0 names the row of the sharded table that mirrors replica j (on the rank that owns it), so
+ * the sharded table stays a faithful view; n_unique_inout += fields touched (pass it on one rank only) */
+int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
+                          int64_t row_stride, float* dense_lin, float* dense_lin_accum, int optimizer,
+                          float lr, const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
+                          int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
+                          float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
+                          int64_t* n_unique_inout, dir_stream_t stream);
+/* cfg4-sized tables are filled on the device: value(global row, k) from a counter hash of (seed, row, k) --
+ * a sum of four 16-bit uniforms, centred and scaled to standard deviation `sd` (|value| < 3.47 sd) -- so any row
+ * can be reproduced on the host without the table (oracle/deepctr_oracle.counter_rows).  Fills
+ * table[i, 0:K] for local row i = global row (i * G + rank); rows past n_rows are zero. */
+int dir_table_init_counter(float* table, int64_t row_stride, int64_t n_local_rows, int K, int G, int rank,
+                           int64_t n_rows, uint64_t seed, float sd, dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-hot / weighted bags: every (sample, field) holds a variable-length list of (id, weight) --

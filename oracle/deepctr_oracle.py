@@ -331,3 +331,34 @@ def input_layer(columns, numeric, indicator_ids, emb):
         where[name] = (c, c + pieces[name].shape[1])
         c += pieces[name].shape[1]
     return np.concatenate(out, axis=1) if out else np.zeros((B, 0), np.float32), where
+
+
+# ----------------------------------------------------------------------------
+# counter-hash table initialisation (cfg4: tables too large to come from the host)
+# ----------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return x ^ (x >> np.uint64(31))
+
+
+def counter_rows(global_rows_, K, seed=1236, sd=None):
+    """Rows of a table filled by `dir_table_init_counter`: value(row, k) = (sum of the four 16-bit fields of
+    mix64(seed ^ mix64(row * 64 + k)) - 131070) * (sd / 37837.2272), one fp32 multiply -- bit-exact on any host.
+    This initialiser is defined by THIS repo (BASELINE cfg4: "initialised on-device by a counter-based RNG");
+    the reference's own is TF's truncated_normal(0, 1/sqrt(K)), models/DeepFM/deepFM.py:385-390 [TF]."""
+    sd = np.float32(1.0 / np.sqrt(K) if sd is None else sd)
+    scale = np.float32(sd / np.float32(37837.2272))
+    rows = np.asarray(global_rows_, dtype=np.uint64).reshape(-1, 1)
+    with np.errstate(over="ignore"):
+        ctr = rows * np.uint64(64) + np.arange(K, dtype=np.uint64)[None, :]
+    h = _mix64(np.uint64(seed) ^ _mix64(ctr))
+    m = np.uint64(0xFFFF)
+    s = ((h & m) + ((h >> np.uint64(16)) & m) + ((h >> np.uint64(32)) & m) + (h >> np.uint64(48))).astype(np.int64)
+    return ((s - 131070).astype(np.float32) * scale).astype(np.float32)

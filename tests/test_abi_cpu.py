@@ -96,14 +96,37 @@ def test_argument_validation_of_the_widened_entry_points(pkg):
     rc = lib.dir_embed_bwd_reduce_update(P, P, 32, P, P, 1, P, None, P, P, P, P, None, 4, 2, 16, 10, None, 0, None, 0,
                                          1, 0.05, ctypes.byref(bad), P, 1 << 20, None, None)
     assert rc == -22 and b"unknown linear optimizer" in lib.dir_last_error()
-    # input layer, column feed, id push, capacity sort
+    # input layer, column feed
     assert lib.dir_input_layer_fwd(None, 0, None, 0, P, 8, P, P, P, 4, 0, P, None) == -22
     assert lib.dir_input_layer_bwd(None, None, 0, 8, 8, None, None) == 0
-    assert lib.dir_ids_push(P, 4, 0, P, P, P, None) == -22
-    assert lib.dir_embed_bwd_sort_in(P, 8, 4, 10, P, 1 << 20, None) == -22          # capacity below the count
+    # the device-driven sharded exchange: the layout helper agrees with itself, every entry point refuses a layout
+    # that was never filled (no launch happens before validation)
+    lay = _lib.PeerLayout()
+    assert lib.dir_peer_layout_init(8, 3, 16, 13, 1000, 5000, ctypes.byref(lay)) == 0
+    offs = [lay.off_hdr, lay.off_ids, lay.off_rows, lay.off_w, lay.off_g, lay.off_g1, lay.off_dense, lay.total_bytes]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert lay.off_ids - lay.off_hdr >= 8 * 4 * 8 and lay.off_rows - lay.off_ids >= 8 * 1000 * 4
+    assert lay.off_w - lay.off_rows >= (5000 + 13) * 16 * 4 and lay.off_g1 - lay.off_g >= 8 * 1000 * 16 * 4
+    assert lay.total_bytes - lay.off_dense >= 8 * 13 * 20 * 4
+    assert lib.dir_peer_layout_init(8, 8, 16, 0, 10, 10, ctypes.byref(lay)) == -22          # rank out of range
+    assert lib.dir_peer_layout_init(2, 0, 12, 0, 10, 10, ctypes.byref(lay)) == -22 and b"K must be" in lib.dir_last_error()
+    assert lib.dir_peer_layout_init(2, 0, 16, 2, 10, 10, ctypes.byref(lay)) == 0            # peer_base / local still NULL
+    ref = ctypes.byref(lay)
+    assert lib.dir_shard_ids_push(ref, P, P, 4, P, None) == -22 and b"peer_base" in lib.dir_last_error()
+    assert lib.dir_shard_slots(ref, P, 10, 1, P, None) == -22
+    assert lib.dir_shard_gather_send(ref, P, 32, None, 1, P, 32, None, None) == -22
+    assert lib.dir_shard_g1_push(ref, P, P, 4, None) == -22
+    assert lib.dir_shard_owner_update(ref, P, P, P, 32, None, None, 1, 10, 1, 0.05, None, None, None) == -22
+    assert lib.dir_shard_dense_apply(ref, P, P, 32, None, None, 1, 0.05, None, P, P, 32, None, None, None, 1, P, None,
+                                     None) == -22
+    assert lib.dir_shard_dense_emit(ref, P, 32, P, None, P, None, P, P, None, P, 4, 3, P, 1 << 20, None) == -22
     with pytest.raises(ValueError):
-        _lib.check(lib.dir_embed_bwd_reduce_emit_to(P, 20, None, None, P, P, None, P, 4, 2, 16, 100, 2, P, None, P, 20,
-                                                    P, 1 << 20, None), "emit_to")      # peer_ptrs missing
+        _lib.check(lib.dir_embed_bwd_reduce_emit_to(ref, None, None, P, P, None, P, P, 4, 2, 100, None, 0, P, P,
+                                                    1 << 20, None), "emit_to")
+    assert lib.dir_shard_dense_inv(None, None, None, 0, 4, 3, 0, None, None, None) == 0      # nothing to do
+    assert lib.dir_shard_unique(P, P, 8, 10, 2, P, 3, 4, P, P, P, P, P, 1 << 20, None) == -22      # 8 is not B * 3
+    assert lib.dir_table_init_counter(None, 16, 4, 16, 2, 0, 8, 1, 0.25, None) == -22
+    assert lib.dir_shard_dense_workspace_bytes(16) > 296 * 64 * 20 * 8
 
 
 def test_integration_md_stub_matches_the_library(pkg):

@@ -1,8 +1,9 @@
-"""GPU parity of the row-sharded path.  With one process (world_size 1) every kernel of the sharded
-pipeline runs -- composite keys, sort, distinct-row numbering, owner gather, forward on the exchanged
-buffer, per-row gradient sums, owner-side merge + update -- and must match the oracle like the
-single-GPU layer does.  With two GPUs (skipped otherwise) two NCCL ranks each feed their own samples
-and the union of their shards must match the oracle run on the concatenated batch."""
+"""GPU parity of the row-sharded path.  With one process (world_size 1) every kernel of the device-driven
+exchange runs against local buffers -- composite keys, sort, distinct-row numbering, id push, the owner's slot
+map, gather + send, forward on the exchanged rows, per-row gradient sums, owner-side merge + update, the
+replicated one-row fields -- and must match the oracle like the single-GPU layer does.  With 2 / 4 / 8 GPUs
+(skipped otherwise) the ranks each feed their own samples over NVLink peer memory and the union of their
+shards must match the oracle run on the concatenated batch."""
 import os
 import socket
 
@@ -66,7 +67,18 @@ def test_world1_matches_oracle(pkg, cuda, B, rows, K, optimizer):
         assert rel_err(layer.accum.cpu().numpy()[urows], acc[urows], floor) <= REL
     ex = layer.last_exchange
     keep = (case["idx"] >= 0) & (case["val"] > 0)
-    assert ex["unique_sent"] == len(urows) and ex["lookups"] == B * F and int(keep.sum()) >= len(urows)
+    # one-row fields are replicated parameters: they do not travel
+    dense_touched = sum(1 for f in range(F) if int(case["rows"][f]) == 1 and keep[:, f].any()) if layer.n_dense else 0
+    assert ex["unique_sent"] == len(urows) - dense_touched and ex["lookups"] == B * F
+    layer.check_errors()
+    # a second step from the updated state (the other exchange buffer; the owner's marks of step 1 were taken back)
+    first2, fm2, emb2 = layer(to_dev(case["idx"]), to_dev(case["val"]))
+    e2, _ = O.embedding_lookup(got_t, case["off"], case["idx"], case["val"], "sum", np.float32)
+    assert np.array_equal(emb2.detach().cpu().numpy().reshape(B, F, K), e2), "step 2 must see step 1's rows"
+    (first2.sum() + fm2.sum() + emb2.sum()).backward()
+    torch.cuda.synchronize()
+    layer.check_errors()
+    assert all(int(sl.abs().sum()) == 0 for sl in layer.slot), "the owner's marks must be cleared after every step"
 
 
 def _free_port():
@@ -77,15 +89,20 @@ def _free_port():
     return p
 
 
-def _rank_main(rank, world, port, out, exchange_mode):
+CASES = {"small": ([50, 1, 9, 1000, 3, 17, 1], 16, 96),          # at world 8: ceil(n_rows / G) = 136 < distinct rows of a rank
+         "wide": ([300, 1, 400, 350, 1, 500], 8, 600)}           # at world 2: ceil(n_rows / G) = 776 < ~1 200 distinct rows
+
+
+def _rank_main(rank, world, port, out, exchange_mode, case_name="small"):
     import torch.distributed as dist
     import dir_b200
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), DIR_B200_EXCHANGE=exchange_mode)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        rows, K, Bl = [50, 1, 9, 1000, 3, 17, 1], 16, 96
-        case = make_case(41, Bl * world, rows, K, weighted=True, prune=True, skew=2.0)   # global batch
+        rows, K, Bl = CASES[case_name]
+        case = make_case(41, Bl * world, rows, K, weighted=True, prune=True,
+                         skew=2.0 if case_name == "small" else None)                     # global batch
         rng, F = case["rng"], case["F"]
         g_first = rng.standard_normal(Bl * world).astype(np.float32)
         g_fm = (rng.standard_normal(Bl * world) * 0.1).astype(np.float32)
@@ -93,7 +110,7 @@ def _rank_main(rank, world, port, out, exchange_mode):
         sl = slice(rank * Bl, (rank + 1) * Bl)
         layer = dir_b200.ShardedEmbeddingFM(F, K, rows, optimizer="adagrad", lr=0.05, max_batch=Bl,
                                             device="cuda").train()
-        assert (layer.peer is not None) == (exchange_mode == "peer"), "exchange mode not honoured"
+        assert (layer.px is not None) == (exchange_mode == "peer"), "exchange mode not honoured"
         layer.load_tables(case["table"], case["w1"])
         d = "cuda"
         first, fm, emb = layer(to_dev(case["idx"][sl], d), to_dev(case["val"][sl], d))
@@ -105,6 +122,9 @@ def _rank_main(rank, world, port, out, exchange_mode):
                 + (emb * to_dev(u[sl].reshape(Bl, -1), d)).sum())
         loss.backward()
         torch.cuda.synchronize()
+        if exchange_mode == "peer":
+            layer.check_errors()
+            assert all(int(sl.abs().sum()) == 0 for sl in layer.slot)
         shards = [torch.empty_like(layer.rows) for _ in range(world)]
         lins = [torch.empty_like(layer.lin_rows) for _ in range(world)]
         dist.all_gather(shards, layer.rows)
@@ -127,6 +147,27 @@ def _rank_main(rank, world, port, out, exchange_mode):
             untouched = np.ones(N, bool)
             untouched[urows] = False
             assert np.array_equal(full[:N, :K][untouched], case["table"][untouched])
+            floor = 0.1 + 2 * np.abs(G) * np.abs(G)
+            assert rel_err(full[:N, K:][urows], acc[urows], floor + 1e-3) <= 10 * REL
+        if exchange_mode == "peer" and layer.n_dense:
+            # every rank's replica of a one-row field equals the owner's row of the sharded table
+            for j, g in enumerate(layer.dense_global_rows):
+                own = [torch.zeros_like(layer.dense_rows[j]) for _ in range(world)]
+                dist.all_gather(own, layer.dense_rows[j].contiguous())
+                assert all(torch.equal(own[0], o) for o in own), "replicas diverged"
+                if rank == g % world:
+                    assert torch.equal(layer.rows[g // world], layer.dense_rows[j])
+        # a presorted second step (id phase on the side stream, one batch ahead) from the updated state
+        idx2, val2 = to_dev(case["idx"][sl], d), to_dev(case["val"][sl], d)
+        h = layer.presort(idx2, val2)
+        f2, m2, e2 = layer(idx2, val2, presorted=h)
+        (f2.sum() + m2.sum() + e2.sum()).backward()
+        torch.cuda.synchronize()
+        if exchange_mode == "peer":
+            layer.check_errors()
+        if rank == 0:
+            e_want, _ = O.embedding_lookup(full[:N, :K], case["off"], case["idx"][sl], case["val"][sl], "sum", np.float32)
+            assert np.array_equal(e2.detach().cpu().numpy().reshape(Bl, F, K), e_want), "step 2 must see step 1's rows"
         out.put((rank, "ok"))
     except Exception as ex:
         import traceback
@@ -136,15 +177,15 @@ def _rank_main(rank, world, port, out, exchange_mode):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("exchange_mode", ["peer", "nccl"])
-def test_multi_rank_nccl_matches_oracle(pkg, cuda, exchange_mode, world):
+@pytest.mark.parametrize("exchange_mode,case_name", [("peer", "small"), ("peer", "wide"), ("nccl", "small")])
+def test_multi_rank_matches_oracle(pkg, cuda, exchange_mode, case_name, world):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, world, port, out, exchange_mode)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, out, exchange_mode, case_name)) for r in range(world)]
     for p in procs:
         p.start()
     res = [out.get(timeout=300) for _ in procs]
