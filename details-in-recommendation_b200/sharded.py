@@ -490,7 +490,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         check(_lib.lib().dir_table_init_counter(ptr(self.table), self.row_stride, self.n_rows, self.embedding_size,
                                                 self.plan.world_size, self.plan.rank, self.plan.n_rows, int(seed), sd,
                                                 _stream()), "dir_table_init_counter")
-        if self.n_dense:
+        if self.n_dense and "dense_rows" in self._buffers:       # (the constructor builds the replicas afterwards)
             self._sync_dense_replicas()
 
     # -- replicated one-row fields ----------------------------------------------------------------------------
