@@ -526,7 +526,7 @@ def run_b200(args):
         except Exception as e:                                   # an extra, never worth the bench line
             print("bench.py: cfg1 CPU timing skipped (%s)" % e, file=sys.stderr)
 
-    stages, nvlink = None, None
+    stages, nvlink, serial = None, None, None
     if world > 1 and getattr(layer, "trace", None) is not None:
         # Stage times of the sharded step: a diagnostic pass AFTER the timed regions.  Eager launches, every stage
         # bracketed by CUDA events on its stream, one device sync per step.  Every rank takes part (the steps
@@ -540,6 +540,20 @@ def run_b200(args):
                 cursor[0] += 1
             torch.cuda.synchronize()
             stages = (layer.trace.report(), layer.trace_pre.report())
+            # the same stages with NOTHING overlapped: the id phase inline on the main stream (exclusive times)
+            torch.cuda.current_stream().wait_stream(side)
+            cur = cursor[0] % R                      # its id work is pending: run it, then go inline
+            first, fm, emb, g, up, _ = model(cur)
+            backward(first, fm, emb, g, up)
+            for s_ in range(4):
+                idx_, val_, y_ = devs[s_ % R]
+                first, fm, emb = layer(idx_, val_)
+                with torch.no_grad():
+                    g = torch.sigmoid(first + fm).sub_(y_.unsqueeze(1))
+                backward(first, fm, emb, g, ups[s_ % R])
+            torch.cuda.synchronize()
+            serial = (layer.trace.report(), layer.trace_pre.report())
+            cursor[0] = -1                           # the rotation is broken from here on: nothing may run() again
         except Exception as e:
             stages = None
             if rank == 0:
@@ -547,7 +561,7 @@ def run_b200(args):
         layer.trace.on = layer.trace_pre.on = False
         if rank == 0 and stages is not None:
             try:
-                main = stages[0]
+                main = serial[0] if serial else stages[0]     # exclusive stage times
                 U = int(layer.last_exchange.get("unique_sent", 0))
                 row_bytes = (K + 1) * 4                                   # (row, first-order weight) per distinct row
                 key = "bwd.emit+push" if "bwd.emit+push" in main else "bwd.emit"
@@ -561,7 +575,8 @@ def run_b200(args):
                         "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src if src == "measured"
                         else "fallback (B200_PROFILING.md)", "traffic": None, "algorithmic_bytes_per_launch": int(nbytes),
                         "us_per_launch": main[key],
-                        "how": "stage time (CUDA events, rank 0) from an eager traced pass after the timed regions"}
+                        "how": "exclusive stage time (CUDA events, rank 0) from an eager, non-overlapped traced pass "
+                               "after the timed regions"}
                 link = U * row_bytes * (world - 1) / world                 # bytes that leave / reach this rank, each way
                 t_fwd = main.get("fwd.gather+send")
                 nvlink = {"bytes_per_direction_per_rank": int(link), "peak": 770.0, "unit": "GB/s",
@@ -585,7 +600,9 @@ def run_b200(args):
                 "cpu_baseline": cpu}
         if stages is not None:
             line["stages_us"] = {"main_stream": {k: round(v, 1) for k, v in stages[0].items()},
-                                 "side_stream": {k: round(v, 1) for k, v in stages[1].items()}}
+                                 "side_stream": {k: round(v, 1) for k, v in stages[1].items()},
+                                 "serial_main": {k: round(v, 1) for k, v in serial[0].items()},
+                                 "serial_id_phase": {k: round(v, 1) for k, v in serial[1].items()}}
             line["nvlink"] = nvlink
         print(json.dumps(line), flush=True)
     if world > 1:
