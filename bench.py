@@ -48,6 +48,8 @@ def parse_args():
     p.add_argument("--no-emit", action="store_true", help="FM only: no embeddings out / upstream in")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--sharded", action="store_true",
+                   help="run the row-sharded layer even on one GPU (every exchange kernel, local buffers): a diagnostic")
     p.add_argument("--feed", default="columns", choices=["columns", "resolved"],
                    help="e2e host format: one column per feature (the reference's input_fn form) or the [B,F] pair")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -254,7 +256,8 @@ def run_b200(args):
     R = max(1, args.rotate)
     torch.manual_seed(dir_b200.synth.SEED_TABLES + rank)
 
-    if world == 1:
+    sharded = world > 1 or args.sharded
+    if not sharded:
         layer = dir_b200.EmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
                                      emit_embeddings=emit, device=dev).train()
     else:
@@ -282,12 +285,12 @@ def run_b200(args):
     # every step still performs exactly one sort.  A running cursor keeps the rotation (and, sharded, the
     # one-batch-ahead id phase) consistent across the warm-up, timed, e2e and trace loops.
     ready_events = {}          # e2e: slot -> event of its H2D copy (the id work of that batch waits for it)
-    handles = [dir_b200.SortedLookups() if world == 1 else dir_b200.ShardedLookups() for _ in range(R)]
+    handles = [dir_b200.SortedLookups() if not sharded else dir_b200.ShardedLookups() for _ in range(R)]
     cursor = [0]
     side = layer.side_stream(dev)
 
     def id_work(nxt, phase="both", inline=False):
-        if world == 1:
+        if not sharded:
             layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=not inline)
         elif inline:
             layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], inline=True, phase=phase)
@@ -316,7 +319,7 @@ def run_b200(args):
         """One step on resident inputs of `slot` plus the id-only work of the next slot."""
         nxt = (slot + 1) % R
         main = torch.cuda.current_stream()
-        if world == 1:
+        if not sharded:
             id_work(nxt, inline=captured)          # forks onto the side stream itself
             first, fm, emb, g, up, logits = model(slot)
             backward(first, fm, emb, g, up)
@@ -345,21 +348,21 @@ def run_b200(args):
 
     # warm every slot eagerly (allocates workspaces), note U per slot
     id_work(0)
-    if world > 1:
+    if sharded:
         torch.cuda.current_stream().wait_stream(side)
     for r in range(R):
         step(r)
         n_rows_touched.append(int(layer.last_n_unique.item()))
     torch.cuda.synchronize()
-    if world > 1:
+    if sharded:
         layer.check_errors()
     cursor[0] = 0                                  # the last step left slot 0's id work ready
 
     graphs, graph_out = [None] * R, [None] * R
-    use_graph = not args.no_graph and (world == 1 or (layer.px is not None and R % 2 == 0))
+    use_graph = not args.no_graph and (not sharded or (layer.px is not None and R % 2 == 0))
     if use_graph:
         try:
-            if world > 1:
+            if sharded:
                 for r in range(R):
                     handles[r].parity = r % 2      # captured: the exchange buffer of a slot is baked in
                     assert handles[r].parity is not None
@@ -368,7 +371,8 @@ def run_b200(args):
                     step(r)
                 torch.cuda.synchronize()
                 assert [h.parity for h in handles] == [r % 2 for r in range(R)], "parity drifted"
-                dist.barrier()
+                if world > 1:
+                    dist.barrier()
             cap_stream = torch.cuda.Stream()
             cap_stream.wait_stream(torch.cuda.current_stream())
             layer.capturing = True
@@ -391,7 +395,7 @@ def run_b200(args):
                 print("bench.py: CUDA graph capture failed (%s); launching eagerly" % e, file=sys.stderr)
             use_graph = False
             torch.cuda.synchronize()
-    if world == 1:
+    if not sharded:
         id_work(0)                                 # slot 0's list for the first step
         torch.cuda.synchronize()
 
@@ -399,7 +403,7 @@ def run_b200(args):
         slot = cursor[0] % R
         cursor[0] += 1
         if use_graph:
-            if world > 1:
+            if sharded:
                 ev = ready_events.get((slot + 1) % R)
                 if ev is not None:                 # e2e: the graph's id branch reads the next batch
                     torch.cuda.current_stream().wait_event(ev)
@@ -475,13 +479,13 @@ def run_b200(args):
                     feeder.prefetch((c0 + s + ahead) % R, host[(c0 + s + ahead) % R])
                 feeder.wait(cur)
                 if s + 1 < n:
-                    if world == 1 and not use_graph:
+                    if not sharded and not use_graph:
                         feeder.wait((c0 + s + 1) % R)        # this step presorts the next batch
                     else:
                         ready_events[(c0 + s + 1) % R] = feeder.ready[(c0 + s + 1) % R]
                 else:
                     ready_events.pop((c0 + s + 1) % R, None)   # the batch after the last one is the resident copy
-                if world == 1 and use_graph and s + 1 < n:
+                if not sharded and use_graph and s + 1 < n:
                     torch.cuda.current_stream().wait_event(feeder.ready[(c0 + s + 1) % R])
                 _, o = run()
                 feeder.release(cur)
@@ -510,7 +514,7 @@ def run_b200(args):
 
     # ---------------- roofline: each C-ABI call timed on its own (rank 0's GPU) ---------------
     roof, kernels = None, []
-    if world == 1:
+    if not sharded:
         roof, kernels = time_calls(dir_b200, RL, layer, cross, devs, ups, w, B, emit, n_rows_touched,
                                    min(50, max(5, args.steps)))
 
@@ -527,7 +531,7 @@ def run_b200(args):
             print("bench.py: cfg1 CPU timing skipped (%s)" % e, file=sys.stderr)
 
     stages, nvlink, serial = None, None, None
-    if world > 1 and getattr(layer, "trace", None) is not None:
+    if sharded and getattr(layer, "trace", None) is not None:
         # Stage times of the sharded step: a diagnostic pass AFTER the timed regions.  Eager launches, every stage
         # bracketed by CUDA events on its stream, one device sync per step.  Every rank takes part (the steps
         # contain the cross-rank barriers); rank 0 reports.
