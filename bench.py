@@ -649,12 +649,28 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     def sort(r):
         check(lib.dir_embed_bwd_sort(ptr(keys), B * n_sel, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
 
+    ows = torch.empty(int(lib.dir_shard_dense_workspace_bytes(K)), dtype=torch.uint8, device=dev)
+    nu = torch.zeros(2, dtype=torch.int64, device=dev)
+    aux = layer.aux_stream(dev)
+
     def upd(r):
+        # as the layer's backward runs it: the one-row fields' column sums on a second stream underneath the sorted
+        # segmented reduce (disjoint rows); the events bracket both
+        cur = torch.cuda.current_stream()
+        if layer.n_onerow_fields:
+            aux.wait_stream(cur)
+            check(lib.dir_embed_bwd_onerow_update(
+                ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
+                layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
+                ptr(ups[r]) if emit else None, B, F, K, ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, None,
+                ptr(ows), ows.numel(), nu[1:].data_ptr(), aux.cuda_stream), "onerow")
         check(lib.dir_embed_bwd_reduce_update(
             ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
             layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
             ptr(ups[r]) if emit else None, B, F, K, layer.n_rows, ptr(layer.sorted_fields), n_sel,
-            ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, None, ptr(ws), ws.numel(), None, st), "update")
+            None, 0, 1, LR, None, ptr(ws), ws.numel(), nu.data_ptr(), st), "update")
+        if layer.n_onerow_fields:
+            cur.wait_stream(aux)
 
     calls = [("dir_shard_keys", mkkeys, 0),
              ("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
@@ -699,7 +715,11 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
         except Exception:
             traffic = None
     roof = {"bound": "hbm", "kernel": top["call"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": top["achieved_gbs"] / peak, "frac_of_nominal_8000": top["achieved_gbs"] / 8000.0, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
+            "frac": top["achieved_gbs"] / peak, "frac_of_nominal_8000": top["achieved_gbs"] / 8000.0,
+            "traffic_source": "profiles/traffic.json: dram__bytes_read + write of one ncu --set full capture of this "
+                              "kernel on this workload, committed with the profile; not re-measured in this run",
+            "call_note": "dir_embed_bwd_reduce_update is timed as the layer runs it: dir_embed_bwd_onerow_update (the "
+                         "one-row fields) on a second stream underneath the sorted segmented reduce", "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
             if src == "measured" else "fallback (B200_PROFILING.md)", "traffic": traffic,
             "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "us_per_launch": top["us"]}
     return roof, table

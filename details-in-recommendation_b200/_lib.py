@@ -44,6 +44,10 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
                                             c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dir_embed_bwd_onerow_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                            c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
+                                            c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_sorted": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

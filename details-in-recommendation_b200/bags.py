@@ -83,9 +83,10 @@ class _EmbeddingBagFunction(torch.autograd.Function):
                     ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride,
                     ptr(w), ptr(slot), ptr(x), ctx.nnz, ptr(emb), ptr(g_first), ptr(g_fm), ptr(S), ptr(u),
                     B, F, K, layer.n_rows, _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
-                    ptr(ws), ws.numel(), ptr(layer.last_n_unique), _stream()), "dir_embed_bag_bwd_reduce_update")
+                    ptr(ws), ws.numel(), ptr(layer._nu_sorted), _stream()), "dir_embed_bag_bwd_reduce_update")
         else:
-            layer.last_n_unique.zero_()
+            layer._nu_sorted.zero_()
+        layer._nu_onerow.zero_()
         g_bias = g_first.sum().reshape(1) if layer.first_order else None
         return None, g_bias, None, None, None, None, None, None
 

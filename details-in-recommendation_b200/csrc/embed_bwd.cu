@@ -28,6 +28,7 @@ constexpr int kTile = 32;     // lookups a warp handles at a time
 constexpr int kChunk = 128;   // lookups per chunk (C): one warp walks one chunk
 constexpr int kLongRun = 32;  // chunks; longer crossing runs go to phase 3
 constexpr uint32_t kNoKey = 0xffffffffu;
+constexpr int kOneRowCtasMax = 444;  // CTAs of the one-row column-sum kernel (three per SM)
 
 struct BwdWorkspace {
   uint32_t* keys;      // [n] sorted global rows
@@ -121,7 +122,7 @@ static BwdWorkspace carve(void* base, int64_t n, int K) {
   w.onerow_flags = reinterpret_cast<int*>(take(64 * 4));
   w.part1 = reinterpret_cast<float*>(take((size_t)nchunks * 2 * 4));
   w.part = reinterpret_cast<float*>(take((size_t)nchunks * 2 * K * 4));
-  w.onerow_part = reinterpret_cast<double*>(take((size_t)296 * 64 * (K + 4) * 8));
+  w.onerow_part = reinterpret_cast<double*>(take((size_t)kOneRowCtasMax * 64 * (K + 4) * 8));
   w.total = off;
   return w;
 }
@@ -621,7 +622,7 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
 // whose result lands near zero otherwise leaves ~3e-5 absolute on G, which Adagrad's lr/sqrt(0.1)
 // slope turns into > 5e-6 on the row (round-1 full-size parity failure).
 constexpr int kOneRowPasses = 4;   // fields per launch = kOneRowPasses * 32 / LPR
-constexpr int kOneRowCtas = 296;   // two per SM
+constexpr int kOneRowCtas = kOneRowCtasMax;
 constexpr int kOneRowMax = 64;     // one-row fields per call
 
 struct OneRowArgs {
@@ -650,11 +651,13 @@ struct OneRowArgs {
 };
 
 template <int LPR, int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, P <= 2 ? 3 : 1)
 embed_bwd_onerow_kernel(const OneRowArgs a, int f0, int nf) {
   constexpr int K = LPR * 4;
   constexpr int SLOTS = 32 / LPR;
-  constexpr int UN = 4;  // samples whose loads are in flight together
+  // samples whose loads are in flight together: with the fp64 accumulators four of them cost 134 registers at
+  // P = 2 (one CTA per SM, 12 % of the warp slots: profiles/r02_sharded_1gpu_ncu.txt); two fit three CTAs per SM
+  constexpr int UN = P <= 2 ? 2 : 4;
   __shared__ double sm4[8][P][32][4];
   __shared__ double sm1[8][P][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1238,4 +1241,45 @@ extern "C" int dir_shard_dense_emit(const dir_peer_layout* layout, const float* 
   }
 #undef DIR_ORE
   return launched("shard_dense_emit");
+}
+
+extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t row_stride, float* lin,
+                                           float* lin_accum, int64_t lin_stride, const int64_t* feature_index,
+                                           const float* feature_value, const int64_t* field_offset,
+                                           const float* g_first, const float* g_fm, const float* S, const float* u,
+                                           int64_t B, int F, int K, const int32_t* onerow_fields, int n_onerow,
+                                           int optimizer, float lr, const dir_linear_opt* linear_opt, void* workspace,
+                                           size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > kOneRowMax)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: B >= 0, F > 0, 0 <= n_onerow <= 64 required");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: unknown optimizer");
+  if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: K must be one of 4, 8, 16, 32, 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_unique_out) cudaMemsetAsync(n_unique_out, 0, 8, st);
+  if (B == 0 || n_onerow == 0) return 0;
+  if (!table || !g_fm || !S || !workspace || !onerow_fields || !field_offset)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: table, g_fm, S, workspace, onerow_fields, field_offset are required");
+  if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "embed_bwd_onerow_update: Adagrad needs accum");
+  LinOpt lo;
+  if (int rc = resolve_lin("embed_bwd_onerow_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
+  if (lin && !g_first) return fail(DIR_EINVAL, "embed_bwd_onerow_update: lin needs g_first");
+  if (row_stride < K || (row_stride & 3)) return fail(DIR_EINVAL, "embed_bwd_onerow_update: row_stride must be >= K, multiple of 4");
+  if (!aligned16(table) || !aligned16(accum) || !aligned16(S) || !aligned16(u))
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: table, accum, S, u must be 16-byte aligned");
+  OneRowWs w = onerow_carve(workspace, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_onerow_update: workspace too small");
+  cudaMemsetAsync(w.flags, 0, kOneRowMax * 4, st);
+  OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value, field_offset,
+               g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.part, w.flags,
+               reinterpret_cast<unsigned long long*>(n_unique_out), lo};
+  switch (K) {
+    case 4: return launch_onerow<1>(o, n_onerow, st);
+    case 8: return launch_onerow<2>(o, n_onerow, st);
+    case 16: return launch_onerow<4>(o, n_onerow, st);
+    case 32: return launch_onerow<8>(o, n_onerow, st);
+    default: return launch_onerow<16>(o, n_onerow, st);
+  }
 }

@@ -146,11 +146,22 @@ class _EmbeddingFMFunction(torch.autograd.Function):
                 else g_fm.reshape(B).contiguous().float())
         if u is not None:
             u = u.contiguous().float()
+        # Two independent pieces next to the sorted segmented reduce -- the one-row fields' column sums (rows no
+        # sorted lookup touches) and the bias gradient -- run on a second stream underneath it.
+        main, aux = torch.cuda.current_stream(), layer.aux_stream(dev)
+        aux.wait_stream(main)
+        g_bias = None
+        with torch.cuda.stream(aux):
+            if layer.first_order:
+                g_bias = g_first.sum().reshape(1)
+                g_bias.record_stream(main)
+            if ctx.handle is not None:
+                layer.apply_onerow_gradients(idx, val, g_first, g_fm, S, u, B)
         if ctx.handle is not None:
             if ctx.handle.event is not None:
-                torch.cuda.current_stream().wait_event(ctx.handle.event)
+                main.wait_event(ctx.handle.event)
             layer.apply_sorted_gradients(ctx.handle, idx, val, g_first, g_fm, S, u, B)
-        g_bias = g_first.sum().reshape(1) if layer.first_order else None
+        main.wait_stream(aux)
         return None, g_bias, None, None, None, None, None
 
 
@@ -239,9 +250,10 @@ class EmbeddingFM(torch.nn.Module):
         self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
-        self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._ws = _Workspace()
-        self._side = None
+        self._nu_sorted = torch.zeros(1, dtype=torch.int64, device=dev)     # distinct rows the sorted reduce updated
+        self._nu_onerow = torch.zeros(1, dtype=torch.int64, device=dev)     # one-row fields whose row was updated
+        self._ws, self._onerow_ws = _Workspace(), _Workspace()
+        self._side = self._aux = None
         self._inline_sort = SortedLookups()
         with torch.no_grad():
             # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
@@ -250,6 +262,11 @@ class EmbeddingFM(torch.nn.Module):
                 self.accum.fill_(initial_accumulator_value)
             if self.w1_accum is not None:
                 self.w1_accum.fill_(initial_accumulator_value)     # Adagrad and Ftrl both start at 0.1 in TF
+
+    @property
+    def last_n_unique(self):
+        """Distinct rows the last backward updated (device int64[1])."""
+        return self._nu_sorted + self._nu_onerow
 
     # views into the interleaved storage
     @property
@@ -418,10 +435,15 @@ class EmbeddingFM(torch.nn.Module):
             self._side = torch.cuda.Stream(device=device, priority=prio)
         return self._side
 
+    def aux_stream(self, device):
+        if self._aux is None:
+            self._aux = torch.cuda.Stream(device=device)
+        return self._aux
+
     @torch.no_grad()
     def apply_sorted_gradients(self, handle, feature_index, feature_value, g_first, g_fm, S, u, B):
         """segmented reduce -> fused row update (dir_embed_bwd_reduce_update) on the (row, position)
-        list `presort` left sorted in the handle's workspace."""
+        list `presort` left sorted in the handle's workspace (the one-row fields: apply_onerow_gradients)."""
         F, K = self.field_size, self.embedding_size
         L = _lib.lib()
         ws = handle.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), S.device)
@@ -432,10 +454,28 @@ class EmbeddingFM(torch.nn.Module):
             ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
             ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
             ptr(u), B, F, K, self.n_rows, ptr(self.sorted_fields), self.n_sorted_fields,
-            ptr(self.onerow_fields), self.n_onerow_fields,
-            _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self), ptr(ws), ws.numel(),
-            ptr(self.last_n_unique),
-            _stream()), "dir_embed_bwd_reduce_update")
+            None, 0, _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self), ptr(ws), ws.numel(),
+            ptr(self._nu_sorted), _stream()), "dir_embed_bwd_reduce_update")
+
+    @torch.no_grad()
+    def apply_onerow_gradients(self, feature_index, feature_value, g_first, g_fm, S, u, B):
+        """One-row (numeric) fields: every sample hits the same row, so the row's gradient is a column sum over the
+        batch (fixed order, fp64-carried) -- no sort; independent of the sorted part (disjoint rows)."""
+        F, K = self.field_size, self.embedding_size
+        L = _lib.lib()
+        if self.n_onerow_fields == 0:
+            self._nu_onerow.zero_()
+            return
+        ows = self._onerow_ws.get(L.dir_shard_dense_workspace_bytes(K), S.device)
+        adagrad = self.optimizer == "adagrad"
+        check(L.dir_embed_bwd_onerow_update(
+            ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
+            ptr(self.w1) if self.first_order else None,
+            ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
+            ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
+            ptr(u), B, F, K, ptr(self.onerow_fields), self.n_onerow_fields, _OPTIMIZERS[self.optimizer], self.lr,
+            linear_opt_struct(self), ptr(ows), ows.numel(), ptr(self._nu_onerow), _stream()),
+            "dir_embed_bwd_onerow_update")
 
 
 class _CrossFunction(torch.autograd.Function):

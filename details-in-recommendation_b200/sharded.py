@@ -281,6 +281,7 @@ class _ShardedFunction(torch.autograd.Function):
             u = u.contiguous().float()
         tr = layer.trace
         tr.mark("between")
+        g_bias = None
         adagrad = layer.optimizer == "adagrad"
         gfp = ptr(g_first) if layer.first_order else None
         n_keys = layer.plan.cap * layer.plan.world_size
@@ -288,6 +289,20 @@ class _ShardedFunction(torch.autograd.Function):
             if layer.px is not None:
                 px, p = layer.px, h.parity
                 n = B * layer.n_sel
+                # Next to the segmented reduce, on a second stream: the replicated one-row fields' column sums over
+                # this rank's samples -> every rank's buffer, and the bias gradient.
+                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev)
+                aux.wait_stream(main)
+                with torch.cuda.stream(aux):
+                    if layer.first_order:
+                        g_bias = g_first.sum().reshape(1)
+                        g_bias.record_stream(main)
+                    if layer.n_dense:
+                        ows = layer._dense_ws.get(L.dir_shard_dense_workspace_bytes(K), dev)
+                        check(L.dir_shard_dense_emit(
+                            px.ref(p), ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val),
+                            ptr(layer.dense_field_offset), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), B, F,
+                            ptr(ows), ows.numel(), aux.cuda_stream), "dir_shard_dense_emit")
                 # per-distinct-row sums on the requester (the sorted list is in the handle's workspace), each
                 # stored straight into its owner's buffer over NVLink as soon as its run is summed
                 ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n, 1), K), dev)
@@ -296,15 +311,8 @@ class _ShardedFunction(torch.autograd.Function):
                     ptr(layer.sparse_fields) if layer.n_sel < F else None, layer.n_sel, ptr(h.g1_local),
                     ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_to")
                 check(L.dir_shard_g1_push(px.ref(p), ptr(h.g1_local), ptr(h.owner_off), n, st), "dir_shard_g1_push")
+                main.wait_stream(aux)
                 tr.mark("bwd.emit+push")
-                if layer.n_dense:
-                    # replicated one-row fields: this rank's column sums -> every rank's buffer
-                    ows = layer._dense_ws.get(L.dir_shard_dense_workspace_bytes(K), dev)
-                    check(L.dir_shard_dense_emit(
-                        px.ref(p), ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val),
-                        ptr(layer.dense_field_offset), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), B, F,
-                        ptr(ows), ows.numel(), st), "dir_shard_dense_emit")
-                    tr.mark("bwd.dense_emit")
                 px.barrier(p, 0)
                 tr.mark("bwd.barrier")
                 # the owner merges the ranks' contributions (rank order) and updates its rows
@@ -355,7 +363,8 @@ class _ShardedFunction(torch.autograd.Function):
                 else:
                     layer.last_n_unique.zero_()
             tr.close_step()
-        g_bias = g_first.sum().reshape(1) if layer.first_order else None
+        if g_bias is None and layer.first_order:
+            g_bias = g_first.sum().reshape(1)
         return None, g_bias, None, None, None, None, None
 
 
@@ -421,7 +430,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._side = None
+        self._side = self._aux = None
         self._inline = ShardedLookups()
         self.trace, self.trace_pre = StageTrace(), StageTrace()
         self.capturing = False
@@ -601,6 +610,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
         if self._side is None:
             self._side = torch.cuda.Stream(device=device, priority=-1)
         return self._side
+
+    def aux_stream(self, device):
+        if self._aux is None:
+            self._aux = torch.cuda.Stream(device=device)
+        return self._aux
 
     def _note_forward(self):
         """Bookkeeping after the rows barrier of a step: every rank has finished the previous step, so the id

@@ -131,6 +131,18 @@ int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, 
                                 const dir_linear_opt* linear_opt, void* workspace,
                                 size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
+/* The one-row fields of dir_embed_bwd_reduce_update on their own.  They touch rows no sorted lookup touches, so
+ * a caller may run them on a second stream next to the sorted part (call that one with n_onerow = 0).  Fixed-order,
+ * fp64-carried column sums over the batch; workspace of dir_shard_dense_workspace_bytes(K); n_unique_out receives
+ * the number of one-row fields whose row was updated. */
+int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t row_stride, float* lin, float* lin_accum,
+                                int64_t lin_stride, const int64_t* feature_index, const float* feature_value,
+                                const int64_t* field_offset, const float* g_first, const float* g_fm,
+                                const float* S, const float* u, int64_t B, int F, int K,
+                                const int32_t* onerow_fields, int n_onerow, int optimizer, float lr,
+                                const dir_linear_opt* linear_opt, void* workspace, size_t workspace_bytes,
+                                int64_t* n_unique_out, dir_stream_t stream);
+
 /* Where step 1 left the sorted (row, position) pairs inside its workspace (read-only views). */
 int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_t** sorted_keys,
                          const uint32_t** sorted_pos);
