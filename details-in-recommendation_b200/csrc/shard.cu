@@ -59,16 +59,31 @@ struct HeadFlag {
   }
 };
 
+// Numbers the distinct keys of the sorted list and, where the owner changes between two neighbouring entries,
+// writes owner_off[g] = number of distinct keys below g * cap for every g in between (g = 0..G; every g is written
+// exactly once because the owners are non-decreasing).
 __global__ void __launch_bounds__(256)
 shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ pos,
-                    const uint32_t* __restrict__ incl, int64_t n, uint32_t pruned, uint32_t cap,
+                    const uint32_t* __restrict__ incl, int64_t n, uint32_t pruned, uint32_t cap, int G,
                     const int32_t* __restrict__ field_sel, int n_sel, int F,
                     uint32_t* __restrict__ uidx, int32_t* __restrict__ ulocal,
-                    int64_t* __restrict__ inv) {
+                    int64_t* __restrict__ inv, int64_t* __restrict__ owner_off) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = __ldg(keys + i);
+  const uint32_t kp = i > 0 ? __ldg(keys + i - 1) : 0u;
   uint32_t p = __ldg(pos + i);
+  const uint32_t inc = __ldg(incl + i);
+  {
+    const int o_cur = (int)(k / cap);                      // G for a pruned entry
+    const int o_prev = i > 0 ? (int)(kp / cap) : -1;
+    if (o_cur != o_prev) {
+      const int64_t before = i > 0 ? (int64_t)__ldg(incl + i - 1) : 0;
+      for (int g = o_prev + 1; g <= o_cur && g <= G; ++g) owner_off[g] = before;
+    }
+    if (i == n - 1)
+      for (int g = o_cur + 1; g <= G; ++g) owner_off[g] = (int64_t)inc;
+  }
   if (field_sel != nullptr) {  // entry of the compact [B, n_sel] list -> position in the [B, F] inputs
     const uint32_t b = p / (uint32_t)n_sel;
     p = b * (uint32_t)F + (uint32_t)__ldg(field_sel + (p - b * (uint32_t)n_sel));
@@ -78,25 +93,10 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
     inv[p] = -1;  // pruned by the forward kernel (id < 0)
     return;
   }
-  const uint32_t u = __ldg(incl + i) - 1u;
+  const uint32_t u = inc - 1u;
   uidx[i] = u;
   inv[p] = (int64_t)u;
-  if (i == 0 || __ldg(keys + i - 1) != k) ulocal[u] = (int32_t)(k % cap);
-}
-
-// owner_off[g] = number of distinct keys below g*cap, g = 0..G  (owner_off[G] = all of them)
-__global__ void shard_bounds_kernel(const uint32_t* __restrict__ keys,
-                                    const uint32_t* __restrict__ incl, int64_t n, int G,
-                                    uint32_t cap, int64_t* __restrict__ owner_off) {
-  const int g = threadIdx.x;
-  if (g > G) return;
-  const uint64_t target = (uint64_t)g * cap;
-  int64_t lo = 0, hi = n;  // lower bound of target
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if ((uint64_t)keys[mid] < target) lo = mid + 1; else hi = mid;
-  }
-  owner_off[g] = lo > 0 ? (int64_t)incl[lo - 1] : 0;
+  if (i == 0 || kp != k) ulocal[u] = (int32_t)(k % cap);
 }
 
 template <int LPR>
@@ -202,10 +202,9 @@ extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sor
   cudaError_t e = cub::DeviceScan::InclusiveSum(w.cub_temp, bytes, flags, w.incl, (int)n_lookups, st);
   if (e != cudaSuccess) return fail(DIR_EIO, "shard_unique: %s", cudaGetErrorString(e));
   shard_number_kernel<<<(unsigned)((n_lookups + 255) / 256), 256, 0, st>>>(
-      sorted_keys, sorted_pos, w.incl, n_lookups, pruned, (uint32_t)cap, field_sel, n_sel, F, uidx, unique_local_rows,
-      inv);
-  shard_bounds_kernel<<<1, 1024, 0, st>>>(sorted_keys, w.incl, n_lookups, G, (uint32_t)cap, owner_off);
-  return launched("shard_unique", 4);
+      sorted_keys, sorted_pos, w.incl, n_lookups, pruned, (uint32_t)cap, G, field_sel, n_sel, F, uidx, unique_local_rows,
+      inv, owner_off);
+  return launched("shard_unique", 3);
 }
 
 extern "C" int dir_rows_gather(const float* table, int64_t row_stride, const float* lin,

@@ -198,77 +198,118 @@ peer_g1_push_kernel(const dir_peer_layout L, const float* __restrict__ g1_local,
   }
 }
 
-// owner: merge + fused update.  LPR lanes per arrival; the arrival of the lowest rank that asked for a row
-// adds the other ranks' sums in rank order and updates the row (row and accumulator share a 128-byte line).
+// owner: merge + fused update.  A warp takes 32 arrivals at a time.  Lane-per-arrival stage: local row, then the
+// row's slot cells -- does an earlier rank merge this row (then this arrival has nothing to do), which later ranks
+// contribute.  Vector stage over the arrivals that lead, compacted: LPR lanes per row, the row / accumulator /
+// gradient loads of PB passes in flight together; the other ranks' sums are added in rank order, then the fused
+// update (row and accumulator share a 128-byte line).
 template <int LPR>
 __global__ void __launch_bounds__(256)
 peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ slot, float* table, float* accum,
                          int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
                          int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
   constexpr int SLOTS = 32 / LPR;
+  constexpr int PB = LPR <= 4 ? 2 : 1;
+  constexpr unsigned FULL = 0xffffffffu;
   __shared__ Arrivals s;
   load_arrivals(L, s);
   const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
-  const float* gbuf = reinterpret_cast<const float*>(L.local + L.off_g);
+  const float4* gbuf = reinterpret_cast<const float4*>(L.local + L.off_g);
   const float* g1buf = reinterpret_cast<const float*>(L.local + L.off_g1);
   const int64_t total = s.pre[L.G];
   const bool adagrad = opt == DIR_OPT_ADAGRAD;
   const int lane = threadIdx.x & 31;
-  const int sub = lane % LPR;
+  const int sub = lane % LPR, grp = lane / LPR;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint64_t pol_row = policy_evict_first();
-  unsigned leaders = 0;
-  for (int64_t a0 = warp * SLOTS; a0 < total; a0 += nwarps * SLOTS) {  // warp-uniform trip count
-    const int64_t a = a0 + lane / LPR;
+  const int G = L.G;
+  unsigned long long leaders = 0;
+  for (int64_t a0 = warp * 32; a0 < total; a0 += nwarps * 32) {  // warp-uniform trip count
+    // ---- lane-per-arrival stage
+    const int64_t a = a0 + lane;
     bool lead = false;
-    int q = 0;
-    int64_t i = 0, r = 0;
+    int64_t e = 0, r = 0;        // e: this arrival's entry of gbuf / g1buf
+    unsigned long long more = 0; // ranks > q that asked for the same row
     if (a < total) {
-      q = seg_of(s.pre, L.G, a);
-      i = a - s.pre[q];
-      r = __ldg(ids + (int64_t)q * L.seg_cap + i);
-      lead = r >= 0 && r < n_local;
-      const uint32_t* sl = slot + r * L.G;
-      for (int p = 0; lead && p < q; ++p) lead = __ldg(sl + p) == 0u;  // an earlier rank merges this row
+      const int q = seg_of(s.pre, G, a);
+      const int64_t i = a - s.pre[q];
+      e = (int64_t)q * L.seg_cap + i;
+      r = __ldg(ids + e);
+      if (r >= 0 && r < n_local) {
+        const uint32_t* sl = slot + r * G;
+        unsigned earlier = 0;
+        for (int p = 0; p < G; ++p) {
+          const uint32_t sp = __ldg(sl + p);
+          if (p < q) earlier |= sp;
+          if (p > q && sp != 0u) more |= 1ull << p;
+        }
+        lead = earlier == 0u;  // else an earlier rank merges this row
+      }
     }
-    if (lead) {
-      const int64_t ro = r * row_stride;
-      float4 T = ld_hint(table + ro + sub * 4, pol_row);
-      float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (adagrad) A = ld_hint(accum + ro + sub * 4, pol_row);
-      const int64_t e = (int64_t)q * L.seg_cap + i;
-      float4 g = __ldg(reinterpret_cast<const float4*>(gbuf) + e * LPR + sub);
-      float g1 = sub == 0 ? __ldg(g1buf + e) : 0.f;
-      const uint32_t* sl = slot + r * L.G;
-      for (int p = q + 1; p < L.G; ++p) {  // rank order
-        const uint32_t sp = __ldg(sl + p);
-        if (sp != 0u) {
-          const int64_t e2 = (int64_t)p * L.seg_cap + (sp - 1u);
-          const float4 o = __ldg(reinterpret_cast<const float4*>(gbuf) + e2 * LPR + sub);
-          g.x = __fadd_rn(g.x, o.x);
-          g.y = __fadd_rn(g.y, o.y);
-          g.z = __fadd_rn(g.z, o.z);
-          g.w = __fadd_rn(g.w, o.w);
-          if (sub == 0) g1 = __fadd_rn(g1, __ldg(g1buf + e2));
+    const unsigned lm = __ballot_sync(FULL, lead);
+    const int nl = __popc(lm);
+    leaders += (unsigned long long)nl;
+    // ---- vector stage over the leading arrivals
+    for (int k0 = 0; k0 < nl; k0 += SLOTS * PB) {
+      int64_t rr[PB], ee[PB];
+      unsigned long long mm[PB];
+      bool on[PB];
+      float4 T[PB], A[PB], g[PB];
+      float g1[PB], w1[PB], n1[PB], z1[PB];
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int n = k0 + j * SLOTS + grp;
+        on[j] = n < nl;
+        const int src = on[j] ? (int)__fns(lm, 0, n + 1) : 0;
+        rr[j] = __shfl_sync(FULL, r, src);
+        ee[j] = __shfl_sync(FULL, e, src);
+        mm[j] = __shfl_sync(FULL, more, src);
+        T[j] = A[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g1[j] = w1[j] = n1[j] = z1[j] = 0.f;
+        if (on[j]) {
+          const int64_t ro = rr[j] * row_stride;
+          T[j] = ld_hint(table + ro + sub * 4, pol_row);
+          if (adagrad) A[j] = ld_hint(accum + ro + sub * 4, pol_row);
+          g[j] = __ldg(gbuf + ee[j] * LPR + sub);
+          if (sub == 0 && lin != nullptr) {
+            g1[j] = __ldg(g1buf + ee[j]);
+            w1[j] = lin[rr[j] * lin_stride];
+            lin_load(lo, lin_accum, rr[j] * lin_stride, n1[j], z1[j]);
+          }
         }
       }
-      T.x = upd(T.x, g.x, lr, A.x, adagrad);
-      T.y = upd(T.y, g.y, lr, A.y, adagrad);
-      T.z = upd(T.z, g.z, lr, A.z, adagrad);
-      T.w = upd(T.w, g.w, lr, A.w, adagrad);
-      *(reinterpret_cast<float4*>(table + ro) + sub) = T;
-      if (adagrad) *(reinterpret_cast<float4*>(accum + ro) + sub) = A;
-      if (lin != nullptr && sub == 0) {
-        const int64_t off = r * lin_stride;
-        float n1, z1;
-        lin_load(lo, lin_accum, off, n1, z1);
-        lin_apply(lo, lin + off, lin_accum + off, lo.z + off, lin[off], n1, z1, g1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        if (!on[j]) continue;
+        unsigned long long m = mm[j];
+        while (m) {  // rank order
+          const int p = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const uint32_t sp = __ldg(slot + rr[j] * G + p);
+          const int64_t e2 = (int64_t)p * L.seg_cap + (sp - 1u);
+          const float4 o = __ldg(gbuf + e2 * LPR + sub);
+          g[j].x = __fadd_rn(g[j].x, o.x);
+          g[j].y = __fadd_rn(g[j].y, o.y);
+          g[j].z = __fadd_rn(g[j].z, o.z);
+          g[j].w = __fadd_rn(g[j].w, o.w);
+          if (sub == 0 && lin != nullptr) g1[j] = __fadd_rn(g1[j], __ldg(g1buf + e2));
+        }
+        const int64_t ro = rr[j] * row_stride;
+        T[j].x = upd(T[j].x, g[j].x, lr, A[j].x, adagrad);
+        T[j].y = upd(T[j].y, g[j].y, lr, A[j].y, adagrad);
+        T[j].z = upd(T[j].z, g[j].z, lr, A[j].z, adagrad);
+        T[j].w = upd(T[j].w, g[j].w, lr, A[j].w, adagrad);
+        *(reinterpret_cast<float4*>(table + ro) + sub) = T[j];
+        if (adagrad) *(reinterpret_cast<float4*>(accum + ro) + sub) = A[j];
+        if (lin != nullptr && sub == 0) {
+          const int64_t off = rr[j] * lin_stride;
+          lin_apply(lo, lin + off, lin_accum + off, lo.z + off, w1[j], n1[j], z1[j], g1[j]);
+        }
       }
     }
-    leaders += __popc(__ballot_sync(0xffffffffu, lead && sub == 0));
   }
-  if (lane == 0 && leaders && n_unique) atomicAdd(n_unique, (unsigned long long)leaders);
+  if (lane == 0 && leaders && n_unique) atomicAdd(n_unique, leaders);
 }
 
 // replicated one-row fields: the G ranks' sums added in rank order, the same update applied to every replica;
