@@ -46,8 +46,17 @@ SIGNATURES = {
                                             c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_onerow_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                            c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
-                                            c_size_t, c_void_p, c_void_p]),
+                                            c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_float,
+                                            c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dir_embed_bwd_reduce_emit_local": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,
+                                                c_int64, c_void_p, c_size_t, c_void_p]),
+    "dir_field_sqnorms_bytes": (c_size_t, [c_int]),
+    "dir_field_sqnorms": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p,
+                                  c_void_p]),
+    "dir_rows_apply_clipped": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_float, c_int,
+                                       c_float, c_void_p, c_void_p, c_void_p]),
     "dir_embed_bwd_sorted": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "dir_shard_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -98,6 +98,8 @@ class EmbeddingBagFM(EmbeddingFM):
     `forward`; `forward_bags` takes the CSR form."""
 
     def __init__(self, field_size, embedding_size, rows_per_field, combiner="mean", **kw):
+        if kw.get("clip_norm") is not None:
+            raise ValueError("EmbeddingBagFM applies its gradients unclipped: clip_norm is an EmbeddingFM option")
         super().__init__(field_size, embedding_size, rows_per_field, combiner=combiner, **kw)
 
     def forward_bags(self, bag_offsets, bag_index, bag_weight=None):

@@ -182,6 +182,7 @@ struct BwdArgs {
   int64_t emit_seg_cap;
   float* emit_g1;
   int emit_G;
+  int emit_read_key;  // kModeEmit over the table itself: rows are read at the key, sums still go to row uidx of `emit`
   // entries actually in the sorted list, read on the device (NULL: n).  `n` then only bounds the launch
   // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
   const int64_t* n_dev;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
         Sb[j] = ub[j] = T[j] = A[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         lw[j] = a1[j] = lz[j] = 0.f;
         if (k[j] != a.pruned_key) {
-          const int64_t ro = (int64_t)rw[j] * a.row_stride;
+          const int64_t ro = (int64_t)((MODE == kModeEmit && a.emit_read_key) ? k[j] : rw[j]) * a.row_stride;
           if (MODE == kModeGiven) {  // the per-lookup gradient was formed by the requester
             ub[j] = ldg_hint(a.gbuf + (int64_t)p * a.gbuf_stride + sub * 4, pol_once);
           } else {
@@ -648,6 +649,7 @@ struct OneRowArgs {
   int* flags;    // [kOneRowMax] some sample had a surviving lookup
   unsigned long long* n_unique;
   LinOpt lo;
+  float clip;    // > 0: tf.clip_by_norm of the field's gradient (its variable has this one row) before the update
 };
 
 template <int LPR, int P>
@@ -781,6 +783,16 @@ __global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneR
 #pragma unroll
       for (int k = 0; k < 8; ++k) v += red[k][cx];
       tot[c] = (float)v;  // the one rounding of the column sum
+    }
+    __syncthreads();
+  }
+  if (a.clip > 0.f) {  // values * clip / max(||values||, clip), the row and the linear weight each a variable
+    if (threadIdx.x == 0) {
+      double sq = 0.0;
+      for (int c = 0; c < K; ++c) sq += (double)tot[c] * tot[c];
+      const float den = fmaxf((float)sqrt(sq), a.clip), den1 = fmaxf(fabsf(tot[K]), a.clip);
+      for (int c = 0; c < K; ++c) tot[c] = __fdiv_rn(__fmul_rn(tot[c], a.clip), den);
+      tot[K] = __fdiv_rn(__fmul_rn(tot[K], a.clip), den1);
     }
     __syncthreads();
   }
@@ -963,7 +975,7 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, nullptr, lo, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -975,7 +987,7 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
                        const uint32_t* uidx, int64_t B, int F, int K, int64_t n_keys, float* gu,
                        int64_t gu_stride, const dir_peer_layout* layout, const int64_t* owner_off, float* g1_local,
                        void* workspace, size_t workspace_bytes, dir_stream_t stream, const int32_t* field_sel,
-                       int n_sel) {
+                       int n_sel, int read_key = 0) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "%s: B >= 0, F > 0 required", what);
   if (field_sel == nullptr) n_sel = F;      // the sorted list covers every field
@@ -1001,7 +1013,7 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
             gu_stride, nullptr, 0,
             owner_off, layout ? layout->peer_base : nullptr, layout ? layout->off_g : 0,
             layout ? (int64_t)layout->rank * layout->seg_cap : 0, layout ? layout->seg_cap : 0, g1_local,
-            layout ? layout->G : 0, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
+            layout ? layout->G : 0, read_key, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -1017,6 +1029,20 @@ extern "C" int dir_embed_bwd_reduce_emit(const float* ubuf, int64_t ubuf_stride,
   return reduce_emit("embed_bwd_reduce_emit", ubuf, ubuf_stride, feature_value, g_first, g_fm, S, u, uidx, B, F,
                      K, n_keys, gu, gu_stride, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream,
                      nullptr, 0);
+}
+
+/* the same per-distinct-row sums for a table that lives HERE (rows read at their global row, sums written to
+ * gu[uidx]): the first pass of the clipped backward (csrc/clip.cu) */
+extern "C" int dir_embed_bwd_reduce_emit_local(const float* table, int64_t row_stride, const float* feature_value,
+                                               const float* g_first, const float* g_fm, const float* S,
+                                               const float* u, const uint32_t* uidx, int64_t B, int F, int K,
+                                               int64_t n_rows, const int32_t* field_sel, int n_sel, float* gu,
+                                               int64_t gu_stride, void* workspace, size_t workspace_bytes,
+                                               dir_stream_t stream) {
+  if (!gu) return dir::fail(DIR_EINVAL, "embed_bwd_reduce_emit_local: gu is required");
+  return reduce_emit("embed_bwd_reduce_emit_local", table, row_stride, feature_value, g_first, g_fm, S, u, uidx, B, F,
+                     K, n_rows, gu, gu_stride, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream,
+                     field_sel, n_sel, 1);
 }
 
 extern "C" int dir_embed_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* feature_value,
@@ -1063,7 +1089,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, 0, 0, 0, nullptr, 0, n_device, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, n_device, lo, nullptr, nullptr, nullptr};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }
@@ -1105,7 +1131,7 @@ extern "C" int dir_embed_bag_bwd_reduce_update(
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, bag_weight, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, nnz, F,
             (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeBag, nullptr, nullptr, 0, nullptr, 0,
-            nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr, lo, entry_slot, entry_x, emb};
+            nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, nullptr, lo, entry_slot, entry_x, emb};
   set_div(a, F);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -1248,11 +1274,12 @@ extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t r
                                            const float* feature_value, const int64_t* field_offset,
                                            const float* g_first, const float* g_fm, const float* S, const float* u,
                                            int64_t B, int F, int K, const int32_t* onerow_fields, int n_onerow,
-                                           int optimizer, float lr, const dir_linear_opt* linear_opt, void* workspace,
-                                           size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream) {
+                                           int optimizer, float lr, const dir_linear_opt* linear_opt, float clip_norm,
+                                           void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
+                                           dir_stream_t stream) {
   using namespace dir;
-  if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > kOneRowMax)
-    return fail(DIR_EINVAL, "embed_bwd_onerow_update: B >= 0, F > 0, 0 <= n_onerow <= 64 required");
+  if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > kOneRowMax || clip_norm < 0.f)
+    return fail(DIR_EINVAL, "embed_bwd_onerow_update: B >= 0, F > 0, 0 <= n_onerow <= 64, clip_norm >= 0 required");
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
     return fail(DIR_EINVAL, "embed_bwd_onerow_update: unknown optimizer");
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
@@ -1274,7 +1301,7 @@ extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t r
   cudaMemsetAsync(w.flags, 0, kOneRowMax * 4, st);
   OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value, field_offset,
                g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.part, w.flags,
-               reinterpret_cast<unsigned long long*>(n_unique_out), lo};
+               reinterpret_cast<unsigned long long*>(n_unique_out), lo, clip_norm};
   switch (K) {
     case 4: return launch_onerow<1>(o, n_onerow, st);
     case 8: return launch_onerow<2>(o, n_onerow, st);

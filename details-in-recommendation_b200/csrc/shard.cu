@@ -90,12 +90,12 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
   }
   if (k == pruned) {
     uidx[i] = 0u;
-    inv[p] = -1;  // pruned by the forward kernel (id < 0)
+    if (inv) inv[p] = -1;  // pruned by the forward kernel (id < 0)
     return;
   }
   const uint32_t u = inc - 1u;
   uidx[i] = u;
-  inv[p] = (int64_t)u;
+  if (inv) inv[p] = (int64_t)u;
   if (i == 0 || kp != k) ulocal[u] = (int32_t)(k % cap);
 }
 
@@ -187,7 +187,7 @@ extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sor
     cudaMemsetAsync(owner_off, 0, (size_t)(G + 1) * 8, st);
     return 0;
   }
-  if (!sorted_keys || !sorted_pos || !uidx || !unique_local_rows || !inv || !workspace)
+  if (!sorted_keys || !sorted_pos || !uidx || !unique_local_rows || !workspace)
     return fail(DIR_EINVAL, "shard_unique: null pointer");
   if (field_sel != nullptr && (n_sel <= 0 || n_sel > F || n_lookups % n_sel != 0))
     return fail(DIR_EINVAL, "shard_unique: with field_sel, 0 < n_sel <= F and n_lookups = B * n_sel are required");

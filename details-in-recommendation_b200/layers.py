@@ -160,7 +160,10 @@ class _EmbeddingFMFunction(torch.autograd.Function):
         if ctx.handle is not None:
             if ctx.handle.event is not None:
                 main.wait_event(ctx.handle.event)
-            layer.apply_sorted_gradients(ctx.handle, idx, val, g_first, g_fm, S, u, B)
+            if layer.clip_norm is None:
+                layer.apply_sorted_gradients(ctx.handle, idx, val, g_first, g_fm, S, u, B)
+            else:
+                layer.apply_sorted_gradients_clipped(ctx.handle, idx, val, g_first, g_fm, S, u, B)
         main.wait_stream(aux)
         return None, g_bias, None, None, None, None, None
 
@@ -178,6 +181,8 @@ class EmbeddingFM(torch.nn.Module):
 
     rows_per_field: N_f per field (one reference embedding variable per column,
     deepFM.py:385-390), stored concatenated; or a single int `feature_size` with global ids.
+    clip_norm: tf.clip_by_norm of every column's gradient before the update (DeepCrossNetwork.py:282-289; one
+    factor per column variable, over its de-duplicated row sums): a two-pass backward, only when set.
     Storage is B200-first: with Adagrad each row and its accumulator share one 128-byte line
     ([N, 2K] fp32), and each first-order weight sits next to its accumulator ([N, 2]).
     """
@@ -189,8 +194,11 @@ class EmbeddingFM(torch.nn.Module):
                  check_bounds: bool = False, lin_interleaved: Optional[bool] = None,
                  linear_optimizer: Optional[str] = None, linear_lr: Optional[float] = None,
                  l1_regularization_strength: float = 0.0, l2_regularization_strength: float = 0.0,
-                 device="cuda"):
+                 clip_norm: Optional[float] = None, device="cuda"):
         super().__init__()
+        if clip_norm is not None and not clip_norm > 0:
+            raise ValueError("clip_norm must be > 0 (or None)")
+        self.clip_norm = None if clip_norm is None else float(clip_norm)
         if lin_interleaved is None:
             lin_interleaved = os.environ.get("DIR_B200_LIN_INTERLEAVED", "0") == "1"
         if field_size <= 0:
@@ -254,6 +262,7 @@ class EmbeddingFM(torch.nn.Module):
         self._nu_onerow = torch.zeros(1, dtype=torch.int64, device=dev)     # one-row fields whose row was updated
         self._ws, self._onerow_ws = _Workspace(), _Workspace()
         self._side = self._aux = None
+        self._clip_bufs = None
         self._inline_sort = SortedLookups()
         with torch.no_grad():
             # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
@@ -474,8 +483,52 @@ class EmbeddingFM(torch.nn.Module):
             ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
             ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
             ptr(u), B, F, K, ptr(self.onerow_fields), self.n_onerow_fields, _OPTIMIZERS[self.optimizer], self.lr,
-            linear_opt_struct(self), ptr(ows), ows.numel(), ptr(self._nu_onerow), _stream()),
+            linear_opt_struct(self), self.clip_norm or 0.0, ptr(ows), ows.numel(), ptr(self._nu_onerow), _stream()),
             "dir_embed_bwd_onerow_update")
+
+    @torch.no_grad()
+    def apply_sorted_gradients_clipped(self, handle, feature_index, feature_value, g_first, g_fm, S, u, B):
+        """The backward with tf.clip_by_norm on every column's gradient (DeepCrossNetwork.py:282-289): a column's
+        factor is known only once all of its row sums are, so the sums go to a buffer first (dir_embed_bwd_reduce_emit_local),
+        the per-column norms are reduced in a fixed order (dir_field_sqnorms) and a second pass scales and applies
+        (dir_rows_apply_clipped)."""
+        if self.shared_table:
+            raise ValueError("clip_norm needs per-field tables (one variable per column, as in the reference)")
+        F, K = self.field_size, self.embedding_size
+        n_sel = self.n_sorted_fields
+        n = B * n_sel
+        if n == 0:
+            self._nu_sorted.zero_()
+            return
+        L = _lib.lib()
+        dev = S.device
+        ws = handle.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), dev)
+        c = self._clip_bufs
+        if c is None or c["n"] < n or c["uidx"].device != dev:
+            c = self._clip_bufs = dict(
+                n=n, uidx=torch.empty(n, dtype=torch.int32, device=dev), urows=torch.empty(n, dtype=torch.int32, device=dev),
+                count=torch.zeros(2, dtype=torch.int64, device=dev), gu=torch.empty((n, K + 4), dtype=torch.float32, device=dev),
+                ws2=torch.empty(max(int(L.dir_shard_unique_workspace_bytes(n)), 1), dtype=torch.uint8, device=dev),
+                part=torch.empty(int(L.dir_field_sqnorms_bytes(F)), dtype=torch.uint8, device=dev))
+        st = _stream()
+        skeys, spos = _lib.c_void_p(), _lib.c_void_p()
+        check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)), "dir_embed_bwd_sorted")
+        check(L.dir_shard_unique(skeys, spos, n, self.n_rows, 1, None, 0, F, ptr(c["uidx"]), ptr(c["urows"]), None,
+                                 ptr(c["count"]), ptr(c["ws2"]), c["ws2"].numel(), st), "dir_shard_unique")
+        check(L.dir_embed_bwd_reduce_emit_local(
+            ptr(self.table), self.row_stride, ptr(feature_value), ptr(g_first) if self.first_order else None, ptr(g_fm),
+            ptr(S), ptr(u), ptr(c["uidx"]), B, F, K, self.n_rows, ptr(self.sorted_fields), n_sel, ptr(c["gu"]), K + 4,
+            ptr(ws), ws.numel(), st), "dir_embed_bwd_reduce_emit_local")
+        n_dev = c["count"].data_ptr() + 8                      # count[1] = distinct rows (dir_shard_unique, G = 1)
+        check(L.dir_field_sqnorms(ptr(c["gu"]), K + 4, ptr(c["urows"]), n_dev, ptr(self.field_offset), F, K,
+                                  self.n_rows, ptr(c["part"]), st), "dir_field_sqnorms")
+        adagrad = self.optimizer == "adagrad"
+        check(L.dir_rows_apply_clipped(
+            ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
+            ptr(self.w1) if self.first_order else None, ptr(self.w1_accum) if self.first_order else None,
+            self.lin_stride, ptr(c["gu"]), K + 4, ptr(c["urows"]), n_dev, n, ptr(self.field_offset), F, K,
+            ptr(c["part"]), self.clip_norm, _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self),
+            ptr(self._nu_sorted), st), "dir_rows_apply_clipped")
 
 
 class _CrossFunction(torch.autograd.Function):

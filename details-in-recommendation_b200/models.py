@@ -126,9 +126,9 @@ class DCN(torch.nn.Module):
     cross_layer_num, dnn_dropout, batch_norm, learning rate and clip norm as in DeepCrossNetwork.py:35-49,
     :282-289; MEAN-reduced loss (:209-225).  x0 is the [B, F*K] embedding output (every field embedded
     to K: BASELINE.json's d = 624 convention).
-    The per-tensor clip_by_norm(100) is applied to the dense gradients; the embedding tables' gradient is
-    applied unclipped (its norm is known only after the fused backward has consumed it; with a MEAN-reduced
-    loss it is orders of magnitude below 100).
+    The per-tensor clip_by_norm(100) is applied to every gradient, as the reference does: the dense ones here, each
+    column's table gradient inside the layer (`EmbeddingFM(clip_norm=...)`, a two-pass backward).  The sharded
+    layer applies its table gradients unclipped (a column's norm would need a cross-rank reduction per step).
     """
 
     def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
@@ -139,6 +139,8 @@ class DCN(torch.nn.Module):
         super().__init__()
         d = field_size * embedding_size
         self.learning_rate, self.clip_norm = float(learning_rate), clip_norm
+        if clip_norm and not sharded:
+            layer_kw = dict(layer_kw, clip_norm=clip_norm)      # every column's gradient is clipped too (:284)
         self.embedding = _embedding_layer(sharded, field_size, embedding_size, list(rows_per_field), optimizer=optimizer,
                                           lr=learning_rate, first_order=False, device=device, **layer_kw)
         self.cross = CrossNetwork(d, cross_layer_num, device=device)

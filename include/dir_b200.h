@@ -140,8 +140,37 @@ int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t row_stride, 
                                 const int64_t* field_offset, const float* g_first, const float* g_fm,
                                 const float* S, const float* u, int64_t B, int F, int K,
                                 const int32_t* onerow_fields, int n_onerow, int optimizer, float lr,
-                                const dir_linear_opt* linear_opt, void* workspace, size_t workspace_bytes,
-                                int64_t* n_unique_out, dir_stream_t stream);
+                                const dir_linear_opt* linear_opt, float clip_norm, void* workspace,
+                                size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tf.clip_by_norm on the tables' gradient (models/DeepCrossNetwork/DeepCrossNetwork.py:282-289: every gradient
+ * is clipped to norm 100 before apply_gradients).  The reference holds one variable per column and [TF]
+ * embedding_lookup_sparse de-duplicates ids before the gather, so a column's gradient is an IndexedSlices of its
+ * per-distinct-row sums and the factor clip / max(||values||, clip) is ONE PER COLUMN, known only once all of the
+ * column's sums are: the clipped backward is two passes (used only when a clip norm is set):
+ *   dir_shard_unique (G = 1)          numbers the distinct rows of the sorted list: uidx, unique rows, their count
+ *   dir_embed_bwd_reduce_emit_local   per-distinct-row sums -> gu[u] = (G[K], g1)
+ *   dir_field_sqnorms                 per column: sum of squares of G and of g1 (fixed order, fp64)
+ *   dir_rows_apply_clipped            scale by the column's factor, fused Adagrad / SGD (and linear) update
+ * clip_norm of dir_embed_bwd_onerow_update (0 = none) does the same for one-row fields, whose variable is one row.
+ *   unique_rows [n_capacity] uint32 global rows (ascending), n_unique_dev device int64 their count,
+ *   partials    dir_field_sqnorms_bytes(F) bytes of scratch written by dir_field_sqnorms
+ */
+int dir_embed_bwd_reduce_emit_local(const float* table, int64_t row_stride, const float* feature_value,
+                                    const float* g_first, const float* g_fm, const float* S, const float* u,
+                                    const uint32_t* uidx, int64_t B, int F, int K, int64_t n_rows,
+                                    const int32_t* field_sel, int n_sel, float* gu, int64_t gu_stride,
+                                    void* workspace, size_t workspace_bytes, dir_stream_t stream);
+size_t dir_field_sqnorms_bytes(int F);
+int dir_field_sqnorms(const float* gu, int64_t gu_stride, const uint32_t* unique_rows,
+                      const int64_t* n_unique_dev, const int64_t* field_offset, int F, int K, int64_t n_rows,
+                      double* partials, dir_stream_t stream);
+int dir_rows_apply_clipped(float* table, float* accum, int64_t row_stride, float* lin, float* lin_accum,
+                           int64_t lin_stride, const float* gu, int64_t gu_stride, const uint32_t* unique_rows,
+                           const int64_t* n_unique_dev, int64_t n_capacity, const int64_t* field_offset, int F,
+                           int K, const double* partials, float clip_norm, int optimizer, float lr,
+                           const dir_linear_opt* linear_opt, int64_t* n_unique_out, dir_stream_t stream);
 
 /* Where step 1 left the sorted (row, position) pairs inside its workspace (read-only views). */
 int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_t** sorted_keys,
@@ -164,7 +193,8 @@ int dir_embed_bwd_sorted(const void* workspace, int64_t n_lookups, const uint32_
  *   uidx[i]               index of sorted entry i's key among the distinct keys
  *   unique_local_rows[u]  local row (at its owner) of distinct key u; grouped by owner, ascending
  *   inv[b*F + f]          int64 index of that lookup's row in the exchanged buffer, -1 if pruned: the
- *                         feature_index to hand to dir_embed_fm_fwd (f = field_sel[j] of the sorted entry)
+ *                         feature_index to hand to dir_embed_fm_fwd (f = field_sel[j] of the sorted entry);
+ *                         may be NULL
  *   owner_off[g], g = 0..G   distinct keys owned by ranks < g (owner_off[G] = their total)
  * dir_shard_dense_inv: one-row (numeric) fields are replicated parameters, not exchanged: inv[b, f] =
  *   tail_row + j where the lookup survives (id == 0, value > 0), else -1.

@@ -114,7 +114,7 @@ def dcn_forward(p, field_offset, idx, val):
 
 def dcn_train_step(p, st, field_offset, idx, val, labels, lr, clip_norm=100.0, clip_tables=True):
     """One Adagrad step with per-tensor clip_by_norm (DeepCrossNetwork.py:282-289); in place.
-    clip_tables=False leaves the embedding gradient unclipped (what the CUDA path does, see models.DCN)."""
+    clip_tables=False leaves the embedding gradient unclipped (what the sharded CUDA layer does, see models.DCN)."""
     dt = p["table"].dtype.type
     logits, c = dcn_forward(p, field_offset, idx, val)
     loss, g = sigmoid_ce_grad(logits, labels.astype(dt), "mean")
@@ -128,7 +128,10 @@ def dcn_train_step(p, st, field_offset, idx, val, labels, lr, clip_norm=100.0, c
     zero = np.zeros(idx.shape[0], dtype=dt)
     rows, G, _, _ = O.embedding_backward(p["table"], field_offset, idx, val, zero, zero, u, "sum", dt)
     clip = (lambda t: tfs.clip_by_norm(t, clip_norm)) if clip_norm else (lambda t: t)
-    O.sparse_adagrad(p["table"], st["table"], rows, clip(G) if clip_tables else G, lr)
+    G_unclipped = G
+    if clip_tables and clip_norm:        # one variable per column: each column's IndexedSlices clipped on its own
+        G = tfs.clip_indexed_slices_per_column(rows, G, field_offset, p["table"].shape[0], clip_norm)
+    O.sparse_adagrad(p["table"], st["table"], rows, G, lr)
     dense_adagrad(p["cross_w"], st["cross_w"], clip(dcw), lr)
     dense_adagrad(p["cross_b"], st["cross_b"], clip(dcb), lr)
     for i in range(len(p["W"])):
@@ -136,7 +139,7 @@ def dcn_train_step(p, st, field_offset, idx, val, labels, lr, clip_norm=100.0, c
         dense_adagrad(p["b"][i], st["b"][i], clip(dbs[i]), lr)
     dense_adagrad(p["Wl"], st["Wl"], clip(dWl), lr)
     dense_adagrad(p["bl"], st["bl"], clip(dbl), lr)
-    return dict(loss=loss, logits=logits, rows=rows, G=G)
+    return dict(loss=loss, logits=logits, rows=rows, G=G, G_unclipped=G_unclipped)
 
 
 # ---------------------------------------------------------------------------- parameter sets

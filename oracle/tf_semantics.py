@@ -71,6 +71,21 @@ def clip_by_norm(values, clip_norm):
     return values * (dt(clip_norm) / max(l2, dt(clip_norm)))
 
 
+def clip_indexed_slices_per_column(rows, values, field_offset, n_rows, clip_norm):
+    """clip_by_norm as the reference applies it to the embedding gradients (DeepCrossNetwork.py:282-289): ONE
+    VARIABLE PER COLUMN (deepFM.py:385-390; tf.feature_column.input_layer creates one per embedding_column), and
+    [TF] embedding_lookup_sparse de-duplicates ids before the gather, so column f's gradient is an IndexedSlices
+    whose `values` are the de-duplicated row sums of that column; each is clipped on its own.
+    rows[U] global rows (ascending), values[U, ...] their sums -> the clipped values."""
+    out = values.copy()
+    off = list(field_offset) + [n_rows]
+    for f in range(len(field_offset)):
+        m = (rows >= off[f]) & (rows < off[f + 1])
+        if m.any():
+            out[m] = clip_by_norm(values[m], clip_norm)
+    return out
+
+
 def sigmoid_cross_entropy_with_logits(labels, logits):
     """max(x,0) - x*z + log1p(exp(-|x|))  (TF's stable form)."""
     x, z = logits, labels

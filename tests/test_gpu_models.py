@@ -106,7 +106,11 @@ def test_dcn_logits_and_one_step(pkg, cuda, clip):
 
     p0, st = _copy(p), FM.adagrad_state(p)
     out = FM.dcn_train_step(p, st, case["off"], case["idx"], case["val"], labels.astype(np.float64), lr,
-                            clip_norm=clip, clip_tables=False)
+                            clip_norm=clip, clip_tables=True)
+    if clip < 1.0:      # the clip must actually bind on at least one column's table gradient
+        off = list(case["off"]) + [case["N"]]
+        norms = [np.linalg.norm(out["G_unclipped"][(out["rows"] >= off[f]) & (out["rows"] < off[f + 1])]) for f in range(F)]
+        assert max(norms) > clip, "clip too loose for this test to mean anything"
     opt = model.dense_optimizer()
     loss = model.train_step(opt, idx, val, y)
     torch.cuda.synchronize()

@@ -116,9 +116,19 @@ def test_dcn_step_matches_autograd():
     out = FM.dcn_train_step(p, st, case["off"], case["idx"], case["val"], labels, 0.05, clip_norm=clip)
     assert np.allclose(out["logits"], logits.detach().numpy(), rtol=1e-12, atol=1e-12)
     touched = out["rows"]
-    # IndexedSlices clip: the norm runs over the de-duplicated row gradients = the touched rows of autograd's
+    # IndexedSlices clip, ONE VARIABLE PER COLUMN (deepFM.py:385-390): each column's norm runs over its own
+    # de-duplicated row gradients = the rows of that column in autograd's dense gradient
     want_T = p0["table"].copy()
-    want_T[touched] = _adagrad(p0["table"][touched], clipped(T.grad)[touched], 0.05)
+    tg = T.grad.numpy().copy()
+    off = list(case["off"]) + [case["N"]]
+    bit = 0
+    for f in range(len(case["off"])):
+        seg = tg[off[f]:off[f + 1]]
+        nrm = np.sqrt((seg * seg).sum())
+        bit += nrm > clip
+        tg[off[f]:off[f + 1]] = seg * (clip / max(nrm, clip))
+    assert bit >= 1, "the clip must bind on at least one column"
+    want_T[touched] = _adagrad(p0["table"][touched], tg[touched], 0.05)
     assert np.allclose(p["table"], want_T, rtol=1e-9, atol=1e-12)
     assert np.allclose(p["cross_w"], _adagrad(p0["cross_w"], clipped(cw.grad), 0.05), rtol=1e-9, atol=1e-12)
     assert np.allclose(p["cross_b"], _adagrad(p0["cross_b"], clipped(cb.grad), 0.05), rtol=1e-9, atol=1e-12)
