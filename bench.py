@@ -373,6 +373,9 @@ def run_b200(args):
                 assert [h.parity for h in handles] == [r % 2 for r in range(R)], "parity drifted"
                 if world > 1:
                     dist.barrier()
+            torch.cuda.synchronize()
+            for h_ in handles:                     # a captured stream may not wait for an event recorded outside the
+                h_.event = None                    # capture; everything those events ordered has completed
             cap_stream = torch.cuda.Stream()
             cap_stream.wait_stream(torch.cuda.current_stream())
             layer.capturing = True

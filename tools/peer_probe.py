@@ -70,6 +70,29 @@ def main():
     lib.probe_launch(3, src.data_ptr(), ids.data_ptr(), own.data_ptr(), n, 296, st)
     torch.cuda.synchronize()
     out["bulk_gather_equals_lsu_gather"] = bool(torch.equal(a, own))
+    # PULL: random 64-byte rows read straight from the PEER's table (variant 1 with src = peer memory, dst = own)
+    if world > 1:
+        tbl = symm_mem.empty(n_src * 32, dtype=torch.float32, device=dev)
+        th = symm_mem.rendezvous(tbl, dist.group.WORLD)
+        tbl.copy_(src)
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer_tbl = th.buffer_ptrs[(rank + 1) % world]
+        for name, sp in (("pull local", tbl.data_ptr()), ("pull peer", peer_tbl)):
+            for variant in (1, 3, 0):
+                for ctas in (148 * 4, 148 * 8, 148 * 16):
+                    for _ in range(3):
+                        lib.probe_launch(variant, sp, ids.data_ptr(), own.data_ptr(), n, ctas, st)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(10):
+                        lib.probe_launch(variant, sp, ids.data_ptr(), own.data_ptr(), n, ctas, st)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    us = e0.elapsed_time(e1) * 100.0
+                    out["%s v%d ctas%d" % (name, variant, ctas)] = (round(us, 1), round(n * 64 / us * 1e-3, 1))
     if world > 1:
         dst_t = hdl.get_buffer((rank + 1) % world, (n * 16,), torch.float32)
         torch.cuda.synchronize()
