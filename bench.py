@@ -552,7 +552,11 @@ def run_b200(args):
             cur = cursor[0] % R                      # its id work is pending: run it, then go inline
             first, fm, emb, g, up, _ = model(cur)
             backward(first, fm, emb, g, up)
-            for s_ in range(4):
+            for s_ in range(9):
+                if s_ == 3:                          # the first inline steps allocate their handle: not timed
+                    torch.cuda.synchronize()
+                    layer.trace.report()
+                    layer.trace_pre.report()
                 idx_, val_, y_ = devs[s_ % R]
                 first, fm, emb = layer(idx_, val_)
                 with torch.no_grad():
@@ -631,7 +635,7 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     S = torch.empty((B, K), device=dev)
     first, fm = torch.empty(B, device=dev), torch.empty(B, device=dev)
     keys = torch.empty(B * F, dtype=torch.int32, device=dev)
-    g = torch.randn(B, device=dev) * 0.1
+    g = (ups[0][:, 0] * 10.0).contiguous() if ups[0] is not None else torch.full((B,), 0.1, device=dev)
     ws = torch.empty(int(lib.dir_embed_bwd_workspace_bytes(B * F, K)), dtype=torch.uint8, device=dev)
     peak, src = RL.measured_peaks()
     U = sum(n_unique) / len(n_unique)
