@@ -48,6 +48,9 @@ def parse_args():
     p.add_argument("--no-emit", action="store_true", help="FM only: no embeddings out / upstream in")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--profile", default="",
+                   help="after the timed regions, trace 6 steps with torch.profiler (CUPTI kernel timeline) and "
+                        "write the chrome trace of rank 0 to this path: a diagnostic, never a bench value")
     p.add_argument("--sharded", action="store_true",
                    help="run the row-sharded layer even on one GPU (every exchange kernel, local buffers): a diagnostic")
     p.add_argument("--feed", default="columns", choices=["columns", "resolved"],
@@ -514,6 +517,17 @@ def run_b200(args):
                       "(ring of %d device slots, H2D on a copy stream), logits read back each step" % (
                           type(layer).__name__, type(feeder).__name__, R)}
         torch.cuda.synchronize()
+
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for s in range(6):
+                run()
+            torch.cuda.synchronize()
+        barrier()
+        if rank == 0:
+            prof.export_chrome_trace(args.profile)
 
     # ---------------- roofline: each C-ABI call timed on its own (rank 0's GPU) ---------------
     roof, kernels = None, []
