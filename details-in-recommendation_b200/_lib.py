@@ -67,7 +67,7 @@ SIGNATURES = {
                                     c_void_p]),
     "dir_peer_layout_init": (c_int, [c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
     "dir_shard_ids_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
-    "dir_shard_slots": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "dir_shard_slots": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "dir_shard_gather_send": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                       c_void_p]),
     "dir_embed_bwd_reduce_emit_to": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

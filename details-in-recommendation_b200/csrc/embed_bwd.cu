@@ -182,6 +182,8 @@ struct BwdArgs {
   int64_t emit_seg_cap;
   float* emit_g1;
   int emit_G;
+  int perm_G, perm_rank;  // > 1: warps take the chunks in an owner-interleaved, rank-rotated order (see chunk_of)
+  int64_t perm_M;
   int emit_read_key;  // kModeEmit over the table itself: rows are read at the key, sums still go to row uidx of `emit`
   // entries actually in the sorted list, read on the device (NULL: n).  `n` then only bounds the launch
   // and lays out the workspace, so a step whose sizes are known on the device alone needs no host read.
@@ -289,7 +291,13 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int slot = lane / LPR;
-  const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // Which chunk this warp walks.  When the sums go straight to their owners over NVLink, the sorted list is
+  // owner-major: in chunk order every rank would write to owner 0 first, then owner 1, ... and that owner's NVLink
+  // ingress would serve all ranks at once.  Virtual chunk v -> chunk ((v + rank) mod G) * M + v / G (M = chunks / G
+  // rounded up) interleaves the owners and starts every rank on a different one.  The chunking itself -- and with it
+  // every sum -- is unchanged.
+  int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (a.perm_G > 1) chunk = (int64_t)((chunk + a.perm_rank) % a.perm_G) * a.perm_M + chunk / a.perm_G;
   const int64_t i0 = chunk * kChunk;
   const int64_t n = entries(a);
   if (i0 >= n) return;  // whole warp
@@ -598,7 +606,8 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
 template <int LPR>
 static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) {
   const int64_t nchunks = (a.n + kChunk - 1) / kChunk;
-  const unsigned rgrid = (unsigned)((nchunks + 7) / 8);
+  const int64_t vchunks = a.perm_G > 1 ? a.perm_M * a.perm_G : nchunks;   // virtual chunks (>= nchunks)
+  const unsigned rgrid = (unsigned)((vchunks + 7) / 8);
   if (a.mode == kModeEmit)
     embed_bwd_reduce_kernel<LPR, kModeEmit><<<rgrid, 256, 0, st>>>(a);
   else if (a.mode == kModeGiven)
@@ -975,7 +984,7 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, nullptr, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, nullptr, lo, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -1013,7 +1022,9 @@ static int reduce_emit(const char* what, const float* ubuf, int64_t ubuf_stride,
             gu_stride, nullptr, 0,
             owner_off, layout ? layout->peer_base : nullptr, layout ? layout->off_g : 0,
             layout ? (int64_t)layout->rank * layout->seg_cap : 0, layout ? layout->seg_cap : 0, g1_local,
-            layout ? layout->G : 0, read_key, nullptr, LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
+            layout ? layout->G : 0, layout ? layout->G : 0, layout ? layout->rank : 0,
+            layout ? ((n + kChunk - 1) / kChunk + layout->G - 1) / layout->G : 0, read_key, nullptr,
+            LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, nullptr, nullptr, nullptr};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -1089,7 +1100,7 @@ extern "C" int dir_rows_reduce_update(float* table, float* accum, int64_t row_st
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "rows_reduce_update: workspace too small");
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, nullptr, nullptr, nullptr, nullptr,
             nullptr, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, 1,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, n_device, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeGiven, nullptr, nullptr, 0, gbuf, gbuf_stride, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, n_device, lo, nullptr, nullptr, nullptr};
   set_div(a, 1);
   return dispatch_bwd(a, K, n_unique_out, static_cast<cudaStream_t>(stream));
 }
@@ -1131,7 +1142,7 @@ extern "C" int dir_embed_bag_bwd_reduce_update(
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, bag_weight, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, nnz, F,
             (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), nullptr, 0, kModeBag, nullptr, nullptr, 0, nullptr, 0,
-            nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, nullptr, lo, entry_slot, entry_x, emb};
+            nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, nullptr, lo, entry_slot, entry_x, emb};
   set_div(a, F);
   return dispatch_bwd(a, K, n_unique_out, st);
 }

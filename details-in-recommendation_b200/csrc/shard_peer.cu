@@ -98,8 +98,10 @@ __device__ __forceinline__ void load_arrivals(const dir_peer_layout& L, Arrivals
 
 // owner: slot[row * G + q] = i + 1 for arrival i of requester q (set = 1), or 0 again (set = 0)
 __global__ void __launch_bounds__(256)
-peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t n_local, int set, int* err) {
+peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t n_local, int set, int* err,
+                  int64_t* zero_counter) {
   __shared__ Arrivals s;
+  if (zero_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_counter = 0;
   load_arrivals(L, s);
   const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
   const int64_t total = s.pre[L.G];
@@ -116,11 +118,14 @@ peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t 
   }
 }
 
-// owner: fused gather + send.  LPR lanes carry one row (16 bytes each) into the requester's rows[base_u + i];
-// a thread handles kRows rows a grid-stride apart, loads first, so several lines per thread are in flight
-// before the first NVLink store.  The first-order weights go out from a lane-per-arrival loop (128-byte
-// contiguous stores per warp).  CTA 0 also refreshes the replicated one-row fields' rows behind my own rows.
-constexpr int kRows = 4;
+// owner: fused gather + send.  The arrivals are cut into tiles of 256 consecutive arrivals of one requester
+// (16 KB of contiguous destination rows); a CTA takes tiles t = blockIdx.x, + gridDim.x, ... where tile t belongs to
+// requester (rank + 1 + t) mod G: every destination is being written all the time, and no two ranks start on the
+// same one (processing requester 0's rows first on every rank makes rank 0's NVLink ingress the bottleneck for all
+// of them).  LPR lanes carry one row (16 bytes each); a thread has up to four row loads in flight before its first
+// NVLink store.  The first-order weights of the tile go out lane-per-arrival (128-byte contiguous stores per warp).
+// CTA 0 also refreshes the replicated one-row fields' rows behind this rank's own rows.
+constexpr int kTileArr = 256;
 template <int LPR>
 __global__ void __launch_bounds__(256)
 peer_gather_send_kernel(const dir_peer_layout L, const float* __restrict__ table, int64_t row_stride,
@@ -128,48 +133,54 @@ peer_gather_send_kernel(const dir_peer_layout L, const float* __restrict__ table
                         const float* __restrict__ dense_table, int64_t dense_stride,
                         const float* __restrict__ dense_lin) {
   constexpr int K = LPR * 4;
+  constexpr int UN = LPR < 4 ? LPR : 4;  // row loads in flight per thread
   __shared__ Arrivals s;
   __shared__ char* s_peer[kMaxG];
+  __shared__ int64_t s_tiles;
   if (threadIdx.x < L.G) s_peer[threadIdx.x] = peer_buf(L, threadIdx.x);
   load_arrivals(L, s);
-  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
-  const int64_t total = s.pre[L.G];
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int sub = (int)(t % LPR);
-  const int64_t step = ((int64_t)gridDim.x * blockDim.x) / LPR;
-  for (int64_t a0 = t / LPR; a0 < total; a0 += step * kRows) {
-    int64_t r[kRows], dst[kRows];
-    int q[kRows];
-    float4 v[kRows];
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-      const int64_t a = a0 + k * step;
-      r[k] = -1;
-      if (a < total) {
-        q[k] = seg_of(s.pre, L.G, a);
-        const int64_t i = a - s.pre[q[k]];
-        r[k] = __ldg(ids + (int64_t)q[k] * L.seg_cap + i);
-        dst[k] = s.base[q[k]] + i;
-        if (dst[k] < 0 || dst[k] >= L.u_cap) r[k] = -1;
-      }
+  if (threadIdx.x == 0) {
+    int64_t m = 0;
+    for (int q = 0; q < L.G; ++q) {
+      const int64_t c = (s.pre[q + 1] - s.pre[q] + kTileArr - 1) / kTileArr;
+      m = c > m ? c : m;
     }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k)
-      if (r[k] >= 0) v[k] = __ldg(reinterpret_cast<const float4*>(table + r[k] * row_stride) + sub);
-#pragma unroll
-    for (int k = 0; k < kRows; ++k)
-      if (r[k] >= 0)
-        *(reinterpret_cast<float4*>(s_peer[q[k]] + L.off_rows) + dst[k] * LPR + sub) = v[k];
+    s_tiles = m;
   }
-  if (lin != nullptr) {
-    const int64_t step1 = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t a = t; a < total; a += step1) {
-      const int q = seg_of(s.pre, L.G, a);
-      const int64_t i = a - s.pre[q];
-      const int64_t r = __ldg(ids + (int64_t)q * L.seg_cap + i);
-      const int64_t d = s.base[q] + i;
-      if (d >= 0 && d < L.u_cap) reinterpret_cast<float*>(s_peer[q] + L.off_w)[d] = __ldg(lin + r * lin_stride);
+  __syncthreads();
+  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
+  const int G = L.G;
+  const int64_t T = s_tiles * G;
+  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+    const int q = (int)((L.rank + 1 + t % G) % G);
+    const int64_t i0 = (t / G) * kTileArr;
+    const int64_t cnt = s.pre[q + 1] - s.pre[q];
+    if (i0 >= cnt) continue;
+    const int n = (int)(cnt - i0 < kTileArr ? cnt - i0 : kTileArr);
+    const int32_t* tid_ids = ids + (int64_t)q * L.seg_cap + i0;
+    const int64_t d0 = s.base[q] + i0;  // first destination row of the tile
+    if (d0 < 0 || d0 + n > L.u_cap) continue;
+    float4* drows = reinterpret_cast<float4*>(s_peer[q] + L.off_rows) + d0 * LPR;
+#pragma unroll
+    for (int k0 = 0; k0 < LPR; k0 += UN) {
+      int64_t r[UN];
+      int e[UN];
+      float4 v[UN];
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        e[k] = threadIdx.x + 256 * (k0 + k);  // float4 of the tile: arrival e / LPR, part e % LPR
+        r[k] = e[k] / LPR < n ? (int64_t)__ldg(tid_ids + e[k] / LPR) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < UN; ++k)
+        if (r[k] >= 0) v[k] = __ldg(reinterpret_cast<const float4*>(table + r[k] * row_stride) + e[k] % LPR);
+#pragma unroll
+      for (int k = 0; k < UN; ++k)
+        if (r[k] >= 0) drows[e[k]] = v[k];
     }
+    if (lin != nullptr && (int)threadIdx.x < n)
+      reinterpret_cast<float*>(s_peer[q] + L.off_w)[d0 + threadIdx.x] =
+          __ldg(lin + (int64_t)__ldg(tid_ids + threadIdx.x) * lin_stride);
   }
   if (blockIdx.x == 0 && L.n_dense > 0 && dense_table != nullptr) {
     float* rows = reinterpret_cast<float*>(L.local + L.off_rows) + L.u_cap * K;
@@ -470,11 +481,12 @@ extern "C" int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* 
 }
 
 extern "C" int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
-                               int* err_flag, dir_stream_t stream) {
+                               int* err_flag, int64_t* zero_counter, dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_slots", layout)) return rc;
   if (!slot || !err_flag || n_local_rows <= 0) return fail(DIR_EINVAL, "shard_slots: slot, err_flag, n_local_rows > 0 required");
-  peer_slots_kernel<<<kPeerCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, slot, n_local_rows, set, err_flag);
+  peer_slots_kernel<<<kPeerCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, slot, n_local_rows, set, err_flag,
+                                                                              zero_counter);
   return launched("shard_slots");
 }
 
@@ -531,8 +543,7 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
   LinOpt lo;
   if (int rc = resolve_lin("shard_owner_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n_unique_out) cudaMemsetAsync(n_unique_out, 0, 8, st);
-  unsigned long long* nu = reinterpret_cast<unsigned long long*>(n_unique_out);
+  unsigned long long* nu = reinterpret_cast<unsigned long long*>(n_unique_out);  // += (zeroed by dir_shard_slots)
 #define DIR_OU(LP) \
   peer_owner_update_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, slot, table, accum, row_stride, lin, lin_accum, \
                                                           lin_stride, lo, optimizer, lr, n_local_rows, nu)

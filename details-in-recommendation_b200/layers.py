@@ -446,7 +446,9 @@ class EmbeddingFM(torch.nn.Module):
 
     def aux_stream(self, device):
         if self._aux is None:
-            self._aux = torch.cuda.Stream(device=device)
+            # high priority: its small kernels must get SM slots while the big segmented reduce is running, not
+            # queue behind that kernel's pending CTAs
+            self._aux = torch.cuda.Stream(device=device, priority=-1)
         return self._aux
 
     @torch.no_grad()

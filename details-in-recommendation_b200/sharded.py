@@ -320,9 +320,10 @@ class _ShardedFunction(torch.autograd.Function):
                     px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
                     layer.row_stride, ptr(layer.w1) if layer.first_order else None,
                     ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
-                    _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer), ptr(layer.last_n_unique), st),
-                    "dir_shard_owner_update")
-                check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, 0, ptr(layer.err_flag), st),
+                    _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
+                    layer._n_unique2.data_ptr() + 8 * p, st), "dir_shard_owner_update")
+                layer._last_parity = p
+                check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, 0, ptr(layer.err_flag), None, st),
                       "dir_shard_slots")
                 layer._slots_set[p] = False
                 tr.mark("bwd.owner_update")
@@ -336,7 +337,7 @@ class _ShardedFunction(torch.autograd.Function):
                         ptr(layer.w1_accum) if layer.first_order else None,
                         ptr(layer.lin_z) if (layer.first_order and layer.lin_z is not None) else None,
                         layer.lin_stride, ptr(layer.dense_shard_row),
-                        ptr(layer.last_n_unique) if layer.plan.rank == 0 else None, st), "dir_shard_dense_apply")
+                        layer._n_unique2.data_ptr() + 8 * p if layer.plan.rank == 0 else None, st), "dir_shard_dense_apply")
                     tr.mark("bwd.dense_apply")
             else:
                 U, R = h.U, h.R
@@ -358,10 +359,11 @@ class _ShardedFunction(torch.autograd.Function):
                         ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride,
                         ptr(grecv), pad, R, K, layer.plan.cap, _OPTIMIZERS[layer.optimizer], layer.lr,
                         linear_opt_struct(layer), None,
-                        ptr(ws3), ws3.numel(), ptr(layer.last_n_unique), st), "dir_rows_reduce_update")
+                        ptr(ws3), ws3.numel(), layer._n_unique2.data_ptr(), st), "dir_rows_reduce_update")
                     tr.mark("bwd.owner_update")
                 else:
-                    layer.last_n_unique.zero_()
+                    layer._n_unique2.zero_()
+                layer._last_parity = 0
             tr.close_step()
         if g_bias is None and layer.first_order:
             g_bias = g_first.sum().reshape(1)
@@ -429,7 +431,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.register_buffer("err_flag", torch.zeros(1, dtype=torch.int32, device=dev))
         self.bias = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
-        self.last_n_unique = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._n_unique2 = torch.zeros(2, dtype=torch.int64, device=dev)   # per exchange buffer: rows the owner updated
+        self._last_parity = 0
         self._side = self._aux = None
         self._inline = ShardedLookups()
         self.trace, self.trace_pre = StageTrace(), StageTrace()
@@ -490,6 +493,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
     @property
     def w1_accum(self):
         return self.lin_acc[:, 0] if self.lin_acc is not None else None
+
+    @property
+    def last_n_unique(self):
+        """Local rows the last backward updated on this rank (+ the replicated one-row fields on rank 0)."""
+        return self._n_unique2[self._last_parity:self._last_parity + 1]
 
     @torch.no_grad()
     def init_counter(self, seed=1236, sd=None):
@@ -613,7 +621,9 @@ class ShardedEmbeddingFM(torch.nn.Module):
 
     def aux_stream(self, device):
         if self._aux is None:
-            self._aux = torch.cuda.Stream(device=device)
+            # high priority: its small kernels must get SM slots while the big segmented reduce is running, not
+            # queue behind that kernel's pending CTAs (profiles/r02_timeline_n2.txt)
+            self._aux = torch.cuda.Stream(device=device, priority=-1)
         return self._aux
 
     def _note_forward(self):
@@ -690,15 +700,15 @@ class ShardedEmbeddingFM(torch.nn.Module):
             if self._fwd_event is not None and not self.capturing:
                 torch.cuda.current_stream().wait_event(self._fwd_event)     # every rank is done with parity p
             if self._slots_set[p]:      # a presorted batch was never run: take its marks back before re-using ids[p]
-                check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag), st),
+                check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag), None, st),
                       "dir_shard_slots")
             check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), B * self.n_sel,
                                        ptr(self.err_flag), st), "dir_shard_ids_push")
             tr.mark("pre.ids_push")
             px.barrier(p, 1)
             tr.mark("pre.barrier")
-            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 1, ptr(self.err_flag), st),
-                  "dir_shard_slots")
+            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 1, ptr(self.err_flag),
+                                    self._n_unique2.data_ptr() + 8 * p, st), "dir_shard_slots")
             self._slots_set[p] = True
             tr.mark("pre.slots")
             return
@@ -769,7 +779,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
             # no backward will come: release the owner's marks of this batch
             p = presorted.parity
             check(_lib.lib().dir_shard_slots(self.px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag),
-                                             _stream()), "dir_shard_slots")
+                                             None, _stream()), "dir_shard_slots")
             self._slots_set[p] = False
         if self.check_bounds:
             if int(self.oob_flag.item()) != 0:

@@ -292,8 +292,10 @@ int dir_peer_layout_init(int G, int rank, int K, int n_dense, int64_t seg_cap, i
                          dir_peer_layout* out);
 int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_local_rows,
                        const int64_t* owner_off, int64_t n_capacity, int* err_flag, dir_stream_t stream);
+/* zero_counter (device int64, may be NULL) is set to 0: the counter dir_shard_owner_update / dir_shard_dense_apply
+ * of the same step then add the rows they update to (no memset node between the step's kernels) */
 int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
-                    int* err_flag, dir_stream_t stream);
+                    int* err_flag, int64_t* zero_counter, dir_stream_t stream);
 /* dense_table / dense_lin: the replicated one-row fields' rows [n_dense] (copied behind this rank's own
  * exchanged rows so that dir_embed_fm_fwd finds them at u_cap + j); NULL when n_dense == 0 */
 int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
@@ -318,10 +320,11 @@ int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table
                          const int64_t* dense_field_offset, const float* g_first, const float* g_fm,
                          const float* S, const float* u, const int32_t* onerow_fields, int64_t B, int F,
                          void* workspace, size_t workspace_bytes, dir_stream_t stream);
+/* n_unique_inout += local rows updated */
 int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                            int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
                            int64_t n_local_rows, int optimizer, float lr, const dir_linear_opt* linear_opt,
-                           int64_t* n_unique_out, dir_stream_t stream);
+                           int64_t* n_unique_inout, dir_stream_t stream);
 /* shard_row[j] >= 0 names the row of the sharded table that mirrors replica j (on the rank that owns it), so
  * the sharded table stays a faithful view; n_unique_inout += fields touched (pass it on one rank only) */
 int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
