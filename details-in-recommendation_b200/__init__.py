@@ -8,8 +8,10 @@ from . import _lib, roofline, synth                          # noqa: F401
 from ._lib import LIB_PATH, build, launch_count             # noqa: F401
 from .bags import EmbeddingBagFM                              # noqa: F401
 from .feeder import ColumnFeeder, HostFeeder                              # noqa: F401
+from . import frontend                                         # noqa: F401
+from .frontend import FeatureFrontEnd                          # noqa: F401
 from .layers import CrossNetwork, EmbeddingFM, InputLayer, SortedLookups # noqa: F401
 from .models import DCN, DeepFM                               # noqa: F401
 from .sharded import ShardedEmbeddingFM, ShardedLookups, ShardPlan  # noqa: F401
 
-__all__ = ["DeepFM", "DCN", "EmbeddingFM", "EmbeddingBagFM", "InputLayer", "CrossNetwork", "ShardedEmbeddingFM", "ShardPlan", "HostFeeder", "ColumnFeeder", "synth", "roofline", "build", "launch_count", "LIB_PATH"]
+__all__ = ["DeepFM", "DCN", "EmbeddingFM", "EmbeddingBagFM", "InputLayer", "CrossNetwork", "ShardedEmbeddingFM", "ShardPlan", "HostFeeder", "ColumnFeeder", "FeatureFrontEnd", "frontend", "synth", "roofline", "build", "launch_count", "LIB_PATH"]

@@ -99,6 +99,12 @@ SIGNATURES = {
                                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p, c_int64, c_int, c_int, c_int64, c_int, c_float, c_void_p,
                                                 c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dir_fingerprint64_host": (c_uint64, [c_void_p, c_int64]),
+    "dir_fingerprint64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dir_hash_bucket": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "dir_vocabulary_lookup": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                      c_int64, c_void_p]),
+    "dir_bucketize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "dir_expand_features": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p]),
     "dir_input_layer_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

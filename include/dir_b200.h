@@ -396,6 +396,32 @@ int dir_expand_features(const void* sparse_index, int index_bytes, const float* 
                         int64_t* feature_index, float* feature_value, dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Front end: raw feature -> index, the step in front of the lookup.  The reference declares its categorical columns
+ * with tf.feature_column.categorical_column_with_hash_bucket / _with_vocabulary_list
+ * (models/DeepCrossNetwork/train.py:57-100, models/ESMM/train.py:65-90) and accepts bucketized_column
+ * (models/DeepCrossNetwork/DeepCrossNetwork.py:58); TensorFlow resolves them per batch on the host.  Here a decoded
+ * batch's strings travel as ONE byte buffer + offsets[n+1] (string i = bytes[offsets[i] .. offsets[i+1])) and are
+ * resolved on the device, one thread per value, straight into a column of feature_index (out_stride = F):
+ *   dir_hash_bucket         [TF] string_to_hash_bucket_fast: Fingerprint64(s) mod hash_bucket_size, Fingerprint64 =
+ *                           FarmHash farmhashna::Hash64 (published algorithm); integer features are hashed through
+ *                           their decimal string, as TF does
+ *   dir_vocabulary_lookup   index of s in the vocabulary list, default_value (-1: pruned by the lookup) when absent;
+ *                           the table is (sorted fingerprints, list index of each) built on the host with
+ *                           dir_fingerprint64_host
+ *   dir_bucketize           [TF] Bucketize: number of boundaries <= value (boundaries ascending)
+ *   dir_fingerprint64       the raw 64-bit fingerprints (as int64 bits)
+ */
+uint64_t dir_fingerprint64_host(const uint8_t* bytes_host, int64_t len);
+int dir_fingerprint64(const uint8_t* bytes, const int64_t* offsets, int64_t n, int64_t* out, dir_stream_t stream);
+int dir_hash_bucket(const uint8_t* bytes, const int64_t* offsets, int64_t n, int64_t num_buckets, int64_t* out,
+                    int64_t out_stride, dir_stream_t stream);
+int dir_vocabulary_lookup(const uint8_t* bytes, const int64_t* offsets, int64_t n,
+                          const uint64_t* vocab_fingerprints, const int64_t* vocab_index, int64_t n_vocab,
+                          int64_t default_value, int64_t* out, int64_t out_stride, dir_stream_t stream);
+int dir_bucketize(const float* values, int64_t n, int64_t value_stride, const float* boundaries, int n_boundaries,
+                  int64_t* out, int64_t out_stride, dir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * tf.feature_column.input_layer in the reference's own DCN convention
  * (models/DeepCrossNetwork/DeepCrossNetwork.py:126 over the columns of train.py:88-100): all dense
  * columns side by side, sorted by column name -- numeric columns 1-wide, indicator columns one-hot,
