@@ -25,7 +25,9 @@
 //
 // The owner never sorts: a requester sends each row at most once, so slot[row][q] (one cell per local row and
 // requester, written without atomics) tells an arrival whether an earlier rank asked for the same row; the first
-// one merges.  Deterministic: no floating-point atomics, sums in rank order.
+// one merges.  Deterministic: no floating-point atomics, sums in rank order.  A cell is (epoch << 24) | (i + 1) and
+// counts only while its epoch is the buffer's current one, so nothing has to be cleared after a step; the epoch
+// (1..255, advanced on the device by the id push) wraps once per 255 uses, when the whole map is zeroed.
 //
 // Reference: the partitioner hook around the embedding variables, models/DeepFM/deepFM.py:163-175 (under a TF
 // parameter-server cluster the variables are sharded by row and ids / IndexedSlices travel over gRPC).
@@ -49,9 +51,15 @@ __device__ __forceinline__ int seg_of(const int64_t* s, int G, int64_t i) {  // 
 // requester: header + distinct local rows to every owner
 __global__ void __launch_bounds__(256)
 peer_ids_push_kernel(const dir_peer_layout L, const int32_t* __restrict__ ulocal,
-                     const int64_t* __restrict__ owner_off, int64_t n_cap, int* err) {
+                     const int64_t* __restrict__ owner_off, int64_t n_cap, int* err, uint32_t* epoch) {
   __shared__ int64_t s_off[kMaxG + 1];
   if (threadIdx.x <= L.G) s_off[threadIdx.x] = owner_off[threadIdx.x];
+  if (epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    // this buffer's slot map enters a new epoch: epoch[0] = current (1..255), epoch[1] = "zero the map first"
+    const uint32_t e = epoch[0];
+    epoch[1] = e >= 255u ? 1u : 0u;
+    epoch[0] = e >= 255u ? 1u : e + 1u;
+  }
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x < L.G) {
     const int o = threadIdx.x;
@@ -96,13 +104,23 @@ __device__ __forceinline__ void load_arrivals(const dir_peer_layout& L, Arrivals
   __syncthreads();
 }
 
-// owner: slot[row * G + q] = i + 1 for arrival i of requester q (set = 1), or 0 again (set = 0)
+// owner: the slot map is zeroed when its epoch wraps (epoch[1] set by the id push): a launch that exits at once
+// 254 times out of 255
 __global__ void __launch_bounds__(256)
-peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t n_local, int set, int* err,
-                  int64_t* zero_counter) {
+peer_slots_reset_kernel(uint32_t* __restrict__ slot, int64_t n_cells, const uint32_t* __restrict__ epoch) {
+  if (epoch[1] == 0u) return;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += step) slot[i] = 0u;
+}
+
+// owner: slot[row * G + q] = (epoch << 24) | (i + 1) for arrival i of requester q
+__global__ void __launch_bounds__(256)
+peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t n_local, int* err,
+                  int64_t* zero_counter, const uint32_t* __restrict__ epoch) {
   __shared__ Arrivals s;
   if (zero_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_counter = 0;
   load_arrivals(L, s);
+  const uint32_t tag = epoch[0] << 24;
   const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
   const int64_t total = s.pre[L.G];
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -114,7 +132,7 @@ peer_slots_kernel(const dir_peer_layout L, uint32_t* __restrict__ slot, int64_t 
       *err = 2;
       continue;
     }
-    slot[r * L.G + q] = set ? (uint32_t)(i + 1) : 0u;
+    slot[r * L.G + q] = tag | (uint32_t)(i + 1);
   }
 }
 
@@ -218,9 +236,11 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ slot, float* table, float* accum,
                          int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
-                         int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
+                         int opt, float lr, int64_t n_local, unsigned long long* n_unique,
+                         const uint32_t* __restrict__ epoch) {
   constexpr int SLOTS = 32 / LPR;
   constexpr int PB = LPR <= 4 ? 2 : 1;
+  const uint32_t tag = epoch[0];  // a cell counts only while it carries the current epoch
   constexpr unsigned FULL = 0xffffffffu;
   __shared__ Arrivals s;
   load_arrivals(L, s);
@@ -249,13 +269,22 @@ peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ s
       r = __ldg(ids + e);
       if (r >= 0 && r < n_local) {
         const uint32_t* sl = slot + r * G;
-        unsigned earlier = 0;
-        for (int p = 0; p < G; ++p) {
-          const uint32_t sp = __ldg(sl + p);
-          if (p < q) earlier |= sp;
-          if (p > q && sp != 0u) more |= 1ull << p;
+        bool earlier = false;
+        uint32_t sv[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) sv[p] = p < G ? __ldg(sl + p) : 0u;  // independent loads, one sector
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const bool on = (sv[p] >> 24) == tag;
+          earlier |= on && p < q;
+          if (on && p > q) more |= 1ull << p;
         }
-        lead = earlier == 0u;  // else an earlier rank merges this row
+        for (int p = 8; p < G; ++p) {
+          const bool on = (__ldg(sl + p) >> 24) == tag;
+          earlier |= on && p < q;
+          if (on && p > q) more |= 1ull << p;
+        }
+        lead = !earlier;  // else an earlier rank merges this row
       }
     }
     const unsigned lm = __ballot_sync(FULL, lead);
@@ -297,7 +326,7 @@ peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ s
         while (m) {  // rank order
           const int p = __ffsll((long long)m) - 1;
           m &= m - 1;
-          const uint32_t sp = __ldg(slot + rr[j] * G + p);
+          const uint32_t sp = __ldg(slot + rr[j] * G + p) & 0xffffffu;
           const int64_t e2 = (int64_t)p * L.seg_cap + (sp - 1u);
           const float4 o = __ldg(gbuf + e2 * LPR + sub);
           g[j].x = __fadd_rn(g[j].x, o.x);
@@ -468,7 +497,7 @@ extern "C" int dir_shard_dense_inv(const int64_t* feature_index, const float* fe
 
 extern "C" int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_local_rows,
                                   const int64_t* owner_off, int64_t n_capacity, int* err_flag,
-                                  dir_stream_t stream) {
+                                  uint32_t* slot_epoch, dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_ids_push", layout)) return rc;
   if (!owner_off || !err_flag || n_capacity < 0 || (n_capacity > 0 && !unique_local_rows))
@@ -476,18 +505,21 @@ extern "C" int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* 
   const int64_t want = (n_capacity + 255) / 256;
   const unsigned grid = (unsigned)(want < 1 ? 1 : (want < kPeerCtas ? want : kPeerCtas));
   peer_ids_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, unique_local_rows, owner_off,
-                                                                           n_capacity, err_flag);
+                                                                           n_capacity, err_flag, slot_epoch);
   return launched("shard_ids_push");
 }
 
-extern "C" int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
-                               int* err_flag, int64_t* zero_counter, dir_stream_t stream) {
+extern "C" int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows,
+                               const uint32_t* slot_epoch, int* err_flag, int64_t* zero_counter, dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_slots", layout)) return rc;
-  if (!slot || !err_flag || n_local_rows <= 0) return fail(DIR_EINVAL, "shard_slots: slot, err_flag, n_local_rows > 0 required");
-  peer_slots_kernel<<<kPeerCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(*layout, slot, n_local_rows, set, err_flag,
-                                                                              zero_counter);
-  return launched("shard_slots");
+  if (!slot || !err_flag || !slot_epoch || n_local_rows <= 0)
+    return fail(DIR_EINVAL, "shard_slots: slot, slot_epoch, err_flag, n_local_rows > 0 required");
+  if (layout->seg_cap >= (1 << 24)) return fail(DIR_EINVAL, "shard_slots: seg_cap must be < 2^24");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  peer_slots_reset_kernel<<<kPeerCtas, 256, 0, st>>>(slot, n_local_rows * layout->G, slot_epoch);
+  peer_slots_kernel<<<kPeerCtas, 256, 0, st>>>(*layout, slot, n_local_rows, err_flag, zero_counter, slot_epoch);
+  return launched("shard_slots", 2);
 }
 
 extern "C" int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
@@ -529,14 +561,15 @@ extern "C" int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_
 
 extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                                       int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
-                                      int64_t n_local_rows, int optimizer, float lr,
+                                      int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
                                       const dir_linear_opt* linear_opt, int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_owner_update", layout)) return rc;
   const int K = layout->K;
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
     return fail(DIR_EINVAL, "shard_owner_update: unknown optimizer");
-  if (!slot || !table || n_local_rows <= 0) return fail(DIR_EINVAL, "shard_owner_update: slot, table, n_local_rows > 0 required");
+  if (!slot || !slot_epoch || !table || n_local_rows <= 0)
+    return fail(DIR_EINVAL, "shard_owner_update: slot, slot_epoch, table, n_local_rows > 0 required");
   if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "shard_owner_update: Adagrad needs accum");
   if (row_stride < K || (row_stride & 3) || !aligned16(table) || !aligned16(accum))
     return fail(DIR_EINVAL, "shard_owner_update: rows must be 16-byte aligned, row_stride >= K and a multiple of 4");
@@ -546,7 +579,7 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
   unsigned long long* nu = reinterpret_cast<unsigned long long*>(n_unique_out);  // += (zeroed by dir_shard_slots)
 #define DIR_OU(LP) \
   peer_owner_update_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, slot, table, accum, row_stride, lin, lin_accum, \
-                                                          lin_stride, lo, optimizer, lr, n_local_rows, nu)
+                                                          lin_stride, lo, optimizer, lr, n_local_rows, nu, slot_epoch)
   switch (K / 4) {
     case 1: DIR_OU(1); break;
     case 2: DIR_OU(2); break;

@@ -320,12 +320,9 @@ class _ShardedFunction(torch.autograd.Function):
                     px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
                     layer.row_stride, ptr(layer.w1) if layer.first_order else None,
                     ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
-                    _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
+                    ptr(layer.slot_epoch[p]), _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
                     layer._n_unique2.data_ptr() + 8 * p, st), "dir_shard_owner_update")
                 layer._last_parity = p
-                check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, 0, ptr(layer.err_flag), None, st),
-                      "dir_shard_slots")
-                layer._slots_set[p] = False
                 tr.mark("bwd.owner_update")
                 if layer.n_dense:
                     check(L.dir_shard_dense_apply(
@@ -379,7 +376,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
     replicated parameter: all-reduce its gradient like any dense parameter.
 
     `max_batch` sizes the exchange buffers (peer flavour).  `presort` may run at most one batch ahead
-    of `forward`; every presorted batch must be run.
+    of `forward`.
     """
 
     def __init__(self, field_size: int, embedding_size: int, rows_per_field: Sequence[int],
@@ -451,8 +448,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.n_dense, self.n_sel = len(onerow), len(sparse)
         self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
         self.register_buffer("sparse_fields", torch.tensor(sparse or [0], dtype=torch.int32, device=dev))
-        self.px, self.slot = None, None
-        self._slots_set = [False, False]
+        self.px, self.slot, self.slot_epoch = None, None, None
         self._ids_issued = self._fwd_issued = 0
         self._fwd_event = None
         # the id exchange of the NEXT batch runs concurrently with this batch's row / gradient exchange: the NCCL
@@ -462,7 +458,11 @@ class ShardedEmbeddingFM(torch.nn.Module):
             seg_cap = max(1, min(self.max_batch * max(self.n_sel, 1), cap))   # rows one requester can ask of one owner
             u_cap = max(1, self.max_batch * max(self.n_sel, 1))               # distinct rows a requester can ask for
             self.px = PeerExchange(process_group, world, rank, K, self.n_dense, seg_cap, u_cap, dev)
+            if seg_cap >= 1 << 24:
+                raise ValueError("max_batch * sparse fields must stay below 2^24 rows per requester and owner")
+            # who asked for which of my rows: one cell per (local row, requester), tagged with the buffer's epoch
             self.slot = [torch.zeros(cap * world, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.slot_epoch = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(2)]
         elif dist.is_initialized() and dist.get_backend(process_group) == "nccl":
             self.side_group = dist.new_group(ranks=dist.get_process_group_ranks(process_group or dist.group.WORLD))
         with torch.no_grad():
@@ -699,17 +699,14 @@ class ShardedEmbeddingFM(torch.nn.Module):
             p, px = h.parity, self.px
             if self._fwd_event is not None and not self.capturing:
                 torch.cuda.current_stream().wait_event(self._fwd_event)     # every rank is done with parity p
-            if self._slots_set[p]:      # a presorted batch was never run: take its marks back before re-using ids[p]
-                check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag), None, st),
-                      "dir_shard_slots")
             check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), B * self.n_sel,
-                                       ptr(self.err_flag), st), "dir_shard_ids_push")
+                                       ptr(self.err_flag), ptr(self.slot_epoch[p]), st), "dir_shard_ids_push")
             tr.mark("pre.ids_push")
             px.barrier(p, 1)
             tr.mark("pre.barrier")
-            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, 1, ptr(self.err_flag),
-                                    self._n_unique2.data_ptr() + 8 * p, st), "dir_shard_slots")
-            self._slots_set[p] = True
+            # the owner marks who asked for which row (cells carry this use's epoch: nothing is cleared afterwards)
+            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, ptr(self.slot_epoch[p]),
+                                    ptr(self.err_flag), self._n_unique2.data_ptr() + 8 * p, st), "dir_shard_slots")
             tr.mark("pre.slots")
             return
         send_counts = h.owner_off[1:] - h.owner_off[:-1]
@@ -775,12 +772,6 @@ class ShardedEmbeddingFM(torch.nn.Module):
             raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
         self._last_handle = presorted
         first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
-        if self.px is not None and not train:
-            # no backward will come: release the owner's marks of this batch
-            p = presorted.parity
-            check(_lib.lib().dir_shard_slots(self.px.ref(p), ptr(self.slot[p]), self.n_rows, 0, ptr(self.err_flag),
-                                             None, _stream()), "dir_shard_slots")
-            self._slots_set[p] = False
         if self.check_bounds:
             if int(self.oob_flag.item()) != 0:
                 self.oob_flag.zero_()

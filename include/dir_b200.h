@@ -253,7 +253,7 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
  *   requester q                                         owner o
  *   dir_shard_ids_push     hdr[q] = (count, base_u), ids[q][0..count)  -->  o's buffer
  *   ---- barrier ----
- *                                                       dir_shard_slots(set)    slot[row * G + q] = i + 1
+ *                                                       dir_shard_slots         slot[row * G + q] = epoch | i + 1
  *                                                       dir_shard_gather_send   T[row] -> q's rows[base_u + i],
  *                                                                               w[row] -> q's w[base_u + i]
  *   ---- barrier ----
@@ -264,11 +264,10 @@ int dir_rows_reduce_update(float* table, float* accum, int64_t row_stride, float
  *   ---- barrier ----
  *                                                       dir_shard_owner_update  ranks' sums added in rank
  *                                                         order (slot tells who else asked), fused update
- *                                                       dir_shard_slots(clear)
  *   dir_shard_dense_apply  (every rank)
  *
- * slot: uint32 [n_local_rows * G], zero before the first step (the owner never sorts: a requester sends a
- * row at most once, so a cell is written by one thread).  err_flag (device int, zero-initialised): 1 = a
+ * slot: uint32 [n_local_rows * G] per exchange buffer, zero before the first step (the owner never sorts: a
+ * requester sends a row at most once, so a cell is written by one thread).  err_flag (device int, zero-initialised): 1 = a
  * requester had more distinct rows than seg_cap / u_cap, 2 = a received local row is out of range; nothing is
  * written out of bounds in either case, the host layer raises.
  */
@@ -290,12 +289,16 @@ typedef struct dir_peer_layout {
 } dir_peer_layout;
 int dir_peer_layout_init(int G, int rank, int K, int n_dense, int64_t seg_cap, int64_t u_cap,
                          dir_peer_layout* out);
+/* slot_epoch: device uint32[2] per exchange buffer, {0, 0} before the first step.  A slot cell is
+ * (epoch << 24) | (i + 1) and counts only while its epoch is the current one, so the map is never cleared after a
+ * step; dir_shard_ids_push advances the epoch (1..255), dir_shard_slots zeroes the whole map when it wraps. */
 int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_local_rows,
-                       const int64_t* owner_off, int64_t n_capacity, int* err_flag, dir_stream_t stream);
+                       const int64_t* owner_off, int64_t n_capacity, int* err_flag, uint32_t* slot_epoch,
+                       dir_stream_t stream);
 /* zero_counter (device int64, may be NULL) is set to 0: the counter dir_shard_owner_update / dir_shard_dense_apply
  * of the same step then add the rows they update to (no memset node between the step's kernels) */
-int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows, int set,
-                    int* err_flag, int64_t* zero_counter, dir_stream_t stream);
+int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows,
+                    const uint32_t* slot_epoch, int* err_flag, int64_t* zero_counter, dir_stream_t stream);
 /* dense_table / dense_lin: the replicated one-row fields' rows [n_dense] (copied behind this rank's own
  * exchanged rows so that dir_embed_fm_fwd finds them at u_cap + j); NULL when n_dense == 0 */
 int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
@@ -323,8 +326,8 @@ int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table
 /* n_unique_inout += local rows updated */
 int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                            int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
-                           int64_t n_local_rows, int optimizer, float lr, const dir_linear_opt* linear_opt,
-                           int64_t* n_unique_inout, dir_stream_t stream);
+                           int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
+                           const dir_linear_opt* linear_opt, int64_t* n_unique_inout, dir_stream_t stream);
 /* shard_row[j] >= 0 names the row of the sharded table that mirrors replica j (on the rank that owns it), so
  * the sharded table stays a faithful view; n_unique_inout += fields touched (pass it on one rank only) */
 int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,

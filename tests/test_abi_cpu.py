@@ -112,11 +112,11 @@ def test_argument_validation_of_the_widened_entry_points(pkg):
     assert lib.dir_peer_layout_init(2, 0, 12, 0, 10, 10, ctypes.byref(lay)) == -22 and b"K must be" in lib.dir_last_error()
     assert lib.dir_peer_layout_init(2, 0, 16, 2, 10, 10, ctypes.byref(lay)) == 0            # peer_base / local still NULL
     ref = ctypes.byref(lay)
-    assert lib.dir_shard_ids_push(ref, P, P, 4, P, None) == -22 and b"peer_base" in lib.dir_last_error()
-    assert lib.dir_shard_slots(ref, P, 10, 1, P, None, None) == -22
+    assert lib.dir_shard_ids_push(ref, P, P, 4, P, P, None) == -22 and b"peer_base" in lib.dir_last_error()
+    assert lib.dir_shard_slots(ref, P, 10, P, P, None, None) == -22
     assert lib.dir_shard_gather_send(ref, P, 32, None, 1, P, 32, None, None) == -22
     assert lib.dir_shard_g1_push(ref, P, P, 4, None) == -22
-    assert lib.dir_shard_owner_update(ref, P, P, P, 32, None, None, 1, 10, 1, 0.05, None, None, None) == -22
+    assert lib.dir_shard_owner_update(ref, P, P, P, 32, None, None, 1, 10, P, 1, 0.05, None, None, None) == -22
     assert lib.dir_shard_dense_apply(ref, P, P, 32, None, None, 1, 0.05, None, P, P, 32, None, None, None, 1, P, None,
                                      None) == -22
     assert lib.dir_shard_dense_emit(ref, P, 32, P, None, P, None, P, P, None, P, 4, 3, P, 1 << 20, None) == -22
