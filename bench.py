@@ -683,13 +683,13 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
             check(lib.dir_embed_bwd_onerow_update(
                 ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
                 layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
-                ptr(ups[r]) if emit else None, B, F, K, ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, None, 0.0,
+                ptr(ups[r]) if emit else None, B, F, K, ptr(layer.onerow_fields), layer.n_onerow_fields, 1, LR, None, None, 0.0,
                 ptr(ows), ows.numel(), nu[1:].data_ptr(), aux.cuda_stream), "onerow")
         check(lib.dir_embed_bwd_reduce_update(
             ptr(layer.table), ptr(layer.accum), layer.row_stride, ptr(layer.w1), ptr(layer.w1_accum),
             layer.lin_stride, ptr(devs[r][0]), ptr(devs[r][1]), ptr(layer.field_offset), ptr(g), ptr(g), ptr(S),
             ptr(ups[r]) if emit else None, B, F, K, layer.n_rows, ptr(layer.sorted_fields), n_sel,
-            None, 0, 1, LR, None, ptr(ws), ws.numel(), nu.data_ptr(), st), "update")
+            None, 0, 1, LR, None, None, ptr(ws), ws.numel(), nu.data_ptr(), st), "update")
         if layer.n_onerow_fields:
             cur.wait_stream(aux)
 

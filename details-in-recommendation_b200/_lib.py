@@ -11,12 +11,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdir_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-OPT_SGD, OPT_ADAGRAD, OPT_FTRL = 0, 1, 2
+OPT_SGD, OPT_ADAGRAD, OPT_FTRL, OPT_PROXIMAL_ADAGRAD = 0, 1, 2, 3
 
 
 class LinearOpt(ctypes.Structure):
     """struct dir_linear_opt (include/dir_b200.h): the linear scope's own optimizer."""
     _fields_ = [("optimizer", c_int), ("lr", c_float), ("l1", c_float), ("l2", c_float), ("z", c_void_p)]
+
+
+class TableOpt(ctypes.Structure):
+    """struct dir_table_opt (include/dir_b200.h): l1 / l2 of a ProximalAdagrad table optimizer."""
+    _fields_ = [("l1", c_float), ("l2", c_float)]
 
 
 class PeerLayout(ctypes.Structure):
@@ -43,10 +48,10 @@ SIGNATURES = {
     "dir_embed_bwd_reduce_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
-                                            c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                            c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_onerow_update": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                            c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_float,
+                                            c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_float,
                                             c_void_p, c_size_t, c_void_p, c_void_p]),
     "dir_embed_bwd_reduce_emit_local": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,

@@ -193,6 +193,7 @@ struct BwdArgs {
   const uint32_t* entry_slot;  // [nnz] slot b*F+f of entry j
   const float* entry_x;        // [nnz] effective scale w_j / norm(bag)
   const float* emb;            // [B*F, K] combined embeddings e_s saved by the forward
+  float l1, l2;                // ProximalAdagrad strengths of the table rows
 };
 
 __device__ __forceinline__ int64_t entries(const BwdArgs& a) {
@@ -233,7 +234,8 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int
     emit_store<LPR>(a, key, sub, G, g1);
     return;
   }
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const bool adagrad = a.opt != DIR_OPT_SGD;  // the rule keeps an accumulator
+  const RowRule rr{a.opt, a.lr, a.l1, a.l2};
   float4* trow = reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub;
   float4 T = *trow;
   float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,10 +244,10 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int
     arow = reinterpret_cast<float4*>(a.accum + (int64_t)key * a.row_stride) + sub;
     A = *arow;
   }
-  T.x = upd(T.x, G.x, a.lr, A.x, adagrad);
-  T.y = upd(T.y, G.y, a.lr, A.y, adagrad);
-  T.z = upd(T.z, G.z, a.lr, A.z, adagrad);
-  T.w = upd(T.w, G.w, a.lr, A.w, adagrad);
+  T.x = upd_rule(T.x, G.x, A.x, rr);
+  T.y = upd_rule(T.y, G.y, A.y, rr);
+  T.z = upd_rule(T.z, G.z, A.z, rr);
+  T.w = upd_rule(T.w, G.w, A.w, rr);
   *trow = T;
   if (adagrad) *arow = A;
   if (a.lin != nullptr && sub == 0) {
@@ -259,11 +261,12 @@ __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int
 // Row update from values already in registers (same arithmetic as apply_update).
 __device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int sub, float4 T,
                                              float4 A, float4 G, float w, float a1, float z1, float g1) {
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
-  T.x = upd(T.x, G.x, a.lr, A.x, adagrad);
-  T.y = upd(T.y, G.y, a.lr, A.y, adagrad);
-  T.z = upd(T.z, G.z, a.lr, A.z, adagrad);
-  T.w = upd(T.w, G.w, a.lr, A.w, adagrad);
+  const bool adagrad = a.opt != DIR_OPT_SGD;
+  const RowRule rr{a.opt, a.lr, a.l1, a.l2};
+  T.x = upd_rule(T.x, G.x, A.x, rr);
+  T.y = upd_rule(T.y, G.y, A.y, rr);
+  T.z = upd_rule(T.z, G.z, A.z, rr);
+  T.w = upd_rule(T.w, G.w, A.w, rr);
   *(reinterpret_cast<float4*>(a.table + (int64_t)key * a.row_stride) + sub) = T;
   if (adagrad) *(reinterpret_cast<float4*>(a.accum + (int64_t)key * a.row_stride) + sub) = A;
   if (a.lin != nullptr && sub == 0) {
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs 
   const int64_t chunk_end = min(n, i0 + (int64_t)kChunk);
   const uint32_t prev_key = i0 > 0 ? __ldg(a.keys + i0 - 1) : kNoKey;
   const uint32_t next_chunk_key = chunk_end < n ? __ldg(a.keys + chunk_end) : kNoKey;
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const bool adagrad = a.opt != DIR_OPT_SGD;
   // L2 policies.  A 64-byte gradient / row gather pulls a whole 128-byte line from HBM (measured,
   // tools/gather_probe.cu); the other half of a `u` line belongs to the neighbouring field of the
   // same sample and is wanted later by some other warp, so `u` lines are asked to stay (evict_last)
@@ -659,6 +662,7 @@ struct OneRowArgs {
   unsigned long long* n_unique;
   LinOpt lo;
   float clip;    // > 0: tf.clip_by_norm of the field's gradient (its variable has this one row) before the update
+  float l1, l2;  // ProximalAdagrad strengths of the table rows
 };
 
 template <int LPR, int P>
@@ -805,7 +809,8 @@ __global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneR
     }
     __syncthreads();
   }
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const bool adagrad = a.opt != DIR_OPT_SGD;
+  const RowRule rr{a.opt, a.lr, a.l1, a.l2};
   const int64_t row = a.field_offset[a.fields[j]];
   if (threadIdx.x < K) {
     float* tp = a.table + row * a.row_stride + threadIdx.x;
@@ -815,7 +820,7 @@ __global__ void __launch_bounds__(256) embed_bwd_onerow_finish_kernel(const OneR
       ap = a.accum + row * a.row_stride + threadIdx.x;
       acc = *ap;
     }
-    *tp = upd(*tp, tot[threadIdx.x], a.lr, acc, adagrad);
+    *tp = upd_rule(*tp, tot[threadIdx.x], acc, rr);
     if (adagrad) *ap = acc;
   } else if (threadIdx.x == K) {
     if (a.lin != nullptr) {
@@ -926,17 +931,19 @@ extern "C" int dir_embed_bwd_reduce_update(
     const int64_t* feature_index, const float* feature_value, const int64_t* field_offset,
     const float* g_first, const float* g_fm, const float* S, const float* u, int64_t B, int F, int K,
     int64_t n_rows, const int32_t* field_sel, int n_sel, const int32_t* onerow_fields, int n_onerow,
-    int optimizer, float lr, const dir_linear_opt* linear_opt, void* workspace, size_t workspace_bytes,
-    int64_t* n_unique_out, dir_stream_t stream) {
+    int optimizer, float lr, const dir_table_opt* table_opt, const dir_linear_opt* linear_opt, void* workspace,
+    size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (B < 0 || F <= 0) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B >= 0, F > 0 required");
   if (B * F >= 0x7fffffffLL) return fail(DIR_EINVAL, "embed_bwd_reduce_update: B*F must be < 2^31");
-  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD && optimizer != DIR_OPT_PROXIMAL_ADAGRAD)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: unknown optimizer");
   if (!table || !g_fm || !S || !workspace)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: table, g_fm, S, workspace are required");
-  if (optimizer == DIR_OPT_ADAGRAD && !accum)
+  if (optimizer != DIR_OPT_SGD && !accum)
     return fail(DIR_EINVAL, "embed_bwd_reduce_update: Adagrad needs accum");
+  const float tl1 = table_opt ? table_opt->l1 : 0.f, tl2 = table_opt ? table_opt->l2 : 0.f;
+  if (tl1 < 0.f || tl2 < 0.f) return fail(DIR_EINVAL, "embed_bwd_reduce_update: l1, l2 must be >= 0");
   LinOpt lo;
   if (int rc = resolve_lin("embed_bwd_reduce_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   if (lin && !g_first) return fail(DIR_EINVAL, "embed_bwd_reduce_update: lin needs g_first");
@@ -964,7 +971,7 @@ extern "C" int dir_embed_bwd_reduce_update(
     cudaMemsetAsync(w.onerow_flags, 0, kOneRowMax * 4, st);
     OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value,
                  field_offset, g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.onerow_part,
-                 w.onerow_flags, w.n_unique, lo};
+                 w.onerow_flags, w.n_unique, lo, 0.f, tl1, tl2};
     int rc;
     switch (K) {
       case 4: rc = launch_onerow<1>(o, n_onerow, st); break;
@@ -984,7 +991,7 @@ extern "C" int dir_embed_bwd_reduce_update(
   }
   BwdArgs a{table, accum, row_stride, lin, lin_accum, lin_stride, feature_value, g_first, g_fm, S,
             u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, n, F,
-            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, nullptr, lo, nullptr, nullptr, nullptr};
+            (uint32_t)n_rows, optimizer, lr, 0u, 0, tune(), field_sel, n_sel, kModeLocal, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, nullptr, lo, nullptr, nullptr, nullptr, tl1, tl2};
   set_div(a, n_sel);
   return dispatch_bwd(a, K, n_unique_out, st);
 }
@@ -1285,14 +1292,16 @@ extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t r
                                            const float* feature_value, const int64_t* field_offset,
                                            const float* g_first, const float* g_fm, const float* S, const float* u,
                                            int64_t B, int F, int K, const int32_t* onerow_fields, int n_onerow,
-                                           int optimizer, float lr, const dir_linear_opt* linear_opt, float clip_norm,
-                                           void* workspace, size_t workspace_bytes, int64_t* n_unique_out,
-                                           dir_stream_t stream) {
+                                           int optimizer, float lr, const dir_table_opt* table_opt,
+                                           const dir_linear_opt* linear_opt, float clip_norm, void* workspace,
+                                           size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream) {
   using namespace dir;
   if (B < 0 || F <= 0 || n_onerow < 0 || n_onerow > kOneRowMax || clip_norm < 0.f)
     return fail(DIR_EINVAL, "embed_bwd_onerow_update: B >= 0, F > 0, 0 <= n_onerow <= 64, clip_norm >= 0 required");
-  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD && optimizer != DIR_OPT_PROXIMAL_ADAGRAD)
     return fail(DIR_EINVAL, "embed_bwd_onerow_update: unknown optimizer");
+  const float tl1 = table_opt ? table_opt->l1 : 0.f, tl2 = table_opt ? table_opt->l2 : 0.f;
+  if (tl1 < 0.f || tl2 < 0.f) return fail(DIR_EINVAL, "embed_bwd_onerow_update: l1, l2 must be >= 0");
   if (K != 4 && K != 8 && K != 16 && K != 32 && K != 64)
     return fail(DIR_EINVAL, "embed_bwd_onerow_update: K must be one of 4, 8, 16, 32, 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1300,7 +1309,7 @@ extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t r
   if (B == 0 || n_onerow == 0) return 0;
   if (!table || !g_fm || !S || !workspace || !onerow_fields || !field_offset)
     return fail(DIR_EINVAL, "embed_bwd_onerow_update: table, g_fm, S, workspace, onerow_fields, field_offset are required");
-  if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "embed_bwd_onerow_update: Adagrad needs accum");
+  if (optimizer != DIR_OPT_SGD && !accum) return fail(DIR_EINVAL, "embed_bwd_onerow_update: Adagrad needs accum");
   LinOpt lo;
   if (int rc = resolve_lin("embed_bwd_onerow_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   if (lin && !g_first) return fail(DIR_EINVAL, "embed_bwd_onerow_update: lin needs g_first");
@@ -1312,7 +1321,7 @@ extern "C" int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t r
   cudaMemsetAsync(w.flags, 0, kOneRowMax * 4, st);
   OneRowArgs o{table, accum, row_stride, lin, lin_accum, lin_stride, feature_index, feature_value, field_offset,
                g_first, g_fm, S, u, onerow_fields, B, F, optimizer, lr, w.part, w.flags,
-               reinterpret_cast<unsigned long long*>(n_unique_out), lo, clip_norm};
+               reinterpret_cast<unsigned long long*>(n_unique_out), lo, clip_norm, tl1, tl2};
   switch (K) {
     case 4: return launch_onerow<1>(o, n_onerow, st);
     case 8: return launch_onerow<2>(o, n_onerow, st);

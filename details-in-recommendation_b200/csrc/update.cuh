@@ -27,6 +27,28 @@ __device__ __forceinline__ float upd(float t, float g, float lr, float& a, bool 
   return __fsub_rn(t, __fmul_rn(lr, g));
 }
 
+// [TF] SparseApplyProximalAdagrad (tf.train.ProximalAdagradOptimizer, the reference's dnn_optimizer in
+// models/ESMM/train.py:137-139), accumulator starting at 0.1:
+//   a += g^2;  eta = lr * rsqrt(a);  p = t - g * eta
+//   t = sign(p) * max(|p| - eta * l1, 0) / (1 + l2 * eta)        (l1 = 0: t = p / (1 + l2 * eta))
+__device__ __forceinline__ float upd_prox(float t, float g, float lr, float& a, float l1, float l2) {
+  a = __fadd_rn(a, __fmul_rn(g, g));
+  const float eta = __fmul_rn(lr, rsqrtf(a));
+  const float p = __fsub_rn(t, __fmul_rn(g, eta));
+  const float den = __fadd_rn(1.f, __fmul_rn(l2, eta));
+  if (l1 > 0.f) return __fdiv_rn(copysignf(fmaxf(__fsub_rn(fabsf(p), __fmul_rn(eta, l1)), 0.f), p), den);
+  return __fdiv_rn(p, den);
+}
+// the rule of a table row: SGD / Adagrad (upd) or ProximalAdagrad
+struct RowRule {
+  int opt;
+  float lr, l1, l2;
+};
+__device__ __forceinline__ float upd_rule(float t, float g, float& a, const RowRule& r) {
+  if (r.opt == DIR_OPT_PROXIMAL_ADAGRAD) return upd_prox(t, g, r.lr, a, r.l1, r.l2);
+  return upd(t, g, r.lr, a, r.opt == DIR_OPT_ADAGRAD);
+}
+
 // One first-order weight with its de-duplicated gradient g.  Ftrl is [TF] SparseApplyFtrl with
 // learning_rate_power = -0.5 and no l2 shrinkage (tf.train.FtrlOptimizer defaults):
 //   n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma*w
@@ -44,6 +66,11 @@ __device__ __forceinline__ void lin_apply(const LinOpt& o, float* wp, float* np,
     *zp = z;
     return;
   }
+  if (o.opt == DIR_OPT_PROXIMAL_ADAGRAD) {
+    *wp = upd_prox(w, g, o.lr, n, o.l1, o.l2);
+    *np = n;
+    return;
+  }
   const bool adagrad = o.opt == DIR_OPT_ADAGRAD;
   *wp = upd(w, g, o.lr, n, adagrad);
   if (adagrad) *np = n;
@@ -59,11 +86,14 @@ inline int resolve_lin(const char* what, const dir_linear_opt* in, int optimizer
                        const float* lin_accum, LinOpt& out) {
   out = LinOpt{optimizer, lr, 0.f, 0.f, nullptr};
   if (in != nullptr) out = LinOpt{in->optimizer, in->lr, in->l1, in->l2, in->z};
-  if (out.opt != DIR_OPT_SGD && out.opt != DIR_OPT_ADAGRAD && out.opt != DIR_OPT_FTRL)
+  if (out.opt != DIR_OPT_SGD && out.opt != DIR_OPT_ADAGRAD && out.opt != DIR_OPT_FTRL &&
+      out.opt != DIR_OPT_PROXIMAL_ADAGRAD)
     return fail(DIR_EINVAL, "%s: unknown linear optimizer", what);
   if (lin != nullptr) {
     if (out.opt != DIR_OPT_SGD && !lin_accum)
-      return fail(DIR_EINVAL, "%s: Adagrad / Ftrl on the linear weights need lin_accum", what);
+      return fail(DIR_EINVAL, "%s: Adagrad / ProximalAdagrad / Ftrl on the linear weights need lin_accum", what);
+    if (out.opt == DIR_OPT_PROXIMAL_ADAGRAD && (out.l1 < 0.f || out.l2 < 0.f))
+      return fail(DIR_EINVAL, "%s: l1, l2 must be >= 0", what);
     if (out.opt == DIR_OPT_FTRL && (!out.z || !(out.lr > 0.f) || out.l1 < 0.f || out.l2 < 0.f))
       return fail(DIR_EINVAL, "%s: Ftrl needs z, lr > 0 and l1, l2 >= 0", what);
   }

@@ -23,13 +23,24 @@ from ._lib import check, ptr
 
 _COMBINERS = ("sum", "mean", "sqrtn")
 _OPTIMIZERS = {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD}
-_LINEAR_OPTIMIZERS = dict(_OPTIMIZERS, ftrl=_lib.OPT_FTRL)
+_TABLE_OPTIMIZERS = dict(_OPTIMIZERS, proximal_adagrad=_lib.OPT_PROXIMAL_ADAGRAD)       # single-GPU layer
+_LINEAR_OPTIMIZERS = dict(_TABLE_OPTIMIZERS, ftrl=_lib.OPT_FTRL)
 _K_OK = (4, 8, 16, 32, 64)
+
+
+def table_opt_struct(layer):
+    """dir_table_opt: l1 / l2 of a ProximalAdagrad table optimizer (None otherwise)."""
+    if getattr(layer, "optimizer", None) != "proximal_adagrad":
+        return None
+    return _lib.ctypes.byref(_lib.TableOpt(layer.optimizer_l1, layer.optimizer_l2))
 
 
 def linear_opt_struct(layer):
     """The dir_linear_opt the C ABI takes (None: the linear weights follow the tables' optimizer)."""
     if layer.linear_optimizer is None:
+        if getattr(layer, "optimizer", None) == "proximal_adagrad":      # same rule, same strengths as the tables
+            return _lib.ctypes.byref(_lib.LinearOpt(_lib.OPT_PROXIMAL_ADAGRAD, layer.lr, layer.optimizer_l1,
+                                                    layer.optimizer_l2, None))
         return None
     z = layer.lin_z.data_ptr() if layer.lin_z is not None else None
     return _lib.ctypes.byref(_lib.LinearOpt(_LINEAR_OPTIMIZERS[layer.linear_optimizer], layer.linear_lr,
@@ -49,8 +60,8 @@ def resolve_linear_optimizer(optimizer, lr, linear_optimizer, linear_lr, l1, l2)
     elif linear_lr is not None:
         linear_optimizer = optimizer
     eff = linear_optimizer or optimizer
-    return (linear_optimizer, float(lr if linear_lr is None else linear_lr), eff in ("adagrad", "ftrl"),
-            eff == "ftrl")
+    return (linear_optimizer, float(lr if linear_lr is None else linear_lr),
+            eff in ("adagrad", "ftrl", "proximal_adagrad"), eff == "ftrl")
 
 
 def _stream():
@@ -114,7 +125,12 @@ class _EmbeddingFMFunction(torch.autograd.Function):
             # the forward kernel and whatever the model does before this layer's backward.
             handle = presorted
             if handle is None:
-                handle = layer.presort(idx, val, handle=layer._inline_sort)
+                # the layer's own handle serves one forward at a time: a second forward before the first one's
+                # backward (two towers sharing the layer) gets a handle of its own
+                mine = layer._inline_sort if not layer._inline_busy else SortedLookups()
+                handle = layer.presort(idx, val, handle=mine)
+                if mine is layer._inline_sort:
+                    layer._inline_busy = True
         check(L.dir_embed_fm_fwd(
             ptr(layer.table), layer.row_stride, ptr(lin), layer.lin_stride,
             ptr(bias) if layer.first_order else None, ptr(idx), ptr(val), ptr(layer.field_offset),
@@ -165,6 +181,8 @@ class _EmbeddingFMFunction(torch.autograd.Function):
             else:
                 layer.apply_sorted_gradients_clipped(ctx.handle, idx, val, g_first, g_fm, S, u, B)
         main.wait_stream(aux)
+        if ctx.handle is layer._inline_sort:
+            layer._inline_busy = False
         return None, g_bias, None, None, None, None, None
 
 
@@ -194,8 +212,12 @@ class EmbeddingFM(torch.nn.Module):
                  check_bounds: bool = False, lin_interleaved: Optional[bool] = None,
                  linear_optimizer: Optional[str] = None, linear_lr: Optional[float] = None,
                  l1_regularization_strength: float = 0.0, l2_regularization_strength: float = 0.0,
-                 clip_norm: Optional[float] = None, device="cuda"):
+                 clip_norm: Optional[float] = None, optimizer_l1: float = 0.0, optimizer_l2: float = 0.0,
+                 device="cuda"):
         super().__init__()
+        if optimizer_l1 < 0 or optimizer_l2 < 0:
+            raise ValueError("optimizer_l1 / optimizer_l2 must be >= 0")
+        self.optimizer_l1, self.optimizer_l2 = float(optimizer_l1), float(optimizer_l2)
         if clip_norm is not None and not clip_norm > 0:
             raise ValueError("clip_norm must be > 0 (or None)")
         self.clip_norm = None if clip_norm is None else float(clip_norm)
@@ -206,8 +228,10 @@ class EmbeddingFM(torch.nn.Module):
         if embedding_size not in _K_OK:
             raise ValueError("embedding_size must be one of %r" % (_K_OK,))
         optimizer = optimizer.lower()
-        if optimizer not in _OPTIMIZERS:
-            raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        if optimizer not in _TABLE_OPTIMIZERS:
+            raise ValueError("optimizer must be 'adagrad', 'sgd' or 'proximal_adagrad'")
+        if optimizer == "proximal_adagrad" and self.clip_norm is not None:
+            raise ValueError("clip_norm is not available with proximal_adagrad")
         self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
         self.linear_optimizer, self.linear_lr, lin_needs_acc, lin_needs_z = resolve_linear_optimizer(
             optimizer, lr, linear_optimizer, linear_lr, self.l1, self.l2)
@@ -231,11 +255,11 @@ class EmbeddingFM(torch.nn.Module):
         self.combiner, self.first_order = combiner, first_order
         self.emit_embeddings, self.check_bounds = emit_embeddings, check_bounds
         K = embedding_size
-        adagrad = optimizer == "adagrad"
+        adagrad = optimizer != "sgd"                     # the rule keeps an accumulator next to the row
         self.row_stride = 2 * K if adagrad else K
         if self.linear_optimizer is not None:
             lin_interleaved = False                 # the interleaved (w, accumulator) pair is the one-optimizer layout
-        self.lin_stride = 2 if (adagrad and lin_interleaved) else 1
+        self.lin_stride = 2 if (optimizer == "adagrad" and lin_interleaved) else 1
         dev = torch.device(device)
         self.register_buffer("field_offset", torch.tensor(offsets, dtype=torch.int64, device=dev))
         self.register_buffer("field_rows", None if rows is None else
@@ -243,7 +267,7 @@ class EmbeddingFM(torch.nn.Module):
         self.register_buffer("rows", torch.empty((n_rows, self.row_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_rows", torch.zeros((n_rows, self.lin_stride), dtype=torch.float32, device=dev))
         self.register_buffer("lin_acc", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)
-                             if (lin_needs_acc and not (adagrad and lin_interleaved)) else None)
+                             if (lin_needs_acc and not (optimizer == "adagrad" and lin_interleaved)) else None)
         self.register_buffer("lin_z", torch.zeros((n_rows, 1), dtype=torch.float32, device=dev)    # Ftrl 'linear' slot
                              if lin_needs_z else None)
         self.register_buffer("oob_flag", torch.zeros(1, dtype=torch.int32, device=dev))
@@ -263,7 +287,7 @@ class EmbeddingFM(torch.nn.Module):
         self._ws, self._onerow_ws = _Workspace(), _Workspace()
         self._side = self._aux = None
         self._clip_bufs = None
-        self._inline_sort = SortedLookups()
+        self._inline_sort, self._inline_busy = SortedLookups(), False
         with torch.no_grad():
             # [TF] embedding_column initializer: truncated_normal(0, 1/sqrt(K)); linear weights zero
             torch.nn.init.trunc_normal_(self.table, 0.0, 1.0 / math.sqrt(K), -2.0 / math.sqrt(K), 2.0 / math.sqrt(K))
@@ -284,7 +308,7 @@ class EmbeddingFM(torch.nn.Module):
 
     @property
     def accum(self):
-        return self.rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+        return self.rows[:, self.embedding_size:] if self.optimizer != "sgd" else None
 
     @property
     def w1(self):
@@ -458,14 +482,15 @@ class EmbeddingFM(torch.nn.Module):
         F, K = self.field_size, self.embedding_size
         L = _lib.lib()
         ws = handle.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), S.device)
-        adagrad = self.optimizer == "adagrad"
+        adagrad = self.optimizer != "sgd"
         check(L.dir_embed_bwd_reduce_update(
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
             ptr(self.w1) if self.first_order else None,
             ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
             ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
             ptr(u), B, F, K, self.n_rows, ptr(self.sorted_fields), self.n_sorted_fields,
-            None, 0, _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self), ptr(ws), ws.numel(),
+            None, 0, _TABLE_OPTIMIZERS[self.optimizer], self.lr, table_opt_struct(self), linear_opt_struct(self),
+            ptr(ws), ws.numel(),
             ptr(self._nu_sorted), _stream()), "dir_embed_bwd_reduce_update")
 
     @torch.no_grad()
@@ -478,14 +503,14 @@ class EmbeddingFM(torch.nn.Module):
             self._nu_onerow.zero_()
             return
         ows = self._onerow_ws.get(L.dir_shard_dense_workspace_bytes(K), S.device)
-        adagrad = self.optimizer == "adagrad"
+        adagrad = self.optimizer != "sgd"
         check(L.dir_embed_bwd_onerow_update(
             ptr(self.table), ptr(self.accum) if adagrad else None, self.row_stride,
             ptr(self.w1) if self.first_order else None,
             ptr(self.w1_accum) if self.first_order else None, self.lin_stride,
             ptr(feature_index), ptr(feature_value), ptr(self.field_offset), ptr(g_first), ptr(g_fm), ptr(S),
-            ptr(u), B, F, K, ptr(self.onerow_fields), self.n_onerow_fields, _OPTIMIZERS[self.optimizer], self.lr,
-            linear_opt_struct(self), self.clip_norm or 0.0, ptr(ows), ows.numel(), ptr(self._nu_onerow), _stream()),
+            ptr(u), B, F, K, ptr(self.onerow_fields), self.n_onerow_fields, _TABLE_OPTIMIZERS[self.optimizer], self.lr,
+            table_opt_struct(self), linear_opt_struct(self), self.clip_norm or 0.0, ptr(ows), ows.numel(), ptr(self._nu_onerow), _stream()),
             "dir_embed_bwd_onerow_update")
 
     @torch.no_grad()

@@ -28,8 +28,9 @@ class _Tower(torch.nn.Module):
     hidden layer, optional dropout and batch normalisation, optional activation-free final layer."""
 
     def __init__(self, d_in, hidden_units, final_units, activation, dropout, batch_norm, bn_momentum,
-                 bn_on_last, init, device):
+                 bn_on_last, init, device, bn_before_dropout=False):
         super().__init__()
+        self.bn_before_dropout = bn_before_dropout
         sizes = [d_in] + [int(h) for h in hidden_units]
         self.hidden = torch.nn.ModuleList(torch.nn.Linear(a, b, device=device) for a, b in zip(sizes[:-1], sizes[1:]))
         n = len(self.hidden)
@@ -47,9 +48,12 @@ class _Tower(torch.nn.Module):
     def forward(self, x):
         for lin, bn in zip(self.hidden, self.bn):
             x = self.activation(lin(x))
+            if self.bn_before_dropout:            # DCN: dense(act) -> batch norm -> dropout (DeepCrossNetwork.py:397-408)
+                x = bn(x)
             if self.dropout is not None and self.training:
                 x = torch.nn.functional.dropout(x, self.dropout, True)
-            x = bn(x)
+            if not self.bn_before_dropout:        # DeepFM: dense(act) -> dropout -> batch norm (deepFM.py:297-306)
+                x = bn(x)
         return self.final(x) if self.final is not None else x
 
 
@@ -145,7 +149,7 @@ class DCN(torch.nn.Module):
                                           lr=learning_rate, first_order=False, device=device, **layer_kw)
         self.cross = CrossNetwork(d, cross_layer_num, device=device)
         self.deep = _Tower(d, hidden_units, 0, dnn_activation_fn, dnn_dropout, batch_norm, 0.999, False,
-                           torch.nn.init.xavier_normal_, device)                                # glorot_normal (:393)
+                           torch.nn.init.xavier_normal_, device, bn_before_dropout=True)        # glorot_normal (:393)
         self.logits = torch.nn.Linear(d + self.deep.out_features, 1, device=device)             # :137
         torch.nn.init.xavier_uniform_(self.logits.weight)      # tf.layers.dense default kernel init
         torch.nn.init.zeros_(self.logits.bias)

@@ -362,6 +362,10 @@ class _ShardedFunction(torch.autograd.Function):
                     layer._n_unique2.zero_()
                 layer._last_parity = 0
             tr.close_step()
+        if h is layer._inline:
+            layer._inline_busy = False
+        if layer.px is not None:
+            layer._in_flight[h.parity] = False
         if g_bias is None and layer.first_order:
             g_bias = g_first.sum().reshape(1)
         return None, g_bias, None, None, None, None, None
@@ -431,7 +435,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self._n_unique2 = torch.zeros(2, dtype=torch.int64, device=dev)   # per exchange buffer: rows the owner updated
         self._last_parity = 0
         self._side = self._aux = None
-        self._inline = ShardedLookups()
+        self._inline, self._inline_busy = ShardedLookups(), False
+        self._in_flight = [False, False]
         self.trace, self.trace_pre = StageTrace(), StageTrace()
         self.capturing = False
         self.exchange_mode = os.environ.get("DIR_B200_EXCHANGE", "peer")
@@ -767,9 +772,19 @@ class ShardedEmbeddingFM(torch.nn.Module):
         idx, val = self._prepare(feature_index, feature_value)
         train = self.training and torch.is_grad_enabled()
         if presorted is None:
-            presorted = self.presort(feature_index, feature_value, handle=self._inline, inline=True)
+            # the layer's own handle serves one forward at a time (a second forward before the first one's backward
+            # gets a handle of its own)
+            mine = self._inline if not self._inline_busy else ShardedLookups()
+            presorted = self.presort(feature_index, feature_value, handle=mine, inline=True)
+            if mine is self._inline and train:
+                self._inline_busy = True
         elif presorted.src != ShardedLookups.key_of(feature_index, feature_value):
             raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
+        if self.px is not None and train:
+            if self._in_flight[presorted.parity] and not self.capturing:
+                raise RuntimeError("ShardedEmbeddingFM: two exchange buffers = at most two batches between forward and "
+                                   "backward; run the backward of an earlier batch first")
+            self._in_flight[presorted.parity] = True
         self._last_handle = presorted
         first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
         if self.check_bounds:

@@ -39,6 +39,9 @@ extern "C" {
 #define DIR_OPT_ADAGRAD 1 /* acc[r] += g*g; T[r] -= lr*g/sqrt(acc[r])  (deepFM.py:61 'Adagrad')    */
 
 #define DIR_OPT_FTRL 2    /* linear weights only: [TF] SparseApplyFtrl (deepFM.py:58 'Ftrl')         */
+#define DIR_OPT_PROXIMAL_ADAGRAD 3 /* [TF] SparseApplyProximalAdagrad (models/ESMM/train.py:137-139):
+                                      a += g*g; eta = lr/sqrt(a); p = T - g*eta;
+                                      T = sign(p) * max(|p| - eta*l1, 0) / (1 + l2*eta); single-GPU layer only */
 
 typedef void* dir_stream_t; /* cudaStream_t */
 
@@ -50,10 +53,15 @@ typedef void* dir_stream_t; /* cudaStream_t */
  *     n' = n + g^2;  sigma = (sqrt(n') - sqrt(n)) / lr;  z += g - sigma * w
  *     w  = |z| > l1 ? (sign(z) * l1 - z) / (sqrt(n') / lr + 2 * l2) : 0
  * n is `lin_accum` (initial_accumulator_value 0.1), z the 'linear' slot (zeros). */
+/* l1 / l2 of a ProximalAdagrad TABLE optimizer (HOST struct; NULL = 0, 0) */
+typedef struct dir_table_opt {
+  float l1, l2;
+} dir_table_opt;
+
 typedef struct dir_linear_opt {
-  int optimizer; /* DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_FTRL */
+  int optimizer; /* DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_FTRL | DIR_OPT_PROXIMAL_ADAGRAD */
   float lr;
-  float l1, l2;  /* Ftrl l1 / l2_regularization_strength */
+  float l1, l2;  /* Ftrl / ProximalAdagrad l1 / l2_regularization_strength */
   float* z;      /* DEVICE: Ftrl 'linear' slot, lin_stride floats apart like lin (NULL otherwise) */
 } dir_linear_opt;
 
@@ -114,6 +122,7 @@ int dir_embed_fm_fwd(const float* table, int64_t row_stride, const float* lin, i
  *   feature_value).  Every sample hits the same row, so these are left out of the sort and reduced
  *   as a column sum over the batch (fixed order); they need feature_index / field_offset.
  *   accum / lin_accum: accumulators with the same strides as table / lin (NULL for SGD).
+ *   optimizer: DIR_OPT_SGD | DIR_OPT_ADAGRAD | DIR_OPT_PROXIMAL_ADAGRAD (table_opt: its l1 / l2, NULL = 0).
  *   linear_opt (host, may be NULL): the linear scope's own optimizer, see dir_linear_opt.
  *   lin == NULL skips the first-order update.  u == NULL means no upstream embedding gradient.
  *   n_unique_out (device int64, may be NULL) receives the number of distinct rows updated.
@@ -127,7 +136,7 @@ int dir_embed_bwd_reduce_update(float* table, float* accum, int64_t row_stride, 
                                 const float* g_first, const float* g_fm, const float* S,
                                 const float* u, int64_t B, int F, int K, int64_t n_rows,
                                 const int32_t* field_sel, int n_sel, const int32_t* onerow_fields,
-                                int n_onerow, int optimizer, float lr,
+                                int n_onerow, int optimizer, float lr, const dir_table_opt* table_opt,
                                 const dir_linear_opt* linear_opt, void* workspace,
                                 size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
@@ -140,7 +149,8 @@ int dir_embed_bwd_onerow_update(float* table, float* accum, int64_t row_stride, 
                                 const int64_t* field_offset, const float* g_first, const float* g_fm,
                                 const float* S, const float* u, int64_t B, int F, int K,
                                 const int32_t* onerow_fields, int n_onerow, int optimizer, float lr,
-                                const dir_linear_opt* linear_opt, float clip_norm, void* workspace,
+                                const dir_table_opt* table_opt, const dir_linear_opt* linear_opt,
+                                float clip_norm, void* workspace,
                                 size_t workspace_bytes, int64_t* n_unique_out, dir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -191,6 +191,22 @@ def sparse_ftrl(var, accum, linear, rows, grad, lr, l1=0.0, l2=0.0):
     linear[rows] = z
 
 
+def sparse_proximal_adagrad(var, accum, rows, grad, lr, l1=0.0, l2=0.0):
+    """[TF] SparseApplyProximalAdagrad behind tf.train.ProximalAdagradOptimizer(learning_rate, initial_accumulator_value
+    = 0.1, l1, l2) -- the reference's dnn_optimizer in models/ESMM/train.py:137-139 -- on de-duplicated rows, in place:
+        a += g^2;  eta = lr / sqrt(a);  p = v - g * eta
+        v = sign(p) * max(|p| - eta * l1, 0) / (1 + l2 * eta)          (l1 = 0: v = p / (1 + l2 * eta))"""
+    dt = var.dtype.type
+    accum[rows] = accum[rows] + grad * grad
+    eta = dt(lr) / np.sqrt(accum[rows])
+    p = var[rows] - grad * eta
+    den = dt(1.0) + dt(l2) * eta
+    if l1 > 0:
+        var[rows] = np.sign(p) * np.maximum(np.abs(p) - eta * dt(l1), dt(0.0)) / den
+    else:
+        var[rows] = p / den
+
+
 def sparse_sgd(var, rows, grad, lr):
     """[TF] ScatterSub of the de-duplicated IndexedSlices: var[r] -= lr*g."""
     var[rows] = var[rows] - var.dtype.type(lr) * grad

@@ -90,11 +90,11 @@ def test_argument_validation_of_the_widened_entry_points(pkg):
     # the linear scope's optimizer: Ftrl without its z slot, an unknown optimizer code
     bad = _lib.LinearOpt(_lib.OPT_FTRL, 0.2, 0.0, 0.0, None)
     rc = lib.dir_embed_bwd_reduce_update(P, P, 32, P, P, 1, P, None, P, P, P, P, None, 4, 2, 16, 10, None, 0, None, 0,
-                                         1, 0.05, ctypes.byref(bad), P, 1 << 20, None, None)
+                                         1, 0.05, None, ctypes.byref(bad), P, 1 << 20, None, None)
     assert rc == -22 and b"Ftrl needs z" in lib.dir_last_error()
     bad = _lib.LinearOpt(9, 0.2, 0.0, 0.0, None)
     rc = lib.dir_embed_bwd_reduce_update(P, P, 32, P, P, 1, P, None, P, P, P, P, None, 4, 2, 16, 10, None, 0, None, 0,
-                                         1, 0.05, ctypes.byref(bad), P, 1 << 20, None, None)
+                                         1, 0.05, None, ctypes.byref(bad), P, 1 << 20, None, None)
     assert rc == -22 and b"unknown linear optimizer" in lib.dir_last_error()
     # input layer, column feed
     assert lib.dir_input_layer_fwd(None, 0, None, 0, P, 8, P, P, P, 4, 0, P, None) == -22

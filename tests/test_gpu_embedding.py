@@ -242,3 +242,39 @@ def test_presort_ahead_of_forward(pkg, cuda):
     loss.backward()
     torch.cuda.synchronize()
     assert torch.equal(layer.rows, ref.rows) and torch.equal(layer.lin_rows, ref.lin_rows)
+
+
+def test_two_forwards_before_the_first_backward(pkg, cuda):
+    """Two towers sharing the layer: forward(A), forward(B), backward(B), backward(A) without presorted handles.  Each
+    forward must keep a sorted list of its own (round-1 advisor finding: the second forward used to overwrite the
+    first one's).  A and B touch disjoint rows, so the result must equal running A and B one after the other."""
+    rows, K, B = [64, 1, 200], 8, 40
+    rng = np.random.default_rng(3)
+    N = sum(rows)
+    table = (rng.standard_normal((N, K)) * 0.3).astype(np.float32)
+    w1 = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    idxA = np.stack([rng.integers(0, 32, B), np.zeros(B, np.int64), rng.integers(0, 100, B)], 1).astype(np.int64)
+    idxB = np.stack([rng.integers(32, 64, B), np.zeros(B, np.int64), rng.integers(100, 200, B)], 1).astype(np.int64)
+    val = np.ones((B, 3), np.float32)
+    val[:, 1] = 0.0                                     # the shared one-row field is pruned: A and B stay disjoint
+
+    def run(interleaved):
+        layer = pkg.EmbeddingFM(3, K, rows, optimizer="adagrad", lr=0.05).train()
+        layer.load_tables(table, w1)
+        a, b = torch.as_tensor(idxA).cuda(), torch.as_tensor(idxB).cuda()
+        v = torch.as_tensor(val).cuda()
+        if interleaved:
+            fa = layer(a, v)
+            fb = layer(b, v)
+            (fb[0].sum() + fb[1].sum() + fb[2].sum()).backward()
+            (fa[0].sum() + fa[1].sum() + fa[2].sum()).backward()
+        else:
+            for x in (a, b):
+                f = layer(x, v)
+                (f[0].sum() + f[1].sum() + f[2].sum()).backward()
+        torch.cuda.synchronize()
+        return layer.rows.clone(), layer.lin_rows.clone()
+
+    r1, l1 = run(True)
+    r2, l2 = run(False)
+    assert torch.equal(r1, r2) and torch.equal(l1, l2)

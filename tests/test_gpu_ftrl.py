@@ -86,3 +86,38 @@ def test_linear_optimizer_arguments(pkg, cuda):
     assert float(layer.w1_accum[0]) == pytest.approx(0.1)
     plain = pkg.EmbeddingFM(2, 8, [4, 4], optimizer="sgd")
     assert plain.lin_z is None and plain.w1_accum is None
+
+
+@pytest.mark.parametrize("l1,l2", [(0.0, 0.0), (0.01, 0.01), (0.3, 0.0), (0.0, 0.5)])
+def test_proximal_adagrad_tables(pkg, cuda, l1, l2):
+    """dnn_optimizer = tf.train.ProximalAdagradOptimizer(lr, l1, l2) (models/ESMM/train.py:137-139) on the tables and,
+    with no separate linear optimizer, on the first-order weights: two steps against the oracle's rule."""
+    from oracle import deepctr_oracle as O
+    from tests._util import REL, make_case, rel_err, to_dev
+    B, rows, K, lr = 300, [40, 1, 700, 5, 1], 8, 0.05
+    case = make_case(23, B, rows, K, weighted=True, prune=True, skew=2.0)
+    rng, F = case["rng"], case["F"]
+    layer = pkg.EmbeddingFM(F, K, rows, optimizer="proximal_adagrad", lr=lr, optimizer_l1=l1, optimizer_l2=l2).train()
+    layer.load_tables(case["table"], case["w1"])
+    t, w = case["table"].astype(np.float64), case["w1"].astype(np.float64)
+    acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+    idx, val = to_dev(case["idx"]), to_dev(case["val"])
+    for step in range(2):
+        g_first = rng.standard_normal(B).astype(np.float32)
+        g_fm = (rng.standard_normal(B) * 0.1).astype(np.float32)
+        u = (rng.standard_normal((B, F, K)) * 0.1).astype(np.float32)
+        first, fm, emb = layer(idx, val)
+        torch.autograd.backward((first, fm, emb), (to_dev(g_first)[:, None], to_dev(g_fm)[:, None], to_dev(u.reshape(B, -1))))
+        urows, G, g1, _ = O.embedding_backward(t, case["off"], case["idx"], case["val"], g_first, g_fm, u, "sum", np.float64)
+        O.sparse_proximal_adagrad(t, acc, urows, G, lr, l1, l2)
+        O.sparse_proximal_adagrad(w, acc1, urows, g1, lr, l1, l2)
+    torch.cuda.synchronize()
+    assert rel_err(layer.table.cpu().numpy(), t, np.abs(case["table"]).max()) <= 2 * REL
+    assert rel_err(layer.w1.cpu().numpy(), w, np.abs(case["w1"]).max() + 1e-3) <= 2 * REL
+    assert rel_err(layer.accum.cpu().numpy(), acc, 0.1 + np.abs(acc).max()) <= 2 * REL
+    if l1 >= 0.3:
+        assert (layer.table.cpu().numpy()[urows] == 0).any(), "a strong l1 must zero some components exactly"
+    with pytest.raises(ValueError):
+        pkg.ShardedEmbeddingFM(F, K, rows, optimizer="proximal_adagrad")
+    with pytest.raises(ValueError):
+        pkg.EmbeddingBagFM(F, K, rows, optimizer="proximal_adagrad")

@@ -329,3 +329,27 @@ def test_cross_rank1_algebra_of_the_kernels():
         assert np.allclose(dx0, wdx0, rtol=1e-10, atol=1e-11)
         assert np.allclose(dw, wdw, rtol=1e-10, atol=1e-11)
         assert np.allclose(db, wdb, rtol=1e-10, atol=1e-11)
+
+
+def test_kat9_proximal_adagrad_closed_forms():
+    """KAT-9: [TF] SparseApplyProximalAdagrad (models/ESMM/train.py:137-139).  l1 = l2 = 0 is plain Adagrad; a large
+    l1 shrinks the weight to exactly 0; l2 alone divides the Adagrad result by 1 + l2 * lr / sqrt(a)."""
+    rows = np.array([1, 3])
+    g = np.array([[0.5, -2.0], [1.0, 0.25]])
+    v0 = np.array([[1.0, 1.0], [0.3, -0.4], [2.0, 2.0], [-0.7, 0.9]])
+    v, a = v0.copy(), np.full_like(v0, 0.1)
+    O.sparse_proximal_adagrad(v, a, rows, g, 0.05)
+    v2, a2 = v0.copy(), np.full_like(v0, 0.1)
+    O.sparse_adagrad(v2, a2, rows, g, 0.05)
+    assert np.allclose(v, v2, rtol=1e-15) and np.allclose(a, a2) and np.array_equal(v[[0, 2]], v0[[0, 2]])
+    v, a = v0.copy(), np.full_like(v0, 0.1)
+    O.sparse_proximal_adagrad(v, a, rows, g, 0.05, l1=1e3)
+    assert np.array_equal(v[rows], np.zeros((2, 2))) and np.array_equal(v[[0, 2]], v0[[0, 2]])
+    v, a = v0.copy(), np.full_like(v0, 0.1)
+    O.sparse_proximal_adagrad(v, a, rows, g, 0.05, l2=0.7)
+    eta = 0.05 / np.sqrt(0.1 + g * g)
+    assert np.allclose(v[rows], (v0[rows] - g * eta) / (1 + 0.7 * eta), rtol=1e-15)
+    v, a = v0.copy(), np.full_like(v0, 0.1)
+    O.sparse_proximal_adagrad(v, a, rows, g, 0.05, l1=0.5, l2=0.7)
+    p = v0[rows] - g * eta
+    assert np.allclose(v[rows], np.sign(p) * np.maximum(np.abs(p) - eta * 0.5, 0) / (1 + 0.7 * eta), rtol=1e-15)
