@@ -20,6 +20,7 @@
 #include <cub/device/dispatch/dispatch_radix_sort.cuh>
 
 #include "common.cuh"
+#include "radix.cuh"
 #include "update.cuh"
 
 namespace dir {
@@ -36,6 +37,8 @@ struct BwdWorkspace {
   uint32_t* pos_in;    // [n] iota
   void* cub_temp;
   size_t cub_bytes;
+  uint32_t* alt_keys;   // [n] the other half of the radix sort's ping-pong (pos_in is the values' other half)
+  uint32_t* radix_hist; // radix_hist_bytes(n)
   float* part;         // [nchunks][2][K]
   float* part1;        // [nchunks][2]
   uint32_t* long_list; // [nchunks / kLongRun + 1]
@@ -115,6 +118,8 @@ static BwdWorkspace carve(void* base, int64_t n, int K) {
   w.pos_in = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = take(w.cub_bytes);
+  w.alt_keys = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
+  w.radix_hist = reinterpret_cast<uint32_t*>(take(radix_hist_bytes(n)));
   // everything whose size does not depend on K comes first: the sort step carves with a dummy K
   w.long_list = reinterpret_cast<uint32_t*>(take((size_t)(nchunks / kLongRun + 1) * 4));
   w.long_count = reinterpret_cast<uint32_t*>(take(16));
@@ -284,8 +289,8 @@ __device__ __forceinline__ void apply_loaded(const BwdArgs& a, uint32_t key, int
 //                           running sum carried from the previous pass.
 //   At the last lookup of a run: the run lies inside the chunk -> update the row right here with the
 //   row / accumulator already in registers; otherwise leave a partial for phase 2 / 3.
-template <int LPR, int MODE>
-__global__ void __launch_bounds__(256, 3) embed_bwd_reduce_kernel(const BwdArgs a) {
+template <int LPR, int MODE, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdArgs a) {
   constexpr int K = LPR * 4;
   constexpr int SLOTS = 32 / LPR;             // lookups per pass
   constexpr int PASSES = LPR;                 // passes per tile of 32 lookups
@@ -612,13 +617,15 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
   const int64_t vchunks = a.perm_G > 1 ? a.perm_M * a.perm_G : nchunks;   // virtual chunks (>= nchunks)
   const unsigned rgrid = (unsigned)((vchunks + 7) / 8);
   if (a.mode == kModeEmit)
-    embed_bwd_reduce_kernel<LPR, kModeEmit><<<rgrid, 256, 0, st>>>(a);
+    if (LPR == 4 && (a.tune & 256)) embed_bwd_reduce_kernel<LPR, kModeEmit, 4><<<rgrid, 256, 0, st>>>(a);
+    else embed_bwd_reduce_kernel<LPR, kModeEmit><<<rgrid, 256, 0, st>>>(a);
   else if (a.mode == kModeGiven)
     embed_bwd_reduce_kernel<LPR, kModeGiven><<<rgrid, 256, 0, st>>>(a);
   else if (a.mode == kModeBag)
     embed_bwd_reduce_kernel<LPR, kModeBag><<<rgrid, 256, 0, st>>>(a);
   else
-    embed_bwd_reduce_kernel<LPR, kModeLocal><<<rgrid, 256, 0, st>>>(a);
+    if (LPR == 4 && (a.tune & 256)) embed_bwd_reduce_kernel<LPR, kModeLocal, 4><<<rgrid, 256, 0, st>>>(a);
+    else embed_bwd_reduce_kernel<LPR, kModeLocal><<<rgrid, 256, 0, st>>>(a);
   constexpr int NG = 256 / LPR;
   embed_bwd_finish_kernel<LPR><<<(unsigned)((nchunks + NG - 1) / NG), 256, 0, st>>>(a, n_unique_out);
   return launched("embed_bwd_reduce_update", 2);
@@ -913,12 +920,19 @@ extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, 
   // K only sizes the tail of the workspace; the sort part does not depend on it
   BwdWorkspace w = carve(workspace, n_capacity, 4);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "embed_bwd_sort: workspace too small");
+  int end_bit = 1;
+  while (end_bit < 32 && (((uint64_t)n_rows) >> end_bit) != 0) ++end_bit;  // n_rows itself is a key
+  if (!(tune() & 512)) {
+    // the hand-written sort (radix.cuh): three small kernels per 8-bit pass, positions implied by the input order
+    const int launches = radix_sort_pairs(sort_keys, n_lookups, end_bit, w.keys, w.pos, w.alt_keys, w.pos_in,
+                                          w.radix_hist, w.long_count, w.n_unique, st);
+    return launched("embed_bwd_sort", launches);
+  }
+  // DIR_B200_TUNE bit 512: cub::DeviceRadixSort, kept as the cross-check / timing baseline
   const unsigned grid = (unsigned)((n_lookups + 255) / 256);
   iota_kernel<<<grid, 256, 0, st>>>(w.pos_in, n_lookups, w.long_count, w.n_unique);
   int rc = launched("embed_bwd_sort/iota");
   if (rc) return rc;
-  int end_bit = 1;
-  while (end_bit < 32 && (((uint64_t)n_rows) >> end_bit) != 0) ++end_bit;  // n_rows itself is a key
   size_t cub_bytes = w.cub_bytes;
   cudaError_t e = sort_pairs(w.cub_temp, cub_bytes, sort_keys, w.keys, (const uint32_t*)w.pos_in, w.pos,
                              (int)n_lookups, end_bit, st, sort_variant());
