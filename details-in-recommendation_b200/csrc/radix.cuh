@@ -2,34 +2,34 @@
 // (uint32 keys of up to 32 bits, values = 0..n-1 implied by the input order), sized for this workload: a few
 // million pairs that live in L2, a key space of 24-30 bits.
 //
-// Per 8-bit pass three small kernels instead of cub's onesweep (whose 290 large tiles of 8 832 pairs are
+// Per 8-bit pass two small kernels instead of cub's onesweep (whose 290 large tiles of 8 832 pairs are
 // latency-bound at this size: 26 us per pass for 27 MB of L2-resident traffic, profiles/r02_sharded_1gpu_ncu.txt):
-//   count    tile histogram of the pass's digit, digit-major [256][tiles]
-//   scan     one CTA per digit: exclusive prefix of its row over the tiles, and the row total
-//   scatter  the tile's pairs re-read, ranked stably inside the tile and written to their places
-// A tile is kRadixTile consecutive pairs, walked warp by warp in order, 32 consecutive pairs at a time:
-// __match_any_sync gives every pair its rank among equal digits of the same 32, a per-warp running count the
-// pairs of earlier rounds, a per-digit prefix over the warps the pairs of earlier warps.  Stable by construction
-// (no atomics decide an order), so equal rows stay in lookup order and the gradient sums stay deterministic.
+//   row scan  one CTA per digit: exclusive prefix of the digit's tile counts over the tiles, and the row total
+//   scatter   a tile's pairs ranked stably inside the tile, staged in shared memory in sorted order and written out
+//             in runs (consecutive threads, consecutive addresses inside a digit's run); while writing, the pair's
+//             NEXT digit is counted into the next pass's tile histogram (integer atomics: counts are order-free),
+//             so only the first pass needs a counting kernel of its own
+// A tile is kRadixTile consecutive pairs, walked warp by warp in order, 32 consecutive pairs at a time: eight
+// ballots give every pair its rank among equal digits of the same 32, a per-warp running count the pairs of
+// earlier rounds, a per-digit prefix over the warps the pairs of earlier warps.  Stable by construction (no atomic
+// decides an order), so equal rows stay in lookup order and the gradient sums stay deterministic.
 // The first pass reads the caller's keys and takes the position from the index (no iota array).
 #pragma once
 #include "common.cuh"
 
 namespace dir {
 
-constexpr int kRadixTile = 4096;   // pairs per CTA
-constexpr int kRadixWarps = 8;     // 256 threads: 16 pairs per thread
+constexpr int kRadixTile = 2048;   // pairs per CTA
+constexpr int kRadixWarps = 8;     // 256 threads: 8 pairs per thread
 constexpr int kRadixRounds = kRadixTile / (kRadixWarps * 32);
 
-struct RadixTemp {
-  uint32_t* alt_keys;  // [n]
-  uint32_t* alt_vals;  // [n]
-  uint32_t* hist;      // [256][tiles] digit-major tile counts, then [256] row totals
-  size_t total;
-};
 inline int64_t radix_tiles(int64_t n) { return (n + kRadixTile - 1) / kRadixTile; }
-inline size_t radix_hist_bytes(int64_t n) { return align_up((size_t)(256 * radix_tiles(n) + 256) * 4, 256); }
+// two histograms ([256][tiles] digit-major tile counts + [256] row totals each): a pass scans one while its
+// scatter fills the other for the next pass
+inline size_t radix_hist_words(int64_t n) { return (size_t)(256 * radix_tiles(n) + 256); }
+inline size_t radix_hist_bytes(int64_t n) { return align_up(2 * radix_hist_words(n) * 4, 256); }
 
+// first pass only: tile histogram of the low digit
 __global__ void __launch_bounds__(256)
 radix_count_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t tiles,
                    uint32_t* __restrict__ hist, uint32_t* zero_a, unsigned long long* zero_b) {
@@ -73,9 +73,11 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* s_w
   return base + inc - v;
 }
 
-// one CTA per digit: the row hist[d][0 .. tiles) becomes its exclusive prefix over the tiles, rowtot[d] its sum
+// one CTA per digit: the row hist[d][0 .. tiles) becomes its exclusive prefix over the tiles, rowtot[d] its sum;
+// the same row of the OTHER histogram is zeroed for the scatter that follows to count into
 __global__ void __launch_bounds__(256)
-radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __restrict__ rowtot) {
+radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __restrict__ rowtot,
+                     uint32_t* __restrict__ next_hist) {
   __shared__ uint32_t s_warp[8];
   uint32_t* row = hist + (int64_t)blockIdx.x * tiles;
   uint32_t carry = 0;
@@ -84,21 +86,28 @@ radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __res
     const uint32_t v = i < tiles ? row[i] : 0u;
     uint32_t tot;
     const uint32_t ex = block_excl_scan256(v, s_warp, &tot);
-    if (i < tiles) row[i] = carry + ex;
+    if (i < tiles) {
+      row[i] = carry + ex;
+      if (next_hist) next_hist[(int64_t)blockIdx.x * tiles + i] = 0u;
+    }
     carry += tot;
   }
   if (threadIdx.x == 0) rowtot[blockIdx.x] = carry;
 }
 
-// FIRST: the values are the indices themselves (vin unused)
+// FIRST: the values are the indices themselves (vin unused).  next_hist != NULL: count digit (shift + 8) of every
+// pair into the tile it lands in.
 template <bool FIRST>
 __global__ void __launch_bounds__(256)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, int64_t n, int shift,
                      int64_t tiles, const uint32_t* __restrict__ hist, uint32_t* __restrict__ kout,
-                     uint32_t* __restrict__ vout) {
+                     uint32_t* __restrict__ vout, uint32_t* __restrict__ next_hist) {
   __shared__ uint32_t wcount[kRadixWarps][256];  // pairs of digit d in warp w's part of the tile, then the prefix
   __shared__ uint32_t gbase[256];                // where digit d of this tile starts in the output
+  __shared__ uint32_t tstart[256];               // where digit d starts inside the sorted tile
   __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_key[kRadixTile], s_val[kRadixTile];
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int d = lane; d < 256; d += 32) wcount[w][d] = 0u;
   {  // digit d starts after all pairs of smaller digits (scan of the 256 row totals) + this digit's earlier tiles
@@ -106,31 +115,35 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     const uint32_t digit_base = block_excl_scan256(__ldg(hist + 256 * tiles + threadIdx.x), s_warp, &tot);
     gbase[threadIdx.x] = digit_base + __ldg(hist + (int64_t)threadIdx.x * tiles + blockIdx.x);
   }
-  __syncwarp();
   // warp w owns pairs [w * R * 32, (w + 1) * R * 32) of the tile, R = kRadixRounds, round r = 32 consecutive pairs
-  const int64_t wbase = (int64_t)blockIdx.x * kRadixTile + (int64_t)w * kRadixRounds * 32;
-  uint32_t key[kRadixRounds], val[kRadixRounds], rank[kRadixRounds];
+  const int64_t tbase = (int64_t)blockIdx.x * kRadixTile;
+  const int64_t wbase = tbase + (int64_t)w * kRadixRounds * 32;
+  uint32_t key[kRadixRounds], rank[kRadixRounds];
 #pragma unroll
   for (int r = 0; r < kRadixRounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
-    key[r] = i < n ? __ldg(kin + i) : 0xffffffffu;
-    val[r] = FIRST ? (uint32_t)i : (i < n ? __ldg(vin + i) : 0u);
+    key[r] = i < n ? __ldg(kin + i) : 0u;
   }
 #pragma unroll
   for (int r = 0; r < kRadixRounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     const bool live = i < n;
     const uint32_t d = (key[r] >> shift) & 255u;
-    // lanes past the end must not match live ones: give them a digit of their own (256 + lane cannot collide)
-    const unsigned peers = __match_any_sync(0xffffffffu, live ? d : 256u + (uint32_t)lane);
+    unsigned peers = __ballot_sync(FULL, live);  // lanes of this round with my digit
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const unsigned m = __ballot_sync(FULL, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? m : ~m;
+    }
     const uint32_t before = live ? wcount[w][d] : 0u;  // pairs of digit d in this warp's earlier rounds
     __syncwarp();
-    rank[r] = before + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    if (live && (peers & ((1u << lane) - 1u)) == 0u) wcount[w][d] = before + (uint32_t)__popc(peers);  // one writer
+    const unsigned lower = peers & ((1u << lane) - 1u);
+    rank[r] = before + (uint32_t)__popc(lower);
+    if (live && lower == 0u) wcount[w][d] = before + (uint32_t)__popc(peers);  // one writer per digit
     __syncwarp();
   }
   __syncthreads();
-  {  // per digit: exclusive prefix over the warps (thread d), in warp order
+  {  // per digit (thread d): exclusive prefix over the warps, then over the digits: the sorted tile's layout
     const int d = threadIdx.x;
     uint32_t run = 0;
 #pragma unroll
@@ -139,6 +152,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
       wcount[ww][d] = run;
       run += c;
     }
+    uint32_t tot;
+    tstart[d] = block_excl_scan256(run, s_warp, &tot);
   }
   __syncthreads();
 #pragma unroll
@@ -146,35 +161,47 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     const int64_t i = wbase + r * 32 + lane;
     if (i < n) {
       const uint32_t d = (key[r] >> shift) & 255u;
-      const uint32_t dst = gbase[d] + wcount[w][d] + rank[r];
-      kout[dst] = key[r];
-      vout[dst] = val[r];
+      const uint32_t pos = tstart[d] + wcount[w][d] + rank[r];
+      s_key[pos] = key[r];
+      s_val[pos] = FIRST ? (uint32_t)i : __ldg(vin + i);
     }
+  }
+  __syncthreads();
+  const int cnt = (int)(n - tbase < kRadixTile ? n - tbase : kRadixTile);
+  for (int j = threadIdx.x; j < cnt; j += 256) {  // sorted order: runs of equal digits go to consecutive addresses
+    const uint32_t k = s_key[j];
+    const uint32_t d = (k >> shift) & 255u;
+    const uint32_t dst = gbase[d] + ((uint32_t)j - tstart[d]);
+    kout[dst] = k;
+    vout[dst] = s_val[j];
+    if (next_hist) atomicAdd(next_hist + (int64_t)((k >> (shift + 8)) & 255u) * tiles + dst / kRadixTile, 1u);
   }
 }
 
 // Sorts (keys[i], i) by the low `end_bit` bits of the key, stable.  The result lands in (kout, vout); (alt_keys,
-// alt_vals) is the other half of the ping-pong.  3 launches per 8-bit pass.
+// alt_vals) is the other half of the ping-pong.  2 launches per 8-bit pass + 1.
 inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32_t* kout, uint32_t* vout,
                             uint32_t* alt_keys, uint32_t* alt_vals, uint32_t* hist, uint32_t* zero_a,
                             unsigned long long* zero_b, cudaStream_t st) {
   const int passes = (end_bit + 7) / 8;
   const int64_t tiles = radix_tiles(n);
+  uint32_t* h[2] = {hist, hist + radix_hist_words(n)};
   const uint32_t* kin = keys;
   const uint32_t* vin = nullptr;
+  radix_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(kin, n, 0, tiles, h[0], zero_a, zero_b);
   for (int p = 0; p < passes; ++p) {
     const bool to_out = ((passes - 1 - p) & 1) == 0;  // the last pass writes (kout, vout)
     uint32_t* kd = to_out ? kout : alt_keys;
     uint32_t* vd = to_out ? vout : alt_vals;
-    radix_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(kin, n, p * 8, tiles, hist, p == 0 ? zero_a : nullptr,
-                                                        p == 0 ? zero_b : nullptr);
-    radix_rowscan_kernel<<<256, 256, 0, st>>>(hist, tiles, hist + 256 * tiles);
-    if (p == 0) radix_scatter_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, hist, kd, vd);
-    else radix_scatter_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, hist, kd, vd);
+    uint32_t* cur = h[p & 1];
+    uint32_t* nxt = p + 1 < passes ? h[(p + 1) & 1] : nullptr;
+    radix_rowscan_kernel<<<256, 256, 0, st>>>(cur, tiles, cur + 256 * tiles, nxt);
+    if (p == 0) radix_scatter_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt);
+    else radix_scatter_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt);
     kin = kd;
     vin = vd;
   }
-  return passes * 3;
+  return passes * 2 + 1;
 }
 
 }  // namespace dir
