@@ -662,6 +662,12 @@ class ShardedEmbeddingFM(torch.nn.Module):
             h.owner_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
             h.shape = (B, F)
         sel = ptr(self.sparse_fields) if (peer and n_sel < F) else None
+        if peer and self.n_dense:
+            # the replicated one-row fields' part of `inv` needs the inputs only: first, off the chain that ends in
+            # the id exchange (keys -> sort -> numbering -> push)
+            check(L.dir_shard_dense_inv(ptr(idx), ptr(val), ptr(self.onerow_fields), self.n_dense, B, F,
+                                        self.px.u_cap, ptr(h.inv),
+                                        ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_dense_inv")
         check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
                                self.plan.n_rows, B, F, G, sel, n_sel, ptr(h.keys),
                                ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
@@ -678,10 +684,6 @@ class ShardedEmbeddingFM(torch.nn.Module):
         ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(n), 1), dev)
         check(L.dir_shard_unique(skeys, spos, n, self.plan.n_rows, G, sel, n_sel, F, ptr(h.uidx), ptr(h.ulocal),
                                  ptr(h.inv), ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
-        if peer and self.n_dense:
-            check(L.dir_shard_dense_inv(ptr(idx), ptr(val), ptr(self.onerow_fields), self.n_dense, B, F,
-                                        self.px.u_cap, ptr(h.inv),
-                                        ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_dense_inv")
         tr.mark("pre.unique")
 
     @torch.no_grad()
