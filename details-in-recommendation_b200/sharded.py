@@ -213,6 +213,15 @@ class _ShardedFunction(torch.autograd.Function):
             # the owner answers the ids it received: one kernel gathers the rows and stores them straight
             # into the requesters' buffers over NVLink
             px, p = layer.px, h.parity
+            if train:
+                # the owner marks who asked for which row (cells carry this use's epoch: nothing is cleared
+                # afterwards).  Only the owner's update needs the marks: a second stream, underneath the row exchange
+                # and the forward; the backward joins it.
+                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev)
+                aux.wait_stream(main)
+                check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, ptr(layer.slot_epoch[p]),
+                                        ptr(layer.err_flag), layer._n_unique2.data_ptr() + 8 * p, aux.cuda_stream),
+                      "dir_shard_slots")
             check(L.dir_shard_gather_send(px.ref(p), ptr(layer.table), layer.row_stride,
                                           ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
                                           ptr(layer.dense_table) if layer.n_dense else None, layer.row_stride,
@@ -711,10 +720,6 @@ class ShardedEmbeddingFM(torch.nn.Module):
             tr.mark("pre.ids_push")
             px.barrier(p, 1)
             tr.mark("pre.barrier")
-            # the owner marks who asked for which row (cells carry this use's epoch: nothing is cleared afterwards)
-            check(L.dir_shard_slots(px.ref(p), ptr(self.slot[p]), self.n_rows, ptr(self.slot_epoch[p]),
-                                    ptr(self.err_flag), self._n_unique2.data_ptr() + 8 * p, st), "dir_shard_slots")
-            tr.mark("pre.slots")
             return
         send_counts = h.owner_off[1:] - h.owner_off[:-1]
         recv_counts = exchange_counts(send_counts, self.side_group)
