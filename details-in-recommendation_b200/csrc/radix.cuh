@@ -28,7 +28,8 @@ inline int64_t radix_tiles(int64_t n) { return (n + kRadixTile - 1) / kRadixTile
 // two histograms ([256][tiles] digit-major tile counts + [256] row totals each): a pass scans one while its
 // scatter fills the other for the next pass
 inline size_t radix_hist_words(int64_t n) { return (size_t)(256 * radix_tiles(n) + 256); }
-inline size_t radix_hist_bytes(int64_t n) { return align_up(2 * radix_hist_words(n) * 4, 256); }
+inline size_t radix_skew_words() { return 256; }  // per low digit: does it hold more than twice its uniform share?
+inline size_t radix_hist_bytes(int64_t n) { return align_up((2 * radix_hist_words(n) + radix_skew_words()) * 4, 256); }
 
 // first pass only: tile histogram of the low digit
 __global__ void __launch_bounds__(256)
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* s_w
 // the same row of the OTHER histogram is zeroed for the scatter that follows to count into
 __global__ void __launch_bounds__(256)
 radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __restrict__ rowtot,
-                     uint32_t* __restrict__ next_hist) {
+                     uint32_t* __restrict__ next_hist, uint32_t* __restrict__ skew, uint32_t skew_above) {
   __shared__ uint32_t s_warp[8];
   uint32_t* row = hist + (int64_t)blockIdx.x * tiles;
   uint32_t carry = 0;
@@ -99,7 +100,10 @@ radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __res
     }
     carry += tot;
   }
-  if (threadIdx.x == 0) rowtot[blockIdx.x] = carry;
+  if (threadIdx.x == 0) {
+    rowtot[blockIdx.x] = carry;
+    if (skew) skew[blockIdx.x] = carry > skew_above ? 1u : 0u;  // first pass: a hot digit means hot rows (Zipf)
+  }
 }
 
 // FIRST: the values are the indices themselves (vin unused).  next_hist != NULL: count digit (shift + 8) of every
@@ -108,7 +112,8 @@ template <bool FIRST>
 __global__ void __launch_bounds__(256)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, int64_t n, int shift,
                      int64_t tiles, const uint32_t* __restrict__ hist, uint32_t* __restrict__ kout,
-                     uint32_t* __restrict__ vout, uint32_t* __restrict__ next_hist) {
+                     uint32_t* __restrict__ vout, uint32_t* __restrict__ next_hist,
+                     const uint32_t* __restrict__ skew) {
   __shared__ uint32_t wcount[kRadixWarps][256];  // pairs of digit d in warp w's part of the tile, then the prefix
   __shared__ uint32_t gbase[256];                // where digit d of this tile starts in the output
   __shared__ uint32_t tstart[256];               // where digit d starts inside the sorted tile
@@ -117,6 +122,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int d = lane; d < 256; d += 32) wcount[w][d] = 0u;
+  // hot rows in this batch?  Then equal keys sit next to each other below and their counter updates are combined.
+  const bool skewed = __syncthreads_or(next_hist != nullptr && __ldg(skew + threadIdx.x) != 0u) != 0;
   {  // digit d starts after all pairs of smaller digits (scan of the 256 row totals) + this digit's earlier tiles
     uint32_t tot;
     const uint32_t digit_base = block_excl_scan256(__ldg(hist + 256 * tiles + threadIdx.x), s_warp, &tot);
@@ -182,11 +189,16 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
     kout[dst] = k;
     vout[dst] = s_val[j];
     if (next_hist) {
-      // integer atomics (counts are order-free), one per distinct counter of the warp: neighbours in sorted order
-      // land in the same tile, and a Zipf-hot row gives 32 equal keys (552 us for cfg5's sort before this)
+      // integer atomics (counts are order-free).  With hot rows (first pass saw a digit holding more than twice its uniform share of the keys) one
+      // per distinct counter of the warp: a Zipf-hot row gives runs of equal keys, 32 atomics on one counter each
+      // (cfg5: 552 us per sort without this, 297 with); uniform ids skip the MATCH (cfg2: 99 us instead of 112)
       const uint32_t c = ((k >> (shift + 8)) & 255u) * (uint32_t)tiles + dst / kRadixTile;
-      const unsigned peers = __match_any_sync(__activemask(), c);
-      if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(next_hist + c, (uint32_t)__popc(peers));
+      if (skewed) {
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        if ((peers & ((1u << lane) - 1u)) == 0u) atomicAdd(next_hist + c, (uint32_t)__popc(peers));
+      } else {
+        atomicAdd(next_hist + c, 1u);
+      }
     }
   }
 }
@@ -199,6 +211,7 @@ inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32
   const int passes = (end_bit + 7) / 8;
   const int64_t tiles = radix_tiles(n);
   uint32_t* h[2] = {hist, hist + radix_hist_words(n)};
+  uint32_t* skew = hist + 2 * radix_hist_words(n);
   const uint32_t* kin = keys;
   const uint32_t* vin = nullptr;
   radix_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(kin, n, 0, tiles, h[0], zero_a, zero_b);
@@ -208,9 +221,10 @@ inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32
     uint32_t* vd = to_out ? vout : alt_vals;
     uint32_t* cur = h[p & 1];
     uint32_t* nxt = p + 1 < passes ? h[(p + 1) & 1] : nullptr;
-    radix_rowscan_kernel<<<256, 256, 0, st>>>(cur, tiles, cur + 256 * tiles, nxt);
-    if (p == 0) radix_scatter_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt);
-    else radix_scatter_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt);
+    radix_rowscan_kernel<<<256, 256, 0, st>>>(cur, tiles, cur + 256 * tiles, nxt, p == 0 ? skew : nullptr,
+                                              (uint32_t)(n / 128));
+    if (p == 0) radix_scatter_kernel<true><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt, skew);
+    else radix_scatter_kernel<false><<<(unsigned)tiles, 256, 0, st>>>(kin, vin, n, p * 8, tiles, cur, kd, vd, nxt, skew);
     kin = kd;
     vin = vd;
   }
