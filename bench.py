@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+DEFAULT_MICRO = 1          # micro-batches of the sharded step (see --micro)
 METRIC = "samples/sec fwd+bwd embedding+FM/cross layer"
 UNIT = "samples/s"
 LR = 0.05
@@ -51,6 +52,9 @@ def parse_args():
     p.add_argument("--profile", default="",
                    help="after the timed regions, trace 6 steps with torch.profiler (CUPTI kernel timeline) and "
                         "write the chrome trace of rank 0 to this path: a diagnostic, never a bench value")
+    p.add_argument("--micro", type=int, default=0, choices=[0, 1, 2],
+                   help="sharded layer: exchange a batch as this many micro-batches (2: the second half's row exchange "
+                        "runs underneath the first half's forward; one owner update per batch either way); 0 = the default")
     p.add_argument("--sharded", action="store_true",
                    help="run the row-sharded layer even on one GPU (every exchange kernel, local buffers): a diagnostic")
     p.add_argument("--feed", default="columns", choices=["columns", "resolved"],
@@ -260,13 +264,15 @@ def run_b200(args):
     torch.manual_seed(dir_b200.synth.SEED_TABLES + rank)
 
     sharded = world > 1 or args.sharded
+    micro = 1
     if not sharded:
         layer = dir_b200.EmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
                                      emit_embeddings=emit, device=dev).train()
     else:
         # cfg4's 880 M rows are filled on the device from a counter hash (no 56 GB host table, no fp32 temporaries)
+        micro = args.micro or DEFAULT_MICRO
         layer = dir_b200.ShardedEmbeddingFM(F, K, list(w.rows_per_field), optimizer="adagrad", lr=LR,
-                                            emit_embeddings=emit, max_batch=B, device=dev,
+                                            emit_embeddings=emit, max_batch=B, device=dev, micro_batches=micro,
                                             init="counter" if w.name == "cfg4" else "trunc_normal").train()
     layer.w1.normal_(0.0, 0.01)            # TF's zero init would make the first-order path trivial
     if getattr(layer, "n_dense", 0):
@@ -289,21 +295,42 @@ def run_b200(args):
     # one-batch-ahead id phase) consistent across the warm-up, timed, e2e and trace loops.
     ready_events = {}          # e2e: slot -> event of its H2D copy (the id work of that batch waits for it)
     handles = [dir_b200.SortedLookups() if not sharded else dir_b200.ShardedLookups() for _ in range(R)]
+    if micro == 2:
+        if B % 2:
+            raise SystemExit("--micro 2 needs an even batch")
+        handles = [[dir_b200.ShardedLookups(), dir_b200.ShardedLookups()] for _ in range(R)]
+    Bh = B // 2
     cursor = [0]
     side = layer.side_stream(dev)
+
+    def half(slot, x):
+        """views of micro-batch x of a slot: ids, values, labels, upstream gradient"""
+        lo, hi = x * Bh, (x + 1) * Bh
+        return devs[slot][0][lo:hi], devs[slot][1][lo:hi], devs[slot][2][lo:hi], (ups[slot][lo:hi] if emit else None)
 
     def id_work(nxt, phase="both", inline=False):
         if not sharded:
             layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], record_event=not inline)
+        elif micro == 2:
+            for x in range(2):
+                idx_, val_, _, _ = half(nxt, x)
+                if inline:
+                    layer.presort(idx_, val_, handle=handles[nxt][x], inline=True, phase=phase, half=x)
+                else:
+                    layer.presort(idx_, val_, handle=handles[nxt][x], fork=False, after=ready_events.get(nxt), half=x)
         elif inline:
             layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], inline=True, phase=phase)
         else:
             layer.presort(devs[nxt][0], devs[nxt][1], handle=handles[nxt], fork=False, after=ready_events.get(nxt))
 
-    def model(slot):
-        idx, val, y = devs[slot]
-        up = ups[slot]
-        first, fm, emb = layer(idx, val, presorted=handles[slot])
+    def model(slot, x=None):
+        if x is None:
+            idx, val, y = devs[slot]
+            up = ups[slot]
+            first, fm, emb = layer(idx, val, presorted=handles[slot])
+        else:
+            idx, val, y, up = half(slot, x)
+            first, fm, emb = layer(idx, val, presorted=handles[slot][x], defer_update=True)
         with torch.no_grad():
             logits = first + fm
             g = torch.sigmoid(logits).sub_(y.unsqueeze(1))          # SUM-reduced CE: no 1/B (deepFM.py:72)
@@ -318,6 +345,37 @@ def run_b200(args):
         else:
             torch.autograd.backward((first, fm), (g, g))
 
+    def step_micro(slot, captured):
+        """The sharded step as two micro-batches: half 1 runs on a second stream and starts its row exchange when
+        half 0's rows have been sent, so its NVLink-bound gather + send runs underneath half 0's forward, and its
+        forward underneath half 0's segmented reduce.  One owner update per batch (finish_step)."""
+        nxt = (slot + 1) % R
+        main, sb = torch.cuda.current_stream(), layer.micro_stream(dev)
+        ha, hb = handles[slot]
+        if captured:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                id_work(nxt, phase="local", inline=True)
+        a = model(slot, 0)
+        sb.wait_event(ha.gs_done)
+        with torch.cuda.stream(sb):
+            b = model(slot, 1)
+        if captured:
+            side.wait_stream(main)
+            side.wait_stream(sb)
+            with torch.cuda.stream(side):
+                id_work(nxt, phase="exchange", inline=True)
+        backward(*a[:5])
+        with torch.cuda.stream(sb):
+            backward(*b[:5])
+        main.wait_stream(sb)
+        layer.finish_step(ha, hb)
+        if captured:
+            main.wait_stream(side)
+        else:
+            id_work(nxt)
+        return torch.cat([a[5], b[5]])
+
     def step(slot, captured=False):
         """One step on resident inputs of `slot` plus the id-only work of the next slot."""
         nxt = (slot + 1) % R
@@ -329,6 +387,8 @@ def run_b200(args):
             if captured:                           # join the side branch inside the graph
                 main.wait_stream(side)
             return logits
+        if micro == 2:
+            return step_micro(slot, captured)
         if not captured:
             first, fm, emb, g, up, logits = model(slot)
             backward(first, fm, emb, g, up)
@@ -366,19 +426,18 @@ def run_b200(args):
     if use_graph:
         try:
             if sharded:
-                for r in range(R):
-                    handles[r].parity = r % 2      # captured: the exchange buffer of a slot is baked in
-                    assert handles[r].parity is not None
                 # one more eager round so that every slot has run with exactly the parity it is captured with
                 for r in range(R):
                     step(r)
                 torch.cuda.synchronize()
-                assert [h.parity for h in handles] == [r % 2 for r in range(R)], "parity drifted"
+                flat = [hs if isinstance(hs, list) else [hs] for hs in handles]
+                assert all(h.parity == r % 2 for r, hs in enumerate(flat) for h in hs), "parity drifted"
                 if world > 1:
                     dist.barrier()
             torch.cuda.synchronize()
-            for h_ in handles:                     # a captured stream may not wait for an event recorded outside the
-                h_.event = None                    # capture; everything those events ordered has completed
+            for hs_ in handles:                    # a captured stream may not wait for an event recorded outside the
+                for h_ in (hs_ if isinstance(hs_, list) else [hs_]):     # capture; everything those events ordered
+                    h_.event = None                                      # has completed
             cap_stream = torch.cuda.Stream()
             cap_stream.wait_stream(torch.cuda.current_stream())
             layer.capturing = True
@@ -548,7 +607,7 @@ def run_b200(args):
             print("bench.py: cfg1 CPU timing skipped (%s)" % e, file=sys.stderr)
 
     stages, nvlink, serial = None, None, None
-    if sharded and getattr(layer, "trace", None) is not None:
+    if sharded and micro == 1 and getattr(layer, "trace", None) is not None:
         # Stage times of the sharded step: a diagnostic pass AFTER the timed regions.  Eager launches, every stage
         # bracketed by CUDA events on its stream, one device sync per step.  Every rank takes part (the steps
         # contain the cross-rank barriers); rank 0 reports.
@@ -612,6 +671,8 @@ def run_b200(args):
                 print("bench.py: stage roofline skipped (%s)" % e, file=sys.stderr)
     if rank == 0:
         cfg = workload_config(w, args, world)
+        if sharded:
+            cfg["micro_batches"] = micro
         cfg.update({"l2_policy": "%d rotating input sets (%.0f MB of ids/values/upstream each) + a %.2f GB table: "
                                  "inputs larger than L2, no flush" % (
                                      R, (B * F * 12 + (B * d * 4 if emit else 0)) / 1e6,

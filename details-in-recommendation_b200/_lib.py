@@ -74,7 +74,7 @@ SIGNATURES = {
     "dir_shard_ids_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dir_shard_slots": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_shard_gather_send": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                      c_void_p]),
+                                      c_int, c_void_p]),
     "dir_embed_bwd_reduce_emit_to": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p,
                                              c_size_t, c_void_p]),
@@ -83,10 +83,11 @@ SIGNATURES = {
     "dir_shard_dense_emit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "dir_shard_owner_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                       c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+                                       c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]),
     "dir_shard_dense_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float,
                                       c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                      c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "dir_table_init_counter": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_uint64, c_float,
                                        c_void_p]),
     "dir_rows_gather": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,

@@ -228,26 +228,38 @@ peer_g1_push_kernel(const dir_peer_layout L, const float* __restrict__ g1_local,
 }
 
 // owner: merge + fused update.  A warp takes 32 arrivals at a time.  Lane-per-arrival stage: local row, then the
-// row's slot cells -- does an earlier rank merge this row (then this arrival has nothing to do), which later ranks
-// contribute.  Vector stage over the arrivals that lead, compacted: LPR lanes per row, the row / accumulator /
-// gradient loads of PB passes in flight together; the other ranks' sums are added in rank order, then the fused
-// update (row and accumulator share a 128-byte line).
-template <int LPR>
+// row's slot cells -- does an earlier requester merge this row (then this arrival has nothing to do), which later
+// ones contribute.  Vector stage over the arrivals that lead, compacted: LPR lanes per row, the row / accumulator /
+// gradient loads of PB passes in flight together; the other requesters' sums are added in a fixed order, then the
+// fused update (row and accumulator share a 128-byte line).
+// NBUF = 2: the batch was exchanged as two micro-batches, each through an exchange buffer (and slot map) of its own;
+// half s of rank q counts as virtual requester s * G + q, and the merge runs over both buffers in that order.
+struct OwnerSrc {
+  const char* local[2];      // the exchange buffers (same layout)
+  const uint32_t* slot[2];
+  const uint32_t* epoch[2];
+};
+
+template <int LPR, int NBUF>
 __global__ void __launch_bounds__(256)
-peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ slot, float* table, float* accum,
+peer_owner_update_kernel(const dir_peer_layout L, const OwnerSrc src, float* table, float* accum,
                          int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
-                         int opt, float lr, int64_t n_local, unsigned long long* n_unique,
-                         const uint32_t* __restrict__ epoch) {
+                         int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
   constexpr int SLOTS = 32 / LPR;
   constexpr int PB = LPR <= 4 ? 2 : 1;
-  const uint32_t tag = epoch[0];  // a cell counts only while it carries the current epoch
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ Arrivals s;
-  load_arrivals(L, s);
-  const int32_t* ids = reinterpret_cast<const int32_t*>(L.local + L.off_ids);
-  const float4* gbuf = reinterpret_cast<const float4*>(L.local + L.off_g);
-  const float* g1buf = reinterpret_cast<const float*>(L.local + L.off_g1);
-  const int64_t total = s.pre[L.G];
+  __shared__ Arrivals s[NBUF];
+  uint32_t tag[NBUF];
+  int64_t tot[NBUF];
+#pragma unroll
+  for (int b = 0; b < NBUF; ++b) {
+    dir_peer_layout Lb = L;
+    Lb.local = const_cast<char*>(src.local[b]);
+    load_arrivals(Lb, s[b]);
+    tag[b] = src.epoch[b][0];  // a cell counts only while it carries its buffer's current epoch
+    tot[b] = s[b].pre[L.G];
+  }
+  const int64_t total = tot[0] + (NBUF > 1 ? tot[NBUF - 1] : 0);
   const bool adagrad = opt == DIR_OPT_ADAGRAD;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, grp = lane / LPR;
@@ -258,33 +270,41 @@ peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ s
   unsigned long long leaders = 0;
   for (int64_t a0 = warp * 32; a0 < total; a0 += nwarps * 32) {  // warp-uniform trip count
     // ---- lane-per-arrival stage
-    const int64_t a = a0 + lane;
+    int64_t a = a0 + lane;
     bool lead = false;
-    int64_t e = 0, r = 0;        // e: this arrival's entry of gbuf / g1buf
-    unsigned long long more = 0; // ranks > q that asked for the same row
+    int64_t e = 0, r = 0;        // e: this arrival's entry of gbuf / g1buf, + (buffer << 40)
+    unsigned long long more = 0; // virtual requesters after this one that asked for the same row
     if (a < total) {
-      const int q = seg_of(s.pre, G, a);
-      const int64_t i = a - s.pre[q];
+      const int b = (NBUF > 1 && a >= tot[0]) ? 1 : 0;
+      if (b) a -= tot[0];
+      const int q = seg_of(s[b].pre, G, a);
+      const int64_t i = a - s[b].pre[q];
       e = (int64_t)q * L.seg_cap + i;
-      r = __ldg(ids + e);
+      r = __ldg(reinterpret_cast<const int32_t*>(src.local[b] + L.off_ids) + e);
+      e |= (int64_t)b << 40;
       if (r >= 0 && r < n_local) {
-        const uint32_t* sl = slot + r * G;
         bool earlier = false;
-        uint32_t sv[8];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) sv[p] = p < G ? __ldg(sl + p) : 0u;  // independent loads, one sector
+        for (int bb = 0; bb < NBUF; ++bb) {
+          const uint32_t* sl = src.slot[bb] + r * G;
+          uint32_t sv[8];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const bool on = (sv[p] >> 24) == tag;
-          earlier |= on && p < q;
-          if (on && p > q) more |= 1ull << p;
+          for (int p = 0; p < 8; ++p) sv[p] = p < G ? __ldg(sl + p) : 0u;  // independent loads, one sector
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const bool on = (sv[p] >> 24) == tag[bb];
+            const int v = bb * G + p, me = b * G + q;
+            earlier |= on && v < me;
+            if (on && v > me) more |= 1ull << v;
+          }
+          for (int p = 8; p < G; ++p) {
+            const bool on = (__ldg(sl + p) >> 24) == tag[bb];
+            const int v = bb * G + p, me = b * G + q;
+            earlier |= on && v < me;
+            if (on && v > me) more |= 1ull << v;
+          }
         }
-        for (int p = 8; p < G; ++p) {
-          const bool on = (__ldg(sl + p) >> 24) == tag;
-          earlier |= on && p < q;
-          if (on && p > q) more |= 1ull << p;
-        }
-        lead = !earlier;  // else an earlier rank merges this row
+        lead = !earlier;  // else an earlier (virtual) requester merges this row
       }
     }
     const unsigned lm = __ballot_sync(FULL, lead);
@@ -301,19 +321,21 @@ peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ s
       for (int j = 0; j < PB; ++j) {
         const int n = k0 + j * SLOTS + grp;
         on[j] = n < nl;
-        const int src = on[j] ? (int)__fns(lm, 0, n + 1) : 0;
-        rr[j] = __shfl_sync(FULL, r, src);
-        ee[j] = __shfl_sync(FULL, e, src);
-        mm[j] = __shfl_sync(FULL, more, src);
+        const int from = on[j] ? (int)__fns(lm, 0, n + 1) : 0;
+        rr[j] = __shfl_sync(FULL, r, from);
+        ee[j] = __shfl_sync(FULL, e, from);
+        mm[j] = __shfl_sync(FULL, more, from);
         T[j] = A[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         g1[j] = w1[j] = n1[j] = z1[j] = 0.f;
         if (on[j]) {
           const int64_t ro = rr[j] * row_stride;
           T[j] = ld_hint(table + ro + sub * 4, pol_row);
           if (adagrad) A[j] = ld_hint(accum + ro + sub * 4, pol_row);
-          g[j] = __ldg(gbuf + ee[j] * LPR + sub);
+          const char* base = src.local[NBUF > 1 ? (int)(ee[j] >> 40) : 0];
+          const int64_t ent = ee[j] & ((1ll << 40) - 1);
+          g[j] = __ldg(reinterpret_cast<const float4*>(base + L.off_g) + ent * LPR + sub);
           if (sub == 0 && lin != nullptr) {
-            g1[j] = __ldg(g1buf + ee[j]);
+            g1[j] = __ldg(reinterpret_cast<const float*>(base + L.off_g1) + ent);
             w1[j] = lin[rr[j] * lin_stride];
             lin_load(lo, lin_accum, rr[j] * lin_stride, n1[j], z1[j]);
           }
@@ -323,17 +345,19 @@ peer_owner_update_kernel(const dir_peer_layout L, const uint32_t* __restrict__ s
       for (int j = 0; j < PB; ++j) {
         if (!on[j]) continue;
         unsigned long long m = mm[j];
-        while (m) {  // rank order
-          const int p = __ffsll((long long)m) - 1;
+        while (m) {  // fixed order: buffer, then rank
+          const int v = __ffsll((long long)m) - 1;
           m &= m - 1;
-          const uint32_t sp = __ldg(slot + rr[j] * G + p) & 0xffffffu;
+          const int bb = NBUF > 1 ? v / G : 0, p = NBUF > 1 ? v - bb * G : v;
+          const uint32_t sp = __ldg(src.slot[bb] + rr[j] * G + p) & 0xffffffu;
           const int64_t e2 = (int64_t)p * L.seg_cap + (sp - 1u);
-          const float4 o = __ldg(gbuf + e2 * LPR + sub);
+          const float4 o = __ldg(reinterpret_cast<const float4*>(src.local[bb] + L.off_g) + e2 * LPR + sub);
           g[j].x = __fadd_rn(g[j].x, o.x);
           g[j].y = __fadd_rn(g[j].y, o.y);
           g[j].z = __fadd_rn(g[j].z, o.z);
           g[j].w = __fadd_rn(g[j].w, o.w);
-          if (sub == 0 && lin != nullptr) g1[j] = __fadd_rn(g1[j], __ldg(g1buf + e2));
+          if (sub == 0 && lin != nullptr)
+            g1[j] = __fadd_rn(g1[j], __ldg(reinterpret_cast<const float*>(src.local[bb] + L.off_g1) + e2));
         }
         const int64_t ro = rr[j] * row_stride;
         T[j].x = upd(T[j].x, g[j].x, lr, A[j].x, adagrad);
@@ -375,16 +399,19 @@ struct DenseApplyArgs {
 };
 
 template <int LPR>
-__global__ void __launch_bounds__(128) peer_dense_apply_kernel(const dir_peer_layout L, const DenseApplyArgs a) {
+__global__ void __launch_bounds__(128)
+peer_dense_apply_kernel(const dir_peer_layout L, const char* local_b, const DenseApplyArgs a) {
   constexpr int K = LPR * 4;
   const int j = blockIdx.x, c = threadIdx.x;
   if (c > K) return;
-  const float* gbuf = reinterpret_cast<const float*>(L.local + L.off_dense);
   float g = 0.f, touched = 0.f;
-  for (int q = 0; q < L.G; ++q) {  // rank order: the same sum on every rank
-    const float* src = gbuf + ((int64_t)q * L.n_dense + j) * (K + 4);
-    g = q == 0 ? src[c] : __fadd_rn(g, src[c]);
-    touched += src[K + 1];
+  for (int b = 0; b < (local_b ? 2 : 1); ++b) {  // buffer (micro-batch), then rank: the same sum on every rank
+    const float* gbuf = reinterpret_cast<const float*>((b ? local_b : L.local) + L.off_dense);
+    for (int q = 0; q < L.G; ++q) {
+      const float* src = gbuf + ((int64_t)q * L.n_dense + j) * (K + 4);
+      g = (b == 0 && q == 0) ? src[c] : __fadd_rn(g, src[c]);
+      touched += src[K + 1];
+    }
   }
   if (touched == 0.f) return;  // no rank had a surviving lookup: the row is not touched
   const int64_t sr = __ldg(a.shard_row + j);
@@ -524,7 +551,8 @@ extern "C" int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, in
 
 extern "C" int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
                                      const float* lin, int64_t lin_stride, const float* dense_table,
-                                     int64_t dense_row_stride, const float* dense_lin, dir_stream_t stream) {
+                                     int64_t dense_row_stride, const float* dense_lin, int ctas_per_sm,
+                                     dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_gather_send", layout)) return rc;
   const int K = layout->K;
@@ -533,9 +561,10 @@ extern "C" int dir_shard_gather_send(const dir_peer_layout* layout, const float*
   if (layout->n_dense > 0 && (!dense_table || dense_row_stride < K))
     return fail(DIR_EINVAL, "shard_gather_send: the replicated rows are required when n_dense > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned gs_grid = (unsigned)(kSMs * (ctas_per_sm >= 1 && ctas_per_sm <= 8 ? ctas_per_sm : 8));
 #define DIR_GS(LP) \
-  peer_gather_send_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, table, row_stride, lin, lin_stride, dense_table, \
-                                                         dense_row_stride, dense_lin)
+  peer_gather_send_kernel<LP><<<gs_grid, 256, 0, st>>>(*layout, table, row_stride, lin, lin_stride, dense_table, \
+                                                       dense_row_stride, dense_lin)
   switch (K / 4) {
     case 1: DIR_GS(1); break;
     case 2: DIR_GS(2); break;
@@ -562,9 +591,17 @@ extern "C" int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_
 extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                                       int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
                                       int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
-                                      const dir_linear_opt* linear_opt, int64_t* n_unique_out, dir_stream_t stream) {
+                                      const dir_linear_opt* linear_opt, const dir_peer_layout* layout_b,
+                                      const uint32_t* slot_b, const uint32_t* slot_epoch_b, int64_t* n_unique_out,
+                                      dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_owner_update", layout)) return rc;
+  if (layout_b != nullptr) {
+    if (int rc = check_layout("shard_owner_update", layout_b)) return rc;
+    if (!slot_b || !slot_epoch_b || layout_b->G != layout->G || layout_b->seg_cap != layout->seg_cap ||
+        layout_b->off_g != layout->off_g || layout->G > 32)
+      return fail(DIR_EINVAL, "shard_owner_update: the second buffer needs its slot map and epoch, the same layout, G <= 32");
+  }
   const int K = layout->K;
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
     return fail(DIR_EINVAL, "shard_owner_update: unknown optimizer");
@@ -577,9 +614,14 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
   if (int rc = resolve_lin("shard_owner_update", linear_opt, optimizer, lr, lin, lin_accum, lo)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* nu = reinterpret_cast<unsigned long long*>(n_unique_out);  // += (zeroed by dir_shard_slots)
-#define DIR_OU(LP) \
-  peer_owner_update_kernel<LP><<<kPeerCtas, 256, 0, st>>>(*layout, slot, table, accum, row_stride, lin, lin_accum, \
-                                                          lin_stride, lo, optimizer, lr, n_local_rows, nu, slot_epoch)
+  OwnerSrc src{{layout->local, layout_b ? layout_b->local : nullptr}, {slot, slot_b}, {slot_epoch, slot_epoch_b}};
+#define DIR_OU(LP)                                                                                                  \
+  if (layout_b)                                                                                                     \
+    peer_owner_update_kernel<LP, 2><<<kPeerCtas, 256, 0, st>>>(*layout, src, table, accum, row_stride, lin, lin_accum, \
+                                                               lin_stride, lo, optimizer, lr, n_local_rows, nu);     \
+  else                                                                                                              \
+    peer_owner_update_kernel<LP, 1><<<kPeerCtas, 256, 0, st>>>(*layout, src, table, accum, row_stride, lin, lin_accum, \
+                                                               lin_stride, lo, optimizer, lr, n_local_rows, nu)
   switch (K / 4) {
     case 1: DIR_OU(1); break;
     case 2: DIR_OU(2); break;
@@ -596,9 +638,16 @@ extern "C" int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense
                                      float lr, const dir_linear_opt* linear_opt, float* shard_table,
                                      float* shard_accum, int64_t shard_row_stride, float* shard_lin,
                                      float* shard_lin_accum, float* shard_lin_z, int64_t shard_lin_stride,
-                                     const int64_t* shard_row, int64_t* n_unique_inout, dir_stream_t stream) {
+                                     const int64_t* shard_row, const dir_peer_layout* layout_b,
+                                     int64_t* n_unique_inout, dir_stream_t stream) {
   using namespace dir;
   if (int rc = check_layout("shard_dense_apply", layout)) return rc;
+  if (layout_b != nullptr) {
+    if (int rc = check_layout("shard_dense_apply", layout_b)) return rc;
+    if (layout_b->off_dense != layout->off_dense || layout_b->G != layout->G)
+      return fail(DIR_EINVAL, "shard_dense_apply: the second buffer must have the same layout");
+  }
+  const char* local_b = layout_b ? layout_b->local : nullptr;
   if (layout->n_dense == 0) return 0;
   if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD) return fail(DIR_EINVAL, "shard_dense_apply: unknown optimizer");
   if (!dense_table || !shard_row || !shard_table) return fail(DIR_EINVAL, "shard_dense_apply: null pointer");
@@ -614,11 +663,11 @@ extern "C" int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = layout->n_dense;
   switch (layout->K / 4) {
-    case 1: peer_dense_apply_kernel<1><<<n, 128, 0, st>>>(*layout, a); break;
-    case 2: peer_dense_apply_kernel<2><<<n, 128, 0, st>>>(*layout, a); break;
-    case 4: peer_dense_apply_kernel<4><<<n, 128, 0, st>>>(*layout, a); break;
-    case 8: peer_dense_apply_kernel<8><<<n, 128, 0, st>>>(*layout, a); break;
-    default: peer_dense_apply_kernel<16><<<n, 128, 0, st>>>(*layout, a); break;
+    case 1: peer_dense_apply_kernel<1><<<n, 128, 0, st>>>(*layout, local_b, a); break;
+    case 2: peer_dense_apply_kernel<2><<<n, 128, 0, st>>>(*layout, local_b, a); break;
+    case 4: peer_dense_apply_kernel<4><<<n, 128, 0, st>>>(*layout, local_b, a); break;
+    case 8: peer_dense_apply_kernel<8><<<n, 128, 0, st>>>(*layout, local_b, a); break;
+    default: peer_dense_apply_kernel<16><<<n, 128, 0, st>>>(*layout, local_b, a); break;
   }
   return launched("shard_dense_apply");
 }

@@ -124,12 +124,12 @@ class PeerExchange:
     and the barrier is a no-op: the same kernels run.  `barrier(p, channel)` is a device-side cross-rank barrier on
     the current stream; a lost barrier traps after BARRIER_TIMEOUT_MS instead of spinning forever."""
 
-    def __init__(self, group, world, rank, K, n_dense, seg_cap, u_cap, device):
+    def __init__(self, group, world, rank, K, n_dense, seg_cap, u_cap, device, n_buf=2):
         L = _lib.lib()
         self.world, self.rank, self.K, self.n_dense = world, rank, K, n_dense
         self.seg_cap, self.u_cap = int(seg_cap), int(u_cap)
         self.layouts, self.bufs, self.handles, self.peer_base = [], [], [], []
-        for _ in range(2):
+        for _ in range(n_buf):
             lay = _lib.PeerLayout()
             check(L.dir_peer_layout_init(world, rank, K, n_dense, self.seg_cap, self.u_cap, _lib.ctypes.byref(lay)),
                   "dir_peer_layout_init")
@@ -183,7 +183,10 @@ class ShardedLookups:
         self.U = self.R = 0
         self.event = None
         self.src = None
-        self.parity = None          # which exchange buffer this batch uses (peer flavour; set by presort)
+        self.parity = None          # which exchange buffers this batch uses (peer flavour; set by presort)
+        self.half = 0               # micro-batch of its batch (0, or 1 when the batch is exchanged as two halves)
+        self.buf = None             # = parity * micro_batches + half: index of the exchange buffer / slot map
+        self.gs_done = None         # event: this half's rows have been sent (the other half's exchange may start)
         self.shape = None
 
     @staticmethod
@@ -194,7 +197,7 @@ class ShardedLookups:
 
 class _ShardedFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, bias, layer, idx, val, train, h):
+    def forward(ctx, anchor, bias, layer, idx, val, train, h, defer=False):
         B, F = idx.shape
         K = layer.embedding_size
         dev = idx.device
@@ -212,24 +215,27 @@ class _ShardedFunction(torch.autograd.Function):
         if layer.px is not None:
             # the owner answers the ids it received: one kernel gathers the rows and stores them straight
             # into the requesters' buffers over NVLink
-            px, p = layer.px, h.parity
+            px, p = layer.px, h.buf
             if train:
                 # the owner marks who asked for which row (cells carry this use's epoch: nothing is cleared
                 # afterwards).  Only the owner's update needs the marks: a second stream, underneath the row exchange
                 # and the forward; the backward joins it.
-                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev)
+                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev, h.half)
                 aux.wait_stream(main)
                 check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, ptr(layer.slot_epoch[p]),
-                                        ptr(layer.err_flag), layer._n_unique2.data_ptr() + 8 * p, aux.cuda_stream),
-                      "dir_shard_slots")
+                                        ptr(layer.err_flag),
+                                        layer._n_unique2.data_ptr() + 8 * h.parity if h.half == 0 else None,
+                                        aux.cuda_stream), "dir_shard_slots")
             check(L.dir_shard_gather_send(px.ref(p), ptr(layer.table), layer.row_stride,
                                           ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
                                           ptr(layer.dense_table) if layer.n_dense else None, layer.row_stride,
-                                          ptr(layer.dense_lin) if (layer.n_dense and layer.first_order) else None, st),
-                  "dir_shard_gather_send")
+                                          ptr(layer.dense_lin) if (layer.n_dense and layer.first_order) else None,
+                                          layer.gather_ctas_per_sm, st), "dir_shard_gather_send")
+            h.gs_done = torch.cuda.Event()
+            h.gs_done.record()
             tr.mark("fwd.gather+send")
             px.barrier(p, 0)
-            layer._note_forward()
+            layer._note_forward(h.half)
             tr.mark("fwd.barrier")
             rows, lin = px.rows(p), px.w(p) if layer.first_order else None
             check(L.dir_embed_fm_fwd(ptr(rows), K, ptr(lin), 1, ptr(bias) if layer.first_order else None,
@@ -256,7 +262,7 @@ class _ShardedFunction(torch.autograd.Function):
         if not layer.first_order:
             first.zero_()
         ctx.layer, ctx.train, ctx.shape, ctx.h = layer, train, (B, F, K), h
-        ctx.idx = idx
+        ctx.idx, ctx.defer = idx, defer
         ctx.set_materialize_grads(False)
         if train:
             if ubuf is None:
@@ -296,18 +302,18 @@ class _ShardedFunction(torch.autograd.Function):
         n_keys = layer.plan.cap * layer.plan.world_size
         with torch.no_grad():
             if layer.px is not None:
-                px, p = layer.px, h.parity
+                px, p = layer.px, h.buf
                 n = B * layer.n_sel
                 # Next to the segmented reduce, on a second stream: the replicated one-row fields' column sums over
                 # this rank's samples -> every rank's buffer, and the bias gradient.
-                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev)
+                main, aux = torch.cuda.current_stream(), layer.aux_stream(dev, h.half)
                 aux.wait_stream(main)
                 with torch.cuda.stream(aux):
                     if layer.first_order:
                         g_bias = g_first.sum().reshape(1)
                         g_bias.record_stream(main)
                     if layer.n_dense:
-                        ows = layer._dense_ws.get(L.dir_shard_dense_workspace_bytes(K), dev)
+                        ows = layer._dense_ws[h.half].get(L.dir_shard_dense_workspace_bytes(K), dev)
                         check(L.dir_shard_dense_emit(
                             px.ref(p), ptr(layer.dense_table), layer.row_stride, ptr(ctx.idx), ptr(val),
                             ptr(layer.dense_field_offset), gfp, ptr(g_fm), ptr(S), ptr(u), ptr(layer.onerow_fields), B, F,
@@ -322,29 +328,8 @@ class _ShardedFunction(torch.autograd.Function):
                 check(L.dir_shard_g1_push(px.ref(p), ptr(h.g1_local), ptr(h.owner_off), n, st), "dir_shard_g1_push")
                 main.wait_stream(aux)
                 tr.mark("bwd.emit+push")
-                px.barrier(p, 0)
-                tr.mark("bwd.barrier")
-                # the owner merges the ranks' contributions (rank order) and updates its rows
-                check(L.dir_shard_owner_update(
-                    px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
-                    layer.row_stride, ptr(layer.w1) if layer.first_order else None,
-                    ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
-                    ptr(layer.slot_epoch[p]), _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
-                    layer._n_unique2.data_ptr() + 8 * p, st), "dir_shard_owner_update")
-                layer._last_parity = p
-                tr.mark("bwd.owner_update")
-                if layer.n_dense:
-                    check(L.dir_shard_dense_apply(
-                        px.ref(p), ptr(layer.dense_table), ptr(layer.dense_accum) if adagrad else None,
-                        layer.row_stride, ptr(layer.dense_lin) if layer.first_order else None,
-                        ptr(layer.dense_lin_acc) if layer.first_order else None, _OPTIMIZERS[layer.optimizer],
-                        layer.lr, layer.dense_linear_opt(), ptr(layer.table), ptr(layer.accum) if adagrad else None,
-                        layer.row_stride, ptr(layer.w1) if layer.first_order else None,
-                        ptr(layer.w1_accum) if layer.first_order else None,
-                        ptr(layer.lin_z) if (layer.first_order and layer.lin_z is not None) else None,
-                        layer.lin_stride, ptr(layer.dense_shard_row),
-                        layer._n_unique2.data_ptr() + 8 * p if layer.plan.rank == 0 else None, st), "dir_shard_dense_apply")
-                    tr.mark("bwd.dense_apply")
+                if not ctx.defer:
+                    layer._owner_step([h])
             else:
                 U, R = h.U, h.R
                 pad = layer.pad_stride
@@ -373,11 +358,11 @@ class _ShardedFunction(torch.autograd.Function):
             tr.close_step()
         if h is layer._inline:
             layer._inline_busy = False
-        if layer.px is not None:
-            layer._in_flight[h.parity] = False
+        if layer.px is not None and not ctx.defer:
+            layer._in_flight[h.buf] = False
         if g_bias is None and layer.first_order:
             g_bias = g_first.sum().reshape(1)
-        return None, g_bias, None, None, None, None, None
+        return None, g_bias, None, None, None, None, None, None
 
 
 class ShardedEmbeddingFM(torch.nn.Module):
@@ -397,8 +382,12 @@ class ShardedEmbeddingFM(torch.nn.Module):
                  first_order: bool = True, emit_embeddings: bool = True, check_bounds: bool = False,
                  process_group=None, max_batch: int = 65536, linear_optimizer: Optional[str] = None,
                  linear_lr: Optional[float] = None, l1_regularization_strength: float = 0.0,
-                 l2_regularization_strength: float = 0.0, init: str = "trunc_normal", device="cuda"):
+                 l2_regularization_strength: float = 0.0, init: str = "trunc_normal", micro_batches: int = 1,
+                 device="cuda"):
         super().__init__()
+        if micro_batches not in (1, 2):
+            raise ValueError("micro_batches must be 1 or 2")
+        self.micro_batches = int(micro_batches)
         if field_size <= 0:
             raise ValueError("empty columns.")                      # deepFM.py:104-105
         if embedding_size not in _K_OK:
@@ -443,9 +432,12 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self._anchor = torch.nn.Parameter(torch.zeros(1, dtype=torch.float32, device=dev))
         self._n_unique2 = torch.zeros(2, dtype=torch.int64, device=dev)   # per exchange buffer: rows the owner updated
         self._last_parity = 0
-        self._side = self._aux = None
+        self._side = self._aux = self._micro = None
         self._inline, self._inline_busy = ShardedLookups(), False
-        self._in_flight = [False, False]
+        self._in_flight = [False] * (2 * self.micro_batches)
+        # gather + send CTAs per SM: NVLink-bound, so with two micro-batches a small grid leaves the SMs to the forward
+        # of the other half that runs next to it
+        self.gather_ctas_per_sm = int(os.environ.get("DIR_B200_GS_CTAS", "8" if self.micro_batches == 1 else "3"))
         self.trace, self.trace_pre = StageTrace(), StageTrace()
         self.capturing = False
         self.exchange_mode = os.environ.get("DIR_B200_EXCHANGE", "peer")
@@ -463,7 +455,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
         self.register_buffer("sparse_fields", torch.tensor(sparse or [0], dtype=torch.int32, device=dev))
         self.px, self.slot, self.slot_epoch = None, None, None
-        self._ids_issued = self._fwd_issued = 0
+        self._ids_issued = self._fwd_issued = 0       # batches (their half 0) whose id exchange / forward was issued
         self._fwd_event = None
         # the id exchange of the NEXT batch runs concurrently with this batch's row / gradient exchange: the NCCL
         # flavour gives it a communicator of its own so the two never queue behind each other
@@ -471,12 +463,15 @@ class ShardedEmbeddingFM(torch.nn.Module):
         if self.exchange_mode == "peer":
             seg_cap = max(1, min(self.max_batch * max(self.n_sel, 1), cap))   # rows one requester can ask of one owner
             u_cap = max(1, self.max_batch * max(self.n_sel, 1))               # distinct rows a requester can ask for
-            self.px = PeerExchange(process_group, world, rank, K, self.n_dense, seg_cap, u_cap, dev)
             if seg_cap >= 1 << 24:
                 raise ValueError("max_batch * sparse fields must stay below 2^24 rows per requester and owner")
+            if self.micro_batches == 2 and world > 32:
+                raise ValueError("two micro-batches need world_size <= 32")
+            n_buf = 2 * self.micro_batches          # two parities (consecutive steps alternate) x micro-batches
+            self.px = PeerExchange(process_group, world, rank, K, self.n_dense, seg_cap, u_cap, dev, n_buf)
             # who asked for which of my rows: one cell per (local row, requester), tagged with the buffer's epoch
-            self.slot = [torch.zeros(cap * world, dtype=torch.int32, device=dev) for _ in range(2)]
-            self.slot_epoch = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.slot = [torch.zeros(cap * world, dtype=torch.int32, device=dev) for _ in range(n_buf)]
+            self.slot_epoch = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(n_buf)]
         elif dist.is_initialized() and dist.get_backend(process_group) == "nccl":
             self.side_group = dist.new_group(ranks=dist.get_process_group_ranks(process_group or dist.group.WORLD))
         with torch.no_grad():
@@ -543,7 +538,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
                              if self.lin_acc is not None else None)
         self.register_buffer("dense_lin_z", torch.zeros(n1, dtype=torch.float32, device=dev)
                              if self.lin_z is not None else None)
-        self._dense_ws = _Workspace()
+        self._dense_ws = [_Workspace(), _Workspace()]
         self._sync_dense_replicas()
 
     @torch.no_grad()
@@ -633,17 +628,74 @@ class ShardedEmbeddingFM(torch.nn.Module):
             self._side = torch.cuda.Stream(device=device, priority=-1)
         return self._side
 
-    def aux_stream(self, device):
+    def aux_stream(self, device, half=0):
         if self._aux is None:
             # high priority: its small kernels must get SM slots while the big segmented reduce is running, not
-            # queue behind that kernel's pending CTAs (profiles/r02_timeline_n2.txt)
-            self._aux = torch.cuda.Stream(device=device, priority=-1)
-        return self._aux
+            # queue behind that kernel's pending CTAs (profiles/r02_timeline_n2.txt); one per micro-batch
+            self._aux = [torch.cuda.Stream(device=device, priority=-1) for _ in range(2)]
+        return self._aux[half]
 
-    def _note_forward(self):
+    def micro_stream(self, device):
+        """The stream the second micro-batch of a step runs on (high priority: its row exchange must not queue
+        behind the first half's forward)."""
+        if self._micro is None:
+            self._micro = torch.cuda.Stream(device=device, priority=-1)
+        return self._micro
+
+    @torch.no_grad()
+    def _owner_step(self, handles):
+        """Grads barrier, then the owner's half: the requesters' sums (of one exchange buffer, or of the two
+        micro-batches' buffers) merged in a fixed order, fused row update; then the replicated one-row fields."""
+        L = _lib.lib()
+        st = _stream()
+        tr = self.trace
+        px = self.px
+        h0 = handles[0]
+        hb = handles[1] if len(handles) > 1 else None
+        p = h0.buf
+        adagrad = self.optimizer == "adagrad"
+        px.barrier(handles[-1].buf, 0)
+        tr.mark("bwd.barrier")
+        check(L.dir_shard_owner_update(
+            px.ref(p), ptr(self.slot[p]), ptr(self.table), ptr(self.accum) if adagrad else None,
+            self.row_stride, ptr(self.w1) if self.first_order else None,
+            ptr(self.w1_accum) if self.first_order else None, self.lin_stride, self.n_rows,
+            ptr(self.slot_epoch[p]), _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self),
+            px.ref(hb.buf) if hb is not None else None, ptr(self.slot[hb.buf]) if hb is not None else None,
+            ptr(self.slot_epoch[hb.buf]) if hb is not None else None,
+            self._n_unique2.data_ptr() + 8 * h0.parity, st), "dir_shard_owner_update")
+        self._last_parity = h0.parity
+        tr.mark("bwd.owner_update")
+        if self.n_dense:
+            check(L.dir_shard_dense_apply(
+                px.ref(p), ptr(self.dense_table), ptr(self.dense_accum) if adagrad else None,
+                self.row_stride, ptr(self.dense_lin) if self.first_order else None,
+                ptr(self.dense_lin_acc) if self.first_order else None, _OPTIMIZERS[self.optimizer],
+                self.lr, self.dense_linear_opt(), ptr(self.table), ptr(self.accum) if adagrad else None,
+                self.row_stride, ptr(self.w1) if self.first_order else None,
+                ptr(self.w1_accum) if self.first_order else None,
+                ptr(self.lin_z) if (self.first_order and self.lin_z is not None) else None,
+                self.lin_stride, ptr(self.dense_shard_row), px.ref(hb.buf) if hb is not None else None,
+                self._n_unique2.data_ptr() + 8 * h0.parity if self.plan.rank == 0 else None, st),
+                "dir_shard_dense_apply")
+            tr.mark("bwd.dense_apply")
+
+    def finish_step(self, handle_a, handle_b):
+        """After the backward of both micro-batches of a batch (run with `defer_update=True`): the one owner update
+        of the batch.  Call it on the stream both backwards have been joined into."""
+        if self.px is None or self.micro_batches != 2:
+            raise RuntimeError("finish_step needs the peer exchange with micro_batches=2")
+        if handle_a.parity != handle_b.parity or (handle_a.half, handle_b.half) != (0, 1):
+            raise ValueError("finish_step takes the two halves (0, 1) of one batch")
+        self._owner_step([handle_a, handle_b])
+        self._in_flight[handle_a.buf] = self._in_flight[handle_b.buf] = False
+        self.trace.close_step()
+
+    def _note_forward(self, half=0):
         """Bookkeeping after the rows barrier of a step: every rank has finished the previous step, so the id
         exchange of the next batch may now overwrite the other parity's buffers."""
-        self._fwd_issued += 1
+        if half == 0:
+            self._fwd_issued += 1
         if not self.capturing:
             self._fwd_event = torch.cuda.Event()
             self._fwd_event.record()
@@ -707,12 +759,16 @@ class ShardedEmbeddingFM(torch.nn.Module):
         K = self.embedding_size
         dev = h.keys.device
         if self.px is not None:
-            if self._ids_issued - self._fwd_issued >= 2 and not self.capturing:
-                raise RuntimeError("ShardedEmbeddingFM.presort may run at most one batch ahead of forward")
-            if h.parity is None or not self.capturing:
-                h.parity = self._ids_issued % 2
-            self._ids_issued += 1
-            p, px = h.parity, self.px
+            if h.half == 0:
+                if self._ids_issued - self._fwd_issued >= 2 and not self.capturing:
+                    raise RuntimeError("ShardedEmbeddingFM.presort may run at most one batch ahead of forward")
+                if h.parity is None or not self.capturing:
+                    h.parity = self._ids_issued % 2
+                self._ids_issued += 1
+            elif h.parity is None or not self.capturing:
+                h.parity = (self._ids_issued - 1) % 2          # the second half follows its batch's first half
+            h.buf = h.parity * self.micro_batches + h.half
+            p, px = h.buf, self.px
             if self._fwd_event is not None and not self.capturing:
                 torch.cuda.current_stream().wait_event(self._fwd_event)     # every rank is done with parity p
             check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), B * self.n_sel,
@@ -737,7 +793,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
 
     @torch.no_grad()
     def presort(self, feature_index, feature_value=None, handle=None, after=None, fork=True, inline=False,
-                phase="both"):
+                phase="both", half=0):
         """Everything of a step that depends on the ids only: composite keys, sort, distinct-row numbering
         (phase "local": touches no peer), then the id exchange and the owner's bookkeeping (phase "exchange").
         By default on the side stream, so that issued for batch i+1 right after enqueueing step i it runs underneath
@@ -751,6 +807,9 @@ class ShardedEmbeddingFM(torch.nn.Module):
         if phase not in ("both", "local", "exchange"):
             raise ValueError("phase must be 'both', 'local' or 'exchange'")
         h = handle if handle is not None else ShardedLookups()
+        if half not in (0, 1) or half >= self.micro_batches:
+            raise ValueError("half must be 0 (or 1 with micro_batches=2)")
+        h.half = half
         if inline:
             if phase != "exchange":
                 self.id_local(h, idx, val)
@@ -775,9 +834,13 @@ class ShardedEmbeddingFM(torch.nn.Module):
         h.src = ShardedLookups.key_of(feature_index, feature_value)
         return h
 
-    def forward(self, feature_index, feature_value=None, presorted=None):
+    def forward(self, feature_index, feature_value=None, presorted=None, defer_update=False):
+        """defer_update=True (micro_batches=2): the backward only ships this half's gradient sums; the caller runs
+        `finish_step(half0, half1)` after both halves' backward."""
         idx, val = self._prepare(feature_index, feature_value)
         train = self.training and torch.is_grad_enabled()
+        if defer_update and (self.px is None or self.micro_batches != 2 or presorted is None):
+            raise ValueError("defer_update needs micro_batches=2, the peer exchange and a presorted handle")
         if presorted is None:
             # the layer's own handle serves one forward at a time (a second forward before the first one's backward
             # gets a handle of its own)
@@ -788,12 +851,13 @@ class ShardedEmbeddingFM(torch.nn.Module):
         elif presorted.src != ShardedLookups.key_of(feature_index, feature_value):
             raise ValueError("presorted handle was made for other feature_index / feature_value tensors")
         if self.px is not None and train:
-            if self._in_flight[presorted.parity] and not self.capturing:
+            if self._in_flight[presorted.buf] and not self.capturing:
                 raise RuntimeError("ShardedEmbeddingFM: two exchange buffers = at most two batches between forward and "
                                    "backward; run the backward of an earlier batch first")
-            self._in_flight[presorted.parity] = True
+            self._in_flight[presorted.buf] = True
         self._last_handle = presorted
-        first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted)
+        first, fm, emb = _ShardedFunction.apply(self._anchor, self.bias, self, idx, val, train, presorted,
+                                                bool(defer_update))
         if self.check_bounds:
             if int(self.oob_flag.item()) != 0:
                 self.oob_flag.zero_()

@@ -310,10 +310,12 @@ int dir_shard_ids_push(const dir_peer_layout* layout, const int32_t* unique_loca
 int dir_shard_slots(const dir_peer_layout* layout, uint32_t* slot, int64_t n_local_rows,
                     const uint32_t* slot_epoch, int* err_flag, int64_t* zero_counter, dir_stream_t stream);
 /* dense_table / dense_lin: the replicated one-row fields' rows [n_dense] (copied behind this rank's own
- * exchanged rows so that dir_embed_fm_fwd finds them at u_cap + j); NULL when n_dense == 0 */
+ * exchanged rows so that dir_embed_fm_fwd finds them at u_cap + j); NULL when n_dense == 0.
+ * ctas_per_sm (1..8, else 8): the kernel is NVLink-bound; a small grid leaves the SMs to a kernel running next to it */
 int dir_shard_gather_send(const dir_peer_layout* layout, const float* table, int64_t row_stride,
                           const float* lin, int64_t lin_stride, const float* dense_table,
-                          int64_t dense_row_stride, const float* dense_lin, dir_stream_t stream);
+                          int64_t dense_row_stride, const float* dense_lin, int ctas_per_sm,
+                          dir_stream_t stream);
 /* dir_embed_bwd_reduce_emit with the transfer fused in: each distinct row's G[K] is stored straight into its
  * owner's buffer over NVLink as soon as its run is summed (no round trip through HBM, the NVLink stores overlap
  * the kernel's gathers); g1 goes to g1_local[u] and is shipped by dir_shard_g1_push.  The sorted list covers
@@ -333,11 +335,16 @@ int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table
                          const int64_t* dense_field_offset, const float* g_first, const float* g_fm,
                          const float* S, const float* u, const int32_t* onerow_fields, int64_t B, int F,
                          void* workspace, size_t workspace_bytes, dir_stream_t stream);
-/* n_unique_inout += local rows updated */
+/* n_unique_inout += local rows updated.  layout_b / slot_b / slot_epoch_b (NULL, or all three): the batch was
+ * exchanged as TWO micro-batches, each through an exchange buffer and slot map of its own (so that the row exchange of
+ * the second overlaps the forward of the first); half s of rank q counts as virtual requester s * G + q and the merge
+ * runs over both buffers in that order -- still one update per row and batch. */
 int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                            int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
                            int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
-                           const dir_linear_opt* linear_opt, int64_t* n_unique_inout, dir_stream_t stream);
+                           const dir_linear_opt* linear_opt, const dir_peer_layout* layout_b,
+                           const uint32_t* slot_b, const uint32_t* slot_epoch_b, int64_t* n_unique_inout,
+                           dir_stream_t stream);
 /* shard_row[j] >= 0 names the row of the sharded table that mirrors replica j (on the rank that owns it), so
  * the sharded table stays a faithful view; n_unique_inout += fields touched (pass it on one rank only) */
 int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
@@ -345,7 +352,7 @@ int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, flo
                           float lr, const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
                           int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
                           float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
-                          int64_t* n_unique_inout, dir_stream_t stream);
+                          const dir_peer_layout* layout_b, int64_t* n_unique_inout, dir_stream_t stream);
 /* cfg4-sized tables are filled on the device: value(global row, k) from a counter hash of (seed, row, k) --
  * a sum of four 16-bit uniforms, centred and scaled to standard deviation `sd` (|value| < 3.47 sd) -- so any row
  * can be reproduced on the host without the table (oracle/deepctr_oracle.counter_rows).  Fills

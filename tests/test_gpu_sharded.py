@@ -215,3 +215,119 @@ def test_slot_epoch_wraps(pkg, cuda):
     ta, tb = a.table.cpu().numpy(), b.table.cpu().numpy()
     assert np.abs(ta - tb).max() <= 1e-4 * max(1.0, np.abs(tb).max())
     assert np.abs(a.w1.cpu().numpy() - b.w1.cpu().numpy()).max() <= 1e-4
+
+
+def _micro_step(layer, idx, val, g_first, g_fm, u, d="cuda"):
+    """One batch as two micro-batches: both halves presorted, forward on two streams, backward, ONE owner update."""
+    B = idx.shape[0]
+    Bh = B // 2
+    hs, outs = [], []
+    ti, tv = to_dev(idx, d), to_dev(val, d)
+    for x in range(2):
+        sl = slice(x * Bh, (x + 1) * Bh)
+        hs.append(layer.presort(ti[sl], tv[sl], half=x))
+    main, sb = torch.cuda.current_stream(), layer.micro_stream(ti.device)
+    fa = layer(ti[:Bh], tv[:Bh], presorted=hs[0], defer_update=True)
+    sb.wait_event(hs[0].gs_done)
+    with torch.cuda.stream(sb):
+        fb = layer(ti[Bh:], tv[Bh:], presorted=hs[1], defer_update=True)
+    tg1, tg2, tu = to_dev(g_first, d), to_dev(g_fm, d), to_dev(u.reshape(B, -1), d)
+    torch.autograd.backward(fa, (tg1[:Bh, None], tg2[:Bh, None], tu[:Bh]))
+    with torch.cuda.stream(sb):
+        torch.autograd.backward(fb, (tg1[Bh:, None], tg2[Bh:, None], tu[Bh:]))
+    main.wait_stream(sb)
+    layer.finish_step(hs[0], hs[1])
+    torch.cuda.synchronize()
+    return torch.cat([fa[2], fb[2]]).detach()
+
+
+@pytest.mark.parametrize("B,rows,K", [(64, [50, 1, 9, 1000, 3, 17, 1], 16), (1024, [10_000] * 26 + [1] * 13, 8),
+                                      (600, [3, 1, 40], 4)])
+def test_world1_two_micro_batches(pkg, cuda, B, rows, K):
+    """The batch exchanged as two micro-batches (each through an exchange buffer and slot map of its own) and merged by
+    ONE owner update: rows that both halves touch must get the summed gradient once (Adagrad: one step per batch)."""
+    case = make_case(53, B, rows, K, weighted=True, prune=True, skew=2.0)
+    rng, F = case["rng"], case["F"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = (rng.standard_normal(B) * 0.1).astype(np.float32)
+    u = (rng.standard_normal((B, F, K)) * 0.1).astype(np.float32)
+    layer = pkg.ShardedEmbeddingFM(F, K, [int(r) for r in rows], optimizer="adagrad", lr=0.05, micro_batches=2).train()
+    layer.load_tables(case["table"], case["w1"])
+    t, w = case["table"].astype(np.float64), case["w1"].astype(np.float64)
+    acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+    for step in range(3):                            # three steps: both parities and a re-used buffer
+        emb = _micro_step(layer, case["idx"], case["val"], g_first, g_fm, u)
+        e, _ = O.embedding_lookup(t.astype(np.float32), case["off"], case["idx"], case["val"], "sum", np.float32)
+        if step == 0:
+            assert np.array_equal(emb.cpu().numpy().reshape(B, F, K), e), "gathered rows must be bit-exact"
+        urows, G, g1, _, Gabs, _ = O.embedding_backward(t, case["off"], case["idx"], case["val"], g_first, g_fm, u,
+                                                        "sum", np.float64, return_abs=True)
+        O.sparse_adagrad(t, acc, urows, G, 0.05)
+        O.sparse_adagrad(w, acc1, urows, g1, 0.05)
+        layer.check_errors()
+        assert int(layer.last_n_unique.item()) == len(urows)
+    got_t, got_w = layer.table.cpu().numpy(), layer.w1.cpu().numpy()
+    assert rel_err(got_t, t, np.abs(case["table"]).max()) <= 3 * REL
+    assert rel_err(got_w, w, np.abs(case["w1"]).max() + 1e-3) <= 3 * REL
+    assert rel_err(layer.accum.cpu().numpy(), acc, 0.1 + np.abs(acc).max()) <= 3 * REL
+
+
+def _rank_main_micro(rank, world, port, out):
+    import torch.distributed as dist
+    import dir_b200
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), DIR_B200_EXCHANGE="peer")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rows, K, Bl = CASES["wide"]
+        case = make_case(43, Bl * world, rows, K, weighted=True, prune=True)
+        rng, F = case["rng"], case["F"]
+        g_first = rng.standard_normal(Bl * world).astype(np.float32)
+        g_fm = (rng.standard_normal(Bl * world) * 0.1).astype(np.float32)
+        u = (rng.standard_normal((Bl * world, F, K)) * 0.1).astype(np.float32)
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        layer = dir_b200.ShardedEmbeddingFM(F, K, rows, optimizer="adagrad", lr=0.05, max_batch=Bl, micro_batches=2,
+                                            device="cuda").train()
+        layer.load_tables(case["table"], case["w1"])
+        t, w = case["table"].astype(np.float64), case["w1"].astype(np.float64)
+        acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+        for step in range(2):
+            emb = _micro_step(layer, case["idx"][sl], case["val"][sl], g_first[sl], g_fm[sl], u[sl])
+            e, _ = O.embedding_lookup(t.astype(np.float32), case["off"], case["idx"], case["val"], "sum", np.float32)
+            if step == 0:
+                assert np.array_equal(emb.cpu().numpy().reshape(Bl, F, K), e[sl])
+            urows, G, g1, _ = O.embedding_backward(t, case["off"], case["idx"], case["val"], g_first, g_fm, u, "sum", np.float64)
+            O.sparse_adagrad(t, acc, urows, G, 0.05)
+            O.sparse_adagrad(w, acc1, urows, g1, 0.05)
+            layer.check_errors()
+        shards = [torch.empty_like(layer.rows) for _ in range(world)]
+        dist.all_gather(shards, layer.rows)
+        if rank == 0:
+            N = case["N"]
+            full = np.zeros((layer.plan.cap * world, 2 * K), np.float32)
+            for r in range(world):
+                full[r::world] = shards[r].cpu().numpy()
+            assert rel_err(full[:N, :K], t, np.abs(case["table"]).max()) <= 3 * REL
+        out.put((rank, "ok"))
+    except Exception:
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_two_micro_batches(pkg, cuda, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main_micro, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
