@@ -241,7 +241,7 @@ struct OwnerSrc {
 };
 
 template <int LPR, int NBUF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LPR <= 4 ? 3 : 1)
 peer_owner_update_kernel(const dir_peer_layout L, const OwnerSrc src, float* table, float* accum,
                          int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
                          int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
