@@ -771,14 +771,43 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
                                     ptr(dx0), ptr(dw), ptr(db), ptr(cws), cws.numel(), st), "cb")
         calls += [("dir_cross_fwd", cf, RL.cross_fwd_bytes(B, d, L)), ("dir_cross_bwd", cb, RL.cross_bwd_bytes(B, d, L))]
 
-    # one pass in order keeps each call's inputs valid; events bracket every call
+    # One pass in order keeps each call's inputs valid; events bracket every call.  Each call is replayed from a
+    # CUDA graph of its own (captured once per input set), so that the bracket holds the call's kernels and not the
+    # host's launch gaps between them (a call is several launches, and the backward forks a second stream); if the
+    # capture fails the calls are launched eagerly.
     evs = {name: [] for name, _, _ in calls}
+    for r in range(R):                              # eager once: workspaces exist, errors surface here
+        for name, fn, _ in calls:
+            fn(r)
+    torch.cuda.synchronize()
+    replay, how = {}, "each call replayed from its own CUDA graph"
+    try:
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            for name, fn, _ in calls:
+                for r in range(R):
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_, stream=cap):
+                        st = torch.cuda.current_stream().cuda_stream      # (the closures read `st`)
+                        fn(r)
+                    replay[(name, r)] = g_
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+    except Exception as e:
+        print("bench.py: per-call graph capture failed (%s); timing eager launches" % e, file=sys.stderr)
+        replay, how = {}, "eager launches (host gaps between a call's kernels included)"
+        torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
     for it in range(3 + iters):
         r = it % R
         for name, fn, _ in calls:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            fn(r)
+            if replay:
+                replay[(name, r)].replay()
+            else:
+                fn(r)
             b.record()
             if it >= 3:
                 evs[name].append((a, b))
@@ -803,7 +832,7 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
             "call_note": "dir_embed_bwd_reduce_update is timed as the layer runs it: dir_embed_bwd_onerow_update (the "
                          "one-row fields) on a second stream underneath the sorted segmented reduce", "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src
             if src == "measured" else "fallback (B200_PROFILING.md)", "traffic": traffic,
-            "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "us_per_launch": top["us"]}
+            "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "us_per_launch": top["us"], "timing": how}
     return roof, table
 
 
