@@ -19,6 +19,8 @@
 // the largest term; the parity tests hold 1e-5 relative against the fp64 oracle).
 //
 // Reference: models/DeepCrossNetwork/DeepCrossNetwork.py:336-367 and TF autodiff of it (:283).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dir {
@@ -654,12 +656,7 @@ cross_bwd_fused_kernel(const float* __restrict__ x0g, const float* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------------------ fused backward, TMA-fed
-// Same arithmetic as cross_bwd_fused_kernel, but the x0 / dy tiles ([kTS][d] each, contiguous in HBM) are
-// brought into a two-stage shared-memory ring by bulk asynchronous copies (cp.async.bulk, the 1-D TMA path,
-// completion counted on an mbarrier): the next tile is in flight while the current one is being consumed, so
-// HBM stays busy through phase B and through the barriers, and phase A reads its rows with LDS instead of
-// LDG + STS.  One CTA per SM (the ring takes 4 * kTS * d * 4 bytes).  d % 4 == 0 only.
+// ------------------------------------------------------------------------------ bulk-copy helpers (1-D TMA)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -690,263 +687,223 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// cross_constants for a CTA of WARPS warps (the default kernels keep the 8-warp original).
-template <int WARPS>
-__device__ __forceinline__ void cross_constants_t(const float* __restrict__ wg, const float* __restrict__ bg,
-                                                  int d, int L, float* s_q, float* s_red) {
-  constexpr int NT = WARPS * 32;
-  constexpr int CPT = (1024 + NT - 1) / NT;  // columns per thread, d <= 1024
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float beta[CPT];
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) beta[j] = 0.f;
-  for (int l = 0; l < L; ++l) {
-    float part = 0.f;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = threadIdx.x + j * NT;
-      if (c < d) {
-        part = fmaf(beta[j], __ldg(wg + l * d + c), part);
-        beta[j] += __ldg(bg + l * d + c);
-      }
-    }
-    part = warp_sum(part);
-    if (lane == 0) s_red[wib] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) t += s_red[w];
-      s_q[l] = t;
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-}
+// ------------------------------------------------------------------------------ backward, per-warp rings
+// The fastest form, for shapes whose batch sums fit in registers (4 * NPL * (LT + 3) <= 184 floats per lane).
+// A warp owns samples gw, gw + W, gw + 2W, ... (W = warps in the grid) and a private ring of `depth` slots in shared
+// memory, each holding one x0 row and one dy row.  Lane 0 refills a slot with two bulk asynchronous copies
+// (cp.async.bulk, completion counted on the slot's mbarrier) as soon as the warp has moved the slot's rows into
+// registers, so depth - 1 rows per warp stay in flight whatever the warp is computing: HBM never waits for a
+// phase change, and no __syncthreads() is executed between the prologue and the final combine.  Everything the two
+// phases of cross_bwd_fused_kernel did per tile happens on the one register copy of the rows:
+//     a, the recurrences, dx0 -> HBM,   acc[l][e] += alpha_l x0[e],   accdy[e] += dy[e]
+// i.e. dw / db are accumulated per warp over its own samples in sample order, then the CTA's eight warps are added
+// in warp order and the per-CTA partials go to cross_bwd_finish2_kernel as before: fixed order, no float atomics.
+// p_l comes from the forward (pg, prefetched one sample ahead) or is recomputed.
+constexpr int kRingMaxDepth = 4;
 
-// NS = samples a warp works on at once (1 or 2): with one CTA per SM registers are plentiful, and two
-// independent samples double the ILP of the shuffle / recurrence chains and share the w loads.
-// WARPS = warps per CTA (8 or 16): sixteen warps walk a whole tile in one phase-A round and give phase B
-// 512 column threads.
-template <int NPL, int NS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-cross_bwd_tma_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
-                     const float* __restrict__ bg, const float* __restrict__ dyg,
-                     const float* __restrict__ pg, int64_t B, int d, int L,
-                     float* __restrict__ dx0g, float* __restrict__ Dpart,
-                     float* __restrict__ dypart, float* __restrict__ dwpart) {
+template <int NPL, int LT>
+__global__ void __launch_bounds__(kCrossWarps * 32, 1)
+cross_bwd_ring_kernel(const float* __restrict__ x0g, const float* __restrict__ wg,
+                      const float* __restrict__ bg, const float* __restrict__ dyg,
+                      const float* __restrict__ pg, int64_t B, int d, int L, int depth,
+                      float* __restrict__ dx0g, float* __restrict__ Dpart,
+                      float* __restrict__ dypart, float* __restrict__ dwpart) {
   constexpr int VEC = 4;
   constexpr int E = VEC * NPL;
   constexpr int DP = E * 32;
-  constexpr int NT = WARPS * 32;
-  constexpr int CI = (E * 32 + NT - 1) / NT;
   extern __shared__ __align__(128) float smem[];
-  float* ring = smem;                          // [2 stages][x0 tile | dy tile], each tile [kTS][d]
-  const int tile_f = kTS * d;                  // floats per tile
-  float* als = ring + 4 * tile_f;              // [kTS][8]
-  float* sD = als + kTS * 8;                   // [WARPS][32]
-  float* s_q = sD + WARPS * 32;                // [32]
-  float* s_red = s_q + 32;                     // [WARPS]
-  float* s_w = s_red + WARPS;                  // [L][DP]
-  __shared__ __align__(8) uint64_t full[2];    // one mbarrier per stage
+  float* ring = smem;  // [kCrossWarps][depth][x0 row | dy row]; at the end [kCrossWarps][DP] for the combine
+  const size_t ring_f = max((size_t)kCrossWarps * depth * 2 * d, (size_t)kCrossWarps * DP);
+  float* s_w = ring + ring_f;                               // [L][DP]
+  float* sD = s_w + L * DP;                                 // [kCrossWarps][32]
+  float* s_q = sD + kCrossWarps * 32;                       // [32]
+  float* s_red = s_q + 32;                                  // [kCrossWarps]
+  __shared__ __align__(8) uint64_t full[kCrossWarps * kRingMaxDepth];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int64_t ntiles = (B + kTS - 1) / kTS;
+  const int64_t W = (int64_t)gridDim.x * kCrossWarps;
+  const int64_t gw = (int64_t)blockIdx.x * kCrossWarps + wib;
+  const int64_t nmine = gw < B ? (B - gw + W - 1) / W : 0;
+  const uint32_t row_bytes = (uint32_t)d * 4u;
 
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < kCrossWarps * kRingMaxDepth; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int64_t tile, int stage) {  // thread 0 only
-    const int64_t b0 = tile * kTS;
-    const int rows = (int)(B - b0 < kTS ? B - b0 : kTS);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
-    float* dst = ring + (size_t)stage * 2 * tile_f;
-    mbar_expect_tx(&full[stage], 2u * bytes);
-    bulk_g2s(dst, x0g + b0 * d, bytes, &full[stage]);
-    bulk_g2s(dst + tile_f, dyg + b0 * d, bytes, &full[stage]);
+  float* myring = ring + (size_t)wib * depth * 2 * d;
+  uint64_t* mybar = full + wib * kRingMaxDepth;
+  auto issue = [&](int64_t k, int slot) {  // lane 0 only
+    const int64_t b = gw + k * W;
+    float* dst = myring + (size_t)slot * 2 * d;
+    mbar_expect_tx(&mybar[slot], 2u * row_bytes);
+    bulk_g2s(dst, x0g + b * d, row_bytes, &mybar[slot]);
+    bulk_g2s(dst + d, dyg + b * d, row_bytes, &mybar[slot]);
   };
-  if (threadIdx.x == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  if (lane == 0)
+    for (int k = 0; k < depth && k < nmine; ++k) issue(k, k);
 
   stage_w<DP>(wg, d, L, s_w);
-  cross_constants_t<WARPS>(wg, bg, d, L, s_q, s_red);
+  cross_constants(wg, bg, d, L, nullptr, s_q, s_red);  // ends with a __syncthreads()
   const float q_mine = lane < L ? s_q[lane] : 0.f;
-  float acc[CI][8], accdy[CI];
+  float acc[LT][E], accdy[E];
 #pragma unroll
-  for (int ci = 0; ci < CI; ++ci) {
-    accdy[ci] = 0.f;
+  for (int e = 0; e < E; ++e) {
+    accdy[e] = 0.f;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) acc[ci][l] = 0.f;
+    for (int l = 0; l < LT; ++l) acc[l][e] = 0.f;
   }
-  float Dacc = 0.f;
+  float Dacc = 0.f;  // lane l: sum over this warp's samples of ds_l
+  float p_next = 0.f;
+  if (pg && nmine > 0 && lane < L) p_next = __ldg(pg + gw * L + lane);
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int64_t b0 = tile * kTS;
-    const int nv = (int)(B - b0 < kTS ? B - b0 : kTS);  // samples in this tile
-    // the other stage was released by the barrier that closed the previous iteration: refill it now
-    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
-    mbar_wait(&full[stage], (uint32_t)((it >> 1) & 1));
-    const float* x0s = ring + (size_t)stage * 2 * tile_f;
-    const float* dys = x0s + tile_f;
-    // ---- phase A: one warp per NS samples, rows read from the ring
+  int slot = 0;
+  uint32_t parity = 0;
 #pragma unroll 1
-    for (int h = 0; h < kTS / WARPS; h += NS) {
-      float x0[NS][E], dx[NS][E], a[NS], p_mine[NS];
-      int tbs[NS];
-      bool live[NS];
+  for (int64_t k = 0; k < nmine; ++k) {
+    const int64_t b = gw + k * W;
+    mbar_wait(&mybar[slot], parity);
+    const float* xs = myring + (size_t)slot * 2 * d;
+    float x0[E], dx[E];
+    float a = 0.f;
 #pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        tbs[s2] = (h + s2) * WARPS + wib;
-        live[s2] = tbs[s2] < nv;
-        a[s2] = 0.f;
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      float4 px = make_float4(0.f, 0.f, 0.f, 0.f), pd = px;
+      if (c < d) {
+        px = *reinterpret_cast<const float4*>(xs + c);
+        pd = *reinterpret_cast<const float4*>(xs + d + c);
+      }
+      x0[i * 4] = px.x; x0[i * 4 + 1] = px.y; x0[i * 4 + 2] = px.z; x0[i * 4 + 3] = px.w;
+      dx[i * 4] = pd.x; dx[i * 4 + 1] = pd.y; dx[i * 4 + 2] = pd.z; dx[i * 4 + 3] = pd.w;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        a = fmaf(dx[i * VEC + e], x0[i * VEC + e], a);
+        accdy[i * VEC + e] += dx[i * VEC + e];
+      }
+    }
+    // the rows are in registers: hand the slot back to the copy engine
+    __syncwarp();
+    if (lane == 0 && k + depth < nmine) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(k + depth, slot);
+    }
+    if (++slot == depth) {
+      slot = 0;
+      parity ^= 1u;
+    }
+    a = warp_sum(a);
+    float p_mine = 0.f;  // lane l keeps p_l = x0 . w_l
+    if (pg) {
+      p_mine = p_next;
+      if (k + 1 < nmine && lane < L) p_next = __ldg(pg + (b + W) * L + lane);
+    } else {
+      for (int l = 0; l < L; ++l) {
+        float dot = 0.f;
+        const float* wl = s_w + l * DP + lane * VEC;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
-          const int c = (i * 32 + lane) * VEC;
-          float4 px = make_float4(0.f, 0.f, 0.f, 0.f), pd = px;
-          if (live[s2] && c < d) {
-            px = *reinterpret_cast<const float4*>(x0s + tbs[s2] * d + c);
-            pd = *reinterpret_cast<const float4*>(dys + tbs[s2] * d + c);
-          }
-          x0[s2][i * 4] = px.x; x0[s2][i * 4 + 1] = px.y; x0[s2][i * 4 + 2] = px.z; x0[s2][i * 4 + 3] = px.w;
-          dx[s2][i * 4] = pd.x; dx[s2][i * 4 + 1] = pd.y; dx[s2][i * 4 + 2] = pd.z; dx[s2][i * 4 + 3] = pd.w;
+          const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) a[s2] = fmaf(dx[s2][i * VEC + e], x0[s2][i * VEC + e], a[s2]);
+          for (int e = 0; e < VEC; ++e) dot = fmaf(x0[i * VEC + e], pw.v[e], dot);
         }
+        dot = warp_sum(dot);
+        if (lane == l) p_mine = dot;
       }
+    }
+    float pv[LT], cv[LT + 1];
+    cv[0] = 1.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < LT; ++l) {
+      pv[l] = __shfl_sync(0xffffffffu, p_mine, l);
+      const float q = __shfl_sync(0xffffffffu, q_mine, l);
+      cv[l + 1] = cv[l] + fmaf(cv[l], pv[l], q);  // layers l >= L have p = q = 0: c stays
+    }
+    float al[LT];
+    float t = 0.f, ds_mine = 0.f;
 #pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2) a[s2] += __shfl_xor_sync(0xffffffffu, a[s2], o);
+    for (int l = LT - 1; l >= 0; --l) {
+      float ds = 0.f;
+      if (l < L) {
+        ds = a + t;
+        t = fmaf(ds, pv[l], t);
       }
+      al[l] = ds * cv[l];
+      if (lane == l) ds_mine = ds;
+    }
+    Dacc += ds_mine;
+    const float cL = cv[LT];
 #pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) p_mine[s2] = 0.f;
-      if (pg) {
+    for (int e = 0; e < E; ++e) dx[e] *= cL;
 #pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2)
-          if (live[s2] && lane < L) p_mine[s2] = __ldg(pg + (b0 + tbs[s2]) * L + lane);
-      } else {
-        for (int l = 0; l < L; ++l) {
-          float dot[NS];
+    for (int l = 0; l < LT; ++l) {
+      if (l < L) {  // warp-uniform
+        const float* wl = s_w + l * DP + lane * VEC;
 #pragma unroll
-          for (int s2 = 0; s2 < NS; ++s2) dot[s2] = 0.f;
-          const float* wl = s_w + l * DP + lane * VEC;
+        for (int i = 0; i < NPL; ++i) {
+          const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
 #pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e)
-#pragma unroll
-              for (int s2 = 0; s2 < NS; ++s2) dot[s2] = fmaf(x0[s2][i * VEC + e], pw.v[e], dot[s2]);
-          }
-#pragma unroll
-          for (int s2 = 0; s2 < NS; ++s2) {
-            dot[s2] = warp_sum(dot[s2]);
-            if (lane == l) p_mine[s2] = dot[s2];
-          }
-        }
-      }
-      float al[NS][8];
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        float pv[8], cv[9];
-        cv[0] = 1.f;
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-          pv[l] = __shfl_sync(0xffffffffu, p_mine[s2], l);
-          const float q = __shfl_sync(0xffffffffu, q_mine, l);
-          cv[l + 1] = cv[l] + fmaf(cv[l], pv[l], q);
-        }
-        float t = 0.f, ds_mine = 0.f, al_mine = 0.f;
-#pragma unroll
-        for (int l = 7; l >= 0; --l) {
-          float ds = 0.f;
-          if (l < L) {
-            ds = a[s2] + t;
-            t = fmaf(ds, pv[l], t);
-          }
-          al[s2][l] = ds * cv[l];
-          if (lane == l) {
-            ds_mine = ds;
-            al_mine = al[s2][l];
-          }
-        }
-        Dacc += ds_mine;
-        if (lane < 8) als[tbs[s2] * 8 + lane] = al_mine;
-        const float cL = cv[8];
-#pragma unroll
-        for (int e = 0; e < E; ++e) dx[s2][e] *= cL;
-      }
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        if (l < L) {
-          const float* wl = s_w + l * DP + lane * VEC;
-#pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const Pack<VEC> pw = lds_pack<VEC>(wl + i * 32 * VEC);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e)
-#pragma unroll
-              for (int s2 = 0; s2 < NS; ++s2) dx[s2][i * VEC + e] = fmaf(al[s2][l], pw.v[e], dx[s2][i * VEC + e]);
-          }
-        }
-      }
-#pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        if (live[s2]) {
-#pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const int c = (i * 32 + lane) * VEC;
-            if (c < d) st_pack<VEC>(dx0g + (b0 + tbs[s2]) * d + c, &dx[s2][i * VEC]);
+          for (int e = 0; e < VEC; ++e) {
+            dx[i * VEC + e] = fmaf(al[l], pw.v[e], dx[i * VEC + e]);
+            acc[l][i * VEC + e] = fmaf(al[l], x0[i * VEC + e], acc[l][i * VEC + e]);
           }
         }
       }
     }
-    __syncthreads();
-    // ---- phase B: thread = column, the tile's samples in order (only the nv live ones: the rest of the
-    // ring slot holds whatever an earlier tile left there)
-    for (int tb = 0; tb < nv; ++tb) {
-      const float4 a0 = *reinterpret_cast<const float4*>(als + tb * 8);
-      const float4 a1 = *reinterpret_cast<const float4*>(als + tb * 8 + 4);
 #pragma unroll
-      for (int ci = 0; ci < CI; ++ci) {
-        const int c = ci * NT + threadIdx.x;
-        if (c < d) {
-          const float xv = x0s[tb * d + c];
-          acc[ci][0] = fmaf(a0.x, xv, acc[ci][0]);
-          acc[ci][1] = fmaf(a0.y, xv, acc[ci][1]);
-          acc[ci][2] = fmaf(a0.z, xv, acc[ci][2]);
-          acc[ci][3] = fmaf(a0.w, xv, acc[ci][3]);
-          acc[ci][4] = fmaf(a1.x, xv, acc[ci][4]);
-          acc[ci][5] = fmaf(a1.y, xv, acc[ci][5]);
-          acc[ci][6] = fmaf(a1.z, xv, acc[ci][6]);
-          acc[ci][7] = fmaf(a1.w, xv, acc[ci][7]);
-          accdy[ci] += dys[tb * d + c];
-        }
-      }
+    for (int i = 0; i < NPL; ++i) {
+      const int c = (i * 32 + lane) * VEC;
+      if (c < d) st_pack<VEC>(dx0g + b * d + c, &dx[i * VEC]);
     }
-    __syncthreads();  // everyone is done with this stage and with als: the stage may be refilled
   }
+  // ---- the CTA's partials: warps in order, one quantity at a time through the (now idle) ring
+  __syncthreads();
+  float* comb = ring;  // [kCrossWarps][DP]
 #pragma unroll
-  for (int ci = 0; ci < CI; ++ci) {
-    const int c = ci * NT + threadIdx.x;
-    if (c < d) {
-      dypart[(int64_t)blockIdx.x * d + c] = accdy[ci];
+  for (int r = 0; r <= LT; ++r) {
+    if (r <= L) {  // block-uniform
 #pragma unroll
-      for (int l = 0; l < 8; ++l)
-        if (l < L) dwpart[((int64_t)blockIdx.x * L + l) * d + c] = acc[ci][l];
+      for (int i = 0; i < NPL; ++i) {
+        float4 v;
+        if (r == 0) {
+          v = make_float4(accdy[i * 4], accdy[i * 4 + 1], accdy[i * 4 + 2], accdy[i * 4 + 3]);
+        } else {
+          const int l = r > 0 ? r - 1 : 0;
+          v = make_float4(acc[l][i * 4], acc[l][i * 4 + 1], acc[l][i * 4 + 2], acc[l][i * 4 + 3]);
+        }
+        *reinterpret_cast<float4*>(comb + wib * DP + (i * 32 + lane) * VEC) = v;
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < d; c += kCrossWarps * 32) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCrossWarps; ++w) tsum += comb[w * DP + c];
+        if (r == 0)
+          dypart[(int64_t)blockIdx.x * d + c] = tsum;
+        else
+          dwpart[((int64_t)blockIdx.x * L + (r - 1)) * d + c] = tsum;
+      }
+      __syncthreads();
     }
   }
   sD[wib * 32 + lane] = Dacc;
   __syncthreads();
   if (threadIdx.x < L) {
-    float t = 0.f;
+    float tsum = 0.f;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) t += sD[w * 32 + threadIdx.x];
-    Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+    for (int w = 0; w < kCrossWarps; ++w) tsum += sD[w * 32 + threadIdx.x];
+    Dpart[(int64_t)blockIdx.x * L + threadIdx.x] = tsum;
+  }
+}
+
+template <int N, int T>
+static void launch_ring(int grid, size_t smem, cudaStream_t st, const float* x0, const float* w, const float* b,
+                        const float* dy, const float* p, int64_t B, int d, int L, int depth, float* dx0,
+                        float* Dpart, float* dypart, float* dwpart) {
+  if constexpr (4 * N * (T + 3) <= 184) {  // the register budget of one lane; other shapes take the tiled kernel
+    cudaFuncSetAttribute(cross_bwd_ring_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cross_bwd_ring_kernel<N, T><<<grid, kCrossWarps * 32, smem, st>>>(x0, w, b, dy, p, B, d, L, depth, dx0, Dpart,
+                                                                       dypart, dwpart);
   }
 }
 
@@ -1113,37 +1070,28 @@ extern "C" int dir_cross_bwd(const float* x0, const float* cross_w, const float*
     return fail(DIR_EINVAL, "cross_bwd: 16-byte alignment required when d % 4 == 0");
   CrossBwdWs w = cross_carve(workspace, B, d, L);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "cross_bwd: workspace too small");
-  if (L <= 8 && (tune() & 128) && sh.vec == 4) {
-    // TMA-fed variant (experiment bit 128): one CTA per SM, two-stage ring of x0 / dy tiles
-    const size_t ring = (size_t)4 * kTS * d * 4;
-    const int tw = (tune() & 512) ? 16 : kCrossWarps;
-    const size_t smemt = ring + ((size_t)kTS * 8 + tw * 32 + 32 + tw + (size_t)L * (4 * sh.npl * 32)) * 4;
-    if (smemt <= 220 * 1024 && w.G1 <= kSMs * 2) {
-#define DIR_BWDT1(N, S, W)                                                                            \
-  {                                                                                                  \
-    cudaFuncSetAttribute(cross_bwd_tma_kernel<N, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                         (int)smemt);                                                                \
-    cross_bwd_tma_kernel<N, S, W><<<w.G1, W * 32, smemt, st>>>(x0, cross_w, cross_b, dy, s, B, d, L, dx0, \
-                                                               w.Dpart, w.dypart, w.dwpart);          \
-  }
-  // +256: two samples per warp (8 warps); +512: sixteen warps per CTA, one sample each
-#define DIR_BWDT(N)                         \
-  if (tune() & 512) DIR_BWDT1(N, 1, 16)     \
-  else if (tune() & 256) DIR_BWDT1(N, 2, 8) \
-  else DIR_BWDT1(N, 1, 8)
-      switch (sh.npl) {
-        case 1: DIR_BWDT(1) break;
-        case 2: DIR_BWDT(2) break;
-        case 3: DIR_BWDT(3) break;
-        case 4: DIR_BWDT(4) break;
-        case 5: DIR_BWDT(5) break;
-        case 6: DIR_BWDT(6) break;
-        default: DIR_BWDT(8) break;
-      }
-#undef DIR_BWDT
-#undef DIR_BWDT1
+  if (L <= 8 && !(tune() & 1024) && sh.vec == 4) {  // DIR_B200_TUNE bit 1024: the tiled kernel, for A/B runs
+    // per-warp rings: needs the batch sums of one warp in registers and at least a two-slot ring in shared memory
+    const int LT = (L + 1) & ~1;
+    const size_t fixed = ((size_t)L * (4 * sh.npl * 32) + kCrossWarps * 32 + 32 + kCrossWarps) * 4;
+    int depth = kRingMaxDepth;
+    while (depth > 1 && fixed + (size_t)kCrossWarps * depth * 2 * d * 4 > 216 * 1024) --depth;
+    if (4 * sh.npl * (LT + 3) <= 184 && depth >= 2) {
+      const size_t ring_f = std::max((size_t)kCrossWarps * depth * 2 * d, (size_t)kCrossWarps * 4 * sh.npl * 32);
+      const size_t smemr = fixed + ring_f * 4;
+      const int64_t want = (B + kCrossWarps - 1) / kCrossWarps;
+      // one CTA per SM, and never more CTAs than the workspace holds partials for (G1 = min(B / 16, two per SM))
+      const int grid = (int)std::min<int64_t>(std::min<int64_t>(want, kSMs), w.G1);
+#define DIR_BWDR(N, T)                                                                                   \
+  if (sh.npl == N && LT == T)                                                                            \
+    launch_ring<N, T>(grid, smemr, st, x0, cross_w, cross_b, dy, s, B, d, L, depth, dx0, w.Dpart, w.dypart, \
+                      w.dwpart);
+#define DIR_BWDR4(N) DIR_BWDR(N, 2) DIR_BWDR(N, 4) DIR_BWDR(N, 6) DIR_BWDR(N, 8)
+      DIR_BWDR4(1) DIR_BWDR4(2) DIR_BWDR4(3) DIR_BWDR4(4) DIR_BWDR4(5) DIR_BWDR4(6) DIR_BWDR4(8)
+#undef DIR_BWDR4
+#undef DIR_BWDR
       cross_bwd_finish2_kernel<<<(d + 7) / 8, 256, 0, st>>>(cross_w, cross_b, w.Dpart, w.dypart, w.dwpart,
-                                                             w.G1, w.G2, d, L, dw, db);
+                                                             grid, grid, d, L, dw, db);
       return launched("cross_bwd", 2);
     }
   }

@@ -9,7 +9,9 @@ from tests._util import REL, rel_err, to_dev
 pytestmark = pytest.mark.gpu
 
 CASES = [(1, 1, 1), (5, 3, 2), (33, 51, 2), (64, 128, 3), (100, 429, 6), (129, 624, 6),
-         (40, 1024, 4), (17, 1000, 1), (300, 52, 8), (9, 7, 32)]
+         (40, 1024, 4), (17, 1000, 1), (300, 52, 8), (9, 7, 32),
+         # enough samples for every warp's ring of the register-accumulating backward to wrap several times
+         (12007, 624, 6), (20011, 128, 3), (9001, 64, 8), (7000, 24, 5), (6001, 768, 4)]
 
 
 def _case(B, d, L, seed=21):

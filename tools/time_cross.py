@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Parity tests of the cross kernels, then CUDA-event timing of dir_cross_fwd / dir_cross_bwd at the cfg3 shape,
 in one process (the DIR_B200_TUNE experiment bits are read once at load):
-    DIR_B200_TUNE=128 | 384 | 640 python tools/time_cross.py     # TMA ring: 8 warps, +2 samples per warp, 16 warps
+    python tools/time_cross.py [--no-tests]
+    DIR_B200_TUNE=1024 python tools/time_cross.py       # the tiled backward instead of the per-warp rings
 """
 import os
 import sys
@@ -11,7 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-rc = pytest.main(["-q", "-x", "-m", "gpu", os.path.join(ROOT, "tests", "test_gpu_cross.py")])
+rc = 0 if "--no-tests" in sys.argv else pytest.main(["-q", "-x", "-m", "gpu", os.path.join(ROOT, "tests", "test_gpu_cross.py")])
 import dir_b200                                                          # noqa: E402
 from dir_b200._lib import check, lib, ptr                                # noqa: E402
 
