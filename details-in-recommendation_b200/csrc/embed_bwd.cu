@@ -231,11 +231,14 @@ constexpr int kModeLocal = 0;  // gradients formed from g, S, u, row; the row is
 constexpr int kModeEmit = 1;   // requester side of a sharded table: per-row sums go to `emit`
 constexpr int kModeGiven = 2;  // owner side: per-lookup gradients arrive in `gbuf`; update in place
 constexpr int kModeBag = 3;    // multi-hot bags: entry j of slot s contributes x_j (g_fm (S - e_s) + u_s)
+constexpr int kModeBagEmit = 4;  // requester side of a sharded table fed with bags: kModeBag's gradients, kModeEmit's sums
+__host__ __device__ constexpr bool mode_emits(int m) { return m == kModeEmit || m == kModeBagEmit; }
+__host__ __device__ constexpr bool mode_bags(int m) { return m == kModeBag || m == kModeBagEmit; }
 
 template <int LPR>
 __device__ __forceinline__ void apply_update(const BwdArgs& a, uint32_t key, int sub, float4 G,
                                              float g1) {
-  if (a.mode == kModeEmit) {  // `key` is the row of the emit buffer here
+  if (mode_emits(a.mode)) {  // `key` is the row of the emit buffer here
     emit_store<LPR>(a, key, sub, G, g1);
     return;
   }
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
   constexpr int PASSES = LPR;                 // passes per tile of 32 lookups
   constexpr int PB = PASSES < 2 ? PASSES : 2; // passes whose loads are in flight together
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool EMIT = mode_emits(MODE), BAG = mode_bags(MODE);
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int slot = lane / LPR;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
   uint32_t key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
   uint32_t pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
   uint32_t row_nx = key_nx;  // row of `table` this lookup reads
-  if (MODE == kModeEmit) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
+  if (EMIT) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
 
   for (int64_t base = i0; base < chunk_end; base += kTile) {
     const uint32_t key = key_nx, row = row_nx;
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
     key_nx = i < chunk_end ? __ldg(a.keys + i) : a.pruned_key;
     pos_nx = i < chunk_end ? __ldg(a.pos + i) : 0u;
     row_nx = key_nx;
-    if (MODE == kModeEmit) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
+    if (EMIT) row_nx = i < chunk_end ? __ldg(a.rowidx + i) : 0u;
 
     // ---- lane-per-lookup stage
     const bool valid = key != a.pruned_key;
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
     heads += __popc(__ballot_sync(FULL, valid && key != keyp));
     const unsigned cont = __ballot_sync(FULL, valid && keyn == key);  // run goes on after this lookup
     float v = 1.f, g2 = 0.f, d1l = 0.f, wraw = 1.f;
-    if (MODE == kModeBag) {  // payload = entry index: fetch its slot, scale and raw weight; pos becomes the slot
+    if (BAG) {  // payload = entry index: fetch its slot, scale and raw weight; pos becomes the slot
       const uint32_t j = pos;
       pos = valid ? __ldg(a.entry_slot + j) : 0u;
       if (valid) {
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
     if (valid) {
       if (MODE == kModeGiven) {
         d1l = __ldg(a.gbuf + (int64_t)pos * a.gbuf_stride + K);
-      } else if (MODE == kModeBag) {
+      } else if (BAG) {
         if (a.g_first) d1l = __fmul_rn(__ldg(a.g_first + b), wraw);   // first order combines with 'sum'
         g2 = __ldg(a.g_fm + b);
       } else {
@@ -407,20 +411,20 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
       for (int j = 0; j < PB; ++j) {
         const int l = (j0 + j) * SLOTS + slot;
         k[j] = __shfl_sync(FULL, key, l);
-        rw[j] = MODE == kModeEmit ? __shfl_sync(FULL, row, l) : k[j];
+        rw[j] = EMIT ? __shfl_sync(FULL, row, l) : k[j];
         const uint32_t p = __shfl_sync(FULL, pos, l);
         const uint32_t bb = MODE == kModeGiven ? 0u : __shfl_sync(FULL, b, l);
         ac[j] = __shfl_sync(FULL, act, l);
         Sb[j] = ub[j] = T[j] = A[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         lw[j] = a1[j] = lz[j] = 0.f;
         if (k[j] != a.pruned_key) {
-          const int64_t ro = (int64_t)((MODE == kModeEmit && a.emit_read_key) ? k[j] : rw[j]) * a.row_stride;
+          const int64_t ro = (int64_t)((EMIT && a.emit_read_key) ? k[j] : rw[j]) * a.row_stride;
           if (MODE == kModeGiven) {  // the per-lookup gradient was formed by the requester
             ub[j] = ldg_hint(a.gbuf + (int64_t)p * a.gbuf_stride + sub * 4, pol_once);
           } else {
             if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
             Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
-            if (MODE == kModeBag) {
+            if (BAG) {
               T[j] = __ldg(reinterpret_cast<const float4*>(a.emb + (int64_t)p * K) + sub);
             } else {
               // coherent load: this warp may rewrite the row further down
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
                                  : ld_hint(a.table + ro + sub * 4, pol_row);
             }
           }
-          if (MODE != kModeEmit && (ac[j] & 3) == 1) {
+          if (!EMIT && (ac[j] & 3) == 1) {
             if (MODE == kModeGiven) T[j] = ld_hint(a.table + ro + sub * 4, pol_row);
             if (MODE == kModeBag) Rw[j] = ld_hint(a.table + ro + sub * 4, pol_row);
             if (adagrad) A[j] = ld_hint(a.accum + ro + sub * 4, pol_row);
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
           // value * (g_fm * (S - value*T) + u), evaluation order of the oracle
           const float x = __shfl_sync(FULL, v, l), gg = __shfl_sync(FULL, g2, l);
           // e of this lookup: value * row, or (bags) the combined embedding of its slot
-          const float xe = MODE == kModeBag ? 1.f : x;
+          const float xe = BAG ? 1.f : x;
           d.x = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].x, __fmul_rn(xe, T[j].x))), ub[j].x));
           d.y = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].y, __fmul_rn(xe, T[j].y))), ub[j].y));
           d.z = __fmul_rn(x, __fadd_rn(__fmul_rn(gg, __fsub_rn(Sb[j].z, __fmul_rn(xe, T[j].z))), ub[j].z));
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
           d1 = __fadd_rn(carry1, d1);
         }
         if ((ac[j] & 3) == 1) {
-          if (MODE == kModeEmit) {
+          if (EMIT) {
             emit_store<LPR>(a, rw[j], sub, d, d1);
           } else {
             apply_loaded(a, rw[j], sub, MODE == kModeBag ? Rw[j] : T[j], A[j], d, lw[j], a1[j], lz[j], d1);
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
           acc.w = __fadd_rn(acc.w, p.w);
           acc1 = __fadd_rn(acc1, a.part1[j * 2]);
         }
-        apply_update<LPR>(a, a.mode == kModeEmit ? __ldg(a.rowidx + end - 1) : key, sub, acc, acc1);
+        apply_update<LPR>(a, mode_emits(a.mode) ? __ldg(a.rowidx + end - 1) : key, sub, acc, acc1);
       }
     }
   }
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const BwdArgs a, 
       const float4 h = *(reinterpret_cast<const float4*>(a.part + (gid * 2 + 1) * K) + sub);
       float4 t = sm[threadIdx.x];
       t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
-      apply_update<LPR>(a, a.mode == kModeEmit ? __ldg(a.rowidx + first - 1) : key, sub, t,
+      apply_update<LPR>(a, mode_emits(a.mode) ? __ldg(a.rowidx + first - 1) : key, sub, t,
                         a.part1[gid * 2 + 1] + sm1[0]);
     }
     __syncthreads();
@@ -623,6 +627,8 @@ static int launch_bwd(const BwdArgs& a, int64_t* n_unique_out, cudaStream_t st) 
     embed_bwd_reduce_kernel<LPR, kModeGiven><<<rgrid, 256, 0, st>>>(a);
   else if (a.mode == kModeBag)
     embed_bwd_reduce_kernel<LPR, kModeBag><<<rgrid, 256, 0, st>>>(a);
+  else if (a.mode == kModeBagEmit)
+    embed_bwd_reduce_kernel<LPR, kModeBagEmit><<<rgrid, 256, 0, st>>>(a);
   else
     if (LPR == 4 && (a.tune & 256)) embed_bwd_reduce_kernel<LPR, kModeLocal, 4><<<rgrid, 256, 0, st>>>(a);
     else embed_bwd_reduce_kernel<LPR, kModeLocal><<<rgrid, 256, 0, st>>>(a);
@@ -1166,6 +1172,44 @@ extern "C" int dir_embed_bag_bwd_reduce_update(
             nullptr, nullptr, 0, 0, 0, nullptr, 0, 0, 0, 0, 0, nullptr, lo, entry_slot, entry_x, emb};
   set_div(a, F);
   return dispatch_bwd(a, K, n_unique_out, st);
+}
+
+/* Bags through a row-sharded table, requester side: the per-entry gradients of dir_embed_bag_bwd_reduce_update,
+ * summed per distinct row and stored straight into the owners' buffers like dir_embed_bwd_reduce_emit_to does
+ * (the sorted list = the entries' composite keys, dir_shard_bag_keys + dir_embed_bwd_sort; uidx / owner_off from
+ * dir_shard_unique).  No row is read: an entry's gradient needs only the bag's combined embedding. */
+extern "C" int dir_embed_bag_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* bag_weight,
+                                                const uint32_t* entry_slot, const float* entry_x, int64_t nnz,
+                                                const float* emb, const float* g_first, const float* g_fm,
+                                                const float* S, const float* u, const uint32_t* uidx,
+                                                const int64_t* owner_off, int64_t B, int F, int64_t n_keys,
+                                                float* g1_local, void* workspace, size_t workspace_bytes,
+                                                dir_stream_t stream) {
+  using namespace dir;
+  const char* what = "embed_bag_bwd_reduce_emit_to";
+  if (!layout || !layout->peer_base || !layout->local || layout->G <= 0 || layout->G > 64)
+    return fail(DIR_EINVAL, "%s: a filled dir_peer_layout is required", what);
+  const int K = layout->K;
+  if (B < 0 || F <= 0 || nnz < 0 || nnz >= 0x7fffffffLL || B * F >= 0x7fffffffLL)
+    return fail(DIR_EINVAL, "%s: B >= 0, F > 0, 0 <= nnz < 2^31, B*F < 2^31 required", what);
+  if (B == 0 || nnz == 0) return 0;
+  if (!entry_slot || !entry_x || !emb || !g_fm || !S || !uidx || !owner_off || !g1_local || !workspace)
+    return fail(DIR_EINVAL, "%s: entry_slot, entry_x, emb, g_fm, S, uidx, owner_off, g1_local, workspace are required",
+                what);
+  if (!aligned16(S) || !aligned16(u) || !aligned16(emb))
+    return fail(DIR_EINVAL, "%s: S, u, emb must be 16-byte aligned", what);
+  if (n_keys <= 0 || n_keys >= 0xffffffffLL) return fail(DIR_EINVAL, "%s: 0 < n_keys < 2^32-1 required", what);
+  BwdWorkspace w = carve(workspace, nnz, K);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "%s: workspace too small", what);
+  BwdArgs a{nullptr, nullptr, K, nullptr, nullptr, 0, bag_weight, g_first, g_fm, S,
+            u, w.keys, w.pos, w.part, w.part1, w.long_list, w.long_count, w.n_unique, nnz, F,
+            (uint32_t)n_keys, DIR_OPT_SGD, 0.f, 0u, 0, tune(), nullptr, 0, kModeBagEmit, uidx, nullptr, 0, nullptr, 0,
+            owner_off, layout->peer_base, layout->off_g, (int64_t)layout->rank * layout->seg_cap, layout->seg_cap,
+            g1_local, layout->G, layout->G, layout->rank,
+            ((nnz + kChunk - 1) / kChunk + layout->G - 1) / layout->G, 0, nullptr,
+            LinOpt{DIR_OPT_SGD, 0.f, 0.f, 0.f, nullptr}, entry_slot, entry_x, emb};
+  set_div(a, F);
+  return dispatch_bwd(a, K, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,10 +12,6 @@
 // The reference has no counterpart: its only hook is the partitioner wrapped around the embedding
 // variables (models/DeepFM/deepFM.py:163-175), which under a TF parameter-server cluster shards
 // variables by row and ships ids / IndexedSlices over gRPC.
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
-
 #include "common.cuh"
 
 namespace dir {
@@ -50,53 +46,188 @@ shard_keys_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val
   keys[o] = keep ? key : (uint32_t)(G * cap);
 }
 
-struct HeadFlag {
-  const uint32_t* keys;
-  uint32_t pruned;
-  __host__ __device__ uint32_t operator()(int i) const {
-    const uint32_t k = keys[i];
-    return (k != pruned && (i == 0 || keys[i - 1] != k)) ? 1u : 0u;
+// ------------------------------------------------------------------------------ numbering the distinct keys
+// Three small kernels over tiles of kUTile sorted entries (the list lives in L2):
+//   count   head flags (entry differs from its left neighbour and is not pruned) per tile
+//   scan    one CTA: exclusive prefix of the tile counts
+//   number  per tile: block scan of the flags on top of the tile's base -> uidx / ulocal / inv / owner_off
+// (no per-entry prefix array goes through memory, no library scan).
+constexpr int kUTile = 2048;  // 256 threads x 8 consecutive entries
+
+__device__ __forceinline__ uint32_t block_sum256(uint32_t v, uint32_t* s_warp /*[8]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) s_warp[w] = v;
+  __syncthreads();
+  uint32_t t = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww) t += s_warp[ww];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+unique_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t pruned, uint32_t* __restrict__ tilecnt) {
+  __shared__ uint32_t s_warp[8];
+  const int64_t i0 = (int64_t)blockIdx.x * kUTile + (int64_t)threadIdx.x * 8;
+  uint32_t prev = (i0 > 0 && i0 - 1 < n) ? __ldg(keys + i0 - 1) : 0u;
+  uint32_t c = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int64_t i = i0 + e;
+    if (i < n) {
+      const uint32_t k = __ldg(keys + i);
+      c += (k != pruned && (i == 0 || k != prev)) ? 1u : 0u;
+      prev = k;
+    }
   }
-};
+  const uint32_t t = block_sum256(c, s_warp);
+  if (threadIdx.x == 0) tilecnt[blockIdx.x] = t;
+}
+
+// in place: tilecnt[t] <- distinct keys in the tiles before t
+__global__ void __launch_bounds__(256) unique_scan_kernel(uint32_t* __restrict__ tilecnt, int64_t tiles) {
+  __shared__ uint32_t s_warp[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (int64_t c0 = 0; c0 < tiles; c0 += 256) {
+    const int64_t i = c0 + threadIdx.x;
+    const uint32_t v = i < tiles ? tilecnt[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const uint32_t c = s_warp[ww];
+      if (ww < w) base += c;
+      tot += c;
+    }
+    __syncthreads();
+    if (i < tiles) tilecnt[i] = carry + base + inc - v;
+    carry += tot;
+  }
+}
 
 // Numbers the distinct keys of the sorted list and, where the owner changes between two neighbouring entries,
 // writes owner_off[g] = number of distinct keys below g * cap for every g in between (g = 0..G; every g is written
 // exactly once because the owners are non-decreasing).
 __global__ void __launch_bounds__(256)
 shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ pos,
-                    const uint32_t* __restrict__ incl, int64_t n, uint32_t pruned, uint32_t cap, int G,
+                    const uint32_t* __restrict__ tilebase, int64_t n, uint32_t pruned, uint32_t cap, int G,
                     const int32_t* __restrict__ field_sel, int n_sel, int F,
                     uint32_t* __restrict__ uidx, int32_t* __restrict__ ulocal,
                     int64_t* __restrict__ inv, int64_t* __restrict__ owner_off) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t k = __ldg(keys + i);
-  const uint32_t kp = i > 0 ? __ldg(keys + i - 1) : 0u;
-  uint32_t p = __ldg(pos + i);
-  const uint32_t inc = __ldg(incl + i);
-  {
-    const int o_cur = (int)(k / cap);                      // G for a pruned entry
-    const int o_prev = i > 0 ? (int)(kp / cap) : -1;
-    if (o_cur != o_prev) {
-      const int64_t before = i > 0 ? (int64_t)__ldg(incl + i - 1) : 0;
-      for (int g = o_prev + 1; g <= o_cur && g <= G; ++g) owner_off[g] = before;
+  __shared__ uint32_t s_warp[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * kUTile + (int64_t)threadIdx.x * 8;
+  uint32_t k[8];
+  const uint32_t kleft = (i0 > 0 && i0 - 1 < n) ? __ldg(keys + i0 - 1) : 0u;
+  uint32_t mine = 0;
+  uint32_t ps[8];
+  const bool vec = (((uintptr_t)keys | (uintptr_t)pos) & 15u) == 0;  // (true for the sort's workspace)
+  if (vec && i0 + 8 <= n) {
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(keys + i0)), a1 = __ldg(reinterpret_cast<const uint4*>(keys + i0) + 1);
+    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pos + i0)), p1 = __ldg(reinterpret_cast<const uint4*>(pos + i0) + 1);
+    k[0] = a0.x; k[1] = a0.y; k[2] = a0.z; k[3] = a0.w; k[4] = a1.x; k[5] = a1.y; k[6] = a1.z; k[7] = a1.w;
+    ps[0] = p0.x; ps[1] = p0.y; ps[2] = p0.z; ps[3] = p0.w; ps[4] = p1.x; ps[5] = p1.y; ps[6] = p1.z; ps[7] = p1.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      k[e] = i0 + e < n ? __ldg(keys + i0 + e) : pruned;
+      ps[e] = i0 + e < n ? __ldg(pos + i0 + e) : 0u;
     }
-    if (i == n - 1)
-      for (int g = o_cur + 1; g <= G; ++g) owner_off[g] = (int64_t)inc;
   }
-  if (field_sel != nullptr) {  // entry of the compact [B, n_sel] list -> position in the [B, F] inputs
-    const uint32_t b = p / (uint32_t)n_sel;
-    p = b * (uint32_t)F + (uint32_t)__ldg(field_sel + (p - b * (uint32_t)n_sel));
+  {
+    uint32_t prev = kleft;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t i = i0 + e;
+      mine += (i < n && k[e] != pruned && (i == 0 || k[e] != prev)) ? 1u : 0u;
+      prev = k[e];
+    }
   }
-  if (k == pruned) {
-    uidx[i] = 0u;
-    if (inv) inv[p] = -1;  // pruned by the forward kernel (id < 0)
-    return;
+  // exclusive prefix of `mine` over the CTA's threads
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
-  const uint32_t u = inc - 1u;
-  uidx[i] = u;
-  if (inv) inv[p] = (int64_t)u;
-  if (i == 0 || kp != k) ulocal[u] = (int32_t)(k % cap);
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww)
+    if (ww < w) wbase += s_warp[ww];
+  uint32_t run = __ldg(tilebase + blockIdx.x) + wbase + inc - mine;  // distinct keys before entry i0
+  uint32_t kp = kleft;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int64_t i = i0 + e;
+    if (i >= n) break;
+    const uint32_t kk = k[e];
+    const bool head = kk != pruned && (i == 0 || kk != kp);
+    const uint32_t before = run;
+    run += head ? 1u : 0u;  // = the inclusive count at i
+    {
+      const int o_cur = (int)(kk / cap);  // G for a pruned entry
+      const int o_prev = i > 0 ? (int)(kp / cap) : -1;
+      if (o_cur != o_prev)
+        for (int g = o_prev + 1; g <= o_cur && g <= G; ++g) owner_off[g] = (int64_t)before;
+      if (i == n - 1)
+        for (int g = o_cur + 1; g <= G; ++g) owner_off[g] = (int64_t)run;
+    }
+    uint32_t p = ps[e];
+    if (field_sel != nullptr) {  // entry of the compact [B, n_sel] list -> position in the [B, F] inputs
+      const uint32_t b = p / (uint32_t)n_sel;
+      p = b * (uint32_t)F + (uint32_t)__ldg(field_sel + (p - b * (uint32_t)n_sel));
+    }
+    if (kk == pruned) {
+      uidx[i] = 0u;
+      if (inv) inv[p] = -1;  // pruned by the forward kernel (id < 0)
+    } else {
+      const uint32_t u = run - 1u;
+      uidx[i] = u;
+      if (inv) inv[p] = (int64_t)u;
+      if (head) ulocal[u] = (int32_t)(kk % cap);
+    }
+    kp = kk;
+  }
+}
+
+// Bags (CSR): one thread per (sample, field) slot walks its entries; entry j gets the composite key of its row,
+// or the pruned key (id < 0, weight <= 0, id beyond the field: the last also raises oob_flag).
+__global__ void __launch_bounds__(256)
+shard_bag_keys_kernel(const int64_t* __restrict__ bag_offsets, const int64_t* __restrict__ bag_index,
+                      const float* __restrict__ bag_weight, const int64_t* __restrict__ field_offset,
+                      const int64_t* __restrict__ field_rows, int64_t n_rows, int64_t n_slots, int F, int G,
+                      int64_t cap, uint32_t* __restrict__ keys, int* oob_flag) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int f = (int)(s % F);
+  const int64_t lo = __ldg(field_offset + f);
+  const int64_t nf = field_rows ? __ldg(field_rows + f) : n_rows - lo;
+  const int64_t j1 = __ldg(bag_offsets + s + 1);
+  for (int64_t j = __ldg(bag_offsets + s); j < j1; ++j) {
+    const int64_t id = __ldg(bag_index + j);
+    const float wv = bag_weight ? __ldg(bag_weight + j) : 1.f;
+    bool keep = id >= 0 && wv > 0.f;
+    if (keep && id >= nf) {
+      keep = false;
+      if (oob_flag) *oob_flag = 1;
+    }
+    const uint32_t row = (uint32_t)(lo + id);
+    uint32_t key = row;
+    if (G > 1) key = (row % (uint32_t)G) * (uint32_t)cap + row / (uint32_t)G;
+    keys[j] = keep ? key : (uint32_t)(G * cap);
+  }
 }
 
 template <int LPR>
@@ -116,31 +247,16 @@ rows_gather_kernel(const float* __restrict__ table, int64_t row_stride, const fl
 }
 
 struct UniqueWs {
-  uint32_t* incl;
-  void* cub_temp;
-  size_t cub_bytes;
+  uint32_t* tilecnt;  // [tiles] head flags per tile, then their exclusive prefix
+  int64_t tiles;
   size_t total;
 };
 
 static UniqueWs unique_carve(void* base, int64_t n) {
   UniqueWs w;
-  char* p = static_cast<char*>(base);
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    char* r = p ? p + off : nullptr;
-    off += align_up(bytes, 256);
-    return r;
-  };
-  w.incl = reinterpret_cast<uint32_t*>(take((size_t)n * 4));
-  size_t bytes = 0;
-  cub::CountingInputIterator<int> cnt(0);
-  cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<int>> it(cnt, HeadFlag{nullptr, 0});
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, (int)n, (cudaStream_t)0);
-  cudaGetLastError();
-  const size_t floor_bytes = (size_t)n / 64 + (1u << 16);
-  w.cub_bytes = bytes > floor_bytes ? bytes : floor_bytes;
-  w.cub_temp = take(w.cub_bytes);
-  w.total = off;
+  w.tiles = (n + kUTile - 1) / kUTile;
+  w.tilecnt = reinterpret_cast<uint32_t*>(base);
+  w.total = align_up((size_t)w.tiles * 4, 256);
   return w;
 }
 
@@ -166,6 +282,24 @@ extern "C" int dir_shard_keys(const int64_t* feature_index, const float* feature
       feature_index, feature_value, field_offset, field_rows, n_rows, n, F, G, cap, field_sel, n_sel, keys,
       oob_flag);
   return launched("shard_keys");
+}
+
+extern "C" int dir_shard_bag_keys(const int64_t* bag_offsets, const int64_t* bag_index, const float* bag_weight,
+                                  int64_t nnz, const int64_t* field_offset, const int64_t* field_rows,
+                                  int64_t n_rows, int64_t B, int F, int G, uint32_t* keys, int* oob_flag,
+                                  dir_stream_t stream) {
+  using namespace dir;
+  if (B < 0 || F <= 0 || G <= 0 || n_rows <= 0 || nnz < 0 || nnz >= 0x7fffffffLL)
+    return fail(DIR_EINVAL, "shard_bag_keys: B >= 0, F > 0, G > 0, n_rows > 0, 0 <= nnz < 2^31 required");
+  const int64_t cap = (n_rows + G - 1) / G;
+  if ((uint64_t)cap * (uint64_t)G >= 0xffffffffULL)
+    return fail(DIR_EINVAL, "shard_bag_keys: ceil(n_rows / G) * G must be < 2^32-1");
+  if (B * F >= 0x7fffffffLL) return fail(DIR_EINVAL, "shard_bag_keys: B*F must be < 2^31");
+  if (B == 0 || nnz == 0) return 0;
+  if (!bag_offsets || !bag_index || !field_offset || !keys) return fail(DIR_EINVAL, "shard_bag_keys: null pointer");
+  shard_bag_keys_kernel<<<(unsigned)((B * F + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bag_offsets, bag_index, bag_weight, field_offset, field_rows, n_rows, B * F, F, G, cap, keys, oob_flag);
+  return launched("shard_bag_keys");
 }
 
 extern "C" size_t dir_shard_unique_workspace_bytes(int64_t n_lookups) {
@@ -195,15 +329,11 @@ extern "C" int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sor
   const uint32_t pruned = (uint32_t)(cap * G);
   UniqueWs w = unique_carve(workspace, n_lookups);
   if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "shard_unique: workspace too small");
-  cub::CountingInputIterator<int> cnt(0);
-  cub::TransformInputIterator<uint32_t, HeadFlag, cub::CountingInputIterator<int>> flags(
-      cnt, HeadFlag{sorted_keys, pruned});
-  size_t bytes = w.cub_bytes;
-  cudaError_t e = cub::DeviceScan::InclusiveSum(w.cub_temp, bytes, flags, w.incl, (int)n_lookups, st);
-  if (e != cudaSuccess) return fail(DIR_EIO, "shard_unique: %s", cudaGetErrorString(e));
-  shard_number_kernel<<<(unsigned)((n_lookups + 255) / 256), 256, 0, st>>>(
-      sorted_keys, sorted_pos, w.incl, n_lookups, pruned, (uint32_t)cap, G, field_sel, n_sel, F, uidx, unique_local_rows,
-      inv, owner_off);
+  unique_count_kernel<<<(unsigned)w.tiles, 256, 0, st>>>(sorted_keys, n_lookups, pruned, w.tilecnt);
+  unique_scan_kernel<<<1, 256, 0, st>>>(w.tilecnt, w.tiles);
+  shard_number_kernel<<<(unsigned)w.tiles, 256, 0, st>>>(
+      sorted_keys, sorted_pos, w.tilecnt, n_lookups, pruned, (uint32_t)cap, G, field_sel, n_sel, F, uidx,
+      unique_local_rows, inv, owner_off);
   return launched("shard_unique", 3);
 }
 

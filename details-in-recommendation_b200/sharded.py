@@ -183,6 +183,7 @@ class ShardedLookups:
         self.U = self.R = 0
         self.event = None
         self.src = None
+        self.n_entries = 0          # lookups in the sorted list (B * sparse fields; bags: nnz)
         self.parity = None          # which exchange buffers this batch uses (peer flavour; set by presort)
         self.half = 0               # micro-batch of its batch (0, or 1 when the batch is exchanged as two halves)
         self.buf = None             # = parity * micro_batches + half: index of the exchange buffer / slot map
@@ -383,7 +384,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
                  process_group=None, max_batch: int = 65536, linear_optimizer: Optional[str] = None,
                  linear_lr: Optional[float] = None, l1_regularization_strength: float = 0.0,
                  l2_regularization_strength: float = 0.0, init: str = "trunc_normal", micro_batches: int = 1,
-                 device="cuda"):
+                 replicate_onerow: bool = True, max_entries: Optional[int] = None, device="cuda"):
         super().__init__()
         if micro_batches not in (1, 2):
             raise ValueError("micro_batches must be 1 or 2")
@@ -449,7 +450,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
             raise ValueError("the peer-memory exchange needs the nccl backend (one process per GPU)")
         # One-row (numeric) fields are replicated parameters in the peer flavour: every sample of every rank hits
         # the same row, so they stay out of the sort and the exchange; their gradients are column sums.
-        onerow = [f for f, r in enumerate(rows) if r == 1][:64] if self.exchange_mode == "peer" else []
+        onerow = ([f for f, r in enumerate(rows) if r == 1][:64]
+                  if (self.exchange_mode == "peer" and replicate_onerow) else [])
         sparse = [f for f in range(field_size) if f not in set(onerow)]
         self.n_dense, self.n_sel = len(onerow), len(sparse)
         self.register_buffer("onerow_fields", torch.tensor(onerow or [0], dtype=torch.int32, device=dev))
@@ -461,8 +463,10 @@ class ShardedEmbeddingFM(torch.nn.Module):
         # flavour gives it a communicator of its own so the two never queue behind each other
         self.side_group = process_group
         if self.exchange_mode == "peer":
-            seg_cap = max(1, min(self.max_batch * max(self.n_sel, 1), cap))   # rows one requester can ask of one owner
-            u_cap = max(1, self.max_batch * max(self.n_sel, 1))               # distinct rows a requester can ask for
+            # lookups of one batch that go through the exchange (bags: entries, `max_entries`)
+            self.max_entries = int(max_entries) if max_entries else self.max_batch * max(self.n_sel, 1)
+            seg_cap = max(1, min(self.max_entries, cap))   # rows one requester can ask of one owner
+            u_cap = max(1, self.max_entries)               # distinct rows a requester can ask for
             if seg_cap >= 1 << 24:
                 raise ValueError("max_batch * sparse fields must stay below 2^24 rows per requester and owner")
             if self.micro_batches == 2 and world > 32:
@@ -722,6 +726,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
             h.inv = torch.empty((B, F), dtype=torch.int64, device=dev)
             h.owner_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
             h.shape = (B, F)
+        h.n_entries = n
         sel = ptr(self.sparse_fields) if (peer and n_sel < F) else None
         if peer and self.n_dense:
             # the replicated one-row fields' part of `inv` needs the inputs only: first, off the chain that ends in
@@ -771,7 +776,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
             p, px = h.buf, self.px
             if self._fwd_event is not None and not self.capturing:
                 torch.cuda.current_stream().wait_event(self._fwd_event)     # every rank is done with parity p
-            check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), B * self.n_sel,
+            check(L.dir_shard_ids_push(px.ref(p), ptr(h.ulocal), ptr(h.owner_off), h.n_entries,
                                        ptr(self.err_flag), ptr(self.slot_epoch[p]), st), "dir_shard_ids_push")
             tr.mark("pre.ids_push")
             px.barrier(p, 1)
@@ -862,5 +867,179 @@ class ShardedEmbeddingFM(torch.nn.Module):
             if int(self.oob_flag.item()) != 0:
                 self.oob_flag.zero_()
                 raise IndexError("feature_index out of range for its field")
+            self.check_errors()
+        return first, fm, emb
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-hot / weighted bags through the row-sharded tables (SURVEY.md section 8, rows f3 x e)
+_COMBINER_CODE = {"sum": 0, "mean": 1, "sqrtn": 2}
+
+
+class _ShardedBagFunction(torch.autograd.Function):
+    """`_ShardedFunction` for bags: the exchange is the same (distinct rows travel once each way), the kernels
+    either side of it are the bag ones -- dir_embed_bag_fm_fwd over the received rows, indexed by `inv` per ENTRY,
+    and dir_embed_bag_bwd_reduce_emit_to for the per-distinct-row sums."""
+
+    @staticmethod
+    def forward(ctx, anchor, bias, layer, off, w, B, train, h):
+        F, K = layer.field_size, layer.embedding_size
+        dev = off.device
+        L = _lib.lib()
+        st = _stream()
+        nnz = h.n_entries
+        px, p = layer.px, h.buf
+        emb = torch.empty((B, F * K), dtype=torch.float32, device=dev)
+        fm = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        first = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        S = torch.empty((B, K), dtype=torch.float32, device=dev) if train else None
+        if train:
+            main, aux = torch.cuda.current_stream(), layer.aux_stream(dev, 0)
+            aux.wait_stream(main)
+            check(L.dir_shard_slots(px.ref(p), ptr(layer.slot[p]), layer.n_rows, ptr(layer.slot_epoch[p]),
+                                    ptr(layer.err_flag), layer._n_unique2.data_ptr() + 8 * h.parity,
+                                    aux.cuda_stream), "dir_shard_slots")
+        check(L.dir_shard_gather_send(px.ref(p), ptr(layer.table), layer.row_stride,
+                                      ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
+                                      None, layer.row_stride, None, layer.gather_ctas_per_sm, st),
+              "dir_shard_gather_send")
+        px.barrier(p, 0)
+        layer._note_forward(0)
+        rows, lin = px.rows(p), px.w(p) if layer.first_order else None
+        slot = x = scratch = None
+        if train and nnz > 0:
+            scratch = torch.empty(nnz, dtype=torch.int32, device=dev)     # (the kernel's sort keys: not used here)
+            slot = torch.empty(nnz, dtype=torch.int32, device=dev)
+            x = torch.empty(nnz, dtype=torch.float32, device=dev)
+        check(L.dir_embed_bag_fm_fwd(
+            ptr(rows), K, ptr(lin), 1, ptr(bias) if layer.first_order else None, ptr(off), ptr(h.inv), ptr(w), nnz,
+            ptr(layer.zero_offset), None, rows.shape[0], B, F, K, _COMBINER_CODE[layer.combiner], ptr(emb), ptr(S),
+            ptr(first), ptr(fm), ptr(scratch), ptr(slot), ptr(x), None, st), "dir_embed_bag_fm_fwd")
+        if not layer.first_order:
+            first.zero_()
+        ctx.layer, ctx.train, ctx.shape, ctx.h = layer, train, (B, F, K), h
+        ctx.set_materialize_grads(False)
+        if train:
+            ctx.save_for_backward(w, slot, x, S, emb)
+        return first, fm, emb
+
+    @staticmethod
+    def backward(ctx, g_first, g_fm, u):
+        if not ctx.train:
+            raise RuntimeError("ShardedEmbeddingBagFM.backward: forward ran without gradient tracking")
+        layer, h = ctx.layer, ctx.h
+        w, slot, x, S, emb = ctx.saved_tensors
+        B, F, K = ctx.shape
+        dev = S.device
+        L = _lib.lib()
+        st = _stream()
+        nnz = h.n_entries
+        g_first = (torch.zeros(B, dtype=torch.float32, device=dev) if g_first is None
+                   else g_first.reshape(B).contiguous().float())
+        g_fm = (torch.zeros(B, dtype=torch.float32, device=dev) if g_fm is None
+                else g_fm.reshape(B).contiguous().float())
+        if u is not None:
+            u = u.contiguous().float()
+        px, p = layer.px, h.buf
+        n_keys = layer.plan.cap * layer.plan.world_size
+        with torch.no_grad():
+            main, aux = torch.cuda.current_stream(), layer.aux_stream(dev, 0)
+            main.wait_stream(aux)                       # the slot marking of the forward
+            if nnz > 0 and B > 0:
+                ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(nnz, K), dev)
+                check(L.dir_embed_bag_bwd_reduce_emit_to(
+                    px.ref(p), ptr(w), ptr(slot), ptr(x), nnz, ptr(emb), ptr(g_first) if layer.first_order else None,
+                    ptr(g_fm), ptr(S), ptr(u), ptr(h.uidx), ptr(h.owner_off), B, F, n_keys, ptr(h.g1_local),
+                    ptr(ws), ws.numel(), st), "dir_embed_bag_bwd_reduce_emit_to")
+            check(L.dir_shard_g1_push(px.ref(p), ptr(h.g1_local), ptr(h.owner_off), nnz, st), "dir_shard_g1_push")
+            layer._owner_step([h])
+        layer._in_flight[h.buf] = False
+        g_bias = g_first.sum().reshape(1) if layer.first_order else None
+        return None, g_bias, None, None, None, None, None, None
+
+
+class ShardedEmbeddingBagFM(ShardedEmbeddingFM):
+    """`EmbeddingBagFM` with its tables sharded by row over a process group: `forward_bags(bag_offsets[B*F+1],
+    bag_index[nnz], bag_weight[nnz] | None)` for THIS rank's samples; `.backward()` updates the rows this rank
+    owns with every rank's gradients.  Every field goes through the exchange (a bag of a one-row field still has
+    a length and weights).  `max_entries` bounds nnz of one call (it sizes the exchange buffers; default
+    max_batch * field_size).  Peer-memory exchange only; one batch at a time (no `presort`, no micro-batches)."""
+
+    def __init__(self, field_size, embedding_size, rows_per_field, combiner="mean", max_entries=None, **kw):
+        if combiner not in _COMBINER_CODE:
+            raise ValueError("combiner must be 'sum', 'mean' or 'sqrtn'")
+        if kw.get("micro_batches", 1) != 1:
+            raise ValueError("ShardedEmbeddingBagFM exchanges a batch in one piece: micro_batches must be 1")
+        super().__init__(field_size, embedding_size, rows_per_field, replicate_onerow=False,
+                         max_entries=max_entries, **kw)
+        if self.px is None:
+            raise ValueError("ShardedEmbeddingBagFM needs the peer-memory exchange (DIR_B200_EXCHANGE=peer)")
+        self.combiner = combiner
+        self._bag_handle = ShardedLookups()
+
+    @torch.no_grad()
+    def _id_local_bags(self, h, off, idx, w, B):
+        """Keys per entry, sort, distinct-row numbering: `inv[j]` = entry j's row in the exchanged buffer."""
+        F, K, G = self.field_size, self.embedding_size, self.plan.world_size
+        dev = off.device
+        L = _lib.lib()
+        st = _stream()
+        nnz = idx.numel()
+        if h.keys is None or h.keys.numel() < max(nnz, 1) or h.keys.device != dev:
+            for name, dt in (("keys", torch.int32), ("uidx", torch.int32), ("ulocal", torch.int32),
+                             ("g1_local", torch.float32), ("inv", torch.int64)):
+                setattr(h, name, torch.empty(max(nnz, 1), dtype=dt, device=dev))
+            h.owner_off = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+        h.shape, h.n_entries = (B, F), nnz
+        check(L.dir_shard_bag_keys(ptr(off), ptr(idx), ptr(w), nnz, ptr(self.field_offset), ptr(self.field_rows),
+                                   self.plan.n_rows, B, F, G, ptr(h.keys),
+                                   ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_bag_keys")
+        ws = h.ws.get(max(L.dir_embed_bwd_workspace_bytes(max(nnz, 1), K), 1), dev)
+        check(L.dir_embed_bwd_sort(ptr(h.keys), nnz, self.plan.cap * G, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
+        skeys = spos = None
+        if nnz > 0:
+            skeys, spos = _lib.c_void_p(), _lib.c_void_p()
+            check(L.dir_embed_bwd_sorted(ptr(ws), nnz, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),
+                  "dir_embed_bwd_sorted")
+        ws2 = h.ws2.get(max(L.dir_shard_unique_workspace_bytes(nnz), 1), dev)
+        check(L.dir_shard_unique(skeys, spos, nnz, self.plan.n_rows, G, None, 0, F, ptr(h.uidx), ptr(h.ulocal),
+                                 ptr(h.inv), ptr(h.owner_off), ptr(ws2), ws2.numel(), st), "dir_shard_unique")
+
+    def forward(self, *a, **kw):
+        raise RuntimeError("ShardedEmbeddingBagFM takes bags: call forward_bags(bag_offsets, bag_index, bag_weight)")
+
+    def presort(self, *a, **kw):
+        raise RuntimeError("ShardedEmbeddingBagFM runs its id phase inside forward_bags")
+
+    def forward_bags(self, bag_offsets, bag_index, bag_weight=None):
+        for t, name in ((bag_offsets, "bag_offsets"), (bag_index, "bag_index"), (bag_weight, "bag_weight")):
+            _need_cuda(t, name)
+        if bag_offsets.dtype != torch.int64 or bag_index.dtype != torch.int64:
+            raise ValueError("bag_offsets and bag_index must be int64")
+        if bag_offsets.dim() != 1 or (bag_offsets.numel() - 1) % self.field_size != 0 or bag_offsets.numel() < 1:
+            raise ValueError("bag_offsets must be [B * field_size + 1]")
+        if bag_weight is not None and bag_weight.shape != bag_index.shape:
+            raise ValueError("bag_weight must have bag_index's shape")
+        B = (bag_offsets.numel() - 1) // self.field_size
+        if B > self.max_batch or bag_index.numel() > self.max_entries:
+            raise ValueError("batch %d / %d entries exceed max_batch=%d / max_entries=%d the exchange buffers were "
+                             "sized for" % (B, bag_index.numel(), self.max_batch, self.max_entries))
+        off, idx = bag_offsets.contiguous(), bag_index.contiguous().reshape(-1)
+        w = None if bag_weight is None else bag_weight.contiguous().float().reshape(-1)
+        train = self.training and torch.is_grad_enabled()
+        h = self._bag_handle
+        h.half, h.event = 0, None
+        self._id_local_bags(h, off, idx, w, B)
+        self.id_exchange(h)
+        if train:
+            if self._in_flight[h.buf]:
+                raise RuntimeError("ShardedEmbeddingBagFM: run the backward of the previous forward_bags first")
+            self._in_flight[h.buf] = True
+        self._last_handle = h
+        first, fm, emb = _ShardedBagFunction.apply(self._anchor, self.bias, self, off, w, B, train, h)
+        if self.check_bounds:
+            if int(self.oob_flag.item()) != 0:
+                self.oob_flag.zero_()
+                raise IndexError("bag_index out of range for its field")
             self.check_errors()
         return first, fm, emb

@@ -213,6 +213,12 @@ int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
                    const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B,
                    int F, int G, const int32_t* field_sel, int n_sel, uint32_t* keys, int* oob_flag,
                    dir_stream_t stream);
+/* Bags (CSR, as dir_embed_bag_fm_fwd takes them): keys[j] for entry j of bag_index, pruned entries (id < 0,
+ * weight <= 0, id beyond its field) get the key G * cap.  The sorted list then indexes ENTRIES: dir_shard_unique
+ * with field_sel = NULL leaves inv[j] = row of entry j in the exchanged buffer. */
+int dir_shard_bag_keys(const int64_t* bag_offsets, const int64_t* bag_index, const float* bag_weight, int64_t nnz,
+                       const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B, int F,
+                       int G, uint32_t* keys, int* oob_flag, dir_stream_t stream);
 size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
 int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
                      int64_t n_rows, int G, const int32_t* field_sel, int n_sel, int F, uint32_t* uidx,
@@ -325,6 +331,15 @@ int dir_embed_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* fea
                                  const uint32_t* uidx, const int64_t* owner_off, int64_t B, int F,
                                  int64_t n_keys, const int32_t* field_sel, int n_sel, float* g1_local,
                                  void* workspace, size_t workspace_bytes, dir_stream_t stream);
+/* The same for bags (models/DeepFM/deepFM.py:53, 77 through a sharded table): the sorted list indexes the nnz
+ * ENTRIES (dir_shard_bag_keys); entry_slot / entry_x / emb are what dir_embed_bag_fm_fwd left (run on the exchanged
+ * row buffer with bag_index = inv), gradients as in dir_embed_bag_bwd_reduce_update. */
+int dir_embed_bag_bwd_reduce_emit_to(const dir_peer_layout* layout, const float* bag_weight,
+                                     const uint32_t* entry_slot, const float* entry_x, int64_t nnz, const float* emb,
+                                     const float* g_first, const float* g_fm, const float* S, const float* u,
+                                     const uint32_t* uidx, const int64_t* owner_off, int64_t B, int F,
+                                     int64_t n_keys, float* g1_local, void* workspace, size_t workspace_bytes,
+                                     dir_stream_t stream);
 int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_local, const int64_t* owner_off,
                       int64_t n_capacity, dir_stream_t stream);
 /* one-row fields: each field's gradient over THIS rank's samples (fixed-order fp64-carried column sums) ->
