@@ -52,38 +52,48 @@ shard_keys_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val
 //   scan    one CTA: exclusive prefix of the tile counts
 //   number  per tile: block scan of the flags on top of the tile's base -> uidx / ulocal / inv / owner_off
 // (no per-entry prefix array goes through memory, no library scan).
-constexpr int kUTile = 2048;  // 256 threads x 8 consecutive entries
+constexpr int kUTile = 2048;  // 8 warps x 8 rounds of 32 consecutive entries
 
-__device__ __forceinline__ uint32_t block_sum256(uint32_t v, uint32_t* s_warp /*[8]*/) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// head flags of the 8 rounds of one warp (round r = entries wbase + r * 32 + lane): bit `lane` of heads[r]
+__device__ __forceinline__ void warp_head_flags(const uint32_t* __restrict__ keys, int64_t n, uint32_t pruned,
+                                                int64_t wbase, int lane, uint32_t (&k)[8], unsigned (&heads)[8],
+                                                uint32_t& kleft) {
+  kleft = (wbase > 0 && wbase - 1 < n) ? __ldg(keys + wbase - 1) : 0u;  // (uniform over the warp)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) s_warp[w] = v;
-  __syncthreads();
-  uint32_t t = 0;
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    k[r] = i < n ? __ldg(keys + i) : pruned;
+  }
+  uint32_t prev_last = kleft;
 #pragma unroll
-  for (int ww = 0; ww < 8; ++ww) t += s_warp[ww];
-  __syncthreads();
-  return t;
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    uint32_t kp = __shfl_up_sync(0xffffffffu, k[r], 1);
+    if (lane == 0) kp = prev_last;
+    heads[r] = __ballot_sync(0xffffffffu, i < n && k[r] != pruned && (i == 0 || k[r] != kp));
+    prev_last = __shfl_sync(0xffffffffu, k[r], 31);
+  }
 }
 
 __global__ void __launch_bounds__(256)
 unique_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t pruned, uint32_t* __restrict__ tilecnt) {
   __shared__ uint32_t s_warp[8];
-  const int64_t i0 = (int64_t)blockIdx.x * kUTile + (int64_t)threadIdx.x * 8;
-  uint32_t prev = (i0 > 0 && i0 - 1 < n) ? __ldg(keys + i0 - 1) : 0u;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * 256;
+  uint32_t k[8], kleft;
+  unsigned heads[8];
+  warp_head_flags(keys, n, pruned, wbase, lane, k, heads, kleft);
   uint32_t c = 0;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int64_t i = i0 + e;
-    if (i < n) {
-      const uint32_t k = __ldg(keys + i);
-      c += (k != pruned && (i == 0 || k != prev)) ? 1u : 0u;
-      prev = k;
-    }
+  for (int r = 0; r < 8; ++r) c += (uint32_t)__popc(heads[r]);
+  if (lane == 0) s_warp[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += s_warp[ww];
+    tilecnt[blockIdx.x] = t;
   }
-  const uint32_t t = block_sum256(c, s_warp);
-  if (threadIdx.x == 0) tilecnt[blockIdx.x] = t;
 }
 
 // in place: tilecnt[t] <- distinct keys in the tiles before t
@@ -126,65 +136,42 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
                     int64_t* __restrict__ inv, int64_t* __restrict__ owner_off) {
   __shared__ uint32_t s_warp[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t i0 = (int64_t)blockIdx.x * kUTile + (int64_t)threadIdx.x * 8;
-  uint32_t k[8];
-  const uint32_t kleft = (i0 > 0 && i0 - 1 < n) ? __ldg(keys + i0 - 1) : 0u;
-  uint32_t mine = 0;
-  uint32_t ps[8];
-  const bool vec = (((uintptr_t)keys | (uintptr_t)pos) & 15u) == 0;  // (true for the sort's workspace)
-  if (vec && i0 + 8 <= n) {
-    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(keys + i0)), a1 = __ldg(reinterpret_cast<const uint4*>(keys + i0) + 1);
-    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pos + i0)), p1 = __ldg(reinterpret_cast<const uint4*>(pos + i0) + 1);
-    k[0] = a0.x; k[1] = a0.y; k[2] = a0.z; k[3] = a0.w; k[4] = a1.x; k[5] = a1.y; k[6] = a1.z; k[7] = a1.w;
-    ps[0] = p0.x; ps[1] = p0.y; ps[2] = p0.z; ps[3] = p0.w; ps[4] = p1.x; ps[5] = p1.y; ps[6] = p1.z; ps[7] = p1.w;
-  } else {
+  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * 256;
+  uint32_t k[8], kleft;
+  unsigned heads[8];
+  warp_head_flags(keys, n, pruned, wbase, lane, k, heads, kleft);
+  uint32_t c = 0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      k[e] = i0 + e < n ? __ldg(keys + i0 + e) : pruned;
-      ps[e] = i0 + e < n ? __ldg(pos + i0 + e) : 0u;
-    }
-  }
-  {
-    uint32_t prev = kleft;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int64_t i = i0 + e;
-      mine += (i < n && k[e] != pruned && (i == 0 || k[e] != prev)) ? 1u : 0u;
-      prev = k[e];
-    }
-  }
-  // exclusive prefix of `mine` over the CTA's threads
-  uint32_t inc = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_warp[w] = inc;
+  for (int r = 0; r < 8; ++r) c += (uint32_t)__popc(heads[r]);
+  if (lane == 0) s_warp[w] = c;
   __syncthreads();
-  uint32_t wbase = 0;
+  uint32_t run = __ldg(tilebase + blockIdx.x);  // distinct keys before this warp's first entry
 #pragma unroll
   for (int ww = 0; ww < 8; ++ww)
-    if (ww < w) wbase += s_warp[ww];
-  uint32_t run = __ldg(tilebase + blockIdx.x) + wbase + inc - mine;  // distinct keys before entry i0
-  uint32_t kp = kleft;
+    if (ww < w) run += s_warp[ww];
+  uint32_t prev_last = kleft;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int64_t i = i0 + e;
-    if (i >= n) break;
-    const uint32_t kk = k[e];
-    const bool head = kk != pruned && (i == 0 || kk != kp);
-    const uint32_t before = run;
-    run += head ? 1u : 0u;  // = the inclusive count at i
+  for (int r = 0; r < 8; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    uint32_t kp = __shfl_up_sync(0xffffffffu, k[r], 1);
+    if (lane == 0) kp = prev_last;
+    prev_last = __shfl_sync(0xffffffffu, k[r], 31);
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t before = run + (uint32_t)__popc(heads[r] & lt);  // distinct keys before entry i
+    const bool head = (heads[r] >> lane) & 1u;
+    const uint32_t incl = before + (head ? 1u : 0u);
+    run += (uint32_t)__popc(heads[r]);
+    if (i >= n) continue;
+    const uint32_t kk = k[r];
     {
       const int o_cur = (int)(kk / cap);  // G for a pruned entry
       const int o_prev = i > 0 ? (int)(kp / cap) : -1;
       if (o_cur != o_prev)
         for (int g = o_prev + 1; g <= o_cur && g <= G; ++g) owner_off[g] = (int64_t)before;
       if (i == n - 1)
-        for (int g = o_cur + 1; g <= G; ++g) owner_off[g] = (int64_t)run;
+        for (int g = o_cur + 1; g <= G; ++g) owner_off[g] = (int64_t)incl;
     }
-    uint32_t p = ps[e];
+    uint32_t p = __ldg(pos + i);
     if (field_sel != nullptr) {  // entry of the compact [B, n_sel] list -> position in the [B, F] inputs
       const uint32_t b = p / (uint32_t)n_sel;
       p = b * (uint32_t)F + (uint32_t)__ldg(field_sel + (p - b * (uint32_t)n_sel));
@@ -193,12 +180,11 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
       uidx[i] = 0u;
       if (inv) inv[p] = -1;  // pruned by the forward kernel (id < 0)
     } else {
-      const uint32_t u = run - 1u;
+      const uint32_t u = incl - 1u;
       uidx[i] = u;
       if (inv) inv[p] = (int64_t)u;
       if (head) ulocal[u] = (int32_t)(kk % cap);
     }
-    kp = kk;
   }
 }
 
