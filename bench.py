@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path over one batch of synthetic Criteo-shaped input
 (BASELINE.json configs[1] by default: 26 sparse + 13 dense fields, 10 M rows, K = 16, B = 65 536,
 embeddings emitted to / upstream gradients consumed from the DNN side):
-    dir_embed_fm_fwd -> g = sigmoid(first + fm) - y -> dir_embed_bwd_sort -> dir_embed_bwd_reduce_update
+    dir_shard_keys_sort (next batch) | dir_embed_fm_fwd -> g = sigmoid(first + fm) - y -> dir_embed_bwd_reduce_update
 (cfg3 adds dir_cross_fwd / dir_cross_bwd between the two halves).  Prints ONE JSON line.
 
   value     device-resident inputs, CUDA-event timed, max over ranks
@@ -716,10 +716,11 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
     U = sum(n_unique) / len(n_unique)
     n_sel = layer.n_sorted_fields
 
-    def mkkeys(r):
+    def keys_sort(r):
         idx, val, _ = devs[r]
-        check(lib.dir_shard_keys(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
-                                 layer.n_rows, B, F, 1, ptr(layer.sorted_fields), n_sel, ptr(keys), None, st), "keys")
+        check(lib.dir_shard_keys_sort(ptr(idx), ptr(val), ptr(layer.field_offset), ptr(layer.field_rows),
+                                      layer.n_rows, B, F, 1, ptr(layer.sorted_fields), n_sel, ptr(keys), None,
+                                      ptr(ws), ws.numel(), st), "keys_sort")
 
     def fwd(r):
         idx, val, _ = devs[r]
@@ -727,9 +728,6 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
                                    ptr(layer.bias), ptr(idx), ptr(val), ptr(layer.field_offset),
                                    ptr(layer.field_rows), layer.n_rows, B, F, K, ptr(emb), ptr(S), ptr(first),
                                    ptr(fm), None, None, st), "fwd")
-
-    def sort(r):
-        check(lib.dir_embed_bwd_sort(ptr(keys), B * n_sel, layer.n_rows, ptr(ws), ws.numel(), st), "sort")
 
     ows = torch.empty(int(lib.dir_shard_dense_workspace_bytes(K)), dtype=torch.uint8, device=dev)
     nu = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -754,9 +752,8 @@ def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
         if layer.n_onerow_fields:
             cur.wait_stream(aux)
 
-    calls = [("dir_shard_keys", mkkeys, 0),
-             ("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
-             ("dir_embed_bwd_sort", sort, 0),
+    calls = [("dir_embed_fm_fwd", fwd, RL.embed_fwd_bytes(B, F, K, True, emit)),
+             ("dir_shard_keys_sort", keys_sort, 0),
              ("dir_embed_bwd_reduce_update", upd, RL.embed_bwd_bytes(B, F, K, U, True, emit, "adagrad"))]
     if cross is not None:
         xL, s = torch.empty((B, d), device=dev), torch.empty((B, L), device=dev)

@@ -70,6 +70,8 @@ SIGNATURES = {
     "dir_embed_bag_bwd_reduce_emit_to": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                                  c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dir_shard_keys_sort": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dir_shard_unique_workspace_bytes": (c_size_t, [c_int64]),
     "dir_shard_unique": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

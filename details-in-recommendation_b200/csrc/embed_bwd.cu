@@ -20,6 +20,7 @@
 #include <cub/device/dispatch/dispatch_radix_sort.cuh>
 
 #include "common.cuh"
+#include "keys.cuh"
 #include "radix.cuh"
 #include "update.cuh"
 
@@ -944,6 +945,70 @@ extern "C" int dir_embed_bwd_sort(const uint32_t* sort_keys, int64_t n_lookups, 
                              (int)n_lookups, end_bit, st, sort_variant());
   if (e != cudaSuccess) return fail(DIR_EIO, "embed_bwd_sort: %s", cudaGetErrorString(e));
   return launched("embed_bwd_sort", (end_bit + 7) / 8 + 2);
+}
+
+namespace dir {
+// dir_shard_keys and the sort's first counting pass in one kernel: a CTA forms the keys of one radix tile (2 048
+// consecutive entries, coalesced rounds of 256) and counts their low digit while they are in registers.
+__global__ void __launch_bounds__(256)
+keys_count_kernel(const KeyArgs a, uint32_t* __restrict__ keys, int64_t tiles, uint32_t* __restrict__ hist,
+                  uint32_t* zero_a, unsigned long long* zero_b) {
+  __shared__ uint32_t sh[256];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // counters of the consumer of the sorted list start at zero
+    *zero_a = 0u;
+    *zero_b = 0ull;
+  }
+  sh[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kRadixTile;
+#pragma unroll
+  for (int r = 0; r < kRadixRounds; ++r) {
+    const int64_t o = base + r * 256 + threadIdx.x;
+    const bool live = o < a.n;
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const uint32_t key = make_key(a, o);
+      keys[o] = key;
+      const uint32_t d = key & 255u;
+      const unsigned peers = __match_any_sync(act, d);  // one atomic per distinct digit of the warp
+      if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+}
+}  // namespace dir
+
+/* dir_shard_keys + dir_embed_bwd_sort in one call: the key kernel counts the first radix digit while the keys
+ * are in registers, so the sort starts without a pass of its own over them. */
+extern "C" int dir_shard_keys_sort(const int64_t* feature_index, const float* feature_value,
+                                   const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows,
+                                   int64_t B, int F, int G, const int32_t* field_sel, int n_sel, uint32_t* keys,
+                                   int* oob_flag, void* workspace, size_t workspace_bytes, dir_stream_t stream) {
+  using namespace dir;
+  KeyArgs a;
+  if (int rc = key_args("shard_keys_sort", feature_index, feature_value, field_offset, field_rows, n_rows, B, F, G,
+                        field_sel, n_sel, oob_flag, a))
+    return rc;
+  const int64_t n = a.n;
+  const int64_t n_keys = G > 1 ? a.cap * G : n_rows;  // the pruned key; every other key is below it
+  if (n == 0 || (tune() & 512))  {  // nothing to fuse (or the library sort was asked for): the two calls
+    if (int rc = dir_shard_keys(feature_index, feature_value, field_offset, field_rows, n_rows, B, F, G, field_sel,
+                                n_sel, keys, oob_flag, stream))
+      return rc;
+    return dir_embed_bwd_sort(keys, n, n_keys, workspace, workspace_bytes, stream);
+  }
+  if (!keys || !workspace) return fail(DIR_EINVAL, "shard_keys_sort: null pointer");
+  BwdWorkspace w = carve(workspace, n, 4);
+  if (workspace_bytes < w.total) return fail(DIR_ENOMEM, "shard_keys_sort: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int end_bit = 1;
+  while (end_bit < 32 && (((uint64_t)n_keys) >> end_bit) != 0) ++end_bit;  // n_keys itself is a key
+  const int64_t tiles = radix_tiles(n);
+  keys_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(a, keys, tiles, w.radix_hist, w.long_count, w.n_unique);
+  const int launches = radix_sort_pairs(keys, n, end_bit, w.keys, w.pos, w.alt_keys, w.pos_in, w.radix_hist,
+                                        w.long_count, w.n_unique, st, /*counted=*/true);
+  return launched("shard_keys_sort", launches + 1);
 }
 
 extern "C" int dir_embed_bwd_reduce_update(

@@ -82,21 +82,36 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* s_w
 }
 
 // one CTA per digit: the row hist[d][0 .. tiles) becomes its exclusive prefix over the tiles, rowtot[d] its sum;
-// the same row of the OTHER histogram is zeroed for the scatter that follows to count into
+// the same row of the OTHER histogram is zeroed for the scatter that follows to count into.  A thread owns up to
+// kRowChunk consecutive tiles, so a row of up to 256 * kRowChunk tiles (8.4 M pairs) takes ONE block scan.
+constexpr int kRowChunk = 16;
 __global__ void __launch_bounds__(256)
 radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __restrict__ rowtot,
                      uint32_t* __restrict__ next_hist, uint32_t* __restrict__ skew, uint32_t skew_above) {
   __shared__ uint32_t s_warp[8];
   uint32_t* row = hist + (int64_t)blockIdx.x * tiles;
+  uint32_t* nrow = next_hist ? next_hist + (int64_t)blockIdx.x * tiles : nullptr;
+  const int64_t per = (tiles + 255) / 256;
+  const int C = (int)(per < kRowChunk ? per : kRowChunk);  // tiles per thread and round
   uint32_t carry = 0;
-  for (int64_t c0 = 0; c0 < tiles; c0 += 256) {
-    const int64_t i = c0 + threadIdx.x;
-    const uint32_t v = i < tiles ? row[i] : 0u;
+  for (int64_t c0 = 0; c0 < tiles; c0 += (int64_t)256 * C) {
+    const int64_t i0 = c0 + (int64_t)threadIdx.x * C;
+    uint32_t v[kRowChunk];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int e = 0; e < kRowChunk; ++e) {
+      v[e] = (e < C && i0 + e < tiles) ? row[i0 + e] : 0u;
+      sum += v[e];
+    }
     uint32_t tot;
-    const uint32_t ex = block_excl_scan256(v, s_warp, &tot);
-    if (i < tiles) {
-      row[i] = carry + ex;
-      if (next_hist) next_hist[(int64_t)blockIdx.x * tiles + i] = 0u;
+    uint32_t run = carry + block_excl_scan256(sum, s_warp, &tot);
+#pragma unroll
+    for (int e = 0; e < kRowChunk; ++e) {
+      if (e < C && i0 + e < tiles) {
+        row[i0 + e] = run;
+        run += v[e];
+        if (nrow) nrow[i0 + e] = 0u;
+      }
     }
     carry += tot;
   }
@@ -207,14 +222,16 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
 // alt_vals) is the other half of the ping-pong.  2 launches per 8-bit pass + 1.
 inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32_t* kout, uint32_t* vout,
                             uint32_t* alt_keys, uint32_t* alt_vals, uint32_t* hist, uint32_t* zero_a,
-                            unsigned long long* zero_b, cudaStream_t st) {
+                            unsigned long long* zero_b, cudaStream_t st, bool counted = false) {
   const int passes = (end_bit + 7) / 8;
   const int64_t tiles = radix_tiles(n);
   uint32_t* h[2] = {hist, hist + radix_hist_words(n)};
   uint32_t* skew = hist + 2 * radix_hist_words(n);
   const uint32_t* kin = keys;
   const uint32_t* vin = nullptr;
-  radix_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(kin, n, 0, tiles, h[0], zero_a, zero_b);
+  // counted: the kernel that produced the keys already left the first pass's tile histogram in h[0] (and zeroed
+  // the consumer's counters)
+  if (!counted) radix_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(kin, n, 0, tiles, h[0], zero_a, zero_b);
   for (int p = 0; p < passes; ++p) {
     const bool to_out = ((passes - 1 - p) & 1) == 0;  // the last pass writes (kout, vout)
     uint32_t* kd = to_out ? kout : alt_keys;
@@ -228,7 +245,7 @@ inline int radix_sort_pairs(const uint32_t* keys, int64_t n, int end_bit, uint32
     kin = kd;
     vin = vd;
   }
-  return passes * 2 + 1;
+  return passes * 2 + (counted ? 0 : 1);
 }
 
 }  // namespace dir

@@ -13,37 +13,14 @@
 // variables (models/DeepFM/deepFM.py:163-175), which under a TF parameter-server cluster shards
 // variables by row and ships ids / IndexedSlices over gRPC.
 #include "common.cuh"
+#include "keys.cuh"
 
 namespace dir {
 
-__global__ void __launch_bounds__(256)
-shard_keys_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val,
-                  const int64_t* __restrict__ field_offset, const int64_t* __restrict__ field_rows,
-                  int64_t n_rows, int64_t n, int F, int G, int64_t cap,
-                  const int32_t* __restrict__ field_sel, int n_sel, uint32_t* __restrict__ keys,
-                  int* oob_flag) {
+__global__ void __launch_bounds__(256) shard_keys_kernel(const KeyArgs a, uint32_t* __restrict__ keys) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // entry of the [B, n_sel] key list
-  if (o >= n) return;
-  int f = (int)((uint32_t)o % (uint32_t)n_sel);  // n < 2^31
-  int64_t i = o;
-  if (field_sel != nullptr) {
-    const uint32_t b = (uint32_t)o / (uint32_t)n_sel;
-    f = __ldg(field_sel + f);
-    i = (int64_t)b * F + f;
-  }
-  const int64_t id = __ldg(idx + i);
-  const float v = val ? __ldg(val + i) : 1.f;
-  const int64_t lo = __ldg(field_offset + f);
-  const int64_t nf = field_rows ? __ldg(field_rows + f) : n_rows - lo;
-  bool keep = id >= 0 && v > 0.f;
-  if (keep && id >= nf) {
-    keep = false;
-    if (oob_flag) *oob_flag = 1;
-  }
-  const uint32_t row = (uint32_t)(lo + id);  // n_rows < 2^32
-  uint32_t key = row;                        // one rank: the key is the global row
-  if (G > 1) key = (row % (uint32_t)G) * (uint32_t)cap + row / (uint32_t)G;
-  keys[o] = keep ? key : (uint32_t)(G * cap);
+  if (o >= a.n) return;
+  keys[o] = make_key(a, o);
 }
 
 // ------------------------------------------------------------------------------ numbering the distinct keys
@@ -253,20 +230,13 @@ extern "C" int dir_shard_keys(const int64_t* feature_index, const float* feature
                               int64_t n_rows, int64_t B, int F, int G, const int32_t* field_sel,
                               int n_sel, uint32_t* keys, int* oob_flag, dir_stream_t stream) {
   using namespace dir;
-  if (B < 0 || F <= 0 || G <= 0 || n_rows <= 0)
-    return fail(DIR_EINVAL, "shard_keys: B >= 0, F > 0, G > 0, n_rows > 0 required");
-  const int64_t cap = (n_rows + G - 1) / G;
-  if ((uint64_t)cap * (uint64_t)G >= 0xffffffffULL)
-    return fail(DIR_EINVAL, "shard_keys: ceil(n_rows / G) * G must be < 2^32-1");
-  if (field_sel == nullptr) n_sel = F;
-  if (n_sel < 0 || n_sel > F) return fail(DIR_EINVAL, "shard_keys: 0 <= n_sel <= F required");
-  if (B * F >= 0x7fffffffLL) return fail(DIR_EINVAL, "shard_keys: B*F must be < 2^31");
-  const int64_t n = B * n_sel;
-  if (n == 0) return 0;
-  if (!feature_index || !field_offset || !keys) return fail(DIR_EINVAL, "shard_keys: null pointer");
-  shard_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      feature_index, feature_value, field_offset, field_rows, n_rows, n, F, G, cap, field_sel, n_sel, keys,
-      oob_flag);
+  KeyArgs a;
+  if (int rc = key_args("shard_keys", feature_index, feature_value, field_offset, field_rows, n_rows, B, F, G,
+                        field_sel, n_sel, oob_flag, a))
+    return rc;
+  if (a.n == 0) return 0;
+  if (!keys) return fail(DIR_EINVAL, "shard_keys: null pointer");
+  shard_keys_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, keys);
   return launched("shard_keys");
 }
 

@@ -447,11 +447,9 @@ class EmbeddingFM(torch.nn.Module):
             if h.keys is None or h.keys.numel() != B * n_sel or h.keys.device != dev:
                 h.keys = torch.empty((B * n_sel,), dtype=torch.int32, device=dev)
                 h.keys.record_stream(side)
-            check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
-                                   self.n_rows, B, F, 1, ptr(self.sorted_fields), n_sel, ptr(h.keys), None,
-                                   side.cuda_stream), "dir_shard_keys")
-            check(L.dir_embed_bwd_sort(ptr(h.keys), B * n_sel, self.n_rows, ptr(ws), ws.numel(),
-                                       side.cuda_stream), "dir_embed_bwd_sort")
+            check(L.dir_shard_keys_sort(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
+                                        self.n_rows, B, F, 1, ptr(self.sorted_fields), n_sel, ptr(h.keys), None,
+                                        ptr(ws), ws.numel(), side.cuda_stream), "dir_shard_keys_sort")
         h.event = None
         if record_event:
             h.event = torch.cuda.Event()

@@ -734,13 +734,12 @@ class ShardedEmbeddingFM(torch.nn.Module):
             check(L.dir_shard_dense_inv(ptr(idx), ptr(val), ptr(self.onerow_fields), self.n_dense, B, F,
                                         self.px.u_cap, ptr(h.inv),
                                         ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_dense_inv")
-        check(L.dir_shard_keys(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
-                               self.plan.n_rows, B, F, G, sel, n_sel, ptr(h.keys),
-                               ptr(self.oob_flag) if self.check_bounds else None, st), "dir_shard_keys")
-        tr.mark("pre.keys")
         ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(B * F, 1), K), dev)
-        check(L.dir_embed_bwd_sort(ptr(h.keys), n, self.plan.cap * G, ptr(ws), ws.numel(), st), "dir_embed_bwd_sort")
-        tr.mark("pre.sort")
+        check(L.dir_shard_keys_sort(ptr(idx), ptr(val), ptr(self.field_offset), ptr(self.field_rows),
+                                    self.plan.n_rows, B, F, G, sel, n_sel, ptr(h.keys),
+                                    ptr(self.oob_flag) if self.check_bounds else None, ptr(ws), ws.numel(), st),
+              "dir_shard_keys_sort")
+        tr.mark("pre.keys+sort")
         if n > 0:
             skeys, spos = _lib.c_void_p(), _lib.c_void_p()
             check(L.dir_embed_bwd_sorted(ptr(ws), n, _lib.ctypes.byref(skeys), _lib.ctypes.byref(spos)),

@@ -219,6 +219,13 @@ int dir_shard_keys(const int64_t* feature_index, const float* feature_value,
 int dir_shard_bag_keys(const int64_t* bag_offsets, const int64_t* bag_index, const float* bag_weight, int64_t nnz,
                        const int64_t* field_offset, const int64_t* field_rows, int64_t n_rows, int64_t B, int F,
                        int G, uint32_t* keys, int* oob_flag, dir_stream_t stream);
+/* dir_shard_keys followed by dir_embed_bwd_sort on the same stream, as one call: the key kernel counts the sort's
+ * first digit while the keys are in registers (one pass over the keys and one launch less).  `keys` is still
+ * written (the sort's first pass reads it); workspace as for dir_embed_bwd_sort with n_lookups = B * n_sel. */
+int dir_shard_keys_sort(const int64_t* feature_index, const float* feature_value, const int64_t* field_offset,
+                        const int64_t* field_rows, int64_t n_rows, int64_t B, int F, int G,
+                        const int32_t* field_sel, int n_sel, uint32_t* keys, int* oob_flag, void* workspace,
+                        size_t workspace_bytes, dir_stream_t stream);
 size_t dir_shard_unique_workspace_bytes(int64_t n_lookups);
 int dir_shard_unique(const uint32_t* sorted_keys, const uint32_t* sorted_pos, int64_t n_lookups,
                      int64_t n_rows, int G, const int32_t* field_sel, int n_sel, int F, uint32_t* uidx,

@@ -278,3 +278,64 @@ def test_two_forwards_before_the_first_backward(pkg, cuda):
     r1, l1 = run(True)
     r2, l2 = run(False)
     assert torch.equal(r1, r2) and torch.equal(l1, l2)
+
+
+def _sorted_lists(ws, n):
+    from dir_b200 import _lib
+    sk, sp = _lib.c_void_p(), _lib.c_void_p()
+    _lib.check(_lib.lib().dir_embed_bwd_sorted(ws.data_ptr(), n, _lib.ctypes.byref(sk), _lib.ctypes.byref(sp)), "sorted")
+    off_k, off_p = sk.value - ws.data_ptr(), sp.value - ws.data_ptr()
+    return (ws[off_k:off_k + 4 * n].view(torch.int32).clone(), ws[off_p:off_p + 4 * n].view(torch.int32).clone())
+
+
+@pytest.mark.parametrize("B,rows", [(200, [9, 1, 30]), (5000, [50, 1, 9, 1000, 3, 17, 1]), (20000, [2000] * 28 + [1, 7])])
+def test_fused_keys_sort_equals_the_two_calls(pkg, cuda, B, rows):
+    """dir_shard_keys_sort = dir_shard_keys + dir_embed_bwd_sort, bit for bit (keys, sorted keys, sorted positions);
+    with and without a field selection; the sorted list is the stable sort of the keys."""
+    from dir_b200 import _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    case = make_case(17, B, rows, 8, weighted=True, prune=True, skew=2.0)
+    F, N = len(rows), case["N"]
+    d_idx, d_val = to_dev(case["idx"]), to_dev(case["val"])
+    fo, fr = to_dev(case["off"].astype(np.int64)), to_dev(np.asarray(rows, np.int64))
+    sel_fields = [f for f, r in enumerate(rows) if r > 1]
+    for sel in (None, to_dev(np.asarray(sel_fields, np.int32))):
+        n_sel = F if sel is None else len(sel_fields)
+        n = B * n_sel
+        sp = None if sel is None else sel.data_ptr()
+        nbytes = int(L.dir_embed_bwd_workspace_bytes(n, 8))
+        k1 = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws1 = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(L.dir_shard_keys(d_idx.data_ptr(), d_val.data_ptr(), fo.data_ptr(), fr.data_ptr(), N, B, F, 1, sp,
+                                    n_sel, k1.data_ptr(), None, st), "keys")
+        _lib.check(L.dir_embed_bwd_sort(k1.data_ptr(), n, N, ws1.data_ptr(), nbytes, st), "sort")
+        k2 = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws2 = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(L.dir_shard_keys_sort(d_idx.data_ptr(), d_val.data_ptr(), fo.data_ptr(), fr.data_ptr(), N, B, F, 1, sp,
+                                         n_sel, k2.data_ptr(), None, ws2.data_ptr(), nbytes, st), "keys_sort")
+        torch.cuda.synchronize()
+        assert torch.equal(k1, k2)
+        (sk1, sp1), (sk2, sp2) = _sorted_lists(ws1, n), _sorted_lists(ws2, n)
+        assert torch.equal(sk1, sk2) and torch.equal(sp1, sp2)
+        want_k, want_p = torch.sort(k1.to(torch.int64) & 0xffffffff, stable=True)
+        assert torch.equal(sk2.to(torch.int64) & 0xffffffff, want_k) and torch.equal(sp2.to(torch.int64), want_p)
+
+
+def test_sort_of_nine_million_pairs(pkg, cuda):
+    """More tiles than one round of the per-digit row scan covers (256 x 16 tiles = 8.4 M pairs), 30-bit keys."""
+    from dir_b200 import _lib
+    L = _lib.lib()
+    n, n_rows = 9_000_011, (1 << 30) - 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    keys64 = torch.randint(0, n_rows + 1, (n,), generator=g, device="cuda", dtype=torch.int64)
+    keys64[::7] = keys64[3]                                   # a long run of one key across many tiles
+    keys = (keys64 & 0xffffffff).to(torch.int32)
+    nbytes = int(L.dir_embed_bwd_workspace_bytes(n, 8))
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(L.dir_embed_bwd_sort(keys.data_ptr(), n, n_rows, ws.data_ptr(), nbytes,
+                                    torch.cuda.current_stream().cuda_stream), "sort")
+    torch.cuda.synchronize()
+    sk, sp = _sorted_lists(ws, n)
+    want_k, want_p = torch.sort(keys64, stable=True)
+    assert torch.equal(sk.to(torch.int64) & 0xffffffff, want_k) and torch.equal(sp.to(torch.int64), want_p)
