@@ -124,7 +124,7 @@ radix_rowscan_kernel(uint32_t* __restrict__ hist, int64_t tiles, uint32_t* __res
 // FIRST: the values are the indices themselves (vin unused).  next_hist != NULL: count digit (shift + 8) of every
 // pair into the tile it lands in.
 template <bool FIRST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin, int64_t n, int shift,
                      int64_t tiles, const uint32_t* __restrict__ hist, uint32_t* __restrict__ kout,
                      uint32_t* __restrict__ vout, uint32_t* __restrict__ next_hist,
@@ -136,22 +136,27 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
   __shared__ uint32_t s_key[kRadixTile], s_val[kRadixTile];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int d = lane; d < 256; d += 32) wcount[w][d] = 0u;
-  // hot rows in this batch?  Then equal keys sit next to each other below and their counter updates are combined.
-  const bool skewed = __syncthreads_or(next_hist != nullptr && __ldg(skew + threadIdx.x) != 0u) != 0;
-  {  // digit d starts after all pairs of smaller digits (scan of the 256 row totals) + this digit's earlier tiles
-    uint32_t tot;
-    const uint32_t digit_base = block_excl_scan256(__ldg(hist + 256 * tiles + threadIdx.x), s_warp, &tot);
-    gbase[threadIdx.x] = digit_base + __ldg(hist + (int64_t)threadIdx.x * tiles + blockIdx.x);
-  }
-  // warp w owns pairs [w * R * 32, (w + 1) * R * 32) of the tile, R = kRadixRounds, round r = 32 consecutive pairs
+  // warp w owns pairs [w * R * 32, (w + 1) * R * 32) of the tile, R = kRadixRounds, round r = 32 consecutive pairs.
+  // Every global load of the tile is issued up front (one round trip to L2 instead of three behind barriers).
   const int64_t tbase = (int64_t)blockIdx.x * kRadixTile;
   const int64_t wbase = tbase + (int64_t)w * kRadixRounds * 32;
-  uint32_t key[kRadixRounds], rank[kRadixRounds];
+  uint32_t key[kRadixRounds], val[kRadixRounds], rank[kRadixRounds];
 #pragma unroll
   for (int r = 0; r < kRadixRounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     key[r] = i < n ? __ldg(kin + i) : 0u;
+    val[r] = FIRST ? (uint32_t)i : (i < n ? __ldg(vin + i) : 0u);
+  }
+  const uint32_t row_total = __ldg(hist + 256 * tiles + threadIdx.x);
+  const uint32_t tiles_before = __ldg(hist + (int64_t)threadIdx.x * tiles + blockIdx.x);
+  const bool hot = next_hist != nullptr && __ldg(skew + threadIdx.x) != 0u;
+  for (int d = lane; d < 256; d += 32) wcount[w][d] = 0u;
+  // hot rows in this batch?  Then equal keys sit next to each other below and their counter updates are combined.
+  const bool skewed = __syncthreads_or(hot) != 0;
+  {  // digit d starts after all pairs of smaller digits (scan of the 256 row totals) + this digit's earlier tiles
+    uint32_t tot;
+    const uint32_t digit_base = block_excl_scan256(row_total, s_warp, &tot);
+    gbase[threadIdx.x] = digit_base + tiles_before;
   }
 #pragma unroll
   for (int r = 0; r < kRadixRounds; ++r) {
@@ -192,7 +197,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restric
       const uint32_t d = (key[r] >> shift) & 255u;
       const uint32_t pos = tstart[d] + wcount[w][d] + rank[r];
       s_key[pos] = key[r];
-      s_val[pos] = FIRST ? (uint32_t)i : __ldg(vin + i);
+      s_val[pos] = val[r];
     }
   }
   __syncthreads();
