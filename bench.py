@@ -531,6 +531,7 @@ def run_b200(args):
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         d2h = out_host[0].numel() * 4
         ahead = 2
+        d2h_stream = torch.cuda.Stream()
 
         def e2e_loop(n):
             # Slot cursor % R holds the batch whose id work the previous step already did from the RESIDENT copy
@@ -554,7 +555,15 @@ def run_b200(args):
                     torch.cuda.current_stream().wait_event(feeder.ready[(c0 + s + 1) % R])
                 _, o = run()
                 feeder.release(cur)
-                out_host[s & 1].copy_(o, non_blocking=True)
+                # the logits go home on a stream of their own: on the compute stream the 0.26 MB copy (and its
+                # latency) would sit between two steps; `o` is the slot's static output, rewritten R steps later
+                done = torch.cuda.Event()
+                done.record()
+                d2h_stream.wait_event(done)
+                o.record_stream(d2h_stream)
+                with torch.cuda.stream(d2h_stream):
+                    out_host[s & 1].copy_(o, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(d2h_stream)
             torch.cuda.current_stream().synchronize()
             ready_events.clear()
 
@@ -573,7 +582,7 @@ def run_b200(args):
                        "dir_expand_features" % (len(sp_f), len(de_f)) if args.feed == "columns"
                        else "resolved: feature_index [B,F] int64 + feature_value [B,F] fp32 + labels [B]",
                "how": "%s.presort/forward/backward fed by %s from pinned host memory "
-                      "(ring of %d device slots, H2D on a copy stream), logits read back each step" % (
+                      "(ring of %d device slots, H2D on a copy stream), logits read back each step on a third stream" % (
                           type(layer).__name__, type(feeder).__name__, R)}
         torch.cuda.synchronize()
 
