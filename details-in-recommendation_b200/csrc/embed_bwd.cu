@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(256, MINB) embed_bwd_reduce_kernel(const BwdAr
           if (MODE == kModeGiven) {  // the per-lookup gradient was formed by the requester
             ub[j] = ldg_hint(a.gbuf + (int64_t)p * a.gbuf_stride + sub * 4, pol_once);
           } else {
-            if (a.u) ub[j] = ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
+            // (DIR_B200_TUNE bit 2048: 64-byte L2 fill for one field's slice of u -- measured slower, the neighbouring
+            // field's slice is no longer left in L2 for the warp that wants it)
+            if (a.u) ub[j] = (tune & 2048) ? ldg_hint64(a.u + (int64_t)p * K + sub * 4, pol_once)
+                                           : ldg_hint(a.u + (int64_t)p * K + sub * 4, pol_once);
             Sb[j] = __ldg(reinterpret_cast<const float4*>(a.S + (int64_t)bb * K) + sub);
             if (BAG) {
               T[j] = __ldg(reinterpret_cast<const float4*>(a.emb + (int64_t)p * K) + sub);

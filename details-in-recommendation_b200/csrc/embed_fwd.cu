@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(256) embed_fm_fwd_kernel(const FwdArgs a) {
       w[j] = 0.f;
       if (keep[j]) {
         const float* rp = a.table + row[j] * a.row_stride + sub * 4;
-        t[j] = (a.tune & 4) ? __ldg(reinterpret_cast<const float4*>(rp)) : ldg_hint(rp, pol_once);
+        // DIR_B200_TUNE bit 2048: 64-byte L2 fill (the accumulator half of the line is not wanted here).  Halves the
+        // gather's DRAM bytes and changes nothing: the gather is bound by the rate of random accesses
+        t[j] = (a.tune & 4) ? __ldg(reinterpret_cast<const float4*>(rp))
+                            : ((a.tune & 2048) ? ldg_hint64(rp, pol_once)
+                                               : ldg_hint(rp, (a.tune & 4096) ? pol_keep : pol_once));
         if (a.lin != nullptr && sub == 0) {
           const float* lp = a.lin + row[j] * a.lin_stride;
           w[j] = (a.tune & 1) ? __ldg(lp) : ldg_hint1(lp, pol_keep);

@@ -12,6 +12,41 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 }
 
 // 4 lanes per row (float4 each), 8 rows per warp-load, UNR loads in flight
+// load flavours of the 16-byte row loads: 2..4 = ld.global.nc with an L2 prefetch-size hint
+template <int MODE>
+__device__ __forceinline__ float4 ld_mode(const float4* p) {
+  float4 r;
+  if (MODE == 2)
+    asm volatile("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else if (MODE == 3)
+    asm volatile("ld.global.nc.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else if (MODE == 4)
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else if (MODE == 5)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else
+    r = __ldg(p);
+  return r;
+}
+
+template <int UNR, int MODE>
+__global__ void gather64m(const float* __restrict__ table, int64_t stride, uint32_t n_rows, int64_t n, float* out) {
+  const int lane = threadIdx.x & 31, sub = lane & 3, slot = lane >> 2;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float4 acc = make_float4(0, 0, 0, 0);
+  const int64_t base = warp * 8 * UNR;
+  if (base >= n) return;
+  float4 t[UNR];
+#pragma unroll
+  for (int j = 0; j < UNR; ++j) {
+    const uint32_t r = hash32((uint32_t)(base + j * 8 + slot)) % n_rows;
+    t[j] = ld_mode<MODE>(reinterpret_cast<const float4*>(table + (int64_t)r * stride) + sub);
+  }
+#pragma unroll
+  for (int j = 0; j < UNR; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
+  if (acc.x == 123.456f) out[0] = acc.y + acc.z + acc.w;
+}
+
 template <int UNR, bool NC>
 __global__ void gather64(const float* __restrict__ table, int64_t stride, uint32_t n_rows, int64_t n, float* out) {
   const int lane = threadIdx.x & 31, sub = lane & 3, slot = lane >> 2;
@@ -96,6 +131,14 @@ int main(int argc, char** argv) {
   printf("gather 64B rows, stride 128B (ldg) : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
   us = timeit([&] { gather64<5, false><<<grid, 256>>>(t, 32, N, n, out); });
   printf("gather 64B rows, stride 128B (ld)  : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
+  us = timeit([&] { gather64m<5, 2><<<grid, 256>>>(t, 32, N, n, out); });
+  printf("gather 64B rows, stride 128B (ld.nc.L2::64B)  : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
+  us = timeit([&] { gather64m<5, 3><<<grid, 256>>>(t, 32, N, n, out); });
+  printf("gather 64B rows, stride 128B (ld.nc.L2::128B) : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
+  us = timeit([&] { gather64m<5, 4><<<grid, 256>>>(t, 32, N, n, out); });
+  printf("gather 64B rows, stride 128B (ld.nc.L2::256B) : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
+  us = timeit([&] { gather64m<5, 5><<<grid, 256>>>(t, 32, N, n, out); });
+  printf("gather 64B rows, stride 128B (ld.nc.L1::no_allocate.L2::64B) : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 64.0 / us / 1e3);
   const unsigned g4 = (unsigned)((n / 8 + 255) / 256);
   us = timeit([&] { gather4<8><<<g4, 256>>>(t, 1, N, n, out); });
   printf("gather 4B, stride 4B               : %8.1f us  %7.1f GB/s algorithmic\n", us, n * 4.0 / us / 1e3);
