@@ -44,6 +44,9 @@ def parse_args():
     p.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                    help="cfg4 = Terabyte-sized tables (880 M rows, 113 GB with accumulators): meant for --gpus >= 2")
     p.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    p.add_argument("--strong", action="store_true",
+                   help="strong scaling: the workload's batch is the GLOBAL batch, split over the ranks "
+                        "(default: weak, the batch is per GPU)")
     p.add_argument("--rotate", type=int, default=4, help="distinct input sets cycled through")
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of CUDA graphs")
     p.add_argument("--no-emit", action="store_true", help="FM only: no embeddings out / upstream in")
@@ -60,7 +63,18 @@ def parse_args():
     p.add_argument("--feed", default="columns", choices=["columns", "resolved"],
                    help="e2e host format: one column per feature (the reference's input_fn form) or the [B,F] pair")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
-    return p.parse_args()
+    args = p.parse_args()
+    if args.strong:                        # per-GPU batch = global batch / ranks; everything below sees a per-GPU batch
+        full = args.batch or dir_synth_batch(args.workload)
+        if full % max(args.gpus, 1):
+            p.error("--strong needs the batch to divide by --gpus")
+        args.batch = full // max(args.gpus, 1)
+    return args
+
+
+def dir_synth_batch(name):
+    import dir_b200
+    return dir_b200.synth.cfg(name).batch
 
 
 def workload_config(w, args, n_gpus):
@@ -689,7 +703,7 @@ def run_b200(args):
                     "cuda_graphs": use_graph, "rows_touched_per_step": int(np.mean(n_rows_touched))})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": cfg, "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "roofline": roof, "kernels": kernels,
                 "cpu_baseline": cpu}
