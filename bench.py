@@ -666,6 +666,16 @@ def run_b200(args):
             if rank == 0:
                 print("bench.py: stage trace skipped (%s)" % e, file=sys.stderr)
         layer.trace.on = layer.trace_pre.on = False
+        # The three exchange calls on their own, each replayed from a CUDA graph (no host gaps, nothing else on the
+        # GPU), every rank at the same time so that the NVLink stores meet the traffic they meet in a step.  They run
+        # on the state the last traced step left behind: ids and headers in the exchange buffers, the sorted list in
+        # the handle, the slot map.  (The owner update re-applies the same sums: timing only, after every parity check.)
+        calls_us = None
+        try:
+            calls_us = time_sharded_calls(dir_b200, layer, devs[8 % R], ups[8 % R], B, barrier)
+        except Exception as e:
+            if rank == 0:
+                print("bench.py: sharded call timing skipped (%s)" % e, file=sys.stderr)
         if rank == 0 and stages is not None:
             try:
                 main = serial[0] if serial else stages[0]     # exclusive stage times
@@ -676,16 +686,19 @@ def run_b200(args):
                 # row the (G[K], g1) sums written to its owner
                 nbytes = 4 * B + (B * d * 4 if emit else 0) + B * F * (8 + 4 + 4 * K) + U * row_bytes
                 peak, src = RL.measured_peaks()
-                gbs = nbytes / main[key] * 1e-3
+                t_emit, how = main[key], ("exclusive stage time (CUDA events, rank 0) from an eager, non-overlapped "
+                                          "traced pass after the timed regions: host gaps included")
+                if calls_us and key.endswith("push"):
+                    t_emit, how = calls_us["dir_embed_bwd_reduce_emit_to"], (
+                        "the call replayed from its own CUDA graph, CUDA events, every rank at the same time")
+                gbs = nbytes / t_emit * 1e-3
                 roof = {"bound": "hbm", "kernel": "dir_embed_bwd_reduce_emit_to" if key.endswith("push") else
                         "dir_embed_bwd_reduce_emit", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                         "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % src if src == "measured"
                         else "fallback (B200_PROFILING.md)", "traffic": None, "algorithmic_bytes_per_launch": int(nbytes),
-                        "us_per_launch": main[key],
-                        "how": "exclusive stage time (CUDA events, rank 0) from an eager, non-overlapped traced pass "
-                               "after the timed regions"}
+                        "us_per_launch": t_emit, "how": how}
                 link = U * row_bytes * (world - 1) / world                 # bytes that leave / reach this rank, each way
-                t_fwd = main.get("fwd.gather+send")
+                t_fwd = calls_us["dir_shard_gather_send"] if calls_us else main.get("fwd.gather+send")
                 nvlink = {"bytes_per_direction_per_rank": int(link), "peak": 770.0, "unit": "GB/s",
                           "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
                           "rows_gather_to_gbs": link / t_fwd * 1e-3 if t_fwd else None,
@@ -713,9 +726,85 @@ def run_b200(args):
                                  "serial_main": {k: round(v, 1) for k, v in serial[0].items()},
                                  "serial_id_phase": {k: round(v, 1) for k, v in serial[1].items()}}
             line["nvlink"] = nvlink
+            if calls_us:
+                line["sharded_calls_us"] = {k: round(v, 1) for k, v in calls_us.items()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_sharded_calls(pkg, layer, dev_set, up, B, barrier, iters=20):
+    """CUDA-event time (us, this rank) of dir_shard_gather_send, dir_embed_bwd_reduce_emit_to and
+    dir_shard_owner_update, each replayed from a CUDA graph of its own, on the state of the layer's last step."""
+    import torch
+    from dir_b200._lib import check, ptr
+    from dir_b200.layers import _OPTIMIZERS, linear_opt_struct
+    L = pkg._lib.lib()
+    h = layer._last_handle
+    px, p = layer.px, h.buf
+    idx, val, _ = dev_set
+    F, K = layer.field_size, layer.embedding_size
+    dev = idx.device
+    adagrad = layer.optimizer == "adagrad"
+    S = torch.randn((B, K), device=dev) * 0.1
+    g1 = torch.randn(B, device=dev) * 0.1
+    n = B * layer.n_sel
+    n_keys = layer.plan.cap * layer.plan.world_size
+    ws = h.ws.get(L.dir_embed_bwd_workspace_bytes(max(n, 1), K), dev)
+    nu = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def gather_send(st):
+        check(L.dir_shard_gather_send(px.ref(p), ptr(layer.table), layer.row_stride,
+                                      ptr(layer.w1) if layer.first_order else None, layer.lin_stride,
+                                      ptr(layer.dense_table) if layer.n_dense else None, layer.row_stride,
+                                      ptr(layer.dense_lin) if (layer.n_dense and layer.first_order) else None,
+                                      layer.gather_ctas_per_sm, st), "gather_send")
+
+    def emit_to(st):
+        check(L.dir_embed_bwd_reduce_emit_to(
+            px.ref(p), ptr(val), ptr(g1) if layer.first_order else None, ptr(g1), ptr(S), ptr(up), ptr(h.uidx),
+            ptr(h.owner_off), B, F, n_keys, ptr(layer.sparse_fields) if layer.n_sel < F else None, layer.n_sel,
+            ptr(h.g1_local), ptr(ws), ws.numel(), st), "emit_to")
+
+    def owner_update(st):
+        check(L.dir_shard_owner_update(
+            px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
+            layer.row_stride, ptr(layer.w1) if layer.first_order else None,
+            ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
+            ptr(layer.slot_epoch[p]), _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
+            None, None, None, nu.data_ptr(), st), "owner_update")
+
+    calls = [("dir_shard_gather_send", gather_send), ("dir_embed_bwd_reduce_emit_to", emit_to),
+             ("dir_shard_owner_update", owner_update)]
+    torch.cuda.synchronize()
+    graphs = {}
+    cap = torch.cuda.Stream()
+    cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cap):
+        for name, fn in calls:
+            fn(cap.cuda_stream)                      # eager once
+        cap.synchronize()
+        for name, fn in calls:
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=cap):
+                fn(torch.cuda.current_stream().cuda_stream)
+            graphs[name] = g_
+    torch.cuda.current_stream().wait_stream(cap)
+    torch.cuda.synchronize()
+    out = {}
+    for name, _ in calls:
+        barrier()
+        evs = []
+        for it in range(3 + iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            graphs[name].replay()
+            b.record()
+            if it >= 3:
+                evs.append((a, b))
+        torch.cuda.synchronize()
+        out[name] = 1e3 * sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    return out
 
 
 def time_calls(pkg, RL, layer, cross, devs, ups, w, B, emit, n_unique, iters):
