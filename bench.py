@@ -771,7 +771,7 @@ def time_sharded_calls(pkg, layer, dev_set, up, B, barrier, iters=20):
             px.ref(p), ptr(layer.slot[p]), ptr(layer.table), ptr(layer.accum) if adagrad else None,
             layer.row_stride, ptr(layer.w1) if layer.first_order else None,
             ptr(layer.w1_accum) if layer.first_order else None, layer.lin_stride, layer.n_rows,
-            ptr(layer.slot_epoch[p]), _OPTIMIZERS[layer.optimizer], layer.lr, linear_opt_struct(layer),
+            ptr(layer.slot_epoch[p]), _OPTIMIZERS[layer.optimizer], layer.lr, None, linear_opt_struct(layer),
             None, None, None, nu.data_ptr(), st), "owner_update")
 
     calls = [("dir_shard_gather_send", gather_send), ("dir_embed_bwd_reduce_emit_to", emit_to),

@@ -244,7 +244,7 @@ template <int LPR, int NBUF>
 __global__ void __launch_bounds__(256, LPR <= 4 ? 3 : 1)
 peer_owner_update_kernel(const dir_peer_layout L, const OwnerSrc src, float* table, float* accum,
                          int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride, const LinOpt lo,
-                         int opt, float lr, int64_t n_local, unsigned long long* n_unique) {
+                         const RowRule rule, int64_t n_local, unsigned long long* n_unique) {
   constexpr int SLOTS = 32 / LPR;
   constexpr int PB = LPR <= 4 ? 2 : 1;
   constexpr unsigned FULL = 0xffffffffu;
@@ -260,7 +260,7 @@ peer_owner_update_kernel(const dir_peer_layout L, const OwnerSrc src, float* tab
     tot[b] = s[b].pre[L.G];
   }
   const int64_t total = tot[0] + (NBUF > 1 ? tot[NBUF - 1] : 0);
-  const bool adagrad = opt == DIR_OPT_ADAGRAD;
+  const bool adagrad = rule.opt != DIR_OPT_SGD;  // the rule keeps an accumulator
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, grp = lane / LPR;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -360,10 +360,10 @@ peer_owner_update_kernel(const dir_peer_layout L, const OwnerSrc src, float* tab
             g1[j] = __fadd_rn(g1[j], __ldg(reinterpret_cast<const float*>(src.local[bb] + L.off_g1) + e2));
         }
         const int64_t ro = rr[j] * row_stride;
-        T[j].x = upd(T[j].x, g[j].x, lr, A[j].x, adagrad);
-        T[j].y = upd(T[j].y, g[j].y, lr, A[j].y, adagrad);
-        T[j].z = upd(T[j].z, g[j].z, lr, A[j].z, adagrad);
-        T[j].w = upd(T[j].w, g[j].w, lr, A[j].w, adagrad);
+        T[j].x = upd_rule(T[j].x, g[j].x, A[j].x, rule);
+        T[j].y = upd_rule(T[j].y, g[j].y, A[j].y, rule);
+        T[j].z = upd_rule(T[j].z, g[j].z, A[j].z, rule);
+        T[j].w = upd_rule(T[j].w, g[j].w, A[j].w, rule);
         *(reinterpret_cast<float4*>(table + ro) + sub) = T[j];
         if (adagrad) *(reinterpret_cast<float4*>(accum + ro) + sub) = A[j];
         if (lin != nullptr && sub == 0) {
@@ -385,8 +385,7 @@ struct DenseApplyArgs {
   float* lin;
   float* lin_accum;
   LinOpt lo;  // lo.z: [n_dense]
-  int opt;
-  float lr;
+  RowRule rr;
   float* s_table;  // the sharded table's copy of the row
   float* s_accum;
   int64_t s_row_stride;
@@ -415,12 +414,12 @@ peer_dense_apply_kernel(const dir_peer_layout L, const char* local_b, const Dens
   }
   if (touched == 0.f) return;  // no rank had a surviving lookup: the row is not touched
   const int64_t sr = __ldg(a.shard_row + j);
-  const bool adagrad = a.opt == DIR_OPT_ADAGRAD;
+  const bool adagrad = a.rr.opt != DIR_OPT_SGD;
   if (c < K) {
     float* tp = a.table + (int64_t)j * a.row_stride + c;
     float acc = 0.f;
     if (adagrad) acc = a.accum[(int64_t)j * a.row_stride + c];
-    const float t = upd(*tp, g, a.lr, acc, adagrad);
+    const float t = upd_rule(*tp, g, acc, a.rr);
     *tp = t;
     if (adagrad) a.accum[(int64_t)j * a.row_stride + c] = acc;
     if (sr >= 0) {
@@ -591,7 +590,8 @@ extern "C" int dir_shard_g1_push(const dir_peer_layout* layout, const float* g1_
 extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                                       int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
                                       int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
-                                      const dir_linear_opt* linear_opt, const dir_peer_layout* layout_b,
+                                      const dir_table_opt* table_opt, const dir_linear_opt* linear_opt,
+                                      const dir_peer_layout* layout_b,
                                       const uint32_t* slot_b, const uint32_t* slot_epoch_b, int64_t* n_unique_out,
                                       dir_stream_t stream) {
   using namespace dir;
@@ -603,11 +603,13 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
       return fail(DIR_EINVAL, "shard_owner_update: the second buffer needs its slot map and epoch, the same layout, G <= 32");
   }
   const int K = layout->K;
-  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD)
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD && optimizer != DIR_OPT_PROXIMAL_ADAGRAD)
     return fail(DIR_EINVAL, "shard_owner_update: unknown optimizer");
+  const RowRule rr{optimizer, lr, table_opt ? table_opt->l1 : 0.f, table_opt ? table_opt->l2 : 0.f};
+  if (rr.l1 < 0.f || rr.l2 < 0.f) return fail(DIR_EINVAL, "shard_owner_update: l1, l2 must be >= 0");
   if (!slot || !slot_epoch || !table || n_local_rows <= 0)
     return fail(DIR_EINVAL, "shard_owner_update: slot, slot_epoch, table, n_local_rows > 0 required");
-  if (optimizer == DIR_OPT_ADAGRAD && !accum) return fail(DIR_EINVAL, "shard_owner_update: Adagrad needs accum");
+  if (optimizer != DIR_OPT_SGD && !accum) return fail(DIR_EINVAL, "shard_owner_update: Adagrad needs accum");
   if (row_stride < K || (row_stride & 3) || !aligned16(table) || !aligned16(accum))
     return fail(DIR_EINVAL, "shard_owner_update: rows must be 16-byte aligned, row_stride >= K and a multiple of 4");
   LinOpt lo;
@@ -618,10 +620,10 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
 #define DIR_OU(LP)                                                                                                  \
   if (layout_b)                                                                                                     \
     peer_owner_update_kernel<LP, 2><<<kPeerCtas, 256, 0, st>>>(*layout, src, table, accum, row_stride, lin, lin_accum, \
-                                                               lin_stride, lo, optimizer, lr, n_local_rows, nu);     \
+                                                               lin_stride, lo, rr, n_local_rows, nu);                \
   else                                                                                                              \
     peer_owner_update_kernel<LP, 1><<<kPeerCtas, 256, 0, st>>>(*layout, src, table, accum, row_stride, lin, lin_accum, \
-                                                               lin_stride, lo, optimizer, lr, n_local_rows, nu)
+                                                               lin_stride, lo, rr, n_local_rows, nu)
   switch (K / 4) {
     case 1: DIR_OU(1); break;
     case 2: DIR_OU(2); break;
@@ -635,7 +637,8 @@ extern "C" int dir_shard_owner_update(const dir_peer_layout* layout, const uint3
 
 extern "C" int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
                                      int64_t row_stride, float* dense_lin, float* dense_lin_accum, int optimizer,
-                                     float lr, const dir_linear_opt* linear_opt, float* shard_table,
+                                     float lr, const dir_table_opt* table_opt, const dir_linear_opt* linear_opt,
+                                     float* shard_table,
                                      float* shard_accum, int64_t shard_row_stride, float* shard_lin,
                                      float* shard_lin_accum, float* shard_lin_z, int64_t shard_lin_stride,
                                      const int64_t* shard_row, const dir_peer_layout* layout_b,
@@ -649,15 +652,17 @@ extern "C" int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense
   }
   const char* local_b = layout_b ? layout_b->local : nullptr;
   if (layout->n_dense == 0) return 0;
-  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD) return fail(DIR_EINVAL, "shard_dense_apply: unknown optimizer");
+  if (optimizer != DIR_OPT_SGD && optimizer != DIR_OPT_ADAGRAD && optimizer != DIR_OPT_PROXIMAL_ADAGRAD)
+    return fail(DIR_EINVAL, "shard_dense_apply: unknown optimizer");
+  const RowRule rr{optimizer, lr, table_opt ? table_opt->l1 : 0.f, table_opt ? table_opt->l2 : 0.f};
   if (!dense_table || !shard_row || !shard_table) return fail(DIR_EINVAL, "shard_dense_apply: null pointer");
-  if (optimizer == DIR_OPT_ADAGRAD && (!dense_accum || !shard_accum))
+  if (optimizer != DIR_OPT_SGD && (!dense_accum || !shard_accum))
     return fail(DIR_EINVAL, "shard_dense_apply: Adagrad needs the accumulators");
   LinOpt lo;
   if (int rc = resolve_lin("shard_dense_apply", linear_opt, optimizer, lr, dense_lin, dense_lin_accum, lo)) return rc;
   if (dense_lin && (!shard_lin || (lo.opt != DIR_OPT_SGD && !shard_lin_accum) || (lo.opt == DIR_OPT_FTRL && !shard_lin_z)))
     return fail(DIR_EINVAL, "shard_dense_apply: the sharded copies of the linear state are required");
-  DenseApplyArgs a{dense_table, dense_accum, row_stride, dense_lin, dense_lin_accum, lo, optimizer, lr,
+  DenseApplyArgs a{dense_table, dense_accum, row_stride, dense_lin, dense_lin_accum, lo, rr,
                    shard_table, shard_accum, shard_row_stride, shard_lin, shard_lin_accum, shard_lin_z,
                    shard_lin_stride, shard_row, reinterpret_cast<unsigned long long*>(n_unique_inout)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);

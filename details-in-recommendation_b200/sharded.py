@@ -30,7 +30,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, ptr
-from .layers import (_K_OK, _OPTIMIZERS, _Workspace, _need_cuda, _stream, linear_opt_struct,
+from .layers import (_K_OK, _OPTIMIZERS, _TABLE_OPTIMIZERS, _Workspace, _need_cuda, _stream, linear_opt_struct,
+                     table_opt_struct,
                      resolve_linear_optimizer)
 
 
@@ -384,7 +385,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
                  process_group=None, max_batch: int = 65536, linear_optimizer: Optional[str] = None,
                  linear_lr: Optional[float] = None, l1_regularization_strength: float = 0.0,
                  l2_regularization_strength: float = 0.0, init: str = "trunc_normal", micro_batches: int = 1,
-                 replicate_onerow: bool = True, max_entries: Optional[int] = None, device="cuda"):
+                 replicate_onerow: bool = True, max_entries: Optional[int] = None, optimizer_l1: float = 0.0,
+                 optimizer_l2: float = 0.0, device="cuda"):
         super().__init__()
         if micro_batches not in (1, 2):
             raise ValueError("micro_batches must be 1 or 2")
@@ -394,8 +396,13 @@ class ShardedEmbeddingFM(torch.nn.Module):
         if embedding_size not in _K_OK:
             raise ValueError("embedding_size must be one of %r" % (_K_OK,))
         optimizer = optimizer.lower()
-        if optimizer not in _OPTIMIZERS:
-            raise ValueError("optimizer must be 'adagrad' or 'sgd'")
+        if optimizer not in _TABLE_OPTIMIZERS:
+            raise ValueError("optimizer must be 'adagrad', 'sgd' or 'proximal_adagrad'")
+        self.optimizer_l1, self.optimizer_l2 = float(optimizer_l1), float(optimizer_l2)
+        if self.optimizer_l1 < 0 or self.optimizer_l2 < 0:
+            raise ValueError("optimizer_l1 / optimizer_l2 must be >= 0")
+        if optimizer == "proximal_adagrad" and os.environ.get("DIR_B200_EXCHANGE", "peer") != "peer":
+            raise ValueError("proximal_adagrad needs the peer-memory exchange (DIR_B200_EXCHANGE=peer)")
         if init not in ("trunc_normal", "counter", "none"):
             raise ValueError("init must be 'trunc_normal', 'counter' or 'none'")
         self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
@@ -412,7 +419,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
         self.optimizer, self.lr = optimizer, float(lr)
         self.first_order, self.emit_embeddings, self.check_bounds = first_order, emit_embeddings, check_bounds
         K = embedding_size
-        adagrad = optimizer == "adagrad"
+        adagrad = optimizer != "sgd"                                # the rule keeps an accumulator next to the row
         self.row_stride = 2 * K if adagrad else K
         self.lin_stride = 1
         self.pad_stride = K + 4                                     # NCCL flavour: (row[K], first-order weight, 3 pad)
@@ -497,7 +504,7 @@ class ShardedEmbeddingFM(torch.nn.Module):
 
     @property
     def accum(self):
-        return self.rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+        return self.rows[:, self.embedding_size:] if self.optimizer != "sgd" else None
 
     @property
     def w1(self):
@@ -572,11 +579,14 @@ class ShardedEmbeddingFM(torch.nn.Module):
 
     @property
     def dense_accum(self):
-        return self.dense_rows[:, self.embedding_size:] if self.optimizer == "adagrad" else None
+        return self.dense_rows[:, self.embedding_size:] if self.optimizer != "sgd" else None
 
     def dense_linear_opt(self):
         """dir_linear_opt for the replicas (same rule as the sharded weights, the replicas' own Ftrl slot)."""
         if self.linear_optimizer is None:
+            if self.optimizer == "proximal_adagrad":        # same rule, same strengths as the tables
+                return _lib.ctypes.byref(_lib.LinearOpt(_lib.OPT_PROXIMAL_ADAGRAD, self.lr, self.optimizer_l1,
+                                                        self.optimizer_l2, None))
             return None
         from .layers import _LINEAR_OPTIMIZERS
         z = self.dense_lin_z.data_ptr() if self.dense_lin_z is not None else None
@@ -657,14 +667,15 @@ class ShardedEmbeddingFM(torch.nn.Module):
         h0 = handles[0]
         hb = handles[1] if len(handles) > 1 else None
         p = h0.buf
-        adagrad = self.optimizer == "adagrad"
+        adagrad = self.optimizer != "sgd"
         px.barrier(handles[-1].buf, 0)
         tr.mark("bwd.barrier")
         check(L.dir_shard_owner_update(
             px.ref(p), ptr(self.slot[p]), ptr(self.table), ptr(self.accum) if adagrad else None,
             self.row_stride, ptr(self.w1) if self.first_order else None,
             ptr(self.w1_accum) if self.first_order else None, self.lin_stride, self.n_rows,
-            ptr(self.slot_epoch[p]), _OPTIMIZERS[self.optimizer], self.lr, linear_opt_struct(self),
+            ptr(self.slot_epoch[p]), _TABLE_OPTIMIZERS[self.optimizer], self.lr, table_opt_struct(self),
+            linear_opt_struct(self),
             px.ref(hb.buf) if hb is not None else None, ptr(self.slot[hb.buf]) if hb is not None else None,
             ptr(self.slot_epoch[hb.buf]) if hb is not None else None,
             self._n_unique2.data_ptr() + 8 * h0.parity, st), "dir_shard_owner_update")
@@ -674,8 +685,8 @@ class ShardedEmbeddingFM(torch.nn.Module):
             check(L.dir_shard_dense_apply(
                 px.ref(p), ptr(self.dense_table), ptr(self.dense_accum) if adagrad else None,
                 self.row_stride, ptr(self.dense_lin) if self.first_order else None,
-                ptr(self.dense_lin_acc) if self.first_order else None, _OPTIMIZERS[self.optimizer],
-                self.lr, self.dense_linear_opt(), ptr(self.table), ptr(self.accum) if adagrad else None,
+                ptr(self.dense_lin_acc) if self.first_order else None, _TABLE_OPTIMIZERS[self.optimizer],
+                self.lr, table_opt_struct(self), self.dense_linear_opt(), ptr(self.table), ptr(self.accum) if adagrad else None,
                 self.row_stride, ptr(self.w1) if self.first_order else None,
                 ptr(self.w1_accum) if self.first_order else None,
                 ptr(self.lin_z) if (self.first_order and self.lin_z is not None) else None,

@@ -364,14 +364,16 @@ int dir_shard_dense_emit(const dir_peer_layout* layout, const float* dense_table
 int dir_shard_owner_update(const dir_peer_layout* layout, const uint32_t* slot, float* table, float* accum,
                            int64_t row_stride, float* lin, float* lin_accum, int64_t lin_stride,
                            int64_t n_local_rows, const uint32_t* slot_epoch, int optimizer, float lr,
-                           const dir_linear_opt* linear_opt, const dir_peer_layout* layout_b,
+                           const dir_table_opt* table_opt, const dir_linear_opt* linear_opt,
+                           const dir_peer_layout* layout_b,
                            const uint32_t* slot_b, const uint32_t* slot_epoch_b, int64_t* n_unique_inout,
                            dir_stream_t stream);
 /* shard_row[j] >= 0 names the row of the sharded table that mirrors replica j (on the rank that owns it), so
  * the sharded table stays a faithful view; n_unique_inout += fields touched (pass it on one rank only) */
 int dir_shard_dense_apply(const dir_peer_layout* layout, float* dense_table, float* dense_accum,
                           int64_t row_stride, float* dense_lin, float* dense_lin_accum, int optimizer,
-                          float lr, const dir_linear_opt* linear_opt, float* shard_table, float* shard_accum,
+                          float lr, const dir_table_opt* table_opt, const dir_linear_opt* linear_opt,
+                          float* shard_table, float* shard_accum,
                           int64_t shard_row_stride, float* shard_lin, float* shard_lin_accum,
                           float* shard_lin_z, int64_t shard_lin_stride, const int64_t* shard_row,
                           const dir_peer_layout* layout_b, int64_t* n_unique_inout, dir_stream_t stream);

@@ -117,9 +117,9 @@ def test_argument_validation_of_the_widened_entry_points(pkg):
     assert lib.dir_shard_gather_send(ref, P, 32, None, 1, P, 32, None, 0, None) == -22
     assert lib.dir_shard_g1_push(ref, P, P, 4, None) == -22
     assert lib.dir_shard_owner_update(ref, P, P, P, 32, None, None, 1, 10, P, 1, 0.05, None, None, None, None, None,
-                                      None) == -22
-    assert lib.dir_shard_dense_apply(ref, P, P, 32, None, None, 1, 0.05, None, P, P, 32, None, None, None, 1, P, None,
-                                     None, None) == -22
+                                      None, None) == -22
+    assert lib.dir_shard_dense_apply(ref, P, P, 32, None, None, 1, 0.05, None, None, P, P, 32, None, None, None, 1, P,
+                                     None, None, None) == -22
     assert lib.dir_shard_dense_emit(ref, P, 32, P, None, P, None, P, P, None, P, 4, 3, P, 1 << 20, None) == -22
     with pytest.raises(ValueError):
         _lib.check(lib.dir_embed_bwd_reduce_emit_to(ref, None, None, P, P, None, P, P, 4, 2, 100, None, 0, P, P,

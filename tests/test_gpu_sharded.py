@@ -82,6 +82,41 @@ def test_world1_matches_oracle(pkg, cuda, B, rows, K, optimizer):
     assert [int(e[0]) for e in layer.slot_epoch] == [1, 1]
 
 
+@pytest.mark.parametrize("B,rows,K", [(64, [50, 1, 9, 1000, 3, 17, 1], 16), (1024, [10_000] * 26 + [1] * 13, 8)])
+@pytest.mark.parametrize("l1,l2", [(0.0, 0.0), (0.002, 0.01)])
+def test_world1_proximal_adagrad(pkg, cuda, B, rows, K, l1, l2):
+    """ProximalAdagrad (models/ESMM/train.py:137-139) through the sharded layer: the owner's update and the
+    replicated one-row fields apply [TF] SparseApplyProximalAdagrad to the de-duplicated sums."""
+    case = make_case(37, B, rows, K, weighted=True, prune=True)
+    rng, F = case["rng"], case["F"]
+    g_first = rng.standard_normal(B).astype(np.float32)
+    g_fm = (rng.standard_normal(B) * 0.1).astype(np.float32)
+    u = (rng.standard_normal((B, F, K)) * 0.1).astype(np.float32)
+    layer = pkg.ShardedEmbeddingFM(F, K, [int(r) for r in rows], optimizer="proximal_adagrad", lr=0.05,
+                                   optimizer_l1=l1, optimizer_l2=l2).train()
+    layer.load_tables(case["table"], case["w1"])
+    first, fm, emb = layer(to_dev(case["idx"]), to_dev(case["val"]))
+    loss = (first[:, 0] * to_dev(g_first)).sum() + (fm[:, 0] * to_dev(g_fm)).sum() + (emb * to_dev(u.reshape(B, -1))).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    layer.check_errors()
+    t, w = case["table"].astype(np.float64), case["w1"].astype(np.float64)
+    acc, acc1 = np.full_like(t, 0.1), np.full_like(w, 0.1)
+    urows, G, g1, _ = O.embedding_backward(t, case["off"], case["idx"], case["val"], g_first, g_fm, u, "sum", np.float64)
+    O.sparse_proximal_adagrad(t, acc, urows, G, 0.05, l1, l2)
+    O.sparse_proximal_adagrad(w, acc1, urows, g1, 0.05, l1, l2)
+    got_t, got_w = layer.table.cpu().numpy(), layer.w1.cpu().numpy()
+    untouched = np.ones(case["N"], bool)
+    untouched[urows] = False
+    assert np.array_equal(got_t[untouched], case["table"][untouched])
+    assert rel_err(got_t[urows], t[urows], np.abs(case["table"]).max()) <= REL
+    assert rel_err(got_w[urows], w[urows], np.abs(case["w1"]).max() + 1e-3) <= REL
+    if l1 > 0:      # the shrinkage really acted on some component
+        plain = case["table"].astype(np.float64).copy()
+        O.sparse_proximal_adagrad(plain, np.full_like(plain, 0.1), urows, G, 0.05, 0.0, 0.0)
+        assert np.abs(plain[urows] - t[urows]).max() > 1e-5
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
