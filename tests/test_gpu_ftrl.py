@@ -117,7 +117,7 @@ def test_proximal_adagrad_tables(pkg, cuda, l1, l2):
     assert rel_err(layer.accum.cpu().numpy(), acc, 0.1 + np.abs(acc).max()) <= 2 * REL
     if l1 >= 0.3:
         assert (layer.table.cpu().numpy()[urows] == 0).any(), "a strong l1 must zero some components exactly"
-    with pytest.raises(ValueError):
-        pkg.ShardedEmbeddingFM(F, K, rows, optimizer="proximal_adagrad")
+    with pytest.raises(ValueError):      # (the sharded layer takes the rule too: tests/test_gpu_sharded.py)
+        pkg.ShardedEmbeddingFM(F, K, rows, optimizer="proximal_adagrad", optimizer_l1=-1.0)
     with pytest.raises(ValueError):
         pkg.EmbeddingBagFM(F, K, rows, optimizer="proximal_adagrad")
