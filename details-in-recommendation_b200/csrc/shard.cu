@@ -29,21 +29,23 @@ __global__ void __launch_bounds__(256) shard_keys_kernel(const KeyArgs a, uint32
 //   scan    one CTA: exclusive prefix of the tile counts
 //   number  per tile: block scan of the flags on top of the tile's base -> uidx / ulocal / inv / owner_off
 // (no per-entry prefix array goes through memory, no library scan).
-constexpr int kUTile = 2048;  // 8 warps x 8 rounds of 32 consecutive entries
+constexpr int kURounds = 2;              // rounds of 32 consecutive entries per warp (small tiles: the numbering
+                                        // kernel's scattered inv stores want many warps in flight)
+constexpr int kUTile = 8 * kURounds * 32;  // 8 warps per CTA
 
-// head flags of the 8 rounds of one warp (round r = entries wbase + r * 32 + lane): bit `lane` of heads[r]
+// head flags of the kURounds rounds of one warp (round r = entries wbase + r * 32 + lane): bit `lane` of heads[r]
 __device__ __forceinline__ void warp_head_flags(const uint32_t* __restrict__ keys, int64_t n, uint32_t pruned,
-                                                int64_t wbase, int lane, uint32_t (&k)[8], unsigned (&heads)[8],
+                                                int64_t wbase, int lane, uint32_t (&k)[kURounds], unsigned (&heads)[kURounds],
                                                 uint32_t& kleft) {
   kleft = (wbase > 0 && wbase - 1 < n) ? __ldg(keys + wbase - 1) : 0u;  // (uniform over the warp)
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < kURounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     k[r] = i < n ? __ldg(keys + i) : pruned;
   }
   uint32_t prev_last = kleft;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < kURounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     uint32_t kp = __shfl_up_sync(0xffffffffu, k[r], 1);
     if (lane == 0) kp = prev_last;
@@ -56,13 +58,13 @@ __global__ void __launch_bounds__(256)
 unique_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t pruned, uint32_t* __restrict__ tilecnt) {
   __shared__ uint32_t s_warp[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * 256;
-  uint32_t k[8], kleft;
-  unsigned heads[8];
+  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * (kURounds * 32);
+  uint32_t k[kURounds], kleft;
+  unsigned heads[kURounds];
   warp_head_flags(keys, n, pruned, wbase, lane, k, heads, kleft);
   uint32_t c = 0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) c += (uint32_t)__popc(heads[r]);
+  for (int r = 0; r < kURounds; ++r) c += (uint32_t)__popc(heads[r]);
   if (lane == 0) s_warp[w] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -73,15 +75,24 @@ unique_count_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t prune
   }
 }
 
-// in place: tilecnt[t] <- distinct keys in the tiles before t
+// in place: tilecnt[t] <- distinct keys in the tiles before t.  One CTA; a thread owns up to 16 consecutive tiles, so
+// up to 4 096 tiles (1 M entries) take one block scan.
 __global__ void __launch_bounds__(256) unique_scan_kernel(uint32_t* __restrict__ tilecnt, int64_t tiles) {
   __shared__ uint32_t s_warp[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t per = (tiles + 255) / 256;
+  const int C = (int)(per < 16 ? per : 16);
   uint32_t carry = 0;
-  for (int64_t c0 = 0; c0 < tiles; c0 += 256) {
-    const int64_t i = c0 + threadIdx.x;
-    const uint32_t v = i < tiles ? tilecnt[i] : 0u;
-    uint32_t inc = v;
+  for (int64_t c0 = 0; c0 < tiles; c0 += (int64_t)256 * C) {
+    const int64_t i0 = c0 + (int64_t)threadIdx.x * C;
+    uint32_t v[16];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      v[e] = (e < C && i0 + e < tiles) ? tilecnt[i0 + e] : 0u;
+      sum += v[e];
+    }
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -97,7 +108,14 @@ __global__ void __launch_bounds__(256) unique_scan_kernel(uint32_t* __restrict__
       tot += c;
     }
     __syncthreads();
-    if (i < tiles) tilecnt[i] = carry + base + inc - v;
+    uint32_t run = carry + base + inc - sum;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (e < C && i0 + e < tiles) {
+        tilecnt[i0 + e] = run;
+        run += v[e];
+      }
+    }
     carry += tot;
   }
 }
@@ -113,13 +131,13 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
                     int64_t* __restrict__ inv, int64_t* __restrict__ owner_off) {
   __shared__ uint32_t s_warp[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * 256;
-  uint32_t k[8], kleft;
-  unsigned heads[8];
+  const int64_t wbase = (int64_t)blockIdx.x * kUTile + w * (kURounds * 32);
+  uint32_t k[kURounds], kleft;
+  unsigned heads[kURounds];
   warp_head_flags(keys, n, pruned, wbase, lane, k, heads, kleft);
   uint32_t c = 0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) c += (uint32_t)__popc(heads[r]);
+  for (int r = 0; r < kURounds; ++r) c += (uint32_t)__popc(heads[r]);
   if (lane == 0) s_warp[w] = c;
   __syncthreads();
   uint32_t run = __ldg(tilebase + blockIdx.x);  // distinct keys before this warp's first entry
@@ -128,7 +146,7 @@ shard_number_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
     if (ww < w) run += s_warp[ww];
   uint32_t prev_last = kleft;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < kURounds; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     uint32_t kp = __shfl_up_sync(0xffffffffu, k[r], 1);
     if (lane == 0) kp = prev_last;
