@@ -505,7 +505,7 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     # ---------------- value: device-resident inputs -------------------------------------------
-    for s in range(args.warmup):
+    for s in range(max(3, args.warmup)):           # never fewer than three untimed steps, whatever --warmup says
         run()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
