@@ -964,17 +964,26 @@ keys_count_kernel(const KeyArgs a, uint32_t* __restrict__ keys, int64_t tiles, u
   sh[threadIdx.x] = 0u;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * kRadixTile;
+  // (sample, selected field) of this thread's first entry; a round later the entry is 256 further on: one division
+  // per thread instead of two per key
+  const uint32_t ns = (uint32_t)a.n_sel;
+  uint32_t b = (uint32_t)(base + threadIdx.x) / ns;
+  uint32_t j = (uint32_t)(base + threadIdx.x) - b * ns;
+  const uint32_t db = 256u / ns, dj = 256u - db * ns;
 #pragma unroll
   for (int r = 0; r < kRadixRounds; ++r) {
     const int64_t o = base + r * 256 + threadIdx.x;
-    const bool live = o < a.n;
-    const unsigned act = __ballot_sync(0xffffffffu, live);
-    if (live) {
-      const uint32_t key = make_key(a, o);
+    if (o < a.n) {
+      const uint32_t key = make_key_bj(a, o, b, (int)j);
       keys[o] = key;
-      const uint32_t d = key & 255u;
-      const unsigned peers = __match_any_sync(act, d);  // one atomic per distinct digit of the warp
-      if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&sh[d], (uint32_t)__popc(peers));
+      // plain shared-memory atomics: the input order mixes fields and samples, so lanes rarely meet on a digit
+      atomicAdd(&sh[key & 255u], 1u);
+    }
+    b += db;
+    j += dj;
+    if (j >= ns) {
+      j -= ns;
+      ++b;
     }
   }
   __syncthreads();

@@ -21,12 +21,19 @@ struct KeyArgs {
   int* oob_flag;
 };
 
+// entry o = b * n_sel + j of the key list, with b and j already split
+__device__ __forceinline__ uint32_t make_key_bj(const KeyArgs& a, int64_t o, uint32_t b, int j);
+
 __device__ __forceinline__ uint32_t make_key(const KeyArgs& a, int64_t o) {
-  int f = (int)((uint32_t)o % (uint32_t)a.n_sel);  // n < 2^31
+  const uint32_t b = (uint32_t)o / (uint32_t)a.n_sel;  // n < 2^31
+  return make_key_bj(a, o, b, (int)((uint32_t)o - b * (uint32_t)a.n_sel));
+}
+
+__device__ __forceinline__ uint32_t make_key_bj(const KeyArgs& a, int64_t o, uint32_t b, int j) {
+  int f = j;
   int64_t i = o;
   if (a.field_sel != nullptr) {
-    const uint32_t b = (uint32_t)o / (uint32_t)a.n_sel;
-    f = __ldg(a.field_sel + f);
+    f = __ldg(a.field_sel + j);
     i = (int64_t)b * a.F + f;
   }
   const int64_t id = __ldg(a.idx + i);
