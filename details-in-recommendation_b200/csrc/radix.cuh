@@ -8,7 +8,9 @@
 //   scatter   a tile's pairs ranked stably inside the tile, staged in shared memory in sorted order and written out
 //             in runs (consecutive threads, consecutive addresses inside a digit's run); while writing, the pair's
 //             NEXT digit is counted into the next pass's tile histogram (integer atomics: counts are order-free),
-//             so only the first pass needs a counting kernel of its own
+//             so only the first pass needs a count of its own -- radix_count_kernel, or the kernel that formed the
+//             keys (keys_count_kernel in embed_bwd.cu: dir_shard_keys_sort).  Every global load of a tile is issued
+//             before the first barrier: the kernel runs as one wave, so a tile's latency is the pass's time
 // A tile is kRadixTile consecutive pairs, walked warp by warp in order, 32 consecutive pairs at a time: eight
 // ballots (measured faster here than one __match_any_sync: 27 vs 30 us per pass) give every pair its rank among
 // equal digits of the same 32, a per-warp running count the pairs of

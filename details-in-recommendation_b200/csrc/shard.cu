@@ -1,14 +1,15 @@
-// Row-sharded tables: routing kernels either side of the NCCL all-to-all.
+// Row-sharded tables: the id-only kernels (keys, distinct-row numbering) and the NCCL flavour's row gather.
 //
 // Tables are sharded by row over G ranks (owner = global row mod G, local row = global row div G:
 // modulo, so hot low-numbered rows spread evenly).  The batch stays data-parallel.  Per step a rank
-//   1. dir_shard_keys      forms one composite key per lookup, (owner, local row), owner-major
-//   2. dir_embed_bwd_sort  sorts (key, lookup position)                      [embed_bwd.cu]
-//   3. dir_shard_unique    numbers the distinct keys: only those cross NVLink
-//   4. all-to-all of the distinct local rows; the owner answers with dir_rows_gather
-//   5. dir_embed_fm_fwd    runs on the received unique-row buffer, indexed by `inv`  [embed_fwd.cu]
-//   6. dir_embed_bwd_reduce_emit sums the gradients of each distinct row locally   [embed_bwd.cu]
-//   7. all-to-all of those sums; the owner runs dir_embed_bwd_sort + dir_rows_reduce_update.
+//   1. dir_shard_keys[_sort]  forms one composite key per lookup, (owner, local row), owner-major, and sorts
+//                             (key, lookup position)                                  [keys.cuh, embed_bwd.cu, radix.cuh]
+//   2. dir_shard_unique       numbers the distinct keys: only those cross NVLink
+//   3. the exchange: ids to the owners, rows back, per-distinct-row gradient sums to the owners -- stored
+//      straight into the peers' buffers by the kernels of shard_peer.cu (default), or through NCCL
+//      all-to-all with dir_rows_gather / dir_embed_bwd_reduce_emit / dir_rows_reduce_update (DIR_B200_EXCHANGE=nccl)
+//   4. dir_embed_fm_fwd       runs on the received unique-row buffer, indexed by `inv`  [embed_fwd.cu]
+// Bags (CSR) take dir_shard_bag_keys instead of step 1's key kernel; everything after it is shared.
 // The reference has no counterpart: its only hook is the partitioner wrapped around the embedding
 // variables (models/DeepFM/deepFM.py:163-175), which under a TF parameter-server cluster shards
 // variables by row and ships ids / IndexedSlices over gRPC.
