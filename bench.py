@@ -728,9 +728,11 @@ def run_b200(args):
             line["nvlink"] = nvlink
             if calls_us:
                 line["sharded_calls_us"] = {k: round(v, 1) for k, v in calls_us.items()}
-        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.destroy_process_group()       # first: whatever NCCL still has to say must not follow the JSON line
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def time_sharded_calls(pkg, layer, dev_set, up, B, barrier, iters=20):
