@@ -117,6 +117,54 @@ def test_world1_proximal_adagrad(pkg, cuda, B, rows, K, l1, l2):
         assert np.abs(plain[urows] - t[urows]).max() > 1e-5
 
 
+@pytest.mark.parametrize("n,n_rows,G,sel", [(3_000_017, 1_000_003, 4, False), (70_001, 500, 8, False),
+                                             (26 * 40_000, 10_000_003, 2, True)])
+def test_unique_numbering_against_numpy(pkg, cuda, n, n_rows, G, sel):
+    """dir_shard_unique on its own, at sizes where the scan of the tile counts takes several rounds: uidx, the
+    distinct local rows, inv and owner_off against numpy on the same sorted list (pruned entries included)."""
+    from dir_b200 import _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(51)
+    cap = (n_rows + G - 1) // G
+    pruned = cap * G
+    rows = rng.integers(0, n_rows, size=n)
+    rows[rng.integers(0, n, size=n // 50)] = -1                            # pruned lookups
+    keys = np.where(rows >= 0, (rows % G) * cap + rows // G, pruned).astype(np.int64)
+    order = np.argsort(keys, kind="stable")
+    skeys, spos = keys[order], order.astype(np.int64)
+    F, n_sel = (39, 26) if sel else (1, 1)
+    fsel = np.r_[0:13, 20:33].astype(np.int32) if sel else None                       # 26 of the 39 fields
+    d_k, d_p = to_dev(skeys.astype(np.uint32).view(np.int32)), to_dev(spos.astype(np.uint32).view(np.int32))
+    uidx = torch.empty(n, dtype=torch.int32, device="cuda")
+    ulocal = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    n_pos = (n // n_sel) * F if sel else n
+    inv = torch.full((n_pos,), -5, dtype=torch.int64, device="cuda")
+    owner_off = torch.full((G + 1,), -3, dtype=torch.int64, device="cuda")
+    ws = torch.empty(max(int(L.dir_shard_unique_workspace_bytes(n)), 1), dtype=torch.uint8, device="cuda")
+    d_sel = to_dev(fsel) if sel else None
+    _lib.check(L.dir_shard_unique(d_k.data_ptr(), d_p.data_ptr(), n, n_rows, G, d_sel.data_ptr() if sel else None,
+                                  n_sel, F, uidx.data_ptr(), ulocal.data_ptr(), inv.data_ptr(), owner_off.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), st), "unique")
+    torch.cuda.synchronize()
+    live = skeys != pruned
+    head = live & np.concatenate([[True], skeys[1:] != skeys[:-1]])
+    incl = np.cumsum(head)
+    want_u = np.where(live, incl - 1, 0)
+    assert np.array_equal(uidx.cpu().numpy(), want_u.astype(np.int32))
+    U = int(head.sum())
+    assert np.array_equal(ulocal.cpu().numpy()[:U], (skeys[head] % cap).astype(np.int32))
+    want_off = np.array([int((skeys[head] < g * cap).sum()) for g in range(G + 1)], np.int64)
+    assert np.array_equal(owner_off.cpu().numpy(), want_off)
+    pos = spos
+    if sel:
+        b, j = spos // n_sel, spos % n_sel
+        pos = b * F + fsel[j]
+    want_inv = np.full(n_pos, -5, np.int64)
+    want_inv[pos] = np.where(live, incl - 1, -1)
+    assert np.array_equal(inv.cpu().numpy(), want_inv)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
